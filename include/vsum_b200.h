@@ -1,0 +1,162 @@
+/* vsum_b200 -- C ABI of the B200-native video-summarisation hot path.
+ *
+ * The reference (BerserkerMother/Video-Summarization) is pure Python and has no FFI layer; its
+ * boundary for this path is the Python call surface of `src/model` and `src/evaluation`
+ * (SURVEY.md section 8(b)).  Each entry point below names the reference function it replaces
+ * (file:line relative to the reference root).  INTEGRATION.md shows the ctypes stub a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative VSUM_E* code; the message for the
+ *     calling thread is available from vsum_last_error().  No C++ exceptions cross the ABI.
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`.
+ *   - `stream` is a cudaStream_t passed as void*.  Nothing synchronises the stream.
+ *   - videos are PACKED (no padding): rows of video v are [cu[v], cu[v+1]) of the flat arrays.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef VSUM_B200_H
+#define VSUM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VSUM_API __attribute__((visibility("default")))
+#else
+#define VSUM_API
+#endif
+
+#define VSUM_OK            0
+#define VSUM_EINVAL       -1   /* bad argument / unsupported shape */
+#define VSUM_ECUDA        -2   /* CUDA runtime or driver error */
+#define VSUM_ENOMEM       -3   /* workspace too small / allocation failed */
+#define VSUM_EUNSUPPORTED -4   /* configuration outside what the sm_100a kernels are built for */
+
+#define VSUM_MAX_LAYERS 16
+
+#define VSUM_MODE_FP32 0       /* fp32 SIMT kernels: <=1e-5 vs the reference's fp32 path */
+#define VSUM_MODE_BF16 1       /* bf16 tcgen05/TMEM/TMA kernels (tf32 for the fp32 feature GEMM) */
+
+#define VSUM_FSCORE_AVG 0      /* evaluation_metrics.py:32-33 ('avg', TVSum) */
+#define VSUM_FSCORE_MAX 1      /* evaluation_metrics.py:30-31 ('max', SumMe) */
+
+VSUM_API int         vsum_abi_version(void);
+VSUM_API const char *vsum_last_error(void);
+/* Number of kernels this library has launched from the calling process (bench accounting). */
+VSUM_API int64_t     vsum_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Frame scorer: replaces SimNet.forward (src/model/simnet.py:32-45) and everything under it
+ * (Embedding 208-217, PositionalEncoding 236-238, Encoder 77-83, EncoderBlock 105-114,
+ * MultiAttentionNetwork 138-164, MLP 180-183, final_layer 42) in eval mode, plus the sigmoid
+ * the callers apply (src/train.py:144).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct vsum_scorer *vsum_scorer_t;
+
+typedef struct {
+    int32_t d_model;       /* simnet.py:10 */
+    int32_t num_heads;
+    int32_t num_layers;
+    int32_t d_ff;          /* 4 * d_model (simnet.py:99,175) */
+    int32_t in_features;   /* 1024 (simnet.py:22) */
+    int32_t num_classes;   /* 1 */
+    int32_t use_pos;       /* simnet.py:212 */
+    int32_t reserved;
+} vsum_scorer_config;
+
+/* fp32 device arrays laid out exactly as the reference state_dict tensors (nn.Linear weight is
+ * [out,in] row-major).  pos_table is [pos_rows, d_model] (simnet.py:224-233). */
+typedef struct {
+    const float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *o_w, *o_b;   /* encoder.module_list.i.sa.* */
+    const float *ln1_g, *ln1_b;                                    /* .norm1 */
+    const float *fc1_w, *fc1_b, *fc2_w, *fc2_b;                    /* .mlp.fc1 / .mlp.fc2 */
+    const float *ln2_g, *ln2_b;                                    /* .norm2 */
+} vsum_layer_weights;
+
+typedef struct {
+    const float *embed_w, *embed_b;      /* embedding_layer.feature_transform */
+    const float *pos_table;              /* embedding_layer.positional_encoding.pos_embedding */
+    int32_t      pos_rows;
+    int32_t      reserved;
+    const float *final_w, *final_b;      /* final_layer */
+    vsum_layer_weights layers[VSUM_MAX_LAYERS];
+} vsum_scorer_weights;
+
+VSUM_API int vsum_scorer_create(vsum_scorer_t *out, const vsum_scorer_config *cfg_host);
+VSUM_API int vsum_scorer_destroy(vsum_scorer_t h);
+/* Copies (and for the bf16 path converts/packs) the weights into handle-owned device memory. */
+VSUM_API int vsum_scorer_load_weights(vsum_scorer_t h, const vsum_scorer_weights *w_host, void *stream);
+/* Bytes of scratch vsum_scorer_forward needs for T packed frames in B videos. */
+VSUM_API size_t vsum_scorer_workspace_bytes(vsum_scorer_t h, int64_t T, int32_t B, int32_t mode);
+/* features [T,in_features] fp32, cu_seqlens int32[B+1].  Key masking follows simnet.py:156-157:
+ * with packed videos no key is ever padded.  scores_out [T,num_classes] fp32 logits (or their
+ * sigmoid when apply_sigmoid != 0, src/train.py:144); feats_out [T,d_model] fp32 or NULL
+ * (the second element of SimNet.forward's tuple).  max_len = longest video in the batch. */
+VSUM_API int vsum_scorer_forward(vsum_scorer_t h, const float *features, const int32_t *cu_seqlens,
+                        int32_t B, int64_t T, int32_t max_len, int32_t mode, int32_t apply_sigmoid,
+                        float *scores_out, float *feats_out, void *workspace,
+                        size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Shot pooling: replaces generate_summary.py:25-46 (upsample by picks, per-shot float32 mean in
+ * numpy's pairwise order widened to fp64, shot lengths, 15 % capacity).
+ *   scores int32-indexed by cu_steps[B+1]; picks by cu_picks[B+1]; change points cps[S_total][2]
+ *   (inclusive) by cu_shots[B+1]; n_frames[B].
+ *   Outputs: val_out fp64[S_total], wt_out int32[S_total], cap_out int32[B].
+ * ------------------------------------------------------------------------------------------ */
+VSUM_API int vsum_shot_mean(const float *scores, const int32_t *cu_steps, const int32_t *picks,
+                   const int32_t *cu_picks, const int32_t *n_frames, const int32_t *cps,
+                   const int32_t *cu_shots, int32_t B, int32_t S_total, double *val_out,
+                   int32_t *wt_out, int32_t *cap_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 0/1 knapsack: replaces knapSack (src/evaluation/knapsack_implementation.py:1-30) for B videos
+ * at once, one video per CTA.  fp64 DP row in shared memory, strict-greater decision bits,
+ * back-track from w = capacity; ties go to the lower-indexed shot exactly as line 26 does.
+ *   take_bits: scratch of vsum_knapsack_scratch_words() 32-bit words; bit_offsets int64[B+1]
+ *   are word offsets of each video's S x ceil((cap+1)/32) decision matrix.
+ *   order int32[B] (optional, may be NULL): video processing order (heaviest first).
+ *   selected_out uint8[S_total]: 1 iff the shot is in the summary.
+ * ------------------------------------------------------------------------------------------ */
+VSUM_API int64_t vsum_knapsack_scratch_words(int32_t n_shots, int32_t capacity);
+VSUM_API int vsum_knapsack(const double *val, const int32_t *wt, const int32_t *cu_shots,
+                  const int32_t *cap, const int64_t *bit_offsets, const int32_t *order, int32_t B,
+                  int32_t max_cap, uint32_t *take_bits, uint8_t *selected_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Summary mask + keyshot F-score: replaces generate_summary.py:51-53 and evaluate_summary
+ * (src/evaluation/evaluation_metrics.py:4-33).
+ *   user_summary: float32, video v holds n_users[v] rows of us_cols[v] columns starting at
+ *   element us_offsets[v] (int64[B+1]).  summary_out int8: video v occupies exactly
+ *   [sum_offsets[v], sum_offsets[v+1]) (int64[B+1]), i.e. last_shot_end+1 entries.  With
+ *   selected == NULL, summary_out is an INPUT holding the masks (evaluate_summary on its own).  counts_ws: scratch of 3*sum(n_users) int64.
+ *   f_out fp64[B]; per_user_out fp64[sum(n_users)] or NULL.  cu_users int32[B+1].
+ * ------------------------------------------------------------------------------------------ */
+VSUM_API int vsum_summary_fscore(const uint8_t *selected, const int32_t *cps, const int32_t *cu_shots,
+                        const float *user_summary, const int64_t *us_offsets,
+                        const int32_t *cu_users, const int32_t *us_cols, int32_t B,
+                        int32_t total_users, int32_t method, int8_t *summary_out,
+                        const int64_t *sum_offsets, int64_t summary_total, int64_t *counts_ws,
+                        double *f_out, double *per_user_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Diagnostics: the two tcgen05 kernels on their own, so tests can pin them individually.
+ *   vsum_debug_gemm_tc05: out[M,N] bf16 = epi(A[M,K] W[N,K]^T + bias); A/W bf16, or fp32 when
+ *     a_is_f32 (tf32 MMA).  epi: 0 bias, 1 bias+ReLU, 3 bias+residual+LayerNorm (N == 256).
+ *   vsum_debug_attention_tc05: qkv [T,768] bf16 -> out [T,256] bf16 (4 heads of 64, scale 1/16);
+ *     scratch_i32 holds 2*(T/128+B)+1 int32.
+ * ------------------------------------------------------------------------------------------ */
+VSUM_API int vsum_debug_gemm_tc05(const void *A, const void *W, const float *bias, const void *residual_bf16,
+                         const float *gamma, const float *beta, void *out_bf16, int64_t M, int32_t N,
+                         int32_t K, int32_t a_is_f32, int32_t epi, void *stream);
+VSUM_API int vsum_debug_attention_tc05(const void *qkv_bf16, const int32_t *cu_seqlens, int32_t B, int64_t T,
+                              void *out_bf16, int32_t *scratch_i32, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSUM_B200_H */

@@ -1,0 +1,325 @@
+// Variable-length (packed, padding-free) multi-head self-attention for the scorer on sm_100a.
+// Replaces src/model/simnet.py:155-161 (QK^T * d_model^-0.5 -> softmax -> PV) for d_model 256,
+// 4 heads of 64.  No [N,N] score tensor is ever materialised and nothing is copied to the host
+// (the reference does both, simnet.py:155,164).
+//
+// One CTA = one (video, head, 128-query tile); two CTAs per SM so one CTA's softmax overlaps the
+// other's MMAs.  Roles: warp 0 TMA producer, warp 1 tcgen05.mma issuer, warp 2 TMEM allocator,
+// warps 4..7 softmax (one query row per thread).
+//   S = Q K^T      : A = Q tile (K-major, SW128), B = K tile (K-major, SW128)   -> TMEM [128 x 128] fp32
+//   softmax        : tcgen05.ld S -> registers, online max/sum in the exp2 domain, P -> bf16 ->
+//                    128B-swizzled shared memory (K-major A operand of the second MMA)
+//   O_j = P V_j    : B = V tile as loaded by TMA ([key][head_dim], i.e. MN-major, SW128)
+//                    -> TMEM [128 x 64] fp32, double buffered; accumulated and rescaled in
+//                    registers: O = (O + O_{j-1}) * exp2(m_{j-1} - m_j)
+// Packed layout: a tile may read rows of the next video (or TMA zero fill past T); those key
+// columns are masked to -inf and those query rows are never stored.
+#include "vsum_kernels.cuh"
+#include "vsum_tc05.cuh"
+
+#include <cstdlib>
+
+namespace vsum {
+namespace {
+
+constexpr int HD = 64;                  // head dim
+constexpr int DM = 256;                 // d_model
+constexpr int NH = 4;
+constexpr int BQ = 128, BKV = 128;
+constexpr int TILE_BYTES = 128 * 128;   // 128 rows x 64 bf16 = 16 KB
+constexpr int ATT_THREADS = 256;
+constexpr int ATT_TMEM_COLS = 256;      // S: 128, O0: 64, O1: 64
+constexpr size_t ATT_SMEM = 1024 + 7 * (size_t)TILE_BYTES + 256;   // Q, K0, V0, K1, V1, P(2 halves)
+
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__restrict__ cu,
+                 const int32_t *__restrict__ tile_video, const int32_t *__restrict__ tile_q0,
+                 const int32_t *__restrict__ n_tiles_ptr, __nv_bfloat16 *__restrict__ out,
+                 float scale_log2e, uint32_t v_lbo, uint32_t v_sbo, uint32_t v_kstep) {
+    if ((int)blockIdx.x >= __ldg(n_tiles_ptr)) return;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sQ = smem;
+    uint8_t *sKV = smem + TILE_BYTES;                 // stage s: K at 2s, V at 2s+1 (tiles)
+    uint8_t *sP = smem + 5 * (size_t)TILE_BYTES;      // two 64-key halves, 16 KB each
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 7 * (size_t)TILE_BYTES);
+    uint64_t *q_full = bars, *kv_full = bars + 1, *kv_empty = bars + 3, *s_full = bars + 5,
+             *s_empty = bars + 6, *p_full = bars + 7, *p_empty = bars + 8, *o_full = bars + 9,
+             *o_empty = bars + 11;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 13);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int vid = __ldg(tile_video + blockIdx.x), q0 = __ldg(tile_q0 + blockIdx.x);
+    const int h = blockIdx.y;
+    const int base = __ldg(cu + vid), n = __ldg(cu + vid + 1) - base;
+    const int nkv = (n + BKV - 1) / BKV;
+
+    if (warp == 0 && lane == 0) tc::tma_prefetch_desc(&tmQKV);
+    if (warp == 1 && lane == 0) {
+        tc::mbar_init(q_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(kv_full + s, 1); tc::mbar_init(kv_empty + s, 1);
+            tc::mbar_init(o_full + s, 1); tc::mbar_init(o_empty + s, 128);
+        }
+        tc::mbar_init(s_full, 1); tc::mbar_init(s_empty, 128);
+        tc::mbar_init(p_full, 128); tc::mbar_init(p_empty, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) {
+        tc::tmem_alloc(tmem_slot, ATT_TMEM_COLS);
+        tc::tmem_relinquish();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tS = tmem_base, tO = tmem_base + 128;
+
+    if (warp < 4) {
+        tc::setmaxnreg_dec<40>();
+        if (warp == 0 && lane == 0) {  // ===== TMA producer =====
+            tc::mbar_arrive_expect_tx(q_full, TILE_BYTES);
+            tc::tma_load_2d(sQ, &tmQKV, q_full, h * HD, base + q0);
+            for (int j = 0; j < nkv; ++j) {
+                const int s = j & 1;
+                tc::mbar_wait(kv_empty + s, ((j >> 1) & 1) ^ 1);
+                tc::mbar_arrive_expect_tx(kv_full + s, 2 * TILE_BYTES);
+                tc::tma_load_2d(sKV + (size_t)(2 * s) * TILE_BYTES, &tmQKV, kv_full + s, DM + h * HD, base + j * BKV);
+                tc::tma_load_2d(sKV + (size_t)(2 * s + 1) * TILE_BYTES, &tmQKV, kv_full + s, 2 * DM + h * HD, base + j * BKV);
+            }
+        } else if (warp == 1 && lane == 0) {  // ===== MMA issuer =====
+            constexpr uint32_t IDESC_QK = tc::make_idesc(1, BQ, BKV, 0, 0);   // S[128x128], both K-major
+            constexpr uint32_t IDESC_PV = tc::make_idesc(1, BQ, HD, 0, 1);    // O[128x64], B (=V) MN-major
+            const uint32_t q_addr = tc::smem_u32(sQ), p_addr = tc::smem_u32(sP);
+            auto issue_qk = [&](int j) {
+                const uint32_t k_addr = tc::smem_u32(sKV + (size_t)(2 * (j & 1)) * TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k)
+                    tc::mma_f16_ss(tS, tc::make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                                   tc::make_smem_desc_sw128(k_addr + k * 32, 16, 1024), IDESC_QK, k != 0);
+                tc::mma_commit(s_full);
+            };
+            tc::mbar_wait(q_full, 0);
+            tc::mbar_wait(kv_full + 0, 0);
+            tc::tc_fence_after();
+            issue_qk(0);
+            for (int j = 0; j < nkv; ++j) {
+                if (j + 1 < nkv) {   // S(j+1) as soon as the softmax warps have S(j) in registers
+                    tc::mbar_wait(kv_full + ((j + 1) & 1), ((j + 1) >> 1) & 1);
+                    tc::mbar_wait(s_empty, j & 1);
+                    tc::tc_fence_after();
+                    issue_qk(j + 1);
+                }
+                tc::mbar_wait(p_full, j & 1);
+                tc::mbar_wait(o_empty + (j & 1), ((j >> 1) & 1) ^ 1);
+                tc::tc_fence_after();
+                const uint32_t v_addr = tc::smem_u32(sKV + (size_t)(2 * (j & 1) + 1) * TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BKV / 16; ++k) {
+                    // A: P half (k/4), 32-byte step inside the 128-byte swizzled row
+                    const uint64_t ad = tc::make_smem_desc_sw128(p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024);
+                    // B: V, 16 keys (= 16 rows of 128 bytes) per step
+                    const uint64_t bd = tc::make_smem_desc_sw128(v_addr + k * v_kstep, v_lbo, v_sbo);
+                    tc::mma_f16_ss(tO + (j & 1) * HD, ad, bd, IDESC_PV, k != 0);
+                }
+                tc::mma_commit(kv_empty + (j & 1));
+                tc::mma_commit(p_empty);
+                tc::mma_commit(o_full + (j & 1));
+            }
+        }
+    } else {  // ===== softmax / accumulate / store: one query row per thread =====
+        tc::setmaxnreg_inc<216>();
+        const int qd = warp - 4, r = qd * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        float m_run = -INFINITY, l_run = 0.f;
+        float o[HD];
+#pragma unroll
+        for (int i = 0; i < HD; ++i) o[i] = 0.f;
+        uint8_t *p_row = sP + (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128;
+        const int sw = r & 7;
+
+        for (int j = 0; j < nkv; ++j) {
+            uint32_t s[128];
+            tc::mbar_wait(s_full, j & 1);
+            tc::tc_fence_after();
+            {
+                uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+                uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+                uint32_t(&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
+                uint32_t(&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
+                tc::tmem_ld32(tS + lane_off + 0, s0);
+                tc::tmem_ld32(tS + lane_off + 32, s1);
+                tc::tmem_ld32(tS + lane_off + 64, s2);
+                tc::tmem_ld32(tS + lane_off + 96, s3);
+            }
+            tc::tmem_wait_ld();
+            tc::tc_fence_before();
+            tc::mbar_arrive(s_empty);
+
+            const int valid = n - j * BKV;               // keys of this tile inside the video
+            if (valid < BKV) {
+#pragma unroll
+                for (int c = 0; c < BKV; ++c)
+                    if (c >= valid) s[c] = 0xff800000u;   // -inf
+            }
+            float mx = __uint_as_float(s[0]);
+#pragma unroll
+            for (int c = 1; c < BKV; ++c) mx = fmaxf(mx, __uint_as_float(s[c]));
+            const float m_new = fmaxf(m_run, mx * scale_log2e);       // exp2 domain (scale > 0)
+            const float alpha = ex2(m_run - m_new);                   // 0 on the first tile
+            float psum = 0.f;
+            tc::mbar_wait(p_empty, (j & 1) ^ 1);                      // PV(j-1) has consumed P
+#pragma unroll
+            for (int c = 0; c < BKV; c += 8) {
+                float pv[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    pv[e] = ex2(fmaf(__uint_as_float(s[c + e]), scale_log2e, -m_new));
+                    psum += pv[e];
+                }
+                uint4 pk;
+                pk.x = pack2(pv[0], pv[1]); pk.y = pack2(pv[2], pv[3]);
+                pk.z = pack2(pv[4], pv[5]); pk.w = pack2(pv[6], pv[7]);
+                const int chunk = (c >> 3) & 7, half = c >> 6;
+                *reinterpret_cast<uint4 *>(p_row + (size_t)half * TILE_BYTES + ((chunk ^ sw) << 4)) = pk;
+            }
+            tc::fence_proxy_async_smem();
+            tc::mbar_arrive(p_full);
+
+            if (j > 0) {    // fold in O_{j-1} = P_{j-1} V_{j-1}, then rescale to the new max
+                const int b = (j - 1) & 1;
+                tc::mbar_wait(o_full + b, ((j - 1) >> 1) & 1);
+                tc::tc_fence_after();
+                uint32_t t0[32], t1[32];
+                tc::tmem_ld32(tO + lane_off + b * HD, t0);
+                tc::tmem_ld32(tO + lane_off + b * HD + 32, t1);
+                tc::tmem_wait_ld();
+                tc::tc_fence_before();
+                tc::mbar_arrive(o_empty + b);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    o[i] = (o[i] + __uint_as_float(t0[i])) * alpha;
+                    o[i + 32] = (o[i + 32] + __uint_as_float(t1[i])) * alpha;
+                }
+            }
+            l_run = fmaf(l_run, alpha, psum);
+            m_run = m_new;
+        }
+        {
+            const int b = (nkv - 1) & 1;
+            tc::mbar_wait(o_full + b, ((nkv - 1) >> 1) & 1);
+            tc::tc_fence_after();
+            uint32_t t0[32], t1[32];
+            tc::tmem_ld32(tO + lane_off + b * HD, t0);
+            tc::tmem_ld32(tO + lane_off + b * HD + 32, t1);
+            tc::tmem_wait_ld();
+            const float inv = 1.0f / l_run;
+            if (q0 + r < n) {
+                __nv_bfloat16 *dst = out + (int64_t)(base + q0 + r) * DM + h * HD;
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    uint4 pk;
+                    pk.x = pack2((o[i + 0] + __uint_as_float(t0[i + 0])) * inv, (o[i + 1] + __uint_as_float(t0[i + 1])) * inv);
+                    pk.y = pack2((o[i + 2] + __uint_as_float(t0[i + 2])) * inv, (o[i + 3] + __uint_as_float(t0[i + 3])) * inv);
+                    pk.z = pack2((o[i + 4] + __uint_as_float(t0[i + 4])) * inv, (o[i + 5] + __uint_as_float(t0[i + 5])) * inv);
+                    pk.w = pack2((o[i + 6] + __uint_as_float(t0[i + 6])) * inv, (o[i + 7] + __uint_as_float(t0[i + 7])) * inv);
+                    *reinterpret_cast<uint4 *>(dst + i) = pk;
+                }
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    uint4 pk;
+                    pk.x = pack2((o[32 + i + 0] + __uint_as_float(t1[i + 0])) * inv, (o[32 + i + 1] + __uint_as_float(t1[i + 1])) * inv);
+                    pk.y = pack2((o[32 + i + 2] + __uint_as_float(t1[i + 2])) * inv, (o[32 + i + 3] + __uint_as_float(t1[i + 3])) * inv);
+                    pk.z = pack2((o[32 + i + 4] + __uint_as_float(t1[i + 4])) * inv, (o[32 + i + 5] + __uint_as_float(t1[i + 5])) * inv);
+                    pk.w = pack2((o[32 + i + 6] + __uint_as_float(t1[i + 6])) * inv, (o[32 + i + 7] + __uint_as_float(t1[i + 7])) * inv);
+                    *reinterpret_cast<uint4 *>(dst + 32 + i) = pk;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, ATT_TMEM_COLS);
+    }
+}
+
+// Tile list (video, first query row) for all videos, in input order.  One block.
+__global__ void __launch_bounds__(1024)
+attn_schedule_kernel(const int32_t *__restrict__ cu, int B, int32_t *__restrict__ tile_video,
+                     int32_t *__restrict__ tile_q0, int32_t *__restrict__ n_tiles_out, int max_tiles) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int v0 = 0; v0 < B; v0 += 1024) {
+        const int v = v0 + threadIdx.x;
+        const int cnt = v < B ? (__ldg(cu + v + 1) - __ldg(cu + v) + BQ - 1) / BQ : 0;
+        int x = cnt;                                    // inclusive scan inside the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = x;
+        __syncthreads();
+        int wbase = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += warp_tot[w];
+        const int start = carry + wbase + x - cnt;
+        for (int t = 0; t < cnt; ++t)
+            if (start + t < max_tiles) { tile_video[start + t] = v; tile_q0[start + t] = t * BQ; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = start + cnt;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_tiles_out = min(carry, max_tiles);
+}
+
+}  // namespace
+
+int launch_attn_schedule(const int32_t *cu_seqlens, int B, int32_t *tile_video, int32_t *tile_q0,
+                         int32_t *n_tiles_out, int max_tiles, cudaStream_t s) {
+    attn_schedule_kernel<<<1, 1024, 0, s>>>(cu_seqlens, B, tile_video, tile_q0, n_tiles_out, max_tiles);
+    VSUM_LAUNCH_OK("attn_schedule_kernel");
+    return VSUM_OK;
+}
+
+int launch_attention_tc05(const __nv_bfloat16 *qkv, const int32_t *cu_seqlens, const int32_t *tile_video,
+                          const int32_t *tile_q0, const int32_t *n_tiles_ptr, int max_tiles, int64_t T,
+                          float scale, __nv_bfloat16 *out, cudaStream_t s) {
+    if (T == 0 || max_tiles == 0) return VSUM_OK;
+    CUtensorMap tm;
+    int rc = make_tensor_map_2d(&tm, qkv, 2, 3 * DM, (uint64_t)T, (uint64_t)3 * DM * 2, 64, 128);
+    if (rc) return rc;
+    static bool configured = false;
+    if (!configured) {
+        VSUM_CUDA_OK(cudaFuncSetAttribute(attn_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+        configured = true;
+    }
+    // V operand descriptor (MN-major, 128B swizzle): 8-key groups are 1024 bytes apart (SBO); the
+    // 64-wide head dim is a single swizzle atom so LBO is unused; one MMA K step = 16 keys = 2048 B.
+    uint32_t v_lbo = 16, v_sbo = 1024, v_kstep = 2048;
+    if (const char *e = getenv("VSUM_ATTN_V_DESC")) {   // debugging aid: "lbo,sbo,kstep"
+        unsigned a, b, c;
+        if (sscanf(e, "%u,%u,%u", &a, &b, &c) == 3) { v_lbo = a; v_sbo = b; v_kstep = c; }
+    }
+    dim3 grid((unsigned)max_tiles, NH);
+    attn_tc05_kernel<<<grid, ATT_THREADS, ATT_SMEM, s>>>(tm, cu_seqlens, tile_video, tile_q0, n_tiles_ptr, out,
+                                                         scale * 1.4426950408889634f, v_lbo, v_sbo, v_kstep);
+    VSUM_LAUNCH_OK("attn_tc05_kernel");
+    return VSUM_OK;
+}
+
+}  // namespace vsum

@@ -1,0 +1,58 @@
+// Shared host/device helpers for libvsum_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "vsum_b200.h"
+
+#if defined(__CUDA_ARCH__) && !defined(__CUDA_ARCH_FEAT_SM100_ALL) && (__CUDA_ARCH__ != 1000)
+#error "libvsum_b200 is written for sm_100a only"
+#endif
+
+namespace vsum {
+
+// Thread-local error text returned by vsum_last_error().
+char *error_buffer();
+int set_error(int code, const char *fmt, ...);
+void count_launch(int n = 1);
+
+#define VSUM_CUDA_OK(expr)                                                                      \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return ::vsum::set_error(VSUM_ECUDA, "%s failed: %s (%s:%d)", #expr,                \
+                                     cudaGetErrorString(_e), __FILE__, __LINE__);               \
+    } while (0)
+
+#define VSUM_REQUIRE(cond, code, ...)                                                           \
+    do {                                                                                        \
+        if (!(cond)) return ::vsum::set_error((code), __VA_ARGS__);                             \
+    } while (0)
+
+// Launch check: catches configuration errors at the call site without synchronising.
+#define VSUM_LAUNCH_OK(name)                                                                    \
+    do {                                                                                        \
+        cudaError_t _e = cudaGetLastError();                                                    \
+        if (_e != cudaSuccess)                                                                  \
+            return ::vsum::set_error(VSUM_ECUDA, "launch of %s failed: %s", name,               \
+                                     cudaGetErrorString(_e));                                   \
+        ::vsum::count_launch();                                                                 \
+    } while (0)
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Largest v in [0, n) with cu[v] <= x (cu ascending, cu[0] = 0, x < cu[n]).
+__device__ __forceinline__ int find_segment(const int32_t *__restrict__ cu, int n, int x) {
+    int lo = 0, hi = n;            // invariant: cu[lo] <= x < cu[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(cu + mid) <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+}  // namespace vsum

@@ -1,0 +1,423 @@
+// Evaluation half of the hot path on sm_100a: shot pooling, 0/1 knapsack, summary mask and
+// keyshot F-score.  All integer / fp32 / fp64 arithmetic is ordered exactly as the reference's
+// numpy + Python code orders it, so results are bit-identical given identical scores
+// (DESIGN.md "Bit-exactness").  These stages are latency / shared-memory bound, not GEMMs.
+#include "vsum_common.cuh"
+
+#include <climits>
+
+namespace vsum {
+
+// ---------------------------------------------------------------------------------------------
+// K10  shot pooling  (reference: src/evaluation/generate_summary.py:25-46)
+// ---------------------------------------------------------------------------------------------
+// The reference materialises frame_scores[n_frames] (each sub-sampled score repeated up to the
+// next pick) and calls ndarray.mean() on each shot's slice.  numpy's float32 pairwise summation
+// visits the slice strictly left to right, so one cursor over the pick list reproduces the
+// upsampled sequence without ever writing it to memory.
+struct FrameStream {
+    const float *scores;
+    const int32_t *picks;
+    int n_scores, n_picks, n_pos, n_frames;
+    int f, seg, seg_end;
+    float v;
+
+    __device__ __forceinline__ int pos(int i) const { return i < n_picks ? __ldg(picks + i) : n_frames; }
+    __device__ __forceinline__ void load_segment() {
+        if (seg < 0) { v = 0.0f; seg_end = pos(0); }
+        else if (seg >= n_pos - 1) { v = 0.0f; seg_end = INT_MAX; }       // past the last position
+        else { v = (seg < n_scores) ? __ldg(scores + seg) : 0.0f; seg_end = pos(seg + 1); }  // line 32-33
+    }
+    __device__ void seek(int frame) {
+        f = frame;
+        int lo = -1, hi = n_pos;              // pos(lo) <= frame < pos(hi)
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (pos(mid) <= frame) lo = mid; else hi = mid;
+        }
+        seg = lo;
+        load_segment();
+    }
+    __device__ __forceinline__ float next() {
+        while (f >= seg_end) { ++seg; load_segment(); }
+        ++f;
+        return v;
+    }
+};
+
+// numpy pairwise_sum leaf (n <= 128): 8 accumulators, fixed combine tree, sequential tail.
+__device__ float leaf_sum(FrameStream &st, int n) {
+    if (n < 8) {
+        float r = -0.0f;
+        for (int i = 0; i < n; ++i) r = __fadd_rn(r, st.next());
+        return r;
+    }
+    float r0 = st.next(), r1 = st.next(), r2 = st.next(), r3 = st.next();
+    float r4 = st.next(), r5 = st.next(), r6 = st.next(), r7 = st.next();
+    const int full = n - (n % 8);
+    for (int i = 8; i < full; i += 8) {
+        r0 = __fadd_rn(r0, st.next()); r1 = __fadd_rn(r1, st.next());
+        r2 = __fadd_rn(r2, st.next()); r3 = __fadd_rn(r3, st.next());
+        r4 = __fadd_rn(r4, st.next()); r5 = __fadd_rn(r5, st.next());
+        r6 = __fadd_rn(r6, st.next()); r7 = __fadd_rn(r7, st.next());
+    }
+    float res = __fadd_rn(__fadd_rn(__fadd_rn(r0, r1), __fadd_rn(r2, r3)),
+                          __fadd_rn(__fadd_rn(r4, r5), __fadd_rn(r6, r7)));
+    for (int i = full; i < n; ++i) res = __fadd_rn(res, st.next());
+    return res;
+}
+
+// Full pairwise recursion (split at n/2 rounded down to a multiple of 8) with an explicit stack.
+__device__ float pairwise_sum_stream(FrameStream &st, int n) {
+    float left_val[32];
+    int right_n[32];
+    bool have_left[32];
+    int sp = 0, cur = n;
+    float val;
+    for (;;) {
+        while (cur > 128) {
+            int n2 = cur >> 1;
+            n2 -= n2 & 7;
+            right_n[sp] = cur - n2; have_left[sp] = false; ++sp;
+            cur = n2;
+        }
+        val = leaf_sum(st, cur);
+        bool descend = false;
+        while (sp > 0) {
+            if (!have_left[sp - 1]) {
+                left_val[sp - 1] = val; have_left[sp - 1] = true;
+                cur = right_n[sp - 1];
+                descend = true;
+                break;
+            }
+            val = __fadd_rn(left_val[sp - 1], val);
+            --sp;
+        }
+        if (!descend) return val;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+shot_mean_kernel(const float *__restrict__ scores, const int32_t *__restrict__ cu_steps,
+                 const int32_t *__restrict__ picks, const int32_t *__restrict__ cu_picks,
+                 const int32_t *__restrict__ n_frames, const int32_t *__restrict__ cps,
+                 const int32_t *__restrict__ cu_shots, int B, int S_total,
+                 double *__restrict__ val_out, int32_t *__restrict__ wt_out,
+                 int32_t *__restrict__ cap_out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S_total) return;
+    const int v = find_segment(cu_shots, B, s);
+    const int lo = __ldg(cps + 2 * s), hi = __ldg(cps + 2 * s + 1);
+    wt_out[s] = hi - lo + 1;                                           // line 41
+    if (s == __ldg(cu_shots + v + 1) - 1)                              // line 45-46
+        cap_out[v] = (int32_t)((double)(hi + 1) * 0.15);
+
+    FrameStream st;
+    st.scores = scores + __ldg(cu_steps + v);
+    st.n_scores = __ldg(cu_steps + v + 1) - __ldg(cu_steps + v);
+    st.picks = picks + __ldg(cu_picks + v);
+    st.n_picks = __ldg(cu_picks + v + 1) - __ldg(cu_picks + v);
+    st.n_frames = __ldg(n_frames + v);
+    st.n_pos = st.n_picks + ((st.n_picks == 0 || st.pos(st.n_picks - 1) != st.n_frames) ? 1 : 0);  // line 29-30
+    const int stop = min(hi + 1, st.n_frames);                         // numpy slices clamp
+    const int n = stop - lo;
+    if (n <= 0) { val_out[s] = __longlong_as_double(0x7ff8000000000000LL); return; }
+    st.seek(lo);
+    const float total = __fadd_rn(0.0f, pairwise_sum_stream(st, n));   // add.reduce starts at +0
+    val_out[s] = (double)__fdiv_rn(total, (float)n);                   // float32 mean -> .item()
+}
+
+// ---------------------------------------------------------------------------------------------
+// K11  0/1 knapsack  (reference: src/evaluation/knapsack_implementation.py:11-28)
+// ---------------------------------------------------------------------------------------------
+// One video per CTA.  The fp64 DP row K[i-1][0..W] lives in shared memory; every thread owns
+// EPT capacities, computes K[i][w] for them from the old row into registers, then the row is
+// overwritten (two barriers per shot).  take[i][w] = (K[i][w] != K[i-1][w]) -- the reference's
+// own back-track test -- is packed with a warp ballot into a bit matrix in global memory (it
+// stays in L2), and warp 0 walks it back from w = W, 32 rows per probe.
+template <int THREADS, int EPT>
+__global__ void __launch_bounds__(THREADS, 1)
+knapsack_kernel(const double *__restrict__ val, const int32_t *__restrict__ wt,
+                const int32_t *__restrict__ cu_shots, const int32_t *__restrict__ cap,
+                const int64_t *__restrict__ bit_offsets, const int32_t *__restrict__ order,
+                uint32_t *__restrict__ take_bits, uint8_t *__restrict__ selected_out) {
+    extern __shared__ double row[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int v = order ? __ldg(order + blockIdx.x) : (int)blockIdx.x;
+    const int s0 = __ldg(cu_shots + v), S = __ldg(cu_shots + v + 1) - s0;
+    const int W = __ldg(cap + v);
+    for (int i = tid; i < S; i += THREADS) selected_out[s0 + i] = 0;
+    if (W < 0 || S <= 0) return;
+    const int width = W + 1;
+    const int words = (width + 31) >> 5;
+    uint32_t *bits = take_bits + __ldg(bit_offsets + v);
+    if (width > THREADS * EPT) return;                    // host guarantees this never happens
+    for (int w = tid; w < width; w += THREADS) row[w] = 0.0;            // K[0][*] = 0
+    __syncthreads();
+
+    for (int i = 0; i < S; ++i) {
+        const int wi = __ldg(wt + s0 + i);
+        const double vi = __ldg(val + s0 + i);
+        double nv[EPT];
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            if (k * THREADS >= width) break;                            // block-uniform
+            const int w = k * THREADS + tid;
+            const bool in = w < width;
+            const double b = in ? row[w] : 0.0;                         // K[i-1][w]
+            const bool can = in && w >= 1 && wi >= 0 && wi <= w;        // line 16-18
+            const double a = can ? vi + row[w - wi] : b;
+            const double m = can ? ((b > a) ? b : a) : b;               // Python max(a, b)
+            const bool take = can && (m != b);                          // line 26
+            nv[k] = m;
+            const unsigned word = __ballot_sync(0xffffffffu, take);
+            if (lane == 0 && (w - lane) < width) bits[(int64_t)i * words + (w >> 5)] = word;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            if (k * THREADS >= width) break;
+            const int w = k * THREADS + tid;
+            if (w < width) row[w] = nv[k];
+        }
+        __syncthreads();
+    }
+
+    if (tid < 32) {                                                     // back-track, line 23-28
+        int w = W, i = S;
+        while (i > 0) {
+            const int r = i - 1 - lane;
+            bool bit = false;
+            if (r >= 0) bit = (__ldcg(bits + (int64_t)r * words + (w >> 5)) >> (w & 31)) & 1u;
+            const unsigned m = __ballot_sync(0xffffffffu, bit);
+            if (m == 0) { i -= 32; continue; }
+            const int rsel = i - 1 - (__ffs(m) - 1);                    // highest row that took
+            if (lane == 0) selected_out[s0 + rsel] = 1;
+            w -= __ldg(wt + s0 + rsel);
+            i = rsel;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K12  summary mask + overlap / F-score
+// (reference: generate_summary.py:51-53, evaluation_metrics.py:12-33)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+summary_mask_kernel(const uint8_t *__restrict__ selected, const int32_t *__restrict__ cps,
+                    const int32_t *__restrict__ cu_shots, const int64_t *__restrict__ sum_offsets,
+                    int8_t *__restrict__ summary_out) {
+    const int v = blockIdx.y;
+    const int s0 = __ldg(cu_shots + v), S = __ldg(cu_shots + v + 1) - s0;
+    if (S <= 0) return;
+    const int len = __ldg(cps + 2 * (s0 + S - 1) + 1) + 1;              // line 51
+    int8_t *out = summary_out + __ldg(sum_offsets + v);
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < len; f += gridDim.x * blockDim.x) {
+        // last shot whose start <= f (shots are ascending and disjoint)
+        int lo = 0, hi = S;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (__ldg(cps + 2 * (s0 + mid)) <= f) lo = mid; else hi = mid;
+        }
+        const bool inside = f >= __ldg(cps + 2 * (s0 + lo)) && f <= __ldg(cps + 2 * (s0 + lo) + 1);
+        out[f] = (inside && selected[s0 + lo]) ? 1 : 0;
+    }
+}
+
+__device__ __forceinline__ long long block_sum_i64(long long x, long long *smem) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) smem[warp] = x;
+    __syncthreads();
+    x = (lane < nw) ? smem[lane] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+// One CTA per (video, user) row: o = sum(S & G), g = sum(G), s = sum(S) as int64
+// (evaluation_metrics.py:20-25).  The user row is streamed with 16-byte loads.
+__global__ void __launch_bounds__(256)
+overlap_kernel(const int8_t *__restrict__ summary, const int64_t *__restrict__ sum_offsets,
+               const float *__restrict__ user_summary, const int64_t *__restrict__ us_offsets,
+               const int32_t *__restrict__ cu_users, const int32_t *__restrict__ us_cols, int B,
+               long long *__restrict__ counts) {
+    __shared__ long long red[32];
+    const int rowid = blockIdx.x;
+    const int v = find_segment(cu_users, B, rowid);
+    const int u = rowid - __ldg(cu_users + v);
+    const int cols = __ldg(us_cols + v);
+    const int slen = (int)(__ldg(sum_offsets + v + 1) - __ldg(sum_offsets + v));
+    const int8_t *sm = summary + __ldg(sum_offsets + v);
+    const float *g = user_summary + __ldg(us_offsets + v) + (int64_t)u * cols;
+    long long o_cnt = 0, g_cnt = 0, s_cnt = 0;
+
+    // head (until g is 16-byte aligned), vector body, tail
+    int head = (int)(((16 - ((uintptr_t)g & 15)) & 15) >> 2);
+    if (head > cols) head = cols;
+    const int nvec = (cols - head) >> 2;
+    for (int c = threadIdx.x; c < head; c += blockDim.x) {
+        const long long gi = (long long)__ldg(g + c);
+        const long long si = c < slen ? (long long)sm[c] : 0;
+        o_cnt += si & gi; g_cnt += gi;
+    }
+    const float4 *g4 = reinterpret_cast<const float4 *>(g + head);
+    for (int q = threadIdx.x; q < nvec; q += blockDim.x) {
+        const float4 x = __ldcs(g4 + q);                                // streamed once
+        const int c = head + 4 * q;
+        const long long g0 = (long long)x.x, g1 = (long long)x.y, g2 = (long long)x.z, g3 = (long long)x.w;
+        g_cnt += g0 + g1 + g2 + g3;
+        if (c + 3 < slen) {
+            o_cnt += ((long long)sm[c] & g0) + ((long long)sm[c + 1] & g1) +
+                     ((long long)sm[c + 2] & g2) + ((long long)sm[c + 3] & g3);
+        } else {
+            if (c < slen) o_cnt += (long long)sm[c] & g0;
+            if (c + 1 < slen) o_cnt += (long long)sm[c + 1] & g1;
+            if (c + 2 < slen) o_cnt += (long long)sm[c + 2] & g2;
+            if (c + 3 < slen) o_cnt += (long long)sm[c + 3] & g3;
+        }
+    }
+    for (int c = head + 4 * nvec + threadIdx.x; c < cols; c += blockDim.x) {
+        const long long gi = (long long)__ldg(g + c);
+        const long long si = c < slen ? (long long)sm[c] : 0;
+        o_cnt += si & gi; g_cnt += gi;
+    }
+    for (int c = threadIdx.x; c < slen; c += blockDim.x) s_cnt += (long long)sm[c];
+
+    o_cnt = block_sum_i64(o_cnt, red);
+    g_cnt = block_sum_i64(g_cnt, red);
+    s_cnt = block_sum_i64(s_cnt, red);
+    if (threadIdx.x == 0) {
+        counts[3 * (int64_t)rowid + 0] = o_cnt;
+        counts[3 * (int64_t)rowid + 1] = g_cnt;
+        counts[3 * (int64_t)rowid + 2] = s_cnt;
+    }
+}
+
+// fp64 ratios in the reference's evaluation order (evaluation_metrics.py:23-33).
+__global__ void __launch_bounds__(128)
+fscore_finalize_kernel(const long long *__restrict__ counts, const int32_t *__restrict__ cu_users,
+                       int B, int method, double *__restrict__ f_out,
+                       double *__restrict__ per_user_out) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= B) return;
+    const int u0 = __ldg(cu_users + v), U = __ldg(cu_users + v + 1) - u0;
+    double acc = 0.0, best = 0.0;
+    for (int u = 0; u < U; ++u) {
+        const long long o = counts[3 * (int64_t)(u0 + u)], g = counts[3 * (int64_t)(u0 + u) + 1],
+                        s = counts[3 * (int64_t)(u0 + u) + 2];
+        const double p = __ddiv_rn((double)o, (double)s);                // 0/0 -> NaN like numpy
+        const double r = __ddiv_rn((double)o, (double)g);
+        double f;
+        if (__dadd_rn(p, r) == 0.0) f = 0.0;
+        else f = __ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, p), r), 100.0), __dadd_rn(p, r));
+        if (per_user_out) per_user_out[u0 + u] = f;
+        if (u == 0) { best = f; acc = __dadd_rn(0.0, f); }
+        else { if (f > best) best = f; acc = __dadd_rn(acc, f); }
+    }
+    f_out[v] = U == 0 ? __longlong_as_double(0x7ff8000000000000LL)
+                      : (method == VSUM_FSCORE_MAX ? best : __ddiv_rn(acc, (double)U));
+}
+
+}  // namespace vsum
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace vsum;
+
+extern "C" int vsum_shot_mean(const float *scores, const int32_t *cu_steps, const int32_t *picks,
+                              const int32_t *cu_picks, const int32_t *n_frames, const int32_t *cps,
+                              const int32_t *cu_shots, int32_t B, int32_t S_total, double *val_out,
+                              int32_t *wt_out, int32_t *cap_out, void *stream) {
+    VSUM_REQUIRE(B >= 0 && S_total >= 0, VSUM_EINVAL, "vsum_shot_mean: negative sizes");
+    if (B == 0 || S_total == 0) return VSUM_OK;
+    VSUM_REQUIRE(scores && cu_steps && picks && cu_picks && n_frames && cps && cu_shots && val_out &&
+                 wt_out && cap_out, VSUM_EINVAL, "vsum_shot_mean: null pointer");
+    const int threads = 128;
+    shot_mean_kernel<<<(unsigned)ceil_div(S_total, threads), threads, 0, (cudaStream_t)stream>>>(
+        scores, cu_steps, picks, cu_picks, n_frames, cps, cu_shots, B, S_total, val_out, wt_out,
+        cap_out);
+    VSUM_LAUNCH_OK("shot_mean_kernel");
+    return VSUM_OK;
+}
+
+extern "C" int64_t vsum_knapsack_scratch_words(int32_t n_shots, int32_t capacity) {
+    if (n_shots <= 0 || capacity < 0) return 0;
+    return (int64_t)n_shots * (((int64_t)capacity + 1 + 31) >> 5);
+}
+
+template <int THREADS, int EPT>
+static int launch_knapsack(const double *val, const int32_t *wt, const int32_t *cu_shots,
+                           const int32_t *cap, const int64_t *bit_offsets, const int32_t *order,
+                           int32_t B, int32_t max_cap, uint32_t *take_bits, uint8_t *selected_out,
+                           cudaStream_t stream) {
+    const size_t smem = (size_t)(max_cap + 1) * sizeof(double);
+    auto kern = knapsack_kernel<THREADS, EPT>;
+    if (smem > 48 * 1024)
+        VSUM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<B, THREADS, smem, stream>>>(val, wt, cu_shots, cap, bit_offsets, order, take_bits, selected_out);
+    VSUM_LAUNCH_OK("knapsack_kernel");
+    return VSUM_OK;
+}
+
+extern "C" int vsum_knapsack(const double *val, const int32_t *wt, const int32_t *cu_shots,
+                             const int32_t *cap, const int64_t *bit_offsets, const int32_t *order,
+                             int32_t B, int32_t max_cap, uint32_t *take_bits,
+                             uint8_t *selected_out, void *stream) {
+    VSUM_REQUIRE(B >= 0 && max_cap >= 0, VSUM_EINVAL, "vsum_knapsack: negative sizes");
+    if (B == 0) return VSUM_OK;
+    VSUM_REQUIRE(val && wt && cu_shots && cap && bit_offsets && take_bits && selected_out, VSUM_EINVAL,
+                 "vsum_knapsack: null pointer");
+    const int width = max_cap + 1;
+    cudaStream_t s = (cudaStream_t)stream;
+#define VSUM_KS(T, E) return launch_knapsack<T, E>(val, wt, cu_shots, cap, bit_offsets, order, B, max_cap, take_bits, selected_out, s)
+    if (width <= 256) VSUM_KS(256, 1);
+    if (width <= 1024) VSUM_KS(512, 2);
+    if (width <= 4096) VSUM_KS(1024, 4);
+    if (width <= 8192) VSUM_KS(1024, 8);
+    if (width <= 14336) VSUM_KS(1024, 14);
+    if (width <= 28672) VSUM_KS(512, 56);
+#undef VSUM_KS
+    return set_error(VSUM_EUNSUPPORTED,
+                     "vsum_knapsack: capacity %d needs %zu B of shared memory for the fp64 DP row; "
+                     "the sm_100a kernel holds at most 28672 capacities (n_frames <= 191146)",
+                     max_cap, (size_t)width * 8);
+}
+
+extern "C" int vsum_summary_fscore(const uint8_t *selected, const int32_t *cps,
+                                   const int32_t *cu_shots, const float *user_summary,
+                                   const int64_t *us_offsets, const int32_t *cu_users,
+                                   const int32_t *us_cols, int32_t B, int32_t total_users,
+                                   int32_t method, int8_t *summary_out, const int64_t *sum_offsets,
+                                   int64_t summary_total, int64_t *counts_ws, double *f_out,
+                                   double *per_user_out, void *stream) {
+    VSUM_REQUIRE(B >= 0 && total_users >= 0, VSUM_EINVAL, "vsum_summary_fscore: negative sizes");
+    if (B == 0) return VSUM_OK;
+    VSUM_REQUIRE(summary_out && sum_offsets && (!selected || (cps && cu_shots)), VSUM_EINVAL,
+                 "vsum_summary_fscore: null pointer");
+    VSUM_REQUIRE(method == VSUM_FSCORE_AVG || method == VSUM_FSCORE_MAX, VSUM_EINVAL,
+                 "vsum_summary_fscore: method must be VSUM_FSCORE_AVG or VSUM_FSCORE_MAX");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (selected) {   // selected == NULL: summary_out already holds the masks (evaluate_summary)
+        const int64_t avg = summary_total / B + 1;
+        dim3 grid((unsigned)max((int64_t)1, min((int64_t)64, ceil_div(avg, 256 * 4))), (unsigned)B);
+        summary_mask_kernel<<<grid, 256, 0, s>>>(selected, cps, cu_shots, sum_offsets, summary_out);
+        VSUM_LAUNCH_OK("summary_mask_kernel");
+    }
+    if (!f_out) return VSUM_OK;                                          // generate_summary only
+    VSUM_REQUIRE(user_summary && us_offsets && cu_users && us_cols && counts_ws, VSUM_EINVAL,
+                 "vsum_summary_fscore: null pointer");
+    if (total_users > 0) {
+        overlap_kernel<<<total_users, 256, 0, s>>>(summary_out, sum_offsets, user_summary,
+                                                   us_offsets, cu_users, us_cols, B,
+                                                   reinterpret_cast<long long *>(counts_ws));
+        VSUM_LAUNCH_OK("overlap_kernel");
+    }
+    fscore_finalize_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, s>>>(
+        reinterpret_cast<const long long *>(counts_ws), cu_users, B, method, f_out, per_user_out);
+    VSUM_LAUNCH_OK("fscore_finalize_kernel");
+    return VSUM_OK;
+}

@@ -1,0 +1,379 @@
+// Per-frame GEMMs of the scorer on the 5th-gen tensor cores (sm_100a):
+//   C[M,N] = epilogue(A[M,K] * W[N,K]^T + bias)
+// A (activations, K contiguous) and W (nn.Linear weight [out,in], K contiguous) are both K-major,
+// staged by TMA into 128B-swizzled shared memory, multiplied by tcgen05.mma (M=128, N=256,
+// fp32 accumulators in TMEM, two accumulator stages), and drained by four epilogue warps with
+// tcgen05.ld while the next tile's MMAs run.  Warp roles: 0 = TMA producer, 1 = MMA issuer,
+// 2 = TMEM allocator, 4..7 = epilogue (one output row per thread, so LayerNorm needs no shuffles).
+//
+// Replaces (reference src/model/simnet.py): Embedding.feature_transform + positional add
+// (211, 236-238) [tf32 MMA straight from the fp32 features], q/k/v Linears (148-153, one packed
+// [768,256] weight), feature_projection + residual + norm1 (163, 107), fc1 + ReLU (181),
+// fc2 + residual + norm2 (182, 110) and final_layer (+ sigmoid, train.py:144) fused into the
+// last norm2 epilogue.
+#include "vsum_kernels.cuh"
+#include "vsum_tc05.cuh"
+
+namespace vsum {
+
+// ------------------------------------------------------------------ tensor maps (host)
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+int make_tensor_map_2d(CUtensorMap *out, const void *base, int elt_bytes, uint64_t inner, uint64_t rows,
+                       uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode_fn();
+    VSUM_REQUIRE(enc != nullptr, VSUM_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    VSUM_REQUIRE(box_inner * elt_bytes == 128, VSUM_EINVAL, "tensor map: box rows must be 128 bytes");
+    VSUM_REQUIRE(((uintptr_t)base & 15) == 0 && (row_stride_bytes & 15) == 0, VSUM_EINVAL,
+                 "tensor map: base and row stride must be 16-byte aligned");
+    cuuint64_t dims[2] = {inner, rows};
+    cuuint64_t strides[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {box_inner, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMapDataType dt = elt_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUresult r = enc(out, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VSUM_REQUIRE(r == CUDA_SUCCESS, VSUM_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return VSUM_OK;
+}
+
+namespace {
+
+constexpr int BM = 128;                 // rows per tile (UMMA M)
+constexpr int BN = 256;                 // columns per tile (UMMA N) -- one full d_model row
+constexpr int STAGES = 4;
+constexpr int A_STAGE = BM * 128;       // 16 KB: 128 rows x 128 B
+constexpr int B_STAGE = BN * 128;       // 32 KB
+constexpr int GEMM_THREADS = 256;
+constexpr int TMEM_COLS = 512;          // 2 accumulator stages x 256 fp32 columns
+constexpr int WRES_MAX_KB = 4;          // weight-stationary variant: K = 256 bf16 -> 4 k-blocks = 128 KB
+constexpr size_t GEMM_SMEM = 1024 /*align*/ + (size_t)STAGES * (A_STAGE + B_STAGE) + 256 /*barriers*/;
+
+struct GemmParams {
+    int64_t M;
+    int N, num_kb, n_tiles;
+    int64_t m_tiles;
+    const float *bias;
+    __nv_bfloat16 *out;
+    const __nv_bfloat16 *residual;
+    const float *gamma, *beta;
+    const float *pos_table;
+    const int32_t *row_pos;
+    int pos_rows;
+    const float *head_w, *head_b;
+    float *scores_out, *feats_out;
+    int apply_sigmoid;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+template <bool TF32, int EPI, bool WRES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // non-WRES: stage s = {A: s*48K, B: s*48K + 16K}.  WRES: W k-blocks at kb*32K, A ring after 128K.
+    uint8_t *ring = smem;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * (A_STAGE + B_STAGE));
+    uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = tfull + 2;
+    uint64_t *wfull = tempty + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(wfull + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int KELTS = TF32 ? 32 : 64;          // elements per 128-byte k-block
+    constexpr uint32_t IDESC = tc::make_idesc(TF32 ? 2 : 1, BM, BN, 0, 0);
+
+    auto a_stage = [&](int s) -> uint8_t * {
+        return WRES ? ring + (size_t)WRES_MAX_KB * B_STAGE + (size_t)s * A_STAGE : ring + (size_t)s * (A_STAGE + B_STAGE);
+    };
+    auto b_stage = [&](int s) -> uint8_t * { return ring + (size_t)s * (A_STAGE + B_STAGE) + A_STAGE; };
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmA);
+        tc::tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); }
+        for (int a = 0; a < 2; ++a) { tc::mbar_init(tfull + a, 1); tc::mbar_init(tempty + a, 128); }
+        tc::mbar_init(wfull, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) {
+        tc::tmem_alloc(tmem_slot, TMEM_COLS);
+        tc::tmem_relinquish();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile walk shared by all roles
+    const int64_t total = WRES ? p.m_tiles : p.m_tiles * p.n_tiles;
+    const int64_t first = blockIdx.x, step = gridDim.x;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer =====
+            if (WRES) {
+                tc::mbar_arrive_expect_tx(wfull, (uint32_t)p.num_kb * B_STAGE);
+                for (int kb = 0; kb < p.num_kb; ++kb)
+                    tc::tma_load_2d(ring + (size_t)kb * B_STAGE, &tmB, wfull, kb * KELTS, (int)blockIdx.y * BN);
+            }
+            uint32_t it = 0;
+            for (int64_t t = first; t < total; t += step) {
+                const int64_t m_blk = WRES ? t : t / p.n_tiles;
+                const int n_blk = WRES ? (int)blockIdx.y : (int)(t % p.n_tiles);
+                for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    tc::mbar_wait(empty + s, ph ^ 1);
+                    tc::mbar_arrive_expect_tx(full + s, WRES ? A_STAGE : A_STAGE + B_STAGE);
+                    tc::tma_load_2d(a_stage(s), &tmA, full + s, kb * KELTS, (int)(m_blk * BM));
+                    if (!WRES) tc::tma_load_2d(b_stage(s), &tmB, full + s, kb * KELTS, n_blk * BN);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer =====
+            if (WRES) { tc::mbar_wait(wfull, 0); }
+            uint32_t it = 0, tl = 0;
+            for (int64_t t = first; t < total; t += step, ++tl) {
+                const int acc = tl & 1;
+                tc::mbar_wait(tempty + acc, ((tl >> 1) & 1) ^ 1);
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    tc::mbar_wait(full + s, (it / STAGES) & 1);
+                    tc::tc_fence_after();
+                    const uint32_t a_addr = tc::smem_u32(a_stage(s));
+                    const uint32_t b_addr = WRES ? tc::smem_u32(ring + (size_t)kb * B_STAGE) : tc::smem_u32(b_stage(s));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {   // 4 x (32 bytes of K) per 128-byte k-block
+                        const uint64_t ad = tc::make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+                        const uint64_t bd = tc::make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                        if (TF32) tc::mma_tf32_ss(d_tmem, ad, bd, IDESC, (kb | k) != 0);
+                        else tc::mma_f16_ss(d_tmem, ad, bd, IDESC, (kb | k) != 0);
+                    }
+                    tc::mma_commit(empty + s);
+                }
+                tc::mma_commit(tfull + acc);
+            }
+        }
+    } else if (warp >= 4) {  // ===== epilogue: thread <-> one output row =====
+        const int q = warp - 4;
+        uint32_t tl = 0;
+        for (int64_t t = first; t < total; t += step, ++tl) {
+            const int64_t m_blk = WRES ? t : t / p.n_tiles;
+            const int n_blk = WRES ? (int)blockIdx.y : (int)(t % p.n_tiles);
+            const int acc = tl & 1;
+            tc::mbar_wait(tfull + acc, (tl >> 1) & 1);
+            tc::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+            const int64_t row = m_blk * BM + q * 32 + lane;
+            const bool valid = row < p.M;
+            const int n0 = n_blk * BN;
+            uint32_t r[32];
+
+            if (EPI == TC_EPI_BIAS || EPI == TC_EPI_BIAS_RELU || EPI == TC_EPI_BIAS_POS) {
+                const float *pos = nullptr;
+                if (EPI == TC_EPI_BIAS_POS && valid)
+                    pos = p.pos_table + (int64_t)min(__ldg(p.row_pos + row), p.pos_rows - 1) * BN;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    tc::tmem_ld32(taddr + c * 32, r);
+                    tc::tmem_wait_ld();
+                    if (valid) {
+                        __nv_bfloat16 *dst = p.out + row * p.N + n0 + c * 32;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            float v[8];
+#pragma unroll
+                            for (int e = 0; e < 8; e += 4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + c * 32 + j + e));
+                                v[e + 0] = __uint_as_float(r[j + e + 0]) + b4.x;
+                                v[e + 1] = __uint_as_float(r[j + e + 1]) + b4.y;
+                                v[e + 2] = __uint_as_float(r[j + e + 2]) + b4.z;
+                                v[e + 3] = __uint_as_float(r[j + e + 3]) + b4.w;
+                                if (EPI == TC_EPI_BIAS_POS) {
+                                    const float4 p4 = __ldg(reinterpret_cast<const float4 *>(pos + c * 32 + j + e));
+                                    v[e + 0] += p4.x; v[e + 1] += p4.y; v[e + 2] += p4.z; v[e + 3] += p4.w;
+                                }
+                                if (EPI == TC_EPI_BIAS_RELU) {
+                                    v[e + 0] = fmaxf(v[e + 0], 0.f); v[e + 1] = fmaxf(v[e + 1], 0.f);
+                                    v[e + 2] = fmaxf(v[e + 2], 0.f); v[e + 3] = fmaxf(v[e + 3], 0.f);
+                                }
+                            }
+                            uint4 pk;
+                            pk.x = pack_bf16(v[0], v[1]); pk.y = pack_bf16(v[2], v[3]);
+                            pk.z = pack_bf16(v[4], v[5]); pk.w = pack_bf16(v[6], v[7]);
+                            *reinterpret_cast<uint4 *>(dst + j) = pk;
+                        }
+                    }
+                }
+            } else {  // TC_EPI_BIAS_RES_LN(_HEAD): N == 256, the tile is the whole row
+                float sum = 0.f, sumsq = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    tc::tmem_ld32(taddr + c * 32, r);
+                    tc::tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint4 rs = make_uint4(0, 0, 0, 0);
+                        if (valid) rs = __ldg(reinterpret_cast<const uint4 *>(p.residual + row * BN + c * 32 + j));
+                        const uint32_t rw[4] = {rs.x, rs.y, rs.z, rs.w};
+#pragma unroll
+                        for (int e = 0; e < 8; e += 2) {
+                            const float2 b2 = __ldg(reinterpret_cast<const float2 *>(p.bias + c * 32 + j + e));
+                            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&rw[e >> 1]);
+                            const float v0 = __uint_as_float(r[j + e]) + b2.x + __low2float(h);
+                            const float v1 = __uint_as_float(r[j + e + 1]) + b2.y + __high2float(h);
+                            sum += v0 + v1;
+                            sumsq = fmaf(v0, v0, fmaf(v1, v1, sumsq));
+                            r[j + e] = __float_as_uint(v0);
+                            r[j + e + 1] = __float_as_uint(v1);
+                        }
+                    }
+                    tc::tmem_st32(taddr + c * 32, r);       // park the pre-norm row in TMEM
+                }
+                tc::tmem_wait_st();
+                const float mean = sum * (1.0f / BN);
+                const float var = fmaxf(sumsq * (1.0f / BN) - mean * mean, 0.f);
+                const float rstd = rsqrtf(var + 1e-5f);
+                float dot = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    tc::tmem_ld32(taddr + c * 32, r);
+                    tc::tmem_wait_ld();
+                    float y[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 g4 = __ldg(reinterpret_cast<const float4 *>(p.gamma + c * 32 + j));
+                        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.beta + c * 32 + j));
+                        y[j + 0] = (__uint_as_float(r[j + 0]) - mean) * rstd * g4.x + b4.x;
+                        y[j + 1] = (__uint_as_float(r[j + 1]) - mean) * rstd * g4.y + b4.y;
+                        y[j + 2] = (__uint_as_float(r[j + 2]) - mean) * rstd * g4.z + b4.z;
+                        y[j + 3] = (__uint_as_float(r[j + 3]) - mean) * rstd * g4.w + b4.w;
+                        if (EPI == TC_EPI_BIAS_RES_LN_HEAD) {
+                            const float4 w4 = __ldg(reinterpret_cast<const float4 *>(p.head_w + c * 32 + j));
+                            dot = fmaf(y[j + 0], w4.x, fmaf(y[j + 1], w4.y, fmaf(y[j + 2], w4.z, fmaf(y[j + 3], w4.w, dot))));
+                        }
+                    }
+                    if (valid) {
+                        if (p.out) {
+                            __nv_bfloat16 *dst = p.out + row * BN + c * 32;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                uint4 pk;
+                                pk.x = pack_bf16(y[j + 0], y[j + 1]); pk.y = pack_bf16(y[j + 2], y[j + 3]);
+                                pk.z = pack_bf16(y[j + 4], y[j + 5]); pk.w = pack_bf16(y[j + 6], y[j + 7]);
+                                *reinterpret_cast<uint4 *>(dst + j) = pk;
+                            }
+                        }
+                        if (EPI == TC_EPI_BIAS_RES_LN_HEAD && p.feats_out) {
+                            float4 *dst = reinterpret_cast<float4 *>(p.feats_out + row * BN + c * 32);
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) dst[j >> 2] = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+                        }
+                    }
+                }
+                if (EPI == TC_EPI_BIAS_RES_LN_HEAD && valid) {
+                    float sc = dot + __ldg(p.head_b);
+                    if (p.apply_sigmoid) sc = 1.0f / (1.0f + __expf(-sc));
+                    p.scores_out[row] = sc;
+                }
+            }
+            tc::tc_fence_before();
+            tc::mbar_arrive(tempty + acc);
+        }
+    }
+    __syncwarp();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <bool TF32, int EPI, bool WRES>
+int launch_variant(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, cudaStream_t s) {
+    auto kern = gemm_tc05_kernel<TF32, EPI, WRES>;
+    static bool configured = false;
+    if (!configured) {
+        VSUM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+        configured = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    dim3 grid;
+    if (WRES) grid = dim3((unsigned)max((int64_t)1, min(p.m_tiles, (int64_t)(sms / p.n_tiles))), (unsigned)p.n_tiles);
+    else grid = dim3((unsigned)min(p.m_tiles * p.n_tiles, (int64_t)sms));
+    kern<<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, p);
+    VSUM_LAUNCH_OK("gemm_tc05_kernel");
+    return VSUM_OK;
+}
+
+}  // namespace
+
+int launch_gemm_tc05(const Tc05GemmArgs &a, cudaStream_t s) {
+    if (a.M == 0) return VSUM_OK;
+    const int elt = a.a_is_f32 ? 4 : 2;
+    const int kelts = 128 / elt;
+    VSUM_REQUIRE(a.N % BN == 0 && a.K % kelts == 0, VSUM_EUNSUPPORTED,
+                 "gemm_tc05: N=%d must be a multiple of 256 and K=%d of %d", a.N, a.K, kelts);
+    VSUM_REQUIRE(a.M < ((int64_t)1 << 31), VSUM_EUNSUPPORTED, "gemm_tc05: M=%lld exceeds the TMA coordinate range", (long long)a.M);
+    const bool full_row = a.epi == TC_EPI_BIAS_POS || a.epi == TC_EPI_BIAS_RES_LN || a.epi == TC_EPI_BIAS_RES_LN_HEAD;
+    VSUM_REQUIRE(!full_row || a.N == BN, VSUM_EUNSUPPORTED, "gemm_tc05: epilogue %d needs N == 256", a.epi);
+    CUtensorMap tmA, tmB;
+    int rc = make_tensor_map_2d(&tmA, a.A, elt, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.K * elt, kelts, BM);
+    if (rc) return rc;
+    rc = make_tensor_map_2d(&tmB, a.W, elt, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.K * elt, kelts, BN);
+    if (rc) return rc;
+    GemmParams p{};
+    p.M = a.M; p.N = a.N; p.num_kb = a.K / kelts; p.n_tiles = a.N / BN; p.m_tiles = ceil_div(a.M, BM);
+    p.bias = a.bias; p.out = a.out; p.residual = a.residual; p.gamma = a.gamma; p.beta = a.beta;
+    p.pos_table = a.pos_table; p.row_pos = a.row_pos; p.pos_rows = 0; p.head_w = a.head_w; p.head_b = a.head_b;
+    p.scores_out = a.scores_out; p.feats_out = a.feats_out; p.apply_sigmoid = a.apply_sigmoid;
+    p.pos_rows = a.pos_rows;
+    const bool wres = !a.a_is_f32 && p.num_kb <= WRES_MAX_KB && p.m_tiles >= 2 * (148 / p.n_tiles);
+    if (a.a_is_f32) {
+        VSUM_REQUIRE(a.epi == TC_EPI_BIAS_POS || a.epi == TC_EPI_BIAS, VSUM_EUNSUPPORTED, "gemm_tc05: tf32 path supports BIAS / BIAS_POS only");
+        if (a.epi == TC_EPI_BIAS_POS) return launch_variant<true, TC_EPI_BIAS_POS, false>(tmA, tmB, p, s);
+        return launch_variant<true, TC_EPI_BIAS, false>(tmA, tmB, p, s);
+    }
+    switch (a.epi) {
+        case TC_EPI_BIAS:
+            return wres ? launch_variant<false, TC_EPI_BIAS, true>(tmA, tmB, p, s) : launch_variant<false, TC_EPI_BIAS, false>(tmA, tmB, p, s);
+        case TC_EPI_BIAS_RELU:
+            return wres ? launch_variant<false, TC_EPI_BIAS_RELU, true>(tmA, tmB, p, s) : launch_variant<false, TC_EPI_BIAS_RELU, false>(tmA, tmB, p, s);
+        case TC_EPI_BIAS_RES_LN:
+            return wres ? launch_variant<false, TC_EPI_BIAS_RES_LN, true>(tmA, tmB, p, s) : launch_variant<false, TC_EPI_BIAS_RES_LN, false>(tmA, tmB, p, s);
+        case TC_EPI_BIAS_RES_LN_HEAD:
+            return launch_variant<false, TC_EPI_BIAS_RES_LN_HEAD, false>(tmA, tmB, p, s);
+        default:
+            return set_error(VSUM_EINVAL, "gemm_tc05: unknown epilogue %d", a.epi);
+    }
+}
+
+}  // namespace vsum

@@ -1,0 +1,293 @@
+// Scorer handle, weight packing and the forward pass (C ABI: vsum_scorer_*).
+// Replaces SimNet.forward (src/model/simnet.py:32-45) over PACKED videos: rows of video v are
+// [cu_seqlens[v], cu_seqlens[v+1]).  Attention never crosses a video boundary, which is exactly
+// what the reference computes for batch size 1 (train.py:139-143) and, for padded batches, for
+// every valid row (padded keys are masked, simnet.py:156-157).
+#include "vsum_kernels.cuh"
+
+#include <cmath>
+#include <new>
+
+using namespace vsum;
+
+struct LayerOffsets {
+    size_t wqkv, bqkv, wo, bo, ln1g, ln1b, fc1w, fc1b, fc2w, fc2b, ln2g, ln2b;   // fp32 blob (floats)
+    size_t h_wqkv, h_wo, h_fc1, h_fc2;                                              // bf16 blob (elements)
+};
+
+struct vsum_scorer {
+    vsum_scorer_config cfg;
+    float *w32 = nullptr;
+    __nv_bfloat16 *w16 = nullptr;
+    float *pos_table = nullptr;
+    int pos_rows = 0;
+    size_t embed_w, embed_b, final_w, final_b, n32 = 0, n16 = 0;
+    LayerOffsets L[VSUM_MAX_LAYERS];
+    bool loaded = false;
+    bool tc05_shape = false;
+};
+
+static size_t take(size_t &cursor, size_t n) {
+    const size_t at = cursor;
+    cursor += (n + 63) / 64 * 64;     // keep every tensor 256-byte aligned
+    return at;
+}
+
+extern "C" int vsum_scorer_create(vsum_scorer_t *out, const vsum_scorer_config *cfg) {
+    VSUM_REQUIRE(out && cfg, VSUM_EINVAL, "vsum_scorer_create: null argument");
+    VSUM_REQUIRE(cfg->d_model > 0 && cfg->num_heads > 0 && cfg->d_model % cfg->num_heads == 0, VSUM_EINVAL,
+                 "vsum_scorer_create: d_model %d / heads %d", cfg->d_model, cfg->num_heads);
+    VSUM_REQUIRE(cfg->num_layers >= 1 && cfg->num_layers <= VSUM_MAX_LAYERS, VSUM_EINVAL,
+                 "vsum_scorer_create: num_layers %d not in [1,%d]", cfg->num_layers, VSUM_MAX_LAYERS);
+    VSUM_REQUIRE(cfg->d_model % 32 == 0 && cfg->d_model <= 1024 && cfg->d_ff % 16 == 0 && cfg->in_features % 16 == 0,
+                 VSUM_EUNSUPPORTED, "vsum_scorer_create: d_model must be a multiple of 32 (<=1024), d_ff and in_features of 16");
+    VSUM_REQUIRE(cfg->num_classes >= 1, VSUM_EINVAL, "vsum_scorer_create: num_classes %d", cfg->num_classes);
+    int ndev = 0;
+    VSUM_CUDA_OK(cudaGetDeviceCount(&ndev));
+    VSUM_REQUIRE(ndev > 0, VSUM_ECUDA, "vsum_scorer_create: no CUDA device (there is no CPU fallback)");
+    vsum_scorer *h = new (std::nothrow) vsum_scorer();
+    VSUM_REQUIRE(h, VSUM_ENOMEM, "vsum_scorer_create: out of host memory");
+    h->cfg = *cfg;
+    const size_t d = cfg->d_model, ff = cfg->d_ff, in = cfg->in_features, C = cfg->num_classes;
+    size_t c32 = 0, c16 = 0;
+    h->embed_w = take(c32, d * in); h->embed_b = take(c32, d);
+    h->final_w = take(c32, C * d); h->final_b = take(c32, C);
+    for (int l = 0; l < cfg->num_layers; ++l) {
+        LayerOffsets &o = h->L[l];
+        o.wqkv = take(c32, 3 * d * d); o.bqkv = take(c32, 3 * d);
+        o.wo = take(c32, d * d); o.bo = take(c32, d);
+        o.ln1g = take(c32, d); o.ln1b = take(c32, d);
+        o.fc1w = take(c32, ff * d); o.fc1b = take(c32, ff);
+        o.fc2w = take(c32, d * ff); o.fc2b = take(c32, d);
+        o.ln2g = take(c32, d); o.ln2b = take(c32, d);
+        o.h_wqkv = take(c16, 3 * d * d); o.h_wo = take(c16, d * d);
+        o.h_fc1 = take(c16, ff * d); o.h_fc2 = take(c16, d * ff);
+    }
+    h->n32 = c32; h->n16 = c16;
+    h->tc05_shape = cfg->d_model == 256 && cfg->num_heads == 4 && cfg->d_ff == 1024 && cfg->num_classes == 1 &&
+                    cfg->in_features % 32 == 0;
+    cudaError_t e = cudaMalloc(&h->w32, c32 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&h->w16, c16 * sizeof(__nv_bfloat16));
+    if (e != cudaSuccess) {
+        cudaFree(h->w32); cudaFree(h->w16); delete h;
+        return set_error(VSUM_ENOMEM, "vsum_scorer_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+    }
+    *out = h;
+    return VSUM_OK;
+}
+
+extern "C" int vsum_scorer_destroy(vsum_scorer_t h) {
+    if (!h) return VSUM_OK;
+    cudaFree(h->w32); cudaFree(h->w16); cudaFree(h->pos_table);
+    delete h;
+    return VSUM_OK;
+}
+
+extern "C" int vsum_scorer_load_weights(vsum_scorer_t h, const vsum_scorer_weights *w, void *stream) {
+    VSUM_REQUIRE(h && w, VSUM_EINVAL, "vsum_scorer_load_weights: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t d = h->cfg.d_model, ff = h->cfg.d_ff, in = h->cfg.in_features, C = h->cfg.num_classes;
+#define CP(dst_off, src, n)                                                                              \
+    do {                                                                                                 \
+        VSUM_REQUIRE((src) != nullptr, VSUM_EINVAL, "vsum_scorer_load_weights: null tensor " #src);      \
+        VSUM_CUDA_OK(cudaMemcpyAsync(h->w32 + (dst_off), (src), (n) * sizeof(float),                     \
+                                     cudaMemcpyDeviceToDevice, s));                                      \
+    } while (0)
+    CP(h->embed_w, w->embed_w, d * in); CP(h->embed_b, w->embed_b, d);
+    CP(h->final_w, w->final_w, C * d); CP(h->final_b, w->final_b, C);
+    if (h->cfg.use_pos) {
+        VSUM_REQUIRE(w->pos_table && w->pos_rows > 0, VSUM_EINVAL, "vsum_scorer_load_weights: use_pos needs pos_table");
+        if (w->pos_rows != h->pos_rows) {
+            cudaFree(h->pos_table); h->pos_table = nullptr; h->pos_rows = 0;
+            VSUM_CUDA_OK(cudaMalloc(&h->pos_table, (size_t)w->pos_rows * d * sizeof(float)));
+            h->pos_rows = w->pos_rows;
+        }
+        VSUM_CUDA_OK(cudaMemcpyAsync(h->pos_table, w->pos_table, (size_t)w->pos_rows * d * sizeof(float),
+                                     cudaMemcpyDeviceToDevice, s));
+    }
+    for (int l = 0; l < h->cfg.num_layers; ++l) {
+        const vsum_layer_weights &lw = w->layers[l];
+        const LayerOffsets &o = h->L[l];
+        CP(o.wqkv, lw.q_w, d * d); CP(o.wqkv + d * d, lw.k_w, d * d); CP(o.wqkv + 2 * d * d, lw.v_w, d * d);
+        CP(o.bqkv, lw.q_b, d); CP(o.bqkv + d, lw.k_b, d); CP(o.bqkv + 2 * d, lw.v_b, d);
+        CP(o.wo, lw.o_w, d * d); CP(o.bo, lw.o_b, d);
+        CP(o.ln1g, lw.ln1_g, d); CP(o.ln1b, lw.ln1_b, d);
+        CP(o.fc1w, lw.fc1_w, ff * d); CP(o.fc1b, lw.fc1_b, ff);
+        CP(o.fc2w, lw.fc2_w, d * ff); CP(o.fc2b, lw.fc2_b, d);
+        CP(o.ln2g, lw.ln2_g, d); CP(o.ln2b, lw.ln2_b, d);
+        int rc;
+        if ((rc = launch_f32_to_bf16(h->w32 + o.wqkv, h->w16 + o.h_wqkv, 3 * d * d, s))) return rc;
+        if ((rc = launch_f32_to_bf16(h->w32 + o.wo, h->w16 + o.h_wo, d * d, s))) return rc;
+        if ((rc = launch_f32_to_bf16(h->w32 + o.fc1w, h->w16 + o.h_fc1, ff * d, s))) return rc;
+        if ((rc = launch_f32_to_bf16(h->w32 + o.fc2w, h->w16 + o.h_fc2, d * ff, s))) return rc;
+    }
+#undef CP
+    h->loaded = true;
+    return VSUM_OK;
+}
+
+namespace {
+struct Carver {
+    uint8_t *base;
+    size_t off = 0;
+    template <class T>
+    T *get(size_t n) {
+        off = align_up(off, 1024);
+        T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+struct Ws32 { int32_t *row_pos; float *xa, *xb, *qkv, *att, *tmp, *hid; };
+struct Ws16 { int32_t *row_pos, *tile_video, *tile_q0, *n_tiles; __nv_bfloat16 *xa, *xb, *qkv, *att, *hid; };
+
+size_t carve32(const vsum_scorer_config &c, int64_t T, void *base, Ws32 &w) {
+    Carver k{(uint8_t *)base};
+    const size_t t = (size_t)T, d = c.d_model;
+    w.row_pos = k.get<int32_t>(t);
+    w.xa = k.get<float>(t * d); w.xb = k.get<float>(t * d); w.qkv = k.get<float>(t * 3 * d);
+    w.att = k.get<float>(t * d); w.tmp = k.get<float>(t * d); w.hid = k.get<float>(t * c.d_ff);
+    return align_up(k.off, 1024);
+}
+size_t carve16(const vsum_scorer_config &c, int64_t T, int max_tiles, void *base, Ws16 &w) {
+    Carver k{(uint8_t *)base};
+    const size_t t = (size_t)T, d = c.d_model;
+    w.row_pos = k.get<int32_t>(t);
+    w.tile_video = k.get<int32_t>(max_tiles); w.tile_q0 = k.get<int32_t>(max_tiles); w.n_tiles = k.get<int32_t>(1);
+    w.xa = k.get<__nv_bfloat16>(t * d); w.xb = k.get<__nv_bfloat16>(t * d);
+    w.qkv = k.get<__nv_bfloat16>(t * 3 * d); w.att = k.get<__nv_bfloat16>(t * d);
+    w.hid = k.get<__nv_bfloat16>(t * c.d_ff);
+    return align_up(k.off, 1024);
+}
+int max_attn_tiles(int64_t T, int32_t B) { return (int)(T / 128 + B); }
+}  // namespace
+
+extern "C" size_t vsum_scorer_workspace_bytes(vsum_scorer_t h, int64_t T, int32_t B, int32_t mode) {
+    if (!h || T <= 0 || B <= 0) return 0;
+    if (mode == VSUM_MODE_FP32) { Ws32 w; return carve32(h->cfg, T, nullptr, w); }
+    Ws16 w;
+    return carve16(h->cfg, T, max_attn_tiles(T, B), nullptr, w);
+}
+
+static int forward_fp32(vsum_scorer_t h, const float *x, const int32_t *cu, int B, int64_t T, int max_len,
+                        int sigm, float *scores, float *feats, void *ws, cudaStream_t s) {
+    const vsum_scorer_config &c = h->cfg;
+    const int d = c.d_model;
+    Ws32 w;
+    carve32(c, T, ws, w);
+    int rc;
+#define RUN(call) do { if ((rc = (call))) return rc; } while (0)
+    RUN(launch_row_positions(cu, B, T, w.row_pos, nullptr, s));
+    RUN(launch_linear_f32(x, h->w32 + h->embed_w, h->w32 + h->embed_b, w.xa, T, d, c.in_features,
+                          c.use_pos ? EPI_BIAS_POS : EPI_BIAS, h->pos_table, w.row_pos, h->pos_rows, s));
+    const float scale = 1.0f / sqrtf((float)d);                         // simnet.py:126: d_model ** -0.5
+    for (int l = 0; l < c.num_layers; ++l) {
+        const LayerOffsets &o = h->L[l];
+        RUN(launch_linear_f32(w.xa, h->w32 + o.wqkv, h->w32 + o.bqkv, w.qkv, T, 3 * d, d, EPI_BIAS, nullptr, nullptr, 0, s));
+        RUN(launch_attention_f32(w.qkv, cu, B, max_len, d, c.num_heads, scale, w.att, s));
+        RUN(launch_linear_f32(w.att, h->w32 + o.wo, h->w32 + o.bo, w.tmp, T, d, d, EPI_BIAS, nullptr, nullptr, 0, s));
+        RUN(launch_add_layernorm_f32(w.tmp, w.xa, h->w32 + o.ln1g, h->w32 + o.ln1b, w.xb, T, d, s));
+        RUN(launch_linear_f32(w.xb, h->w32 + o.fc1w, h->w32 + o.fc1b, w.hid, T, c.d_ff, d, EPI_BIAS_RELU, nullptr, nullptr, 0, s));
+        RUN(launch_linear_f32(w.hid, h->w32 + o.fc2w, h->w32 + o.fc2b, w.tmp, T, d, c.d_ff, EPI_BIAS, nullptr, nullptr, 0, s));
+        RUN(launch_add_layernorm_f32(w.tmp, w.xb, h->w32 + o.ln2g, h->w32 + o.ln2b, w.xa, T, d, s));
+    }
+    RUN(launch_head_f32(w.xa, h->w32 + h->final_w, h->w32 + h->final_b, scores, T, d, c.num_classes, sigm, s));
+    if (feats) VSUM_CUDA_OK(cudaMemcpyAsync(feats, w.xa, (size_t)T * d * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return VSUM_OK;
+}
+
+static int forward_bf16(vsum_scorer_t h, const float *x, const int32_t *cu, int B, int64_t T, int sigm,
+                        float *scores, float *feats, void *ws, cudaStream_t s) {
+    const vsum_scorer_config &c = h->cfg;
+    VSUM_REQUIRE(h->tc05_shape, VSUM_EUNSUPPORTED,
+                 "the sm_100a tcgen05 scorer is built for d_model=256, heads=4, d_ff=1024, num_classes=1 "
+                 "(got d_model=%d heads=%d d_ff=%d classes=%d); use VSUM_MODE_FP32",
+                 c.d_model, c.num_heads, c.d_ff, c.num_classes);
+    const int max_tiles = max_attn_tiles(T, B);
+    Ws16 w;
+    carve16(c, T, max_tiles, ws, w);
+    int rc;
+    RUN(launch_row_positions(cu, B, T, w.row_pos, nullptr, s));
+    RUN(launch_attn_schedule(cu, B, w.tile_video, w.tile_q0, w.n_tiles, max_tiles, s));
+    Tc05GemmArgs g{};
+    g.A = x; g.W = h->w32 + h->embed_w; g.M = T; g.N = 256; g.K = c.in_features; g.a_is_f32 = 1;
+    g.epi = c.use_pos ? TC_EPI_BIAS_POS : TC_EPI_BIAS; g.bias = h->w32 + h->embed_b; g.out = w.xa;
+    g.pos_table = h->pos_table; g.row_pos = w.row_pos; g.pos_rows = h->pos_rows;
+    RUN(launch_gemm_tc05(g, s));
+    const float scale = 1.0f / 16.0f;                                   // 256 ** -0.5
+    for (int l = 0; l < c.num_layers; ++l) {
+        const LayerOffsets &o = h->L[l];
+        const bool last = l == c.num_layers - 1;
+        Tc05GemmArgs q{};
+        q.A = w.xa; q.W = h->w16 + o.h_wqkv; q.M = T; q.N = 768; q.K = 256; q.epi = TC_EPI_BIAS;
+        q.bias = h->w32 + o.bqkv; q.out = w.qkv;
+        RUN(launch_gemm_tc05(q, s));
+        RUN(launch_attention_tc05(w.qkv, cu, w.tile_video, w.tile_q0, w.n_tiles, max_tiles, T, scale, w.att, s));
+        Tc05GemmArgs p{};
+        p.A = w.att; p.W = h->w16 + o.h_wo; p.M = T; p.N = 256; p.K = 256; p.epi = TC_EPI_BIAS_RES_LN;
+        p.bias = h->w32 + o.bo; p.residual = w.xa; p.gamma = h->w32 + o.ln1g; p.beta = h->w32 + o.ln1b; p.out = w.xb;
+        RUN(launch_gemm_tc05(p, s));
+        Tc05GemmArgs f1{};
+        f1.A = w.xb; f1.W = h->w16 + o.h_fc1; f1.M = T; f1.N = 1024; f1.K = 256; f1.epi = TC_EPI_BIAS_RELU;
+        f1.bias = h->w32 + o.fc1b; f1.out = w.hid;
+        RUN(launch_gemm_tc05(f1, s));
+        Tc05GemmArgs f2{};
+        f2.A = w.hid; f2.W = h->w16 + o.h_fc2; f2.M = T; f2.N = 256; f2.K = 1024;
+        f2.epi = last ? TC_EPI_BIAS_RES_LN_HEAD : TC_EPI_BIAS_RES_LN;
+        f2.bias = h->w32 + o.fc2b; f2.residual = w.xb; f2.gamma = h->w32 + o.ln2g; f2.beta = h->w32 + o.ln2b;
+        f2.out = last ? nullptr : w.xa;
+        f2.head_w = h->w32 + h->final_w; f2.head_b = h->w32 + h->final_b; f2.scores_out = scores; f2.feats_out = feats;
+        f2.apply_sigmoid = sigm;
+        RUN(launch_gemm_tc05(f2, s));
+    }
+#undef RUN
+    return VSUM_OK;
+}
+
+extern "C" int vsum_scorer_forward(vsum_scorer_t h, const float *features, const int32_t *cu_seqlens,
+                                   int32_t B, int64_t T, int32_t max_len, int32_t mode, int32_t apply_sigmoid,
+                                   float *scores_out, float *feats_out, void *workspace, size_t workspace_bytes,
+                                   void *stream) {
+    VSUM_REQUIRE(h, VSUM_EINVAL, "vsum_scorer_forward: null handle");
+    VSUM_REQUIRE(h->loaded, VSUM_EINVAL, "vsum_scorer_forward: call vsum_scorer_load_weights first");
+    VSUM_REQUIRE(B >= 0 && T >= 0 && max_len >= 0, VSUM_EINVAL, "vsum_scorer_forward: negative sizes");
+    if (B == 0 || T == 0) return VSUM_OK;
+    VSUM_REQUIRE(features && cu_seqlens && scores_out && workspace, VSUM_EINVAL, "vsum_scorer_forward: null pointer");
+    VSUM_REQUIRE(mode == VSUM_MODE_FP32 || mode == VSUM_MODE_BF16, VSUM_EINVAL, "vsum_scorer_forward: unknown mode %d", mode);
+    VSUM_REQUIRE(T < ((int64_t)1 << 31), VSUM_EUNSUPPORTED, "vsum_scorer_forward: T=%lld frames exceed one call", (long long)T);
+    VSUM_REQUIRE(!h->cfg.use_pos || max_len <= h->pos_rows, VSUM_EINVAL,
+                 "vsum_scorer_forward: video of %d frames exceeds the positional table (%d rows); the reference "
+                 "fails the same way past its 2000-row table (simnet.py:188)", max_len, h->pos_rows);
+    const size_t need = vsum_scorer_workspace_bytes(h, T, B, mode);
+    VSUM_REQUIRE(workspace_bytes >= need, VSUM_ENOMEM, "vsum_scorer_forward: workspace %zu < %zu bytes", workspace_bytes, need);
+    VSUM_REQUIRE(((uintptr_t)workspace & 1023) == 0 && ((uintptr_t)features & 15) == 0, VSUM_EINVAL,
+                 "vsum_scorer_forward: workspace must be 1024-byte and features 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (mode == VSUM_MODE_FP32)
+        return forward_fp32(h, features, cu_seqlens, B, T, max_len, apply_sigmoid, scores_out, feats_out, workspace, s);
+    return forward_bf16(h, features, cu_seqlens, B, T, apply_sigmoid, scores_out, feats_out, workspace, s);
+}
+
+// ---- diagnostics -----------------------------------------------------------------------------
+extern "C" int vsum_debug_gemm_tc05(const void *A, const void *W, const float *bias, const void *residual,
+                                    const float *gamma, const float *beta, void *out, int64_t M, int32_t N,
+                                    int32_t K, int32_t a_is_f32, int32_t epi, void *stream) {
+    VSUM_REQUIRE(A && W && bias && out, VSUM_EINVAL, "vsum_debug_gemm_tc05: null pointer");
+    VSUM_REQUIRE(epi == TC_EPI_BIAS || epi == TC_EPI_BIAS_RELU || epi == TC_EPI_BIAS_RES_LN, VSUM_EINVAL,
+                 "vsum_debug_gemm_tc05: epi %d", epi);
+    Tc05GemmArgs g{};
+    g.A = A; g.W = W; g.M = M; g.N = N; g.K = K; g.a_is_f32 = a_is_f32; g.epi = epi; g.bias = bias;
+    g.out = (__nv_bfloat16 *)out; g.residual = (const __nv_bfloat16 *)residual; g.gamma = gamma; g.beta = beta;
+    return launch_gemm_tc05(g, (cudaStream_t)stream);
+}
+
+extern "C" int vsum_debug_attention_tc05(const void *qkv, const int32_t *cu_seqlens, int32_t B, int64_t T,
+                                         void *out, int32_t *scratch, void *stream) {
+    VSUM_REQUIRE(qkv && cu_seqlens && out && scratch, VSUM_EINVAL, "vsum_debug_attention_tc05: null pointer");
+    const int max_tiles = (int)(T / 128 + B);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = launch_attn_schedule(cu_seqlens, B, scratch, scratch + max_tiles, scratch + 2 * max_tiles, max_tiles, s);
+    if (rc) return rc;
+    return launch_attention_tc05((const __nv_bfloat16 *)qkv, cu_seqlens, scratch, scratch + max_tiles,
+                                 scratch + 2 * max_tiles, max_tiles, T, 1.0f / 16.0f, (__nv_bfloat16 *)out, s);
+}

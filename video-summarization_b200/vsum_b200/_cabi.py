@@ -1,0 +1,98 @@
+"""ctypes binding of `libvsum_b200.so` (declared in `include/vsum_b200.h`).
+
+The library is built in-tree by `__graft_entry__.build()` / `make -C video-summarization_b200/csrc`.
+There is no fallback of any kind: if the shared object is missing, or a call fails, this module
+raises -- the product path never routes through PyTorch eager ops or the CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvsum_b200.so")
+
+VSUM_MAX_LAYERS = 16
+MODE_FP32, MODE_BF16 = 0, 1
+FSCORE_AVG, FSCORE_MAX = 0, 1
+
+# every symbol include/vsum_b200.h declares (checked by tests/test_cabi_symbols.py)
+EXPORTS = (
+    "vsum_abi_version", "vsum_last_error", "vsum_launch_count",
+    "vsum_scorer_create", "vsum_scorer_destroy", "vsum_scorer_load_weights",
+    "vsum_scorer_workspace_bytes", "vsum_scorer_forward",
+    "vsum_shot_mean", "vsum_knapsack_scratch_words", "vsum_knapsack", "vsum_summary_fscore",
+    "vsum_debug_gemm_tc05", "vsum_debug_attention_tc05",
+)
+
+
+class VsumError(RuntimeError):
+    pass
+
+
+class ScorerConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("d_model", "num_heads", "num_layers", "d_ff", "in_features",
+                                          "num_classes", "use_pos", "reserved")]
+
+
+_LAYER_FIELDS = ("q_w", "q_b", "k_w", "k_b", "v_w", "v_b", "o_w", "o_b", "ln1_g", "ln1_b",
+                 "fc1_w", "fc1_b", "fc2_w", "fc2_b", "ln2_g", "ln2_b")
+
+
+class LayerWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _LAYER_FIELDS]
+
+
+class ScorerWeights(C.Structure):
+    _fields_ = [("embed_w", C.c_void_p), ("embed_b", C.c_void_p), ("pos_table", C.c_void_p),
+                ("pos_rows", C.c_int32), ("reserved", C.c_int32),
+                ("final_w", C.c_void_p), ("final_b", C.c_void_p),
+                ("layers", LayerWeights * VSUM_MAX_LAYERS)]
+
+
+_lib = None
+
+
+def load():
+    """Load the shared object once.  Raises VsumError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VsumError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C video-summarization_b200/csrc`.  vsum_b200 has no CPU or PyTorch fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    L.vsum_abi_version.restype = C.c_int
+    L.vsum_last_error.restype = C.c_char_p
+    L.vsum_launch_count.restype = i64
+    L.vsum_scorer_create.argtypes = [C.POINTER(vp), C.POINTER(ScorerConfig)]
+    L.vsum_scorer_destroy.argtypes = [vp]
+    L.vsum_scorer_load_weights.argtypes = [vp, C.POINTER(ScorerWeights), vp]
+    L.vsum_scorer_workspace_bytes.restype = C.c_size_t
+    L.vsum_scorer_workspace_bytes.argtypes = [vp, i64, i32, i32]
+    L.vsum_scorer_forward.argtypes = [vp, vp, vp, i32, i64, i32, i32, i32, vp, vp, vp, C.c_size_t, vp]
+    L.vsum_shot_mean.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]
+    L.vsum_knapsack_scratch_words.restype = i64
+    L.vsum_knapsack_scratch_words.argtypes = [i32, i32]
+    L.vsum_knapsack.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp]
+    L.vsum_summary_fscore.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, i64, vp, vp, vp, vp]
+    L.vsum_debug_gemm_tc05.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]
+    L.vsum_debug_attention_tc05.argtypes = [vp, vp, i32, i64, vp, vp, vp]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if fn.restype is C.c_int and name not in ("vsum_abi_version",):
+            fn.restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().vsum_last_error()
+        raise VsumError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+def launch_count() -> int:
+    return int(load().vsum_launch_count())

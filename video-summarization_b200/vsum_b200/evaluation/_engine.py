@@ -1,0 +1,211 @@
+"""Host side of the evaluation half of the hot path: packs per-video metadata (change points,
+picks, user summaries) into flat arrays, moves them to the GPU and drives the three C-ABI calls
+
+    vsum_shot_mean -> vsum_knapsack -> vsum_summary_fscore
+
+that replace `generate_summary` + `knapSack` + `evaluate_summary` of the reference
+(`src/evaluation/generate_summary.py:6-57`, `knapsack_implementation.py:1-30`,
+`evaluation_metrics.py:4-33`).  No arithmetic of the path happens here: the host only
+concatenates arrays and computes buffer sizes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import _cabi
+
+
+def _device(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise _cabi.VsumError("vsum_b200.evaluation needs a CUDA device: the B200 kernels have no CPU fallback")
+    return torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+
+
+def _cu(counts) -> np.ndarray:
+    out = np.zeros(len(counts) + 1, dtype=np.int64)
+    np.cumsum(np.asarray(counts, dtype=np.int64), out=out[1:])
+    return out
+
+
+def capacity_of(last_end: int) -> int:
+    """Buffer sizing only (the kernel computes the capacity itself, generate_summary.py:45-46)."""
+    return int((int(last_end) + 1) * 0.15)
+
+
+@dataclass
+class HostEvalBatch:
+    """Flat host arrays for B videos.  Everything here is input data or a buffer size."""
+    B: int
+    picks: np.ndarray            # int32[sum N_picks]
+    cu_picks: np.ndarray         # int32[B+1]
+    n_frames: np.ndarray         # int32[B]
+    cps: np.ndarray              # int32[S_total,2]
+    cu_shots: np.ndarray         # int32[B+1]
+    bit_offsets: np.ndarray      # int64[B+1]  word offsets of each video's decision-bit matrix
+    order: np.ndarray            # int32[B]    heaviest knapsack first
+    max_cap: int
+    sum_offsets: np.ndarray      # int64[B+1]  summary v occupies [sum_offsets[v], sum_offsets[v+1])
+    user_summary: Optional[np.ndarray]   # float32 flat
+    us_offsets: Optional[np.ndarray]     # int64[B+1]
+    cu_users: Optional[np.ndarray]       # int32[B+1]
+    us_cols: Optional[np.ndarray]        # int32[B]
+
+    @staticmethod
+    def build(change_points: Sequence[np.ndarray], n_frames: Sequence, picks: Sequence[np.ndarray],
+              user_summaries: Optional[Sequence[np.ndarray]] = None) -> "HostEvalBatch":
+        B = len(change_points)
+        cps_list = [np.ascontiguousarray(np.asarray(c).reshape(-1, 2), dtype=np.int32) for c in change_points]
+        pk_list = []
+        for p in picks:
+            p = np.asarray(p)
+            pk_list.append(p.astype(np.int32) if p.dtype != np.int32 else p)     # generate_summary.py:27-28
+        n_shots = [len(c) for c in cps_list]
+        last_end = [int(c[-1, 1]) if len(c) else -1 for c in cps_list]
+        caps = [capacity_of(e) if e >= 0 else 0 for e in last_end]
+        words = [s * ((c + 1 + 31) // 32) for s, c in zip(n_shots, caps)]
+        work = np.asarray([s * (c + 1) for s, c in zip(n_shots, caps)], dtype=np.int64)
+        us = us_off = cu_users = us_cols = None
+        if user_summaries is not None:
+            mats = [np.ascontiguousarray(np.asarray(u), dtype=np.float32).reshape(len(u), -1) for u in user_summaries]
+            us = np.concatenate([m.reshape(-1) for m in mats]) if B else np.zeros(0, np.float32)
+            us_off = _cu([m.size for m in mats])
+            cu_users = _cu([m.shape[0] for m in mats]).astype(np.int32)
+            us_cols = np.asarray([m.shape[1] for m in mats], dtype=np.int32)
+        return HostEvalBatch(
+            B=B,
+            picks=np.concatenate(pk_list).astype(np.int32, copy=False) if B else np.zeros(0, np.int32),
+            cu_picks=_cu([len(p) for p in pk_list]).astype(np.int32),
+            n_frames=np.asarray([int(np.asarray(n)) for n in n_frames], dtype=np.int32),
+            cps=np.concatenate(cps_list) if B else np.zeros((0, 2), np.int32),
+            cu_shots=_cu(n_shots).astype(np.int32),
+            bit_offsets=_cu(words),
+            order=np.argsort(-work, kind="stable").astype(np.int32),
+            max_cap=max(caps) if B else 0,
+            sum_offsets=_cu([e + 1 for e in last_end]),
+            user_summary=us, us_offsets=us_off, cu_users=cu_users, us_cols=us_cols)
+
+
+class DeviceEvalBatch:
+    """The same arrays resident in HBM."""
+
+    def __init__(self, hb: HostEvalBatch, device=None, pin: bool = False):
+        self.host = hb
+        self.device = dev = _device(device)
+
+        def up(a):
+            t = torch.from_numpy(np.ascontiguousarray(a))
+            if pin:
+                t = t.pin_memory()
+            return t.to(dev, non_blocking=True)
+
+        self.picks, self.cu_picks, self.n_frames = up(hb.picks), up(hb.cu_picks), up(hb.n_frames)
+        self.cps, self.cu_shots = up(hb.cps), up(hb.cu_shots)
+        self.bit_offsets, self.order, self.sum_offsets = up(hb.bit_offsets), up(hb.order), up(hb.sum_offsets)
+        self.has_users = hb.user_summary is not None
+        if self.has_users:
+            self.user_summary, self.us_offsets = up(hb.user_summary), up(hb.us_offsets)
+            self.cu_users, self.us_cols = up(hb.cu_users), up(hb.us_cols)
+        self.h2d_bytes = sum(a.nbytes for a in (hb.picks, hb.cu_picks, hb.n_frames, hb.cps, hb.cu_shots,
+                                                hb.bit_offsets, hb.order, hb.sum_offsets))
+        if self.has_users:
+            self.h2d_bytes += hb.user_summary.nbytes + hb.us_offsets.nbytes + hb.cu_users.nbytes + hb.us_cols.nbytes
+
+
+_scratch: dict = {}
+
+
+def _scratch_buf(key: str, nbytes: int, dev: torch.device) -> torch.Tensor:
+    k = (key, dev.index)
+    t = _scratch.get(k)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(int(nbytes * 1.25), 1024), dtype=torch.uint8, device=dev)
+        _scratch[k] = t
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def summarize(db: DeviceEvalBatch, scores: torch.Tensor, cu_steps: torch.Tensor, method: str = "avg",
+              want_f: bool = True, want_per_user: bool = False) -> dict:
+    """scores float32[T] on db.device, cu_steps int32[B+1] on db.device.  Returns device tensors:
+    val fp64[S], wt int32[S], cap int32[B], selected uint8[S], summary int8[sum], f fp64[B]."""
+    hb, dev = db.host, db.device
+    L = _cabi.load()
+    if method not in ("avg", "max"):
+        method = "avg"          # evaluation_metrics.py:30-33: anything but 'max' averages
+    B, S = hb.B, int(hb.cu_shots[-1])
+    if scores.dtype != torch.float32 or not scores.is_contiguous() or scores.device != dev:
+        raise ValueError("scores must be a contiguous float32 tensor on the batch's device")
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        val = torch.empty(S, dtype=torch.float64, device=dev)
+        wt = torch.empty(S, dtype=torch.int32, device=dev)
+        cap = torch.empty(B, dtype=torch.int32, device=dev)
+        selected = torch.empty(S, dtype=torch.uint8, device=dev)
+        summary = torch.empty(int(hb.sum_offsets[-1]), dtype=torch.int8, device=dev)
+        out = dict(val=val, wt=wt, cap=cap, selected=selected, summary=summary, f=None, per_user=None)
+        if B == 0:
+            return out
+        _cabi.check(L.vsum_shot_mean(scores.data_ptr(), cu_steps.data_ptr(), db.picks.data_ptr(),
+                                     db.cu_picks.data_ptr(), db.n_frames.data_ptr(), db.cps.data_ptr(),
+                                     db.cu_shots.data_ptr(), B, S, val.data_ptr(), wt.data_ptr(),
+                                     cap.data_ptr(), stream), "vsum_shot_mean")
+        bits = _scratch_buf("bits", int(hb.bit_offsets[-1]) * 4, dev)
+        _cabi.check(L.vsum_knapsack(val.data_ptr(), wt.data_ptr(), db.cu_shots.data_ptr(), cap.data_ptr(),
+                                    db.bit_offsets.data_ptr(), db.order.data_ptr(), B, hb.max_cap,
+                                    bits.data_ptr(), selected.data_ptr(), stream), "vsum_knapsack")
+        f = per_user = counts = None
+        total_users = 0
+        if want_f:
+            if not db.has_users:
+                raise ValueError("F-score requested but the batch was built without user summaries")
+            total_users = int(hb.cu_users[-1])
+            f = torch.empty(B, dtype=torch.float64, device=dev)
+            counts = _scratch_buf("counts", max(total_users, 1) * 24, dev)
+            if want_per_user:
+                per_user = torch.empty(total_users, dtype=torch.float64, device=dev)
+        _cabi.check(L.vsum_summary_fscore(
+            selected.data_ptr(), db.cps.data_ptr(), db.cu_shots.data_ptr(),
+            _ptr(db.user_summary) if want_f else None, _ptr(db.us_offsets) if want_f else None,
+            _ptr(db.cu_users) if want_f else None, _ptr(db.us_cols) if want_f else None,
+            B, total_users, _cabi.FSCORE_MAX if method == "max" else _cabi.FSCORE_AVG,
+            summary.data_ptr(), db.sum_offsets.data_ptr(), int(hb.sum_offsets[-1]), _ptr(counts),
+            _ptr(f), _ptr(per_user), stream), "vsum_summary_fscore")
+        out["f"], out["per_user"] = f, per_user
+    return out
+
+
+def fscore_of_masks(summaries: Sequence[np.ndarray], user_summaries: Sequence[np.ndarray], method: str,
+                    device=None) -> np.ndarray:
+    """`evaluate_summary` for arbitrary 0/1 masks (selected == NULL path of vsum_summary_fscore)."""
+    dev = _device(device)
+    L = _cabi.load()
+    B = len(summaries)
+    masks = [np.ascontiguousarray(np.asarray(s), dtype=np.int8) for s in summaries]
+    mats = [np.ascontiguousarray(np.asarray(u), dtype=np.float32).reshape(len(u), -1) for u in user_summaries]
+    sum_off = _cu([len(m) for m in masks])
+    us_off = _cu([m.size for m in mats])
+    cu_users = _cu([m.shape[0] for m in mats]).astype(np.int32)
+    us_cols = np.asarray([m.shape[1] for m in mats], dtype=np.int32)
+    total_users = int(cu_users[-1])
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        d_mask = t(np.concatenate(masks) if B else np.zeros(0, np.int8))
+        d_us = t(np.concatenate([m.reshape(-1) for m in mats]) if B else np.zeros(0, np.float32))
+        d_sum_off, d_us_off, d_cu_users, d_cols = t(sum_off), t(us_off), t(cu_users), t(us_cols)
+        f = torch.empty(B, dtype=torch.float64, device=dev)
+        counts = _scratch_buf("counts", max(total_users, 1) * 24, dev)
+        _cabi.check(L.vsum_summary_fscore(
+            None, None, None, d_us.data_ptr(), d_us_off.data_ptr(), d_cu_users.data_ptr(), d_cols.data_ptr(),
+            B, total_users, _cabi.FSCORE_MAX if method == "max" else _cabi.FSCORE_AVG,
+            d_mask.data_ptr(), d_sum_off.data_ptr(), int(sum_off[-1]), counts.data_ptr(), f.data_ptr(), None,
+            stream), "vsum_summary_fscore")
+        return f.cpu().numpy()

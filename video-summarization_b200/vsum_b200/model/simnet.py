@@ -1,0 +1,248 @@
+"""`SimNet` frame scorer with the reference's constructor, `forward` contract and `state_dict`
+keys (reference `src/model/simnet.py:8-56`), executed by the sm_100a kernels behind the C ABI
+(`vsum_scorer_forward`).  The nn.Module tree below only HOLDS parameters under the reference's
+names so checkpoints load with `strict=True` in both directions; no PyTorch op computes the
+scores.
+
+Seeded-init parity: the reference's `Encoder` builds two extra blocks and throws them away
+(`simnet.py:71-75`), which consumes init RNG before `final_layer` is drawn.  `_Encoder` replays
+that consumption so `torch.manual_seed(s); SimNet(...)` yields bit-identical weights here and
+there (tests/test_model_host.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Optional, Sequence
+
+import torch
+from torch import Tensor, nn
+
+from .. import _cabi
+
+_REF_TABLE_ROWS = 2000      # simnet.py:188 -- Embedding(max_len=2000) regardless of SimNet.max_len
+
+
+def sinusoid_table(rows: int, d_model: int) -> Tensor:
+    """fp32 table computed with the reference's exact expression order (simnet.py:224-231) on the
+    host, so rows < 2000 are bit-identical to the reference buffer."""
+    angle = torch.exp(-torch.arange(0, d_model, 2) * math.log(10000) / d_model)
+    pos = torch.arange(0, rows).reshape(rows, 1)
+    tab = torch.zeros((rows, d_model))
+    tab[:, 0::2] = torch.sin(pos * angle)
+    tab[:, 1::2] = torch.cos(pos * angle)
+    return tab
+
+
+class _PositionalEncoding(nn.Module):
+    def __init__(self, d_model: int, rows: int):
+        super().__init__()
+        self.register_buffer("pos_embedding", sinusoid_table(rows, d_model).unsqueeze(0))
+
+
+class _Embedding(nn.Module):
+    def __init__(self, in_features: int, d_model: int, use_pos: bool, use_cls: bool):
+        super().__init__()
+        self.feature_transform = nn.Linear(in_features, d_model)
+        if use_pos:
+            self.positional_encoding = _PositionalEncoding(d_model, _REF_TABLE_ROWS)
+        if use_cls:
+            self.cls_token = nn.Parameter(torch.zeros((1, 1, d_model)))
+
+
+class _Attention(nn.Module):
+    def __init__(self, d_model: int):
+        super().__init__()
+        self.q = nn.Linear(d_model, d_model)
+        self.k = nn.Linear(d_model, d_model)
+        self.v = nn.Linear(d_model, d_model)
+        self.feature_projection = nn.Linear(d_model, d_model)
+
+
+class _FeedForward(nn.Module):
+    def __init__(self, d_model: int, expand: int = 4):
+        super().__init__()
+        self.fc1 = nn.Linear(d_model, expand * d_model)
+        self.fc2 = nn.Linear(expand * d_model, d_model)
+
+
+class _Block(nn.Module):
+    def __init__(self, d_model: int):
+        super().__init__()
+        self.sa = _Attention(d_model)
+        self.mlp = _FeedForward(d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+
+
+class _Encoder(nn.Module):
+    def __init__(self, d_model: int, num_layers: int):
+        super().__init__()
+        self.module_list = nn.ModuleList([_Block(d_model) for _ in range(num_layers)])
+        for _ in range(2):          # RNG replay of the two discarded blocks (simnet.py:72-74)
+            _Block(d_model)
+        self.module_score = nn.ModuleList([])
+
+
+class SimNet(nn.Module):
+    """Drop-in for the reference `SimNet`.  Extra, optional attribute: `precision` ("bf16" uses
+    the tcgen05 kernels and needs d_model=256, heads=4; "fp32" uses the fp32 SIMT kernels)."""
+
+    def __init__(self, num_heads: int = 8, d_model: int = 512, num_layers: int = 4,
+                 sparsity: float = 0.5, use_cls: bool = False, dropout: float = 0.2,
+                 num_classes: int = 1, use_pos: bool = True, max_len=2500):
+        super().__init__()
+        if use_cls:
+            raise NotImplementedError(
+                "use_cls=True is never used by the reference's callers (train.py:33, "
+                "simnet_pretrain.py:30) and hard-codes a CUDA tensor there (simnet.py:49); not built")
+        self.num_heads, self.d_model, self.num_layers = num_heads, d_model, num_layers
+        self.sparsity, self.use_cls, self.max_len = sparsity, use_cls, max_len
+        self.num_classes, self.in_features, self.use_pos = num_classes, 1024, use_pos
+        self.dropout = dropout
+        self.embedding_layer = _Embedding(self.in_features, d_model, use_pos, use_cls)
+        self.encoder = _Encoder(d_model, num_layers)
+        self.final_layer = nn.Linear(d_model, num_classes)
+
+        tc05 = d_model == 256 and num_heads == 4 and num_classes == 1
+        self.precision = os.environ.get("VSUM_PRECISION", "bf16" if tc05 else "fp32")
+        self._handle = None
+        self._weights_key = None
+        self._table: Optional[Tensor] = None
+        self._workspace: Optional[Tensor] = None
+
+    # ------------------------------------------------------------------ C-ABI plumbing
+    def _mode(self) -> int:
+        if self.precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {self.precision!r}")
+        return _cabi.MODE_BF16 if self.precision == "bf16" else _cabi.MODE_FP32
+
+    def _ensure_handle(self):
+        if self._handle is None:
+            cfg = _cabi.ScorerConfig(self.d_model, self.num_heads, self.num_layers, 4 * self.d_model,
+                                     self.in_features, self.num_classes, int(self.use_pos), 0)
+            h = C.c_void_p()
+            _cabi.check(_cabi.load().vsum_scorer_create(C.byref(h), C.byref(cfg)), "vsum_scorer_create")
+            self._handle = h
+        return self._handle
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None:
+                _cabi.load().vsum_scorer_destroy(self._handle)
+        except Exception:
+            pass
+
+    def _table_for(self, rows_needed: int, device) -> Tensor:
+        """Positional rows.  The registered buffer keeps the reference shape [1,2000,d]; longer
+        videos (BASELINE configs go to N=8192, where the reference itself raises) extend the same
+        formula."""
+        buf = self.embedding_layer.positional_encoding.pos_embedding
+        if rows_needed <= buf.shape[1]:
+            return buf[0]
+        if self._table is None or self._table.shape[0] < rows_needed or self._table.device != device:
+            rows = 1 << (rows_needed - 1).bit_length()
+            self._table = sinusoid_table(rows, self.d_model).to(device)
+            self._weights_key = None
+        return self._table
+
+    def _sync_weights(self, max_len: int, device, stream: int):
+        params = list(self.parameters())
+        table = self._table_for(max_len, device) if self.use_pos else None
+        key = (tuple((p.data_ptr(), p._version) for p in params),
+               None if table is None else (table.data_ptr(), table.shape[0]))
+        if key == self._weights_key:
+            return
+        for p in params:
+            if p.device != device or p.dtype != torch.float32 or not p.is_contiguous():
+                raise _cabi.VsumError("SimNet parameters must be contiguous fp32 tensors on the input's device")
+        w = _cabi.ScorerWeights()
+        emb = self.embedding_layer.feature_transform
+        w.embed_w, w.embed_b = emb.weight.data_ptr(), emb.bias.data_ptr()
+        if table is not None:
+            table = table.contiguous()
+            w.pos_table, w.pos_rows = table.data_ptr(), table.shape[0]
+        w.final_w, w.final_b = self.final_layer.weight.data_ptr(), self.final_layer.bias.data_ptr()
+        for i, blk in enumerate(self.encoder.module_list):
+            lw = w.layers[i]
+            lw.q_w, lw.q_b = blk.sa.q.weight.data_ptr(), blk.sa.q.bias.data_ptr()
+            lw.k_w, lw.k_b = blk.sa.k.weight.data_ptr(), blk.sa.k.bias.data_ptr()
+            lw.v_w, lw.v_b = blk.sa.v.weight.data_ptr(), blk.sa.v.bias.data_ptr()
+            lw.o_w, lw.o_b = blk.sa.feature_projection.weight.data_ptr(), blk.sa.feature_projection.bias.data_ptr()
+            lw.ln1_g, lw.ln1_b = blk.norm1.weight.data_ptr(), blk.norm1.bias.data_ptr()
+            lw.fc1_w, lw.fc1_b = blk.mlp.fc1.weight.data_ptr(), blk.mlp.fc1.bias.data_ptr()
+            lw.fc2_w, lw.fc2_b = blk.mlp.fc2.weight.data_ptr(), blk.mlp.fc2.bias.data_ptr()
+            lw.ln2_g, lw.ln2_b = blk.norm2.weight.data_ptr(), blk.norm2.bias.data_ptr()
+        _cabi.check(_cabi.load().vsum_scorer_load_weights(self._ensure_handle(), C.byref(w), C.c_void_p(stream)),
+                    "vsum_scorer_load_weights")
+        self._weights_key = key
+
+    def _workspace_for(self, nbytes: int, device) -> Tensor:
+        ws = self._workspace
+        if ws is None or ws.numel() < nbytes + 1024 or ws.device != device:
+            ws = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
+            self._workspace = ws
+        return ws
+
+    # ------------------------------------------------------------------ packed entry point
+    @torch.no_grad()
+    def forward_packed(self, features: Tensor, cu_seqlens: Tensor, seqlens_host: Sequence[int],
+                       apply_sigmoid: bool = False, want_feats: bool = True):
+        """features [T,1024] fp32 on a CUDA device, rows of video v = [cu[v], cu[v+1]).
+        Returns (scores [T,num_classes] fp32, feats [T,d_model] fp32 | None)."""
+        if not features.is_cuda:
+            raise _cabi.VsumError("vsum_b200 runs on CUDA devices only (no CPU fallback); move the input with .cuda()")
+        if features.dtype != torch.float32 or features.dim() != 2 or features.shape[1] != self.in_features:
+            raise ValueError(f"features must be float32 [T,{self.in_features}], got {tuple(features.shape)} {features.dtype}")
+        features = features.contiguous()
+        dev = features.device
+        T, B = features.shape[0], len(seqlens_host)
+        max_len = max(seqlens_host) if B else 0
+        scores = torch.empty((T, self.num_classes), dtype=torch.float32, device=dev)
+        feats = torch.empty((T, self.d_model), dtype=torch.float32, device=dev) if want_feats else None
+        if T == 0:
+            return scores, feats
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            self._sync_weights(max_len, dev, stream)
+            L, mode = _cabi.load(), self._mode()
+            need = L.vsum_scorer_workspace_bytes(self._handle, T, B, mode)
+            ws = self._workspace_for(need, dev)
+            ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+            _cabi.check(L.vsum_scorer_forward(
+                self._handle, features.data_ptr(), cu_seqlens.data_ptr(), B, T, max_len, mode,
+                int(apply_sigmoid), scores.data_ptr(), feats.data_ptr() if want_feats else None,
+                ws_ptr, ws.numel() - (ws_ptr - ws.data_ptr()), stream), "vsum_scorer_forward")
+        return scores, feats
+
+    # ------------------------------------------------------------------ reference contract
+    def forward(self, x, mask=None, vis_attention=None, model_score=False):
+        """x [bs,n,1024]; mask bool [bs,n], True = padded frame (src/train.py:118).  A non-tensor
+        mask is ignored like the reference does (simnet.py:38, train.py:162).  Returns
+        (scores [bs,n,num_classes], feats [bs,n,d_model]); with `model_score=True` the second
+        element is the same tensor because the reference's score stack is empty (simnet.py:80-83)."""
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                "vsum_b200 round 1 ships the scorer forward only; call under torch.no_grad() / model.eval(). "
+                "The backward kernels (SURVEY.md section 8 row a1/K7) are the next row.")
+        bs, n, _ = x.shape
+        dev = x.device
+        if isinstance(mask, Tensor):
+            keep = ~mask
+            lens = keep.sum(dim=1)
+            ramp = torch.arange(n, device=dev).unsqueeze(0) < lens.unsqueeze(1)
+            lens_host = [int(v) for v in lens.tolist()]
+            if not bool((ramp == keep).all()):
+                raise _cabi.VsumError("only suffix padding (pad_sequence layout, dataset.py:157-161) is supported")
+            packed = x[keep]                                       # [T,1024] gather of the valid frames
+            cu = torch.zeros(bs + 1, dtype=torch.int32, device=dev)
+            cu[1:] = lens.cumsum(0).to(torch.int32)
+            s, f = self.forward_packed(packed, cu, lens_host)
+            scores = torch.zeros((bs, n, self.num_classes), dtype=torch.float32, device=dev)
+            feats = torch.zeros((bs, n, self.d_model), dtype=torch.float32, device=dev)
+            scores[keep], feats[keep] = s, f                       # padded rows stay 0 (the loss masks them)
+            return scores, feats
+        cu = torch.arange(0, (bs + 1) * n, n, dtype=torch.int32, device=dev)
+        s, f = self.forward_packed(x.reshape(bs * n, -1), cu, [n] * bs)
+        return s.view(bs, n, self.num_classes), f.view(bs, n, self.d_model)
