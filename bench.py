@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Headline benchmark: summarised videos / second through the whole hot path
+
+    features -> transformer scorer (bf16 tcgen05) -> sigmoid -> shot pooling -> knapsack 15 %
+             -> keyshot mask -> F-score (-> F-score gather across ranks)
+
+on BASELINE.json's throughput-sweep workload (config 5): synthetic videos with N log-uniform in
+[128, 8192] frames, 1024-d fp32 features, 20 annotators, sharded over N GPUs of one node
+(weak scaling: every rank gets --videos videos per step).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on host cores
+
+Prints ONE JSON line on rank 0 (contract in the task statement / DESIGN.md "Measurement").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "video-summarization_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+MODEL_KW = dict(num_heads=4, d_model=256, num_layers=4, sparsity=0., use_cls=False, dropout=0.3,
+                num_classes=1, use_pos=True)                 # run_finetune.sh:1 / train.py:29-34
+N_LO, N_HI, N_USERS = 128, 8192, 20
+METRIC, UNIT = "summarized_videos_per_sec", "videos/s"
+REF_SAMPLE_N = (256, 1024, 4096)        # one video per third of the log-uniform length range
+
+
+def workload_name(videos):
+    return (f"config5 throughput sweep: {videos} synthetic videos/GPU/step, N log-uniform [{N_LO},{N_HI}], "
+            f"1024-d fp32 features, {N_USERS} users, scorer d256/h4/L4 + knapsack 15% + F-score(avg)")
+
+
+def attention_flops(seqlens, d=256, layers=4):
+    """QK^T + PV, per layer launch: 4 * N^2 * d per video."""
+    return float(sum(4.0 * n * n * d for n in seqlens))
+
+
+def scorer_flops(seqlens, d=256, layers=4, in_features=1024):
+    return float(sum(n * (2 * in_features * d + layers * (24 * d * d + 4 * n * d) + 2 * d) for n in seqlens))
+
+
+# --------------------------------------------------------------------------------------------
+# clocks: sampled DURING the timed region
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's CPU algorithm (oracle port) on host cores
+# --------------------------------------------------------------------------------------------
+def cpu_reference_step(sd, sample_videos):
+    """One pass of the reference's val_step + eval_metrics body (minus scipy correlations) over
+    the sample, in the reference's own execution model: torch fp32 on CPU for the scorer, pure
+    Python loops for pooling / knapsack / F-score (oracle/ref_port.py)."""
+    import torch
+    from oracle import ref_port, scorer_ref
+    fs = []
+    for v in sample_videos:
+        logits, _ = scorer_ref.scorer_forward(sd, torch.from_numpy(v.features).unsqueeze(0), num_heads=4)
+        scores = torch.sigmoid(logits.view(1, -1)).squeeze(0).numpy()                  # train.py:144,148
+        summary, *_ = ref_port.summarize_video(v.change_points, scores, v.n_frames, v.picks)
+        fs.append(ref_port.fscore_video(summary, v.user_summary, "avg"))
+    return float(np.mean(fs))
+
+
+def reference_setup():
+    import torch
+    from vsum_b200.model import SimNet
+    from vsum_b200.synthetic import make_video
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(1234)
+    sd = SimNet(**MODEL_KW).state_dict()
+    sample = [make_video(5000 + i, n, n_users=N_USERS) for i, n in enumerate(REF_SAMPLE_N)]
+    return sd, sample, cores
+
+
+def run_cpu_baseline(steps=1, warmup=0):
+    sd, sample, cores = reference_setup()
+    for _ in range(warmup):
+        cpu_reference_step(sd, sample)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_step(sd, sample)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": len(sample) / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(sample)} videos, N={list(REF_SAMPLE_N)} (one per third of the log-uniform length range), "
+                      f"{dt:.2f} s/step; torch fp32 CPU scorer ({cores} threads) + pure-Python pooling/knapsack/F-score "
+                      "as the reference runs them"}, dt
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, dt = run_cpu_baseline(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.videos), "l2": "n/a (CPU)"},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------
+def main_b200(args):
+    import torch
+    import torch.distributed as dist
+    from vsum_b200 import _cabi
+    from vsum_b200.model import SimNet
+    from vsum_b200.pipeline import DeviceBatch, Summarizer, pack_videos
+    from vsum_b200.synthetic import make_video, video_length
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; the B200 path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- workload: weak scaling, rank r owns videos [r*V, (r+1)*V) of the global id space
+    V = args.videos
+    ids = [rank * V + i for i in range(V)]
+    videos = [make_video(v, video_length(v, N_LO, N_HI), n_users=N_USERS, with_features=False) for v in ids]
+    hb = pack_videos(videos, pin=True, with_features=False)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    feats_dev = torch.rand((hb.n_steps, 1024), device=dev, generator=g)        # rng.random-like features in [0,1)
+    hb.features.copy_(feats_dev)                                                # pinned host copy for the e2e leg
+    torch.manual_seed(1234)
+    model = SimNet(**MODEL_KW).to(dev).eval()
+    summ = Summarizer(model, "avg")
+    db = DeviceBatch(hb, dev, features=feats_dev)
+    f_all = torch.empty(world * V, dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step_resident():
+        f = summ.run_device(db)
+        if world > 1:
+            dist.all_gather_into_tensor(f_all, f)           # the path's only exchange (F-score gather)
+        return f
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- value: inputs resident in HBM (features 1024*4 B/frame >> L2, nothing to flush)
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    launches0 = _cabi.launch_count()
+    _cabi.profile_begin()
+    with ClockSampler(local) as clocks:
+        ms_total = timed(step_resident, args.steps)
+    prof = _cabi.profile_end()
+    launches = _cabi.launch_count() - launches0
+    ms_step = ms_total / args.steps
+    value = world * V / (ms_step * 1e-3)
+
+    # ---- e2e: host (pinned) buffers in, F-scores out, copies inside the timed region
+    def step_e2e():
+        f = summ.run_host(hb, dev)
+        return f
+    for _ in range(2):
+        step_e2e()
+    e2e_steps = max(2, min(args.steps, 5))
+    ms_e2e = timed(step_e2e, e2e_steps) / e2e_steps
+    e2e_value = world * V / (ms_e2e * 1e-3)
+
+    if world > 1:
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))       # kernel timed inside a long step
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+        att_ms, att_n = prof.get("attention", (0.0, 0))
+        att_flops = attention_flops(hb.seqlens)                            # per launch (one layer, whole batch)
+        achieved = att_flops / (att_ms / max(att_n, 1) * 1e-3) / 1e12 if att_ms > 0 else None
+        kernel_ms = {k: round(v[0] / args.steps, 4) for k, v in prof.items() if v[1]}
+        gpu_ms = sum(kernel_ms.values())
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(V), "videos_per_gpu_per_step": V, "frames_per_gpu_per_step": hb.n_steps,
+                       "l2": "inputs (fp32 features, %.2f GB/GPU) are larger than L2; no flush needed" % (hb.n_steps * 4096 / 1e9),
+                       "parallelism": f"videos sharded over {world} GPU(s), F-score all-gather"},
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(db.h2d_bytes) * world,
+                    "d2h_bytes_per_step": 8 * V * world, "ms_per_step": ms_e2e},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "attn_tc05_kernel (varlen QK^T/softmax/PV, tcgen05)", "bound": "tensor",
+                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
+                         "peak_source": peak_src,
+                         "flops_per_launch": att_flops, "launch_ms": att_ms / max(att_n, 1),
+                         "share_of_step": (att_ms / args.steps) / gpu_ms if gpu_ms else None},
+            "scorer_tflops": scorer_flops(hb.seqlens) / (sum(v for k, v in kernel_ms.items() if k in (
+                "embed_gemm", "qkv_gemm", "attention", "oproj_ln_gemm", "fc1_gemm", "fc2_ln_gemm")) * 1e-3) / 1e12
+            if gpu_ms else None,
+            "kernel_ms_per_step": kernel_ms,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"], _ = run_cpu_baseline(1, 0)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--videos", type=int, default=256, help="videos per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_b200(a)

@@ -144,6 +144,16 @@ VSUM_API int vsum_summary_fscore(const uint8_t *selected, const int32_t *cps, co
                         double *f_out, double *per_user_out, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Per-kernel timing (bench.py's roofline leg): between begin and end every kernel launch of
+ * this library is bracketed by CUDA events on its own stream; end() synchronises those events
+ * and returns summed milliseconds and launch counts per category.
+ * ------------------------------------------------------------------------------------------ */
+VSUM_API int vsum_profile_begin(void);
+VSUM_API int vsum_profile_end(float *ms_out_host, int32_t *count_out_host, int32_t ncat);
+VSUM_API int32_t vsum_profile_num_categories(void);
+VSUM_API const char *vsum_profile_category_name(int32_t i);
+
+/* ------------------------------------------------------------------------------------------
  * Diagnostics: the two tcgen05 kernels on their own, so tests can pin them individually.
  *   vsum_debug_gemm_tc05: out[M,N] bf16 = epi(A[M,K] W[N,K]^T + bias); A/W bf16, or fp32 when
  *     a_is_f32 (tf32 MMA).  epi: 0 bias, 1 bias+ReLU, 3 bias+residual+LayerNorm (N == 256).

@@ -1,0 +1,122 @@
+"""GPU parity (bit-exact): shot pooling, knapsack, summary mask and F-score kernels, called
+through the C ABI, against the C oracle and the golden fixtures of the reference."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import bits_equal
+from oracle import c_oracle
+from vsum_b200.evaluation import _engine, eval_fscores, eval_metrics, evaluate_summary, generate_summary, knapSack
+from vsum_b200.synthetic import make_scores, make_video
+
+pytestmark = pytest.mark.gpu
+
+
+def run_batch(videos, scores, method="avg"):
+    hb = _engine.HostEvalBatch.build([v.change_points for v in videos], [np.array(v.n_frames) for v in videos],
+                                     [v.picks for v in videos], [v.user_summary for v in videos])
+    db = _engine.DeviceEvalBatch(hb)
+    cu = torch.from_numpy(_engine._cu([len(s) for s in scores]).astype(np.int32)).to(db.device)
+    out = _engine.summarize(db, torch.from_numpy(np.concatenate(scores)).to(db.device), cu, method, want_per_user=True)
+    torch.cuda.synchronize()
+    return hb, {k: (v.cpu().numpy() if v is not None else None) for k, v in out.items()}
+
+
+def check_against_oracle(videos, scores, method):
+    hb, out = run_batch(videos, scores, method)
+    for i, (v, sc) in enumerate(zip(videos, scores)):
+        want = c_oracle.video(sc, v.picks, v.n_frames, v.change_points, v.user_summary, method)
+        s0, s1 = hb.cu_shots[i], hb.cu_shots[i + 1]
+        assert bits_equal(out["val"][s0:s1], want["val"]), f"shot means differ, video {i} (N={v.n_steps})"
+        assert bits_equal(out["wt"][s0:s1], want["wt"])
+        assert int(out["cap"][i]) == want["cap"]
+        assert bits_equal(out["selected"][s0:s1], want["selected"]), f"knapsack selection differs, video {i} (N={v.n_steps})"
+        assert bits_equal(out["summary"][hb.sum_offsets[i]:hb.sum_offsets[i + 1]], want["summary"])
+        assert bits_equal(np.float64(out["f"][i]), np.float64(want["f"])), f"F differs, video {i}"
+
+
+def test_golden_videos_bit_exact(eval_golden):
+    cases = [tuple(int(x) for x in r) for r in eval_golden["cases"]]
+    videos = [make_video(vid, n, n_users=u, with_features=False) for vid, n, u in cases]
+    scores = [make_scores(vid, n) for vid, n, _ in cases]
+    for k, method in enumerate(("avg", "max")):
+        hb, out = run_batch(videos, scores, method)
+        for i, (vid, n, u) in enumerate(cases):
+            summ = out["summary"][hb.sum_offsets[i]:hb.sum_offsets[i + 1]]
+            want = np.unpackbits(eval_golden[f"summary_{vid}"])[:len(summ)].astype(np.int8)
+            assert bits_equal(summ, want), (vid, n)
+            assert bits_equal(out["val"][hb.cu_shots[i]:hb.cu_shots[i + 1]], eval_golden[f"means_{vid}"]), (vid, n)
+            assert bits_equal(np.float64(out["f"][i]), np.float64(eval_golden[f"f_{vid}"][k])), (vid, n, method)
+
+
+@pytest.mark.parametrize("method", ["avg", "max"])
+def test_random_batch_against_oracle(method):
+    rng = np.random.default_rng(21)
+    ns = [int(x) for x in np.exp(rng.uniform(np.log(1), np.log(3000), 160))]
+    videos = [make_video(1000 + i, n, n_users=int(rng.integers(1, 21)), with_features=False) for i, n in enumerate(ns)]
+    check_against_oracle(videos, [make_scores(1000 + i, n) for i, n in enumerate(ns)], method)
+
+
+def test_full_size_videos_against_oracle():
+    # BASELINE config 5 upper end: N = 8192 (S ~ 819 shots, capacity ~ 18.4 k frames)
+    ns = [8192, 8192, 6000, 4096, 128]
+    videos = [make_video(2000 + i, n, n_users=20, with_features=False) for i, n in enumerate(ns)]
+    check_against_oracle(videos, [make_scores(2000 + i, n) for i, n in enumerate(ns)], "avg")
+
+
+def test_ties_and_degenerate_scores():
+    # constant scores make every shot's value equal: exercises the tie rule (line 26) at scale
+    videos = [make_video(3000 + i, n, n_users=5, with_features=False) for i, n in enumerate([300, 1000, 2500])]
+    for const in (0.5, 1.0, 0.0):
+        check_against_oracle(videos, [np.full(v.n_steps, const, np.float32) for v in videos], "avg")
+    # two-level scores: many exact ties between shots of different lengths
+    rng = np.random.default_rng(1)
+    scores = [rng.choice(np.array([0.25, 0.75], np.float32), v.n_steps) for v in videos]
+    check_against_oracle(videos, scores, "max")
+
+
+def test_nothing_fits_gives_nan():
+    cps = np.array([[0, 99]], dtype=np.int32)
+    us = np.ones((2, 100), dtype=np.float32)
+    hb = _engine.HostEvalBatch.build([cps], [np.array(100)], [np.arange(0, 100, 15, dtype=np.int32)], [us])
+    db = _engine.DeviceEvalBatch(hb)
+    out = _engine.summarize(db, torch.full((7,), 0.5, device=db.device), torch.tensor([0, 7], dtype=torch.int32, device=db.device))
+    assert out["summary"].sum().item() == 0 and np.isnan(out["f"].cpu().numpy()[0])
+
+
+def test_reference_call_surface(eval_golden):
+    assert knapSack(7, [2, 2, 1, 1, 1, 2], [4, 4, 2, 2, 2, 4], 6) == [0, 1, 2, 3, 4]   # knapsack_implementation.py:35-41
+    assert knapSack(2, [2, 1, 1], [2, 1, 1], 3) == [0] and knapSack(2, [1, 1, 2], [1, 1, 2], 3) == [0, 1]
+    assert knapSack(0, [1], [1.0], 1) == []
+    rng = np.random.default_rng(2)
+    for _ in range(20):
+        n = int(rng.integers(1, 40))
+        wt, val, W = rng.integers(1, 50, n), rng.choice(rng.random(6), n), int(rng.integers(0, 200))
+        assert knapSack(W, wt, [float(x) for x in val], n) == c_oracle.knapsack(W, wt, val)
+    v = make_video(6, 300, n_users=20, with_features=False)
+    sc = make_scores(6, 300)
+    summ = generate_summary([v.change_points], [sc], [np.array(v.n_frames)], [v.picks])
+    assert len(summ) == 1 and summ[0].dtype == np.int8
+    assert bits_equal(summ[0], np.unpackbits(eval_golden["summary_6"])[:len(summ[0])].astype(np.int8))
+    for k, method in enumerate(("avg", "max")):
+        assert bits_equal(np.float64(evaluate_summary(summ[0], v.user_summary, method)), np.float64(eval_golden["f_6"][k]))
+    # summary shorter / longer than the user matrix (evaluation_metrics.py:12-15)
+    short, us = np.array([1, 0, 1], np.int8), np.array([[1, 1, 0, 1, 0]], np.float32)
+    assert bits_equal(np.float64(evaluate_summary(short, us, "avg")), np.float64(c_oracle.fscore(short, us, "avg")[0]))
+    long_ = np.ones(9, np.int8)
+    assert bits_equal(np.float64(evaluate_summary(long_, us, "max")), np.float64(c_oracle.fscore(long_, us, "max")[0]))
+
+
+def test_eval_metrics_golden():
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "eval_metrics_golden.npz"))
+    data, users = {}, {}
+    for vid, n in zip(g["ids"], g["ns"]):
+        v = make_video(int(vid), int(n), n_users=20, with_features=False, with_user_scores=True)
+        data[v.name], users[v.name] = make_scores(int(vid), int(n)), v.as_user()
+    f, tau, rho = eval_metrics(data, users)
+    assert bits_equal(np.float64(f), np.float64(g["result"][0]))          # F: bit-exact
+    assert abs(tau - g["result"][1]) < 1e-12 and abs(rho - g["result"][2]) < 1e-12   # scipy on host, as the reference
+    per_video = eval_fscores(data, users)
+    assert bits_equal(np.float64(np.mean(per_video)), np.float64(f))

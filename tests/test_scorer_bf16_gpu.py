@@ -1,0 +1,64 @@
+"""GPU parity: bf16 tcgen05 scorer (the throughput path) against the reference's fp32 outputs
+(golden fixtures).  Tolerance 1e-2 on the importance scores (BASELINE.json); logits are compared
+with the same absolute tolerance because sigmoid is 1/4-Lipschitz."""
+import numpy as np
+import pytest
+import torch
+
+from vsum_b200.model import SimNet
+from vsum_b200.synthetic import make_video
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def models(seeded_model_kwargs):
+    torch.manual_seed(1234)
+    bf = SimNet(**seeded_model_kwargs).cuda().eval()
+    assert bf.precision == "bf16"
+    torch.manual_seed(1234)
+    fp = SimNet(**seeded_model_kwargs).cuda().eval()
+    fp.precision = "fp32"
+    return bf, fp
+
+
+def sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def test_golden_scores(models, scorer_golden):
+    bf, _ = models
+    for vid, n in [tuple(int(x) for x in r) for r in scorer_golden["cases"]] + [(106, 2300)]:
+        x = torch.from_numpy(make_video(vid, n).features).unsqueeze(0).cuda()
+        with torch.no_grad():
+            logits, feats = bf(x)
+        got = logits.view(-1).cpu().numpy()
+        want = scorer_golden[f"logits_{vid}"]
+        np.testing.assert_allclose(sigmoid(got), sigmoid(want), rtol=TOL, atol=0)
+        np.testing.assert_allclose(got, want, rtol=0, atol=4 * TOL)
+        assert feats.shape == (1, n, 256) and torch.isfinite(feats).all()
+
+
+def test_bf16_tracks_fp32_on_packed_varlen(models):
+    bf, fp = models
+    lens = [700, 128, 1, 129, 2500, 64]
+    vids = [make_video(600 + i, n) for i, n in enumerate(lens)]
+    feats = torch.from_numpy(np.concatenate([v.features for v in vids])).cuda()
+    cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32).cuda()
+    a, fa = bf.forward_packed(feats, cu, lens, apply_sigmoid=True)
+    b, fb = fp.forward_packed(feats, cu, lens, apply_sigmoid=True)
+    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=TOL, atol=0)
+    assert (fa - fb).abs().max().item() < 0.15          # bf16 residual stream, unit-variance features
+    # without the feature output (the throughput configuration) the scores are unchanged
+    c, none = bf.forward_packed(feats, cu, lens, apply_sigmoid=True, want_feats=False)
+    assert none is None and torch.equal(a, c)
+
+
+def test_deterministic(models):
+    bf, _ = models
+    x = torch.from_numpy(make_video(700, 900).features).unsqueeze(0).cuda()
+    with torch.no_grad():
+        a, _ = bf(x)
+        b, _ = bf(x)
+    assert torch.equal(a, b)

@@ -316,6 +316,7 @@ int launch_attention_tc05(const __nv_bfloat16 *qkv, const int32_t *cu_seqlens, c
         if (sscanf(e, "%u,%u,%u", &a, &b, &c) == 3) { v_lbo = a; v_sbo = b; v_kstep = c; }
     }
     dim3 grid((unsigned)max_tiles, NH);
+    ProfScope prof(PROF_ATTN, s);
     attn_tc05_kernel<<<grid, ATT_THREADS, ATT_SMEM, s>>>(tm, cu_seqlens, tile_video, tile_q0, n_tiles_ptr, out,
                                                          scale * 1.4426950408889634f, v_lbo, v_sbo, v_kstep);
     VSUM_LAUNCH_OK("attn_tc05_kernel");

@@ -42,6 +42,18 @@ void count_launch(int n = 1);
         ::vsum::count_launch();                                                                 \
     } while (0)
 
+// Optional per-kernel timing with CUDA events on the launching stream (vsum_profile_begin/end).
+enum ProfCategory {
+    PROF_EMBED = 0, PROF_QKV, PROF_ATTN, PROF_OPROJ_LN, PROF_FC1, PROF_FC2_LN, PROF_SHOT_MEAN, PROF_KNAPSACK,
+    PROF_MASK, PROF_OVERLAP, PROF_FSCORE, PROF_OTHER, PROF_NUM
+};
+struct ProfScope {
+    int idx;
+    cudaStream_t stream;
+    ProfScope(int category, cudaStream_t s);
+    ~ProfScope();
+};
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

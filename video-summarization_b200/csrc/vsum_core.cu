@@ -3,6 +3,8 @@
 
 #include <atomic>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 namespace vsum {
 
@@ -21,7 +23,59 @@ int set_error(int code, const char *fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// ---- profiling -------------------------------------------------------------------------------
+struct ProfRecord { int cat; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRecord> g_prof_recs;      // event pool, reused across sessions
+static size_t g_prof_used = 0;
+
+ProfScope::ProfScope(int category, cudaStream_t s) : idx(-1), stream(s) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (g_prof_used == g_prof_recs.size()) {
+        ProfRecord r{};
+        if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+        g_prof_recs.push_back(r);
+    }
+    idx = (int)g_prof_used++;
+    g_prof_recs[idx].cat = category;
+    cudaEventRecord(g_prof_recs[idx].a, stream);
+}
+ProfScope::~ProfScope() {
+    if (idx >= 0) cudaEventRecord(g_prof_recs[idx].b, stream);
+}
+
+static const char *kProfNames[PROF_NUM] = {"embed_gemm", "qkv_gemm", "attention", "oproj_ln_gemm", "fc1_gemm",
+                                           "fc2_ln_gemm", "shot_mean", "knapsack", "summary_mask", "overlap",
+                                           "fscore_finalize", "other"};
+
 }  // namespace vsum
+
+extern "C" int vsum_profile_begin(void) {
+    std::lock_guard<std::mutex> lk(vsum::g_prof_mu);
+    vsum::g_prof_used = 0;
+    vsum::g_prof_on = true;
+    return VSUM_OK;
+}
+extern "C" int vsum_profile_end(float *ms_out, int32_t *count_out, int32_t ncat) {
+    std::lock_guard<std::mutex> lk(vsum::g_prof_mu);
+    vsum::g_prof_on = false;
+    for (int i = 0; i < ncat; ++i) { if (ms_out) ms_out[i] = 0.f; if (count_out) count_out[i] = 0; }
+    for (size_t i = 0; i < vsum::g_prof_used; ++i) {
+        const vsum::ProfRecord &r = vsum::g_prof_recs[i];
+        float ms = 0.f;
+        VSUM_CUDA_OK(cudaEventSynchronize(r.b));
+        VSUM_CUDA_OK(cudaEventElapsedTime(&ms, r.a, r.b));
+        if (r.cat < ncat) { if (ms_out) ms_out[r.cat] += ms; if (count_out) count_out[r.cat] += 1; }
+    }
+    vsum::g_prof_used = 0;
+    return VSUM_OK;
+}
+extern "C" int32_t vsum_profile_num_categories(void) { return vsum::PROF_NUM; }
+extern "C" const char *vsum_profile_category_name(int32_t i) {
+    return (i >= 0 && i < vsum::PROF_NUM) ? vsum::kProfNames[i] : "";
+}
 
 extern "C" int vsum_abi_version(void) { return 1; }
 extern "C" const char *vsum_last_error(void) { return vsum::error_buffer(); }

@@ -337,6 +337,7 @@ extern "C" int vsum_shot_mean(const float *scores, const int32_t *cu_steps, cons
     VSUM_REQUIRE(scores && cu_steps && picks && cu_picks && n_frames && cps && cu_shots && val_out &&
                  wt_out && cap_out, VSUM_EINVAL, "vsum_shot_mean: null pointer");
     const int threads = 128;
+    ProfScope prof(PROF_SHOT_MEAN, (cudaStream_t)stream);
     shot_mean_kernel<<<(unsigned)ceil_div(S_total, threads), threads, 0, (cudaStream_t)stream>>>(
         scores, cu_steps, picks, cu_picks, n_frames, cps, cu_shots, B, S_total, val_out, wt_out,
         cap_out);
@@ -358,6 +359,7 @@ static int launch_knapsack(const double *val, const int32_t *wt, const int32_t *
     auto kern = knapsack_kernel<THREADS, EPT>;
     if (smem > 48 * 1024)
         VSUM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope prof(PROF_KNAPSACK, stream);
     kern<<<B, THREADS, smem, stream>>>(val, wt, cu_shots, cap, bit_offsets, order, take_bits, selected_out);
     VSUM_LAUNCH_OK("knapsack_kernel");
     return VSUM_OK;
@@ -404,6 +406,7 @@ extern "C" int vsum_summary_fscore(const uint8_t *selected, const int32_t *cps,
     if (selected) {   // selected == NULL: summary_out already holds the masks (evaluate_summary)
         const int64_t avg = summary_total / B + 1;
         dim3 grid((unsigned)max((int64_t)1, min((int64_t)64, ceil_div(avg, 256 * 4))), (unsigned)B);
+        ProfScope prof(PROF_MASK, s);
         summary_mask_kernel<<<grid, 256, 0, s>>>(selected, cps, cu_shots, sum_offsets, summary_out);
         VSUM_LAUNCH_OK("summary_mask_kernel");
     }
@@ -411,11 +414,13 @@ extern "C" int vsum_summary_fscore(const uint8_t *selected, const int32_t *cps,
     VSUM_REQUIRE(user_summary && us_offsets && cu_users && us_cols && counts_ws, VSUM_EINVAL,
                  "vsum_summary_fscore: null pointer");
     if (total_users > 0) {
+        ProfScope prof(PROF_OVERLAP, s);
         overlap_kernel<<<total_users, 256, 0, s>>>(summary_out, sum_offsets, user_summary,
                                                    us_offsets, cu_users, us_cols, B,
                                                    reinterpret_cast<long long *>(counts_ws));
         VSUM_LAUNCH_OK("overlap_kernel");
     }
+    ProfScope prof(PROF_FSCORE, s);
     fscore_finalize_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, s>>>(
         reinterpret_cast<const long long *>(counts_ws), cu_users, B, method, f_out, per_user_out);
     VSUM_LAUNCH_OK("fscore_finalize_kernel");

@@ -316,7 +316,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <bool TF32, int EPI, bool WRES>
-int launch_variant(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, cudaStream_t s) {
+int launch_variant(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, cudaStream_t s, int cat) {
     auto kern = gemm_tc05_kernel<TF32, EPI, WRES>;
     static bool configured = false;
     if (!configured) {
@@ -329,6 +329,7 @@ int launch_variant(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmPar
     dim3 grid;
     if (WRES) grid = dim3((unsigned)max((int64_t)1, min(p.m_tiles, (int64_t)(sms / p.n_tiles))), (unsigned)p.n_tiles);
     else grid = dim3((unsigned)min(p.m_tiles * p.n_tiles, (int64_t)sms));
+    ProfScope prof(cat, s);
     kern<<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, p);
     VSUM_LAUNCH_OK("gemm_tc05_kernel");
     return VSUM_OK;
@@ -359,18 +360,18 @@ int launch_gemm_tc05(const Tc05GemmArgs &a, cudaStream_t s) {
     const bool wres = !a.a_is_f32 && p.num_kb <= WRES_MAX_KB && p.m_tiles >= 2 * (148 / p.n_tiles);
     if (a.a_is_f32) {
         VSUM_REQUIRE(a.epi == TC_EPI_BIAS_POS || a.epi == TC_EPI_BIAS, VSUM_EUNSUPPORTED, "gemm_tc05: tf32 path supports BIAS / BIAS_POS only");
-        if (a.epi == TC_EPI_BIAS_POS) return launch_variant<true, TC_EPI_BIAS_POS, false>(tmA, tmB, p, s);
-        return launch_variant<true, TC_EPI_BIAS, false>(tmA, tmB, p, s);
+        if (a.epi == TC_EPI_BIAS_POS) return launch_variant<true, TC_EPI_BIAS_POS, false>(tmA, tmB, p, s, a.prof_cat);
+        return launch_variant<true, TC_EPI_BIAS, false>(tmA, tmB, p, s, a.prof_cat);
     }
     switch (a.epi) {
         case TC_EPI_BIAS:
-            return wres ? launch_variant<false, TC_EPI_BIAS, true>(tmA, tmB, p, s) : launch_variant<false, TC_EPI_BIAS, false>(tmA, tmB, p, s);
+            return wres ? launch_variant<false, TC_EPI_BIAS, true>(tmA, tmB, p, s, a.prof_cat) : launch_variant<false, TC_EPI_BIAS, false>(tmA, tmB, p, s, a.prof_cat);
         case TC_EPI_BIAS_RELU:
-            return wres ? launch_variant<false, TC_EPI_BIAS_RELU, true>(tmA, tmB, p, s) : launch_variant<false, TC_EPI_BIAS_RELU, false>(tmA, tmB, p, s);
+            return wres ? launch_variant<false, TC_EPI_BIAS_RELU, true>(tmA, tmB, p, s, a.prof_cat) : launch_variant<false, TC_EPI_BIAS_RELU, false>(tmA, tmB, p, s, a.prof_cat);
         case TC_EPI_BIAS_RES_LN:
-            return wres ? launch_variant<false, TC_EPI_BIAS_RES_LN, true>(tmA, tmB, p, s) : launch_variant<false, TC_EPI_BIAS_RES_LN, false>(tmA, tmB, p, s);
+            return wres ? launch_variant<false, TC_EPI_BIAS_RES_LN, true>(tmA, tmB, p, s, a.prof_cat) : launch_variant<false, TC_EPI_BIAS_RES_LN, false>(tmA, tmB, p, s, a.prof_cat);
         case TC_EPI_BIAS_RES_LN_HEAD:
-            return launch_variant<false, TC_EPI_BIAS_RES_LN_HEAD, false>(tmA, tmB, p, s);
+            return launch_variant<false, TC_EPI_BIAS_RES_LN_HEAD, false>(tmA, tmB, p, s, a.prof_cat);
         default:
             return set_error(VSUM_EINVAL, "gemm_tc05: unknown epilogue %d", a.epi);
     }

@@ -64,6 +64,7 @@ struct Tc05GemmArgs {
     float *scores_out;        // [M]
     float *feats_out;         // [M,256] fp32 or NULL
     int apply_sigmoid;
+    int prof_cat;             // ProfCategory for vsum_profile_*
 };
 int launch_gemm_tc05(const Tc05GemmArgs &a, cudaStream_t s);
 

@@ -212,7 +212,7 @@ static int forward_bf16(vsum_scorer_t h, const float *x, const int32_t *cu, int 
     Tc05GemmArgs g{};
     g.A = x; g.W = h->w32 + h->embed_w; g.M = T; g.N = 256; g.K = c.in_features; g.a_is_f32 = 1;
     g.epi = c.use_pos ? TC_EPI_BIAS_POS : TC_EPI_BIAS; g.bias = h->w32 + h->embed_b; g.out = w.xa;
-    g.pos_table = h->pos_table; g.row_pos = w.row_pos; g.pos_rows = h->pos_rows;
+    g.pos_table = h->pos_table; g.row_pos = w.row_pos; g.pos_rows = h->pos_rows; g.prof_cat = PROF_EMBED;
     RUN(launch_gemm_tc05(g, s));
     const float scale = 1.0f / 16.0f;                                   // 256 ** -0.5
     for (int l = 0; l < c.num_layers; ++l) {
@@ -220,16 +220,17 @@ static int forward_bf16(vsum_scorer_t h, const float *x, const int32_t *cu, int 
         const bool last = l == c.num_layers - 1;
         Tc05GemmArgs q{};
         q.A = w.xa; q.W = h->w16 + o.h_wqkv; q.M = T; q.N = 768; q.K = 256; q.epi = TC_EPI_BIAS;
-        q.bias = h->w32 + o.bqkv; q.out = w.qkv;
+        q.bias = h->w32 + o.bqkv; q.out = w.qkv; q.prof_cat = PROF_QKV;
         RUN(launch_gemm_tc05(q, s));
         RUN(launch_attention_tc05(w.qkv, cu, w.tile_video, w.tile_q0, w.n_tiles, max_tiles, T, scale, w.att, s));
         Tc05GemmArgs p{};
         p.A = w.att; p.W = h->w16 + o.h_wo; p.M = T; p.N = 256; p.K = 256; p.epi = TC_EPI_BIAS_RES_LN;
         p.bias = h->w32 + o.bo; p.residual = w.xa; p.gamma = h->w32 + o.ln1g; p.beta = h->w32 + o.ln1b; p.out = w.xb;
+        p.prof_cat = PROF_OPROJ_LN;
         RUN(launch_gemm_tc05(p, s));
         Tc05GemmArgs f1{};
         f1.A = w.xb; f1.W = h->w16 + o.h_fc1; f1.M = T; f1.N = 1024; f1.K = 256; f1.epi = TC_EPI_BIAS_RELU;
-        f1.bias = h->w32 + o.fc1b; f1.out = w.hid;
+        f1.bias = h->w32 + o.fc1b; f1.out = w.hid; f1.prof_cat = PROF_FC1;
         RUN(launch_gemm_tc05(f1, s));
         Tc05GemmArgs f2{};
         f2.A = w.hid; f2.W = h->w16 + o.h_fc2; f2.M = T; f2.N = 256; f2.K = 1024;
@@ -237,7 +238,7 @@ static int forward_bf16(vsum_scorer_t h, const float *x, const int32_t *cu, int 
         f2.bias = h->w32 + o.fc2b; f2.residual = w.xb; f2.gamma = h->w32 + o.ln2g; f2.beta = h->w32 + o.ln2b;
         f2.out = last ? nullptr : w.xa;
         f2.head_w = h->w32 + h->final_w; f2.head_b = h->w32 + h->final_b; f2.scores_out = scores; f2.feats_out = feats;
-        f2.apply_sigmoid = sigm;
+        f2.apply_sigmoid = sigm; f2.prof_cat = PROF_FC2_LN;
         RUN(launch_gemm_tc05(f2, s));
     }
 #undef RUN
@@ -277,6 +278,7 @@ extern "C" int vsum_debug_gemm_tc05(const void *A, const void *W, const float *b
                  "vsum_debug_gemm_tc05: epi %d", epi);
     Tc05GemmArgs g{};
     g.A = A; g.W = W; g.M = M; g.N = N; g.K = K; g.a_is_f32 = a_is_f32; g.epi = epi; g.bias = bias;
+    g.prof_cat = PROF_OTHER;
     g.out = (__nv_bfloat16 *)out; g.residual = (const __nv_bfloat16 *)residual; g.gamma = gamma; g.beta = beta;
     return launch_gemm_tc05(g, (cudaStream_t)stream);
 }

@@ -23,6 +23,7 @@ EXPORTS = (
     "vsum_scorer_workspace_bytes", "vsum_scorer_forward",
     "vsum_shot_mean", "vsum_knapsack_scratch_words", "vsum_knapsack", "vsum_summary_fscore",
     "vsum_debug_gemm_tc05", "vsum_debug_attention_tc05",
+    "vsum_profile_begin", "vsum_profile_end", "vsum_profile_num_categories", "vsum_profile_category_name",
 )
 
 
@@ -80,6 +81,10 @@ def load():
     L.vsum_summary_fscore.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, i64, vp, vp, vp, vp]
     L.vsum_debug_gemm_tc05.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]
     L.vsum_debug_attention_tc05.argtypes = [vp, vp, i32, i64, vp, vp, vp]
+    L.vsum_profile_end.argtypes = [vp, vp, i32]
+    L.vsum_profile_num_categories.restype = i32
+    L.vsum_profile_category_name.restype = C.c_char_p
+    L.vsum_profile_category_name.argtypes = [i32]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("vsum_abi_version",):
@@ -96,3 +101,17 @@ def check(rc: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(load().vsum_launch_count())
+
+
+def profile_begin() -> None:
+    check(load().vsum_profile_begin(), "vsum_profile_begin")
+
+
+def profile_end() -> dict:
+    """{category: (total milliseconds, launches)} for every kernel launched since profile_begin()."""
+    L = load()
+    n = int(L.vsum_profile_num_categories())
+    ms = (C.c_float * n)()
+    cnt = (C.c_int32 * n)()
+    check(L.vsum_profile_end(ms, cnt, n), "vsum_profile_end")
+    return {L.vsum_profile_category_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
