@@ -29,12 +29,35 @@ constexpr int BQ = 128, BKV = 128;
 constexpr int TILE_BYTES = 128 * 128;   // 128 rows x 64 bf16 = 16 KB
 constexpr int ATT_THREADS = 256;
 constexpr int ATT_TMEM_COLS = 256;      // S: 128, O0: 64, O1: 64
-constexpr size_t ATT_SMEM = 1024 + 7 * (size_t)TILE_BYTES + 256;   // Q, K0, V0, K1, V1, P(2 halves)
+constexpr size_t ATT_SMEM = 7 * (size_t)TILE_BYTES + 128;   // Q, K0, V0, K1, V1, P(2 halves) + barriers: 2 CTAs / SM
 
 __device__ __forceinline__ float ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+// Packed fp32x2 arithmetic (sm_100): halves the FFMA / FADD issue slots of the softmax.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(*reinterpret_cast<uint64_t *>(&d))
+        : "l"(*reinterpret_cast<const uint64_t *>(&a)), "l"(*reinterpret_cast<const uint64_t *>(&b)),
+          "l"(*reinterpret_cast<const uint64_t *>(&c)));
+    return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    float2 d;
+    asm("add.rn.f32x2 %0, %1, %2;"
+        : "=l"(*reinterpret_cast<uint64_t *>(&d))
+        : "l"(*reinterpret_cast<const uint64_t *>(&a)), "l"(*reinterpret_cast<const uint64_t *>(&b)));
+    return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    float2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;"
+        : "=l"(*reinterpret_cast<uint64_t *>(&d))
+        : "l"(*reinterpret_cast<const uint64_t *>(&a)), "l"(*reinterpret_cast<const uint64_t *>(&b)));
+    return d;
 }
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -47,8 +70,8 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
                  const int32_t *__restrict__ n_tiles_ptr, __nv_bfloat16 *__restrict__ out,
                  float scale_log2e, uint32_t v_lbo, uint32_t v_sbo, uint32_t v_kstep) {
     if ((int)blockIdx.x >= __ldg(n_tiles_ptr)) return;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem[];    // no alignment slack: it would cost the 2nd CTA / SM
+    if ((tc::smem_u32(smem) & 1023u) != 0) __trap();     // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t *sQ = smem;
     uint8_t *sKV = smem + TILE_BYTES;                 // stage s: K at 2s, V at 2s+1 (tiles)
     uint8_t *sP = smem + 5 * (size_t)TILE_BYTES;      // two 64-key halves, 16 KB each
@@ -141,12 +164,18 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
         tc::setmaxnreg_inc<216>();
         const int qd = warp - 4, r = qd * 32 + lane;
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        float m_run = -INFINITY, l_run = 0.f;
+        float m_run = -INFINITY, l_run = 0.f;   // m_run: exponent reference (exp2 domain), <= row max + 8
         float o[HD];
 #pragma unroll
         for (int i = 0; i < HD; ++i) o[i] = 0.f;
         uint8_t *p_row = sP + (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128;
         const int sw = r & 7;
+
+        uint32_t p_off[8];                       // swizzled 16-byte chunk offsets of this row
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) p_off[ch] = (uint32_t)((ch ^ sw) << 4);
+        const uint32_t p_row_u32 = tc::smem_u32(p_row);
+        const float2 c2 = make_float2(scale_log2e, scale_log2e);
 
         for (int j = 0; j < nkv; ++j) {
             uint32_t s[128];
@@ -172,31 +201,47 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
                 for (int c = 0; c < BKV; ++c)
                     if (c >= valid) s[c] = 0xff800000u;   // -inf
             }
-            float mx = __uint_as_float(s[0]);
+            // 8 independent chains (a single 128-long fmax / fadd chain costs 128 x 4 cycles of latency)
+            float mx8[8];
 #pragma unroll
-            for (int c = 1; c < BKV; ++c) mx = fmaxf(mx, __uint_as_float(s[c]));
-            const float m_new = fmaxf(m_run, mx * scale_log2e);       // exp2 domain (scale > 0)
-            const float alpha = ex2(m_run - m_new);                   // 0 on the first tile
-            float psum = 0.f;
+            for (int e = 0; e < 8; ++e) mx8[e] = __uint_as_float(s[e]);
+#pragma unroll
+            for (int c = 8; c < BKV; c += 8)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) mx8[e] = fmaxf(mx8[e], __uint_as_float(s[c + e]));
+            const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
+                                   fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]))) * scale_log2e;
+            // Lazy rescale: the exponent reference m_run only moves when the row max grew by more
+            // than 2^8, so P stays <= 256 (exact in the fp32/bf16 exponent range) and the O / l
+            // correction is skipped on almost every tile.  The branch is warp-uniform.
+            float alpha = 1.0f;
+            const bool bump = mx > m_run + 8.0f;
+            if (__any_sync(0xffffffffu, bump)) {
+                if (bump) { alpha = ex2(m_run - mx); m_run = mx; }      // alpha = 0 on the first tile
+            }
+            const float2 nm2 = make_float2(-m_run, -m_run);
+            float2 ps[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
             tc::mbar_wait(p_empty, (j & 1) ^ 1);                      // PV(j-1) has consumed P
 #pragma unroll
             for (int c = 0; c < BKV; c += 8) {
-                float pv[8];
+                float2 pv[4];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    pv[e] = ex2(fmaf(__uint_as_float(s[c + e]), scale_log2e, -m_new));
-                    psum += pv[e];
+                for (int e = 0; e < 4; ++e) {
+                    const float2 x = ffma2(make_float2(__uint_as_float(s[c + 2 * e]), __uint_as_float(s[c + 2 * e + 1])), c2, nm2);
+                    pv[e] = make_float2(ex2(x.x), ex2(x.y));
+                    ps[e] = fadd2(ps[e], pv[e]);
                 }
-                uint4 pk;
-                pk.x = pack2(pv[0], pv[1]); pk.y = pack2(pv[2], pv[3]);
-                pk.z = pack2(pv[4], pv[5]); pk.w = pack2(pv[6], pv[7]);
-                const int chunk = (c >> 3) & 7, half = c >> 6;
-                *reinterpret_cast<uint4 *>(p_row + (size_t)half * TILE_BYTES + ((chunk ^ sw) << 4)) = pk;
+                const uint32_t addr = p_row_u32 + (uint32_t)(c >> 6) * TILE_BYTES + p_off[(c >> 3) & 7];
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack2(pv[0].x, pv[0].y)),
+                             "r"(pack2(pv[1].x, pv[1].y)), "r"(pack2(pv[2].x, pv[2].y)), "r"(pack2(pv[3].x, pv[3].y))
+                             : "memory");
             }
             tc::fence_proxy_async_smem();
             tc::mbar_arrive(p_full);
+            const float2 pq = fadd2(fadd2(ps[0], ps[1]), fadd2(ps[2], ps[3]));
+            const float psum = pq.x + pq.y;
 
-            if (j > 0) {    // fold in O_{j-1} = P_{j-1} V_{j-1}, then rescale to the new max
+            if (j > 0) {    // fold in O_{j-1} = P_{j-1} V_{j-1}; rescale only when the reference max moved
                 const int b = (j - 1) & 1;
                 tc::mbar_wait(o_full + b, ((j - 1) >> 1) & 1);
                 tc::tc_fence_after();
@@ -207,13 +252,21 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
                 tc::tc_fence_before();
                 tc::mbar_arrive(o_empty + b);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    o[i] = (o[i] + __uint_as_float(t0[i])) * alpha;
-                    o[i + 32] = (o[i + 32] + __uint_as_float(t1[i])) * alpha;
+                for (int i = 0; i < 32; i += 2) {
+                    float2 a0 = fadd2(make_float2(o[i], o[i + 1]), make_float2(__uint_as_float(t0[i]), __uint_as_float(t0[i + 1])));
+                    float2 a1 = fadd2(make_float2(o[i + 32], o[i + 33]), make_float2(__uint_as_float(t1[i]), __uint_as_float(t1[i + 1])));
+                    o[i] = a0.x; o[i + 1] = a0.y; o[i + 32] = a1.x; o[i + 33] = a1.y;
+                }
+                if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+                    const float2 al2 = make_float2(alpha, alpha);
+#pragma unroll
+                    for (int i = 0; i < HD; i += 2) {
+                        const float2 a = fmul2(make_float2(o[i], o[i + 1]), al2);
+                        o[i] = a.x; o[i + 1] = a.y;
+                    }
                 }
             }
             l_run = fmaf(l_run, alpha, psum);
-            m_run = m_new;
         }
         {
             const int b = (nkv - 1) & 1;
