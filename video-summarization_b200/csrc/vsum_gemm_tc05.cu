@@ -60,18 +60,19 @@ constexpr int BN = 256;                 // columns per tile (UMMA N) -- one full
 constexpr int STAGES = 4;
 constexpr int A_STAGE = BM * 128;       // 16 KB: 128 rows x 128 B
 constexpr int B_STAGE = BN * 128;       // 32 KB
+constexpr int RING_BYTES = STAGES * (A_STAGE + B_STAGE);   // 192 KB (WRES: 128 KB of W + 4 x 16 KB of A)
+constexpr int STG_BYTES = BM * 128;     // 16 KB: one [128 rows x 64 bf16] SW128 staging tile
 constexpr int GEMM_THREADS = 256;
 constexpr int TMEM_COLS = 512;          // 2 accumulator stages x 256 fp32 columns
 constexpr int WRES_MAX_KB = 4;          // weight-stationary variant: K = 256 bf16 -> 4 k-blocks = 128 KB
-constexpr size_t GEMM_SMEM = 1024 /*align*/ + (size_t)STAGES * (A_STAGE + B_STAGE) + 256 /*barriers*/;
+constexpr size_t GEMM_SMEM = (size_t)RING_BYTES + 2 * STG_BYTES + 256 /*barriers*/;
+constexpr int EPI_BAR = 1;              // named barrier of the 128 epilogue threads
 
 struct GemmParams {
     int64_t M;
     int N, num_kb, n_tiles;
     int64_t m_tiles;
     const float *bias;
-    __nv_bfloat16 *out;
-    const __nv_bfloat16 *residual;
     const float *gamma, *beta;
     const float *pos_table;
     const int32_t *row_pos;
@@ -79,29 +80,44 @@ struct GemmParams {
     const float *head_w, *head_b;
     float *scores_out, *feats_out;
     int apply_sigmoid;
+    int store_out;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&h);
 }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 
+// The epilogue never touches global memory row-by-row (that costs one L1 wavefront per row and
+// instruction): bf16 outputs are written to a 128B-swizzled staging tile and leave through TMA
+// stores, the LayerNorm residual arrives through TMA loads into the same two staging tiles.
 template <bool TF32, int EPI, bool WRES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                  const GemmParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((tc::smem_u32(smem) & 1023u) != 0) __trap();
     // non-WRES: stage s = {A: s*48K, B: s*48K + 16K}.  WRES: W k-blocks at kb*32K, A ring after 128K.
     uint8_t *ring = smem;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * (A_STAGE + B_STAGE));
+    uint8_t *stg = smem + RING_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + RING_BYTES + 2 * STG_BYTES);
     uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = tfull + 2;
-    uint64_t *wfull = tempty + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(wfull + 1);
+    uint64_t *wfull = tempty + 2, *rfull = wfull + 1;     // rfull[2]: residual staging tiles
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(rfull + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int KELTS = TF32 ? 32 : 64;          // elements per 128-byte k-block
     constexpr uint32_t IDESC = tc::make_idesc(TF32 ? 2 : 1, BM, BN, 0, 0);
+    constexpr bool IS_LN = EPI == TC_EPI_BIAS_RES_LN || EPI == TC_EPI_BIAS_RES_LN_HEAD;
 
     auto a_stage = [&](int s) -> uint8_t * {
         return WRES ? ring + (size_t)WRES_MAX_KB * B_STAGE + (size_t)s * A_STAGE : ring + (size_t)s * (A_STAGE + B_STAGE);
@@ -111,10 +127,12 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmA);
         tc::tma_prefetch_desc(&tmB);
+        tc::tma_prefetch_desc(&tmOut);
+        tc::tma_prefetch_desc(&tmRes);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); }
-        for (int a = 0; a < 2; ++a) { tc::mbar_init(tfull + a, 1); tc::mbar_init(tempty + a, 128); }
+        for (int a = 0; a < 2; ++a) { tc::mbar_init(tfull + a, 1); tc::mbar_init(tempty + a, 128); tc::mbar_init(rfull + a, 1); }
         tc::mbar_init(wfull, 1);
         tc::fence_barrier_init();
     }
@@ -181,79 +199,111 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp >= 4) {  // ===== epilogue: thread <-> one output row =====
         const int q = warp - 4;
-        uint32_t tl = 0;
+        const int r = q * 32 + lane;                        // row inside the tile
+        const bool leader = r == 0;
+        // this row's eight 16-byte chunks inside a [128 x 64 bf16] SW128 staging tile
+        const uint32_t stg_row = tc::smem_u32(stg) + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+        uint32_t sw_off[8];
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) sw_off[ch] = (uint32_t)((ch ^ (r & 7)) << 4);
+        uint32_t tl = 0, res_it = 0;
         for (int64_t t = first; t < total; t += step, ++tl) {
             const int64_t m_blk = WRES ? t : t / p.n_tiles;
             const int n_blk = WRES ? (int)blockIdx.y : (int)(t % p.n_tiles);
             const int acc = tl & 1;
+            const int64_t row = m_blk * BM + r;
+            const bool valid = row < p.M;
+            const int n0 = n_blk * BN;
+            if (IS_LN && leader) {   // residual chunks 0,1 on their way while the MMAs still run
+                tc::bulk_wait_read<0>();                     // earlier stores no longer read the staging tiles
+                for (int cc = 0; cc < 2; ++cc) {
+                    tc::mbar_arrive_expect_tx(rfull + cc, STG_BYTES);
+                    tc::tma_load_2d(stg + cc * STG_BYTES, &tmRes, rfull + cc, cc * 64, (int)(m_blk * BM));
+                }
+            }
             tc::mbar_wait(tfull + acc, (tl >> 1) & 1);
             tc::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-            const int64_t row = m_blk * BM + q * 32 + lane;
-            const bool valid = row < p.M;
-            const int n0 = n_blk * BN;
-            uint32_t r[32];
+            uint32_t ra[32], rb[32];
 
-            if (EPI == TC_EPI_BIAS || EPI == TC_EPI_BIAS_RELU || EPI == TC_EPI_BIAS_POS) {
+            if (!IS_LN) {
                 const float *pos = nullptr;
                 if (EPI == TC_EPI_BIAS_POS && valid)
                     pos = p.pos_table + (int64_t)min(__ldg(p.row_pos + row), p.pos_rows - 1) * BN;
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
-                    tc::tmem_ld32(taddr + c * 32, r);
+                for (int cc = 0; cc < 4; ++cc) {             // 64 output columns per pass
+                    tc::tmem_ld32(taddr + cc * 64, ra);
+                    tc::tmem_ld32(taddr + cc * 64 + 32, rb);
                     tc::tmem_wait_ld();
-                    if (valid) {
-                        __nv_bfloat16 *dst = p.out + row * p.N + n0 + c * 32;
+                    if (cc == 3) { tc::tc_fence_before(); tc::mbar_arrive(tempty + acc); }   // accumulator drained
+                    if (leader) tc::bulk_wait_read<1>();      // the store that last used this staging tile is done reading
+                    tc::bar_sync(EPI_BAR, 128);
+                    const uint32_t dst = stg_row + (uint32_t)(cc & 1) * STG_BYTES;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            float v[8];
-#pragma unroll
-                            for (int e = 0; e < 8; e += 4) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + c * 32 + j + e));
-                                v[e + 0] = __uint_as_float(r[j + e + 0]) + b4.x;
-                                v[e + 1] = __uint_as_float(r[j + e + 1]) + b4.y;
-                                v[e + 2] = __uint_as_float(r[j + e + 2]) + b4.z;
-                                v[e + 3] = __uint_as_float(r[j + e + 3]) + b4.w;
-                                if (EPI == TC_EPI_BIAS_POS) {
-                                    const float4 p4 = __ldg(reinterpret_cast<const float4 *>(pos + c * 32 + j + e));
-                                    v[e + 0] += p4.x; v[e + 1] += p4.y; v[e + 2] += p4.z; v[e + 3] += p4.w;
-                                }
-                                if (EPI == TC_EPI_BIAS_RELU) {
-                                    v[e + 0] = fmaxf(v[e + 0], 0.f); v[e + 1] = fmaxf(v[e + 1], 0.f);
-                                    v[e + 2] = fmaxf(v[e + 2], 0.f); v[e + 3] = fmaxf(v[e + 3], 0.f);
-                                }
-                            }
-                            uint4 pk;
-                            pk.x = pack_bf16(v[0], v[1]); pk.y = pack_bf16(v[2], v[3]);
-                            pk.z = pack_bf16(v[4], v[5]); pk.w = pack_bf16(v[6], v[7]);
-                            *reinterpret_cast<uint4 *>(dst + j) = pk;
+                    for (int ch = 0; ch < 8; ++ch) {         // 8 columns -> one 16-byte chunk
+                        const uint32_t *src = ch < 4 ? &ra[ch * 8] : &rb[(ch - 4) * 8];
+                        const float *bp = p.bias + n0 + cc * 64 + ch * 8;
+                        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bp)), b1 = __ldg(reinterpret_cast<const float4 *>(bp + 4));
+                        float v[8] = {__uint_as_float(src[0]) + b0.x, __uint_as_float(src[1]) + b0.y, __uint_as_float(src[2]) + b0.z,
+                                      __uint_as_float(src[3]) + b0.w, __uint_as_float(src[4]) + b1.x, __uint_as_float(src[5]) + b1.y,
+                                      __uint_as_float(src[6]) + b1.z, __uint_as_float(src[7]) + b1.w};
+                        if (EPI == TC_EPI_BIAS_POS && valid) {
+                            const float4 p0 = __ldg(reinterpret_cast<const float4 *>(pos + cc * 64 + ch * 8));
+                            const float4 p1 = __ldg(reinterpret_cast<const float4 *>(pos + cc * 64 + ch * 8 + 4));
+                            v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w;
+                            v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
                         }
+                        if (EPI == TC_EPI_BIAS_RELU) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+                        }
+                        sts128(dst + sw_off[ch], pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                    }
+                    tc::fence_proxy_async_smem();
+                    tc::bar_sync(EPI_BAR, 128);
+                    if (leader) {
+                        tc::tma_store_2d(stg + (cc & 1) * STG_BYTES, &tmOut, n0 + cc * 64, (int)(m_blk * BM));
+                        tc::bulk_commit();
                     }
                 }
-            } else {  // TC_EPI_BIAS_RES_LN(_HEAD): N == 256, the tile is the whole row
+            } else {  // bias + residual + LayerNorm (+ head): N == 256, the tile is the whole row
                 float sum = 0.f, sumsq = 0.f;
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
-                    tc::tmem_ld32(taddr + c * 32, r);
+                for (int cc = 0; cc < 4; ++cc) {
+                    tc::tmem_ld32(taddr + cc * 64, ra);
+                    tc::tmem_ld32(taddr + cc * 64 + 32, rb);
+                    tc::mbar_wait(rfull + (cc & 1), (res_it >> 1) & 1);
+                    ++res_it;
+                    const uint32_t srcrow = stg_row + (uint32_t)(cc & 1) * STG_BYTES;
+                    uint4 rs[8];
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch) rs[ch] = lds128(srcrow + sw_off[ch]);
                     tc::tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        uint4 rs = make_uint4(0, 0, 0, 0);
-                        if (valid) rs = __ldg(reinterpret_cast<const uint4 *>(p.residual + row * BN + c * 32 + j));
-                        const uint32_t rw[4] = {rs.x, rs.y, rs.z, rs.w};
+                    for (int ch = 0; ch < 8; ++ch) {
+                        uint32_t *a = ch < 4 ? &ra[ch * 8] : &rb[(ch - 4) * 8];
+                        const float *bp = p.bias + cc * 64 + ch * 8;
+                        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bp)), b1 = __ldg(reinterpret_cast<const float4 *>(bp + 4));
+                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                        const uint32_t rw[4] = {rs[ch].x, rs[ch].y, rs[ch].z, rs[ch].w};
 #pragma unroll
                         for (int e = 0; e < 8; e += 2) {
-                            const float2 b2 = __ldg(reinterpret_cast<const float2 *>(p.bias + c * 32 + j + e));
                             const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&rw[e >> 1]);
-                            const float v0 = __uint_as_float(r[j + e]) + b2.x + __low2float(h);
-                            const float v1 = __uint_as_float(r[j + e + 1]) + b2.y + __high2float(h);
+                            const float v0 = __uint_as_float(a[e]) + bb[e] + __low2float(h);
+                            const float v1 = __uint_as_float(a[e + 1]) + bb[e + 1] + __high2float(h);
                             sum += v0 + v1;
                             sumsq = fmaf(v0, v0, fmaf(v1, v1, sumsq));
-                            r[j + e] = __float_as_uint(v0);
-                            r[j + e + 1] = __float_as_uint(v1);
+                            a[e] = __float_as_uint(v0);
+                            a[e + 1] = __float_as_uint(v1);
                         }
                     }
-                    tc::tmem_st32(taddr + c * 32, r);       // park the pre-norm row in TMEM
+                    tc::tmem_st32(taddr + cc * 64, ra);       // park the pre-norm row in TMEM
+                    tc::tmem_st32(taddr + cc * 64 + 32, rb);
+                    tc::bar_sync(EPI_BAR, 128);               // everyone has read this residual tile
+                    if (leader && cc < 2) {
+                        tc::mbar_arrive_expect_tx(rfull + cc, STG_BYTES);
+                        tc::tma_load_2d(stg + cc * STG_BYTES, &tmRes, rfull + cc, (cc + 2) * 64, (int)(m_blk * BM));
+                    }
                 }
                 tc::tmem_wait_st();
                 const float mean = sum * (1.0f / BN);
@@ -261,38 +311,46 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const float rstd = rsqrtf(var + 1e-5f);
                 float dot = 0.f;
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
-                    tc::tmem_ld32(taddr + c * 32, r);
+                for (int cc = 0; cc < 4; ++cc) {
+                    tc::tmem_ld32(taddr + cc * 64, ra);
+                    tc::tmem_ld32(taddr + cc * 64 + 32, rb);
                     tc::tmem_wait_ld();
-                    float y[32];
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 g4 = __ldg(reinterpret_cast<const float4 *>(p.gamma + c * 32 + j));
-                        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.beta + c * 32 + j));
-                        y[j + 0] = (__uint_as_float(r[j + 0]) - mean) * rstd * g4.x + b4.x;
-                        y[j + 1] = (__uint_as_float(r[j + 1]) - mean) * rstd * g4.y + b4.y;
-                        y[j + 2] = (__uint_as_float(r[j + 2]) - mean) * rstd * g4.z + b4.z;
-                        y[j + 3] = (__uint_as_float(r[j + 3]) - mean) * rstd * g4.w + b4.w;
-                        if (EPI == TC_EPI_BIAS_RES_LN_HEAD) {
-                            const float4 w4 = __ldg(reinterpret_cast<const float4 *>(p.head_w + c * 32 + j));
-                            dot = fmaf(y[j + 0], w4.x, fmaf(y[j + 1], w4.y, fmaf(y[j + 2], w4.z, fmaf(y[j + 3], w4.w, dot))));
-                        }
+                    if (cc == 3) { tc::tc_fence_before(); tc::mbar_arrive(tempty + acc); }
+                    if (p.store_out) {
+                        if (leader) tc::bulk_wait_read<1>();
+                        tc::bar_sync(EPI_BAR, 128);
                     }
-                    if (valid) {
-                        if (p.out) {
-                            __nv_bfloat16 *dst = p.out + row * BN + c * 32;
+                    const uint32_t dst = stg_row + (uint32_t)(cc & 1) * STG_BYTES;
 #pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
-                                uint4 pk;
-                                pk.x = pack_bf16(y[j + 0], y[j + 1]); pk.y = pack_bf16(y[j + 2], y[j + 3]);
-                                pk.z = pack_bf16(y[j + 4], y[j + 5]); pk.w = pack_bf16(y[j + 6], y[j + 7]);
-                                *reinterpret_cast<uint4 *>(dst + j) = pk;
+                    for (int ch = 0; ch < 8; ++ch) {
+                        const uint32_t *a = ch < 4 ? &ra[ch * 8] : &rb[(ch - 4) * 8];
+                        const int c0 = cc * 64 + ch * 8;
+                        const float4 g0 = __ldg(reinterpret_cast<const float4 *>(p.gamma + c0)), g1 = __ldg(reinterpret_cast<const float4 *>(p.gamma + c0 + 4));
+                        const float4 e0 = __ldg(reinterpret_cast<const float4 *>(p.beta + c0)), e1 = __ldg(reinterpret_cast<const float4 *>(p.beta + c0 + 4));
+                        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                        const float be[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+                        float y[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) y[e] = (__uint_as_float(a[e]) - mean) * rstd * gg[e] + be[e];
+                        if (EPI == TC_EPI_BIAS_RES_LN_HEAD) {
+                            const float4 w0 = __ldg(reinterpret_cast<const float4 *>(p.head_w + c0)), w1 = __ldg(reinterpret_cast<const float4 *>(p.head_w + c0 + 4));
+                            dot = fmaf(y[0], w0.x, fmaf(y[1], w0.y, fmaf(y[2], w0.z, fmaf(y[3], w0.w, dot))));
+                            dot = fmaf(y[4], w1.x, fmaf(y[5], w1.y, fmaf(y[6], w1.z, fmaf(y[7], w1.w, dot))));
+                            if (p.feats_out && valid) {
+                                float4 *fo = reinterpret_cast<float4 *>(p.feats_out + row * BN + c0);
+                                fo[0] = make_float4(y[0], y[1], y[2], y[3]);
+                                fo[1] = make_float4(y[4], y[5], y[6], y[7]);
                             }
                         }
-                        if (EPI == TC_EPI_BIAS_RES_LN_HEAD && p.feats_out) {
-                            float4 *dst = reinterpret_cast<float4 *>(p.feats_out + row * BN + c * 32);
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) dst[j >> 2] = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+                        if (p.store_out)
+                            sts128(dst + sw_off[ch], pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
+                    }
+                    if (p.store_out) {
+                        tc::fence_proxy_async_smem();
+                        tc::bar_sync(EPI_BAR, 128);
+                        if (leader) {
+                            tc::tma_store_2d(stg + (cc & 1) * STG_BYTES, &tmOut, cc * 64, (int)(m_blk * BM));
+                            tc::bulk_commit();
                         }
                     }
                 }
@@ -302,9 +360,8 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     p.scores_out[row] = sc;
                 }
             }
-            tc::tc_fence_before();
-            tc::mbar_arrive(tempty + acc);
         }
+        if (leader) tc::bulk_wait_all<0>();                  // all output tiles have landed
     }
     __syncwarp();
     tc::tc_fence_before();
@@ -316,7 +373,8 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <bool TF32, int EPI, bool WRES>
-int launch_variant(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmParams &p, cudaStream_t s, int cat) {
+int launch_variant(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmOut, const CUtensorMap &tmRes,
+                   const GemmParams &p, cudaStream_t s, int cat) {
     auto kern = gemm_tc05_kernel<TF32, EPI, WRES>;
     static bool configured = false;
     if (!configured) {
@@ -330,7 +388,7 @@ int launch_variant(const CUtensorMap &tmA, const CUtensorMap &tmB, const GemmPar
     if (WRES) grid = dim3((unsigned)max((int64_t)1, min(p.m_tiles, (int64_t)(sms / p.n_tiles))), (unsigned)p.n_tiles);
     else grid = dim3((unsigned)min(p.m_tiles * p.n_tiles, (int64_t)sms));
     ProfScope prof(cat, s);
-    kern<<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, p);
+    kern<<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmOut, tmRes, p);
     VSUM_LAUNCH_OK("gemm_tc05_kernel");
     return VSUM_OK;
 }
@@ -351,27 +409,38 @@ int launch_gemm_tc05(const Tc05GemmArgs &a, cudaStream_t s) {
     if (rc) return rc;
     rc = make_tensor_map_2d(&tmB, a.W, elt, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.K * elt, kelts, BN);
     if (rc) return rc;
+    CUtensorMap tmOut = tmA, tmRes = tmA;                    // unused maps alias a valid one
+    if (a.out) {
+        rc = make_tensor_map_2d(&tmOut, a.out, 2, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.N * 2, 64, BM);
+        if (rc) return rc;
+    }
+    if (full_row && a.epi != TC_EPI_BIAS_POS) {
+        VSUM_REQUIRE(a.residual && a.gamma && a.beta, VSUM_EINVAL, "gemm_tc05: LayerNorm epilogue needs residual, gamma, beta");
+        rc = make_tensor_map_2d(&tmRes, a.residual, 2, (uint64_t)BN, (uint64_t)a.M, (uint64_t)BN * 2, 64, BM);
+        if (rc) return rc;
+    }
+    VSUM_REQUIRE(a.out || a.epi == TC_EPI_BIAS_RES_LN_HEAD, VSUM_EINVAL, "gemm_tc05: epilogue %d needs an output", a.epi);
     GemmParams p{};
     p.M = a.M; p.N = a.N; p.num_kb = a.K / kelts; p.n_tiles = a.N / BN; p.m_tiles = ceil_div(a.M, BM);
-    p.bias = a.bias; p.out = a.out; p.residual = a.residual; p.gamma = a.gamma; p.beta = a.beta;
-    p.pos_table = a.pos_table; p.row_pos = a.row_pos; p.pos_rows = 0; p.head_w = a.head_w; p.head_b = a.head_b;
+    p.bias = a.bias; p.gamma = a.gamma; p.beta = a.beta;
+    p.pos_table = a.pos_table; p.row_pos = a.row_pos; p.pos_rows = a.pos_rows; p.head_w = a.head_w; p.head_b = a.head_b;
     p.scores_out = a.scores_out; p.feats_out = a.feats_out; p.apply_sigmoid = a.apply_sigmoid;
-    p.pos_rows = a.pos_rows;
+    p.store_out = a.out != nullptr;
     const bool wres = !a.a_is_f32 && p.num_kb <= WRES_MAX_KB && p.m_tiles >= 2 * (148 / p.n_tiles);
     if (a.a_is_f32) {
         VSUM_REQUIRE(a.epi == TC_EPI_BIAS_POS || a.epi == TC_EPI_BIAS, VSUM_EUNSUPPORTED, "gemm_tc05: tf32 path supports BIAS / BIAS_POS only");
-        if (a.epi == TC_EPI_BIAS_POS) return launch_variant<true, TC_EPI_BIAS_POS, false>(tmA, tmB, p, s, a.prof_cat);
-        return launch_variant<true, TC_EPI_BIAS, false>(tmA, tmB, p, s, a.prof_cat);
+        if (a.epi == TC_EPI_BIAS_POS) return launch_variant<true, TC_EPI_BIAS_POS, false>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat);
+        return launch_variant<true, TC_EPI_BIAS, false>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat);
     }
     switch (a.epi) {
         case TC_EPI_BIAS:
-            return wres ? launch_variant<false, TC_EPI_BIAS, true>(tmA, tmB, p, s, a.prof_cat) : launch_variant<false, TC_EPI_BIAS, false>(tmA, tmB, p, s, a.prof_cat);
+            return wres ? launch_variant<false, TC_EPI_BIAS, true>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat) : launch_variant<false, TC_EPI_BIAS, false>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat);
         case TC_EPI_BIAS_RELU:
-            return wres ? launch_variant<false, TC_EPI_BIAS_RELU, true>(tmA, tmB, p, s, a.prof_cat) : launch_variant<false, TC_EPI_BIAS_RELU, false>(tmA, tmB, p, s, a.prof_cat);
+            return wres ? launch_variant<false, TC_EPI_BIAS_RELU, true>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat) : launch_variant<false, TC_EPI_BIAS_RELU, false>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat);
         case TC_EPI_BIAS_RES_LN:
-            return wres ? launch_variant<false, TC_EPI_BIAS_RES_LN, true>(tmA, tmB, p, s, a.prof_cat) : launch_variant<false, TC_EPI_BIAS_RES_LN, false>(tmA, tmB, p, s, a.prof_cat);
+            return wres ? launch_variant<false, TC_EPI_BIAS_RES_LN, true>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat) : launch_variant<false, TC_EPI_BIAS_RES_LN, false>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat);
         case TC_EPI_BIAS_RES_LN_HEAD:
-            return launch_variant<false, TC_EPI_BIAS_RES_LN_HEAD, false>(tmA, tmB, p, s, a.prof_cat);
+            return launch_variant<false, TC_EPI_BIAS_RES_LN_HEAD, false>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat);
         default:
             return set_error(VSUM_EINVAL, "gemm_tc05: unknown epilogue %d", a.epi);
     }
