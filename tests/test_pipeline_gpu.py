@@ -36,3 +36,23 @@ def test_end_to_end_against_oracle(seeded_model_kwargs, precision):
     f_host = summ.run_host(hb)                                # host buffers in, original order out
     assert bits_equal(f_host[hb.order], f)
     assert bits_equal(np.float64(np.mean(f_host)), np.float64(np.mean(f[np.argsort(hb.order)])))
+
+
+def test_pipelined_submission_matches_single_stream(seeded_model_kwargs):
+    torch.manual_seed(1234)
+    model = SimNet(**seeded_model_kwargs).cuda().eval()
+    vids = [make_video(850 + i, video_length(850 + i, 60, 1200), n_users=20) for i in range(12)]
+    hb = pack_videos(vids)
+    summ = Summarizer(model, "avg")
+    want = summ.run_device(DeviceBatch(hb)).cpu().numpy()
+    db = DeviceBatch(hb)
+    outs = [summ.submit_device(db, i & 1) for i in range(4)]
+    summ.drain()
+    torch.cuda.synchronize()
+    for f in outs:
+        assert bits_equal(f.cpu().numpy(), want)
+    dbe = [DeviceBatch(hb, pin_meta=True) for _ in range(2)]
+    hosts = [summ.submit_host(dbe[i & 1], 2 + (i & 1)) for i in range(4)]
+    summ.drain()
+    torch.cuda.synchronize()
+    assert bits_equal(hosts[-1].numpy(), want) and bits_equal(hosts[-2].numpy(), want)

@@ -90,30 +90,34 @@ class HostEvalBatch:
             user_summary=us, us_offsets=us_off, cu_users=cu_users, us_cols=us_cols)
 
 
+_FIELDS = ("picks", "cu_picks", "n_frames", "cps", "cu_shots", "bit_offsets", "order", "sum_offsets")
+_USER_FIELDS = ("user_summary", "us_offsets", "cu_users", "us_cols")
+
+
 class DeviceEvalBatch:
-    """The same arrays resident in HBM."""
+    """The same arrays resident in HBM.  `refill` re-uploads a (same-shaped) host batch into the
+    existing device buffers from pinned staging copies, for the pipelined end-to-end path."""
 
     def __init__(self, hb: HostEvalBatch, device=None, pin: bool = False):
         self.host = hb
         self.device = dev = _device(device)
-
-        def up(a):
-            t = torch.from_numpy(np.ascontiguousarray(a))
+        self.has_users = hb.user_summary is not None
+        self._names = _FIELDS + (_USER_FIELDS if self.has_users else ())
+        self._staging = {}
+        for name in self._names:
+            t = torch.from_numpy(np.ascontiguousarray(getattr(hb, name)))
             if pin:
                 t = t.pin_memory()
-            return t.to(dev, non_blocking=True)
+                self._staging[name] = t
+            setattr(self, name, t.to(dev, non_blocking=True))
+        self.h2d_bytes = sum(getattr(hb, name).nbytes for name in self._names)
 
-        self.picks, self.cu_picks, self.n_frames = up(hb.picks), up(hb.cu_picks), up(hb.n_frames)
-        self.cps, self.cu_shots = up(hb.cps), up(hb.cu_shots)
-        self.bit_offsets, self.order, self.sum_offsets = up(hb.bit_offsets), up(hb.order), up(hb.sum_offsets)
-        self.has_users = hb.user_summary is not None
-        if self.has_users:
-            self.user_summary, self.us_offsets = up(hb.user_summary), up(hb.us_offsets)
-            self.cu_users, self.us_cols = up(hb.cu_users), up(hb.us_cols)
-        self.h2d_bytes = sum(a.nbytes for a in (hb.picks, hb.cu_picks, hb.n_frames, hb.cps, hb.cu_shots,
-                                                hb.bit_offsets, hb.order, hb.sum_offsets))
-        if self.has_users:
-            self.h2d_bytes += hb.user_summary.nbytes + hb.us_offsets.nbytes + hb.cu_users.nbytes + hb.us_cols.nbytes
+    def refill(self) -> None:
+        """Host -> device copy of every array again (pinned staging, current stream)."""
+        if not self._staging:
+            raise ValueError("refill() needs a batch built with pin=True")
+        for name in self._names:
+            getattr(self, name).copy_(self._staging[name], non_blocking=True)
 
 
 _scratch: dict = {}

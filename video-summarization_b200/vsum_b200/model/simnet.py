@@ -188,9 +188,11 @@ class SimNet(nn.Module):
     # ------------------------------------------------------------------ packed entry point
     @torch.no_grad()
     def forward_packed(self, features: Tensor, cu_seqlens: Tensor, seqlens_host: Sequence[int],
-                       apply_sigmoid: bool = False, want_feats: bool = True):
+                       apply_sigmoid: bool = False, want_feats: bool = True,
+                       scores_out: Optional[Tensor] = None):
         """features [T,1024] fp32 on a CUDA device, rows of video v = [cu[v], cu[v+1]).
-        Returns (scores [T,num_classes] fp32, feats [T,d_model] fp32 | None)."""
+        Returns (scores [T,num_classes] fp32, feats [T,d_model] fp32 | None).  `scores_out` lets a
+        pipelined caller supply the (contiguous fp32 [T,num_classes]) output buffer."""
         if not features.is_cuda:
             raise _cabi.VsumError("vsum_b200 runs on CUDA devices only (no CPU fallback); move the input with .cuda()")
         if features.dtype != torch.float32 or features.dim() != 2 or features.shape[1] != self.in_features:
@@ -199,7 +201,12 @@ class SimNet(nn.Module):
         dev = features.device
         T, B = features.shape[0], len(seqlens_host)
         max_len = max(seqlens_host) if B else 0
-        scores = torch.empty((T, self.num_classes), dtype=torch.float32, device=dev)
+        if scores_out is not None:
+            if scores_out.shape != (T, self.num_classes) or scores_out.dtype != torch.float32 or not scores_out.is_contiguous():
+                raise ValueError("scores_out must be a contiguous float32 [T,num_classes] tensor")
+            scores = scores_out
+        else:
+            scores = torch.empty((T, self.num_classes), dtype=torch.float32, device=dev)
         feats = torch.empty((T, self.d_model), dtype=torch.float32, device=dev) if want_feats else None
         if T == 0:
             return scores, feats

@@ -57,19 +57,48 @@ def pack_videos(videos: Sequence[SyntheticVideo], pin: bool = True, with_feature
 class DeviceBatch:
     """A HostBatch resident in HBM."""
 
-    def __init__(self, hb: HostBatch, device=None, features: Optional[torch.Tensor] = None):
+    def __init__(self, hb: HostBatch, device=None, features: Optional[torch.Tensor] = None, pin_meta: bool = False):
         self.host = hb
-        self.meta = _engine.DeviceEvalBatch(hb.meta, device, pin=False)
+        self.meta = _engine.DeviceEvalBatch(hb.meta, device, pin=pin_meta)
         dev = self.meta.device
         self.features = features if features is not None else hb.features.to(dev, non_blocking=True)
-        self.cu_steps = torch.from_numpy(hb.cu_steps).to(dev, non_blocking=True)
+        self._cu_host = torch.from_numpy(hb.cu_steps)
+        if pin_meta:
+            self._cu_host = self._cu_host.pin_memory()
+        self.cu_steps = self._cu_host.to(dev, non_blocking=True)
         self.h2d_bytes = self.meta.h2d_bytes + hb.features.numel() * 4 + hb.cu_steps.nbytes
+
+    def refill(self) -> None:
+        """Copy features + metadata of the host batch into the existing device buffers again."""
+        self.features.copy_(self.host.features, non_blocking=True)
+        self.cu_steps.copy_(self._cu_host, non_blocking=True)
+        self.meta.refill()
+
+
+class _Slot:
+    def __init__(self):
+        self.scores = None      # fp32 [T,1] score buffer owned by the slot
+        self.done = None        # event: evaluation of the batch that last used this slot finished
+        self.f_host = None      # pinned fp64 [B] landing buffer (end-to-end path)
+        self.copied = None      # event: H2D of this slot finished
 
 
 class Summarizer:
+    """Runs the path for batches of packed videos.  Two execution styles:
+
+    * `run_device` / `run_host`: one batch, everything on the current stream (used by the parity tests);
+    * `submit_device` / `submit_host` + `drain`: software pipeline over consecutive batches -- the
+      scorer of batch k+1 runs on the main stream while shot pooling / knapsack / F-score of batch k
+      run on a side stream (the knapsack of the longest video is a serial ~ms tail on ONE SM), and,
+      for host batches, the H2D copy of batch k+1 runs on a copy stream.
+    """
+
     def __init__(self, model: SimNet, eval_method: str = "avg"):
         self.model = model
         self.eval_method = eval_method
+        self._side = None
+        self._copy = None
+        self._slots = {}
 
     @torch.no_grad()
     def run_device(self, db: DeviceBatch, want_intermediates: bool = False):
@@ -92,3 +121,69 @@ class Summarizer:
         f = np.empty_like(f_packed)
         f[hb.order] = f_packed
         return f
+
+    # ------------------------------------------------------------------ pipelined execution
+    def _streams(self, dev):
+        if self._side is None:
+            self._side = torch.cuda.Stream(dev)
+            self._copy = torch.cuda.Stream(dev)
+        return torch.cuda.current_stream(dev), self._side, self._copy
+
+    def _slot(self, slot: int, db: DeviceBatch) -> _Slot:
+        st = self._slots.setdefault(slot, _Slot())
+        T = db.features.shape[0]
+        if st.scores is None or st.scores.shape[0] != T or st.scores.device != db.features.device:
+            st.scores = torch.empty((T, 1), dtype=torch.float32, device=db.features.device)
+        return st
+
+    @torch.no_grad()
+    def submit_device(self, db: DeviceBatch, slot: int) -> torch.Tensor:
+        """Queue one resident batch.  Returns the per-video F tensor, valid after `drain()` (or
+        after waiting on the slot).  Use two slots alternately."""
+        dev = db.features.device
+        main, side, _ = self._streams(dev)
+        st = self._slot(slot, db)
+        if st.done is not None:
+            main.wait_event(st.done)                      # the score buffer of this slot is free again
+        if st.copied is not None:
+            main.wait_event(st.copied)
+        self.model.forward_packed(db.features, db.cu_steps, db.host.seqlens, apply_sigmoid=True,
+                                  want_feats=False, scores_out=st.scores)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            f = _engine.summarize(db.meta, st.scores.view(-1), db.cu_steps, self.eval_method)["f"]
+            st.done = torch.cuda.Event()
+            st.done.record(side)
+        return f
+
+    @torch.no_grad()
+    def submit_host(self, db: DeviceBatch, slot: int) -> torch.Tensor:
+        """Queue one HOST batch through device buffers `db` (built with pin_meta=True): H2D on the
+        copy stream, compute as in submit_device, D2H of the F-scores into a pinned buffer on the
+        side stream.  Returns the pinned fp64 [B] tensor (packed order), valid after `drain()`."""
+        dev = db.features.device
+        main, side, copy = self._streams(dev)
+        st = self._slot(slot, db)
+        with torch.cuda.stream(copy):
+            if st.done is not None:
+                copy.wait_event(st.done)                  # previous user of these device buffers finished
+            db.refill()
+            st.copied = torch.cuda.Event()
+            st.copied.record(copy)
+        f = self.submit_device(db, slot)
+        if st.f_host is None or st.f_host.shape[0] != f.shape[0]:
+            st.f_host = torch.empty(f.shape[0], dtype=torch.float64, pin_memory=True)
+        with torch.cuda.stream(side):
+            st.f_host.copy_(f, non_blocking=True)
+            st.done = torch.cuda.Event()
+            st.done.record(side)
+        return st.f_host
+
+    def drain(self, dev=None) -> None:
+        """Make the current stream wait for everything queued on the side / copy streams."""
+        if self._side is not None:
+            main = torch.cuda.current_stream(dev)
+            main.wait_stream(self._side)
+            main.wait_stream(self._copy)
