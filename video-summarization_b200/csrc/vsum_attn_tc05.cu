@@ -27,8 +27,8 @@ constexpr int DM = 256;                 // d_model
 constexpr int NH = 4;
 constexpr int BQ = 128, BKV = 128;
 constexpr int TILE_BYTES = 128 * 128;   // 128 rows x 64 bf16 = 16 KB
-constexpr int ATT_THREADS = 256;
-constexpr int ATT_TMEM_COLS = 256;      // S: 128, O0: 64, O1: 64
+constexpr int ATT_THREADS = 384;        // 4 control warps + 8 softmax warps
+constexpr int ATT_TMEM_COLS = 256;      // S: [0,128)  O: [128,192)  row-max / row-sum exchange: [192,198)
 constexpr size_t ATT_SMEM = 7 * (size_t)TILE_BYTES + 128;   // Q, K0, V0, K1, V1, P(2 halves) + barriers: 2 CTAs / SM
 
 __device__ __forceinline__ float ex2(float x) {
@@ -52,18 +52,16 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
         : "l"(*reinterpret_cast<const uint64_t *>(&a)), "l"(*reinterpret_cast<const uint64_t *>(&b)));
     return d;
 }
-__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
-    float2 d;
-    asm("mul.rn.f32x2 %0, %1, %2;"
-        : "=l"(*reinterpret_cast<uint64_t *>(&d))
-        : "l"(*reinterpret_cast<const uint64_t *>(&a)), "l"(*reinterpret_cast<const uint64_t *>(&b)));
-    return d;
-}
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
+// One CTA = (video, head, 128 queries); 2 CTAs / SM.  Each query row is shared by TWO softmax
+// threads (64 key columns each, warps q+4 and q+8 of the same TMEM lane quarter), which puts four
+// softmax warps on every SM sub-partition -- the MUFU pipe, not issue latency, becomes the limit.
+// O accumulates in TMEM across KV tiles; the exponent reference only moves when the row max grew
+// by more than 2^8 (lazy rescale), so the read-modify-write of O is rare.
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__restrict__ cu,
                  const int32_t *__restrict__ tile_video, const int32_t *__restrict__ tile_q0,
@@ -77,25 +75,21 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
     uint8_t *sP = smem + 5 * (size_t)TILE_BYTES;      // two 64-key halves, 16 KB each
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 7 * (size_t)TILE_BYTES);
     uint64_t *q_full = bars, *kv_full = bars + 1, *kv_empty = bars + 3, *s_full = bars + 5,
-             *s_empty = bars + 6, *p_full = bars + 7, *p_empty = bars + 8, *o_full = bars + 9,
-             *o_empty = bars + 11;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 13);
+             *s_empty = bars + 6, *p_full = bars + 7, *p_empty = bars + 8;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 9);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int vid = __ldg(tile_video + blockIdx.x), q0 = __ldg(tile_q0 + blockIdx.x);
-    const int h = blockIdx.y;
+    const int h_idx = blockIdx.y;
     const int base = __ldg(cu + vid), n = __ldg(cu + vid + 1) - base;
     const int nkv = (n + BKV - 1) / BKV;
 
     if (warp == 0 && lane == 0) tc::tma_prefetch_desc(&tmQKV);
     if (warp == 1 && lane == 0) {
         tc::mbar_init(q_full, 1);
-        for (int s = 0; s < 2; ++s) {
-            tc::mbar_init(kv_full + s, 1); tc::mbar_init(kv_empty + s, 1);
-            tc::mbar_init(o_full + s, 1); tc::mbar_init(o_empty + s, 128);
-        }
-        tc::mbar_init(s_full, 1); tc::mbar_init(s_empty, 128);
-        tc::mbar_init(p_full, 128); tc::mbar_init(p_empty, 1);
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(kv_full + s, 1); tc::mbar_init(kv_empty + s, 1); }
+        tc::mbar_init(s_full, 1); tc::mbar_init(s_empty, 256);
+        tc::mbar_init(p_full, 256); tc::mbar_init(p_empty, 1);
         tc::fence_barrier_init();
     }
     if (warp == 2) {
@@ -106,19 +100,19 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tS = tmem_base, tO = tmem_base + 128;
+    const uint32_t tS = tmem_base, tO = tmem_base + 128, tX = tmem_base + 192;
 
     if (warp < 4) {
-        tc::setmaxnreg_dec<40>();
+        tc::setmaxnreg_dec<32>();
         if (warp == 0 && lane == 0) {  // ===== TMA producer =====
             tc::mbar_arrive_expect_tx(q_full, TILE_BYTES);
-            tc::tma_load_2d(sQ, &tmQKV, q_full, h * HD, base + q0);
+            tc::tma_load_2d(sQ, &tmQKV, q_full, h_idx * HD, base + q0);
             for (int j = 0; j < nkv; ++j) {
                 const int s = j & 1;
                 tc::mbar_wait(kv_empty + s, ((j >> 1) & 1) ^ 1);
                 tc::mbar_arrive_expect_tx(kv_full + s, 2 * TILE_BYTES);
-                tc::tma_load_2d(sKV + (size_t)(2 * s) * TILE_BYTES, &tmQKV, kv_full + s, DM + h * HD, base + j * BKV);
-                tc::tma_load_2d(sKV + (size_t)(2 * s + 1) * TILE_BYTES, &tmQKV, kv_full + s, 2 * DM + h * HD, base + j * BKV);
+                tc::tma_load_2d(sKV + (size_t)(2 * s) * TILE_BYTES, &tmQKV, kv_full + s, DM + h_idx * HD, base + j * BKV);
+                tc::tma_load_2d(sKV + (size_t)(2 * s + 1) * TILE_BYTES, &tmQKV, kv_full + s, 2 * DM + h_idx * HD, base + j * BKV);
             }
         } else if (warp == 1 && lane == 0) {  // ===== MMA issuer =====
             constexpr uint32_t IDESC_QK = tc::make_idesc(1, BQ, BKV, 0, 0);   // S[128x128], both K-major
@@ -143,8 +137,7 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
                     tc::tc_fence_after();
                     issue_qk(j + 1);
                 }
-                tc::mbar_wait(p_full, j & 1);
-                tc::mbar_wait(o_empty + (j & 1), ((j >> 1) & 1) ^ 1);
+                tc::mbar_wait(p_full, j & 1);          // P(j) written and O rescaled where needed
                 tc::tc_fence_after();
                 const uint32_t v_addr = tc::smem_u32(sKV + (size_t)(2 * (j & 1) + 1) * TILE_BYTES);
 #pragma unroll
@@ -153,77 +146,84 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
                     const uint64_t ad = tc::make_smem_desc_sw128(p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024);
                     // B: V, 16 keys (= 16 rows of 128 bytes) per step
                     const uint64_t bd = tc::make_smem_desc_sw128(v_addr + k * v_kstep, v_lbo, v_sbo);
-                    tc::mma_f16_ss(tO + (j & 1) * HD, ad, bd, IDESC_PV, k != 0);
+                    tc::mma_f16_ss(tO, ad, bd, IDESC_PV, (j | k) != 0);     // O accumulates over all KV tiles
                 }
                 tc::mma_commit(kv_empty + (j & 1));
                 tc::mma_commit(p_empty);
-                tc::mma_commit(o_full + (j & 1));
             }
         }
-    } else {  // ===== softmax / accumulate / store: one query row per thread =====
-        tc::setmaxnreg_inc<216>();
-        const int qd = warp - 4, r = qd * 32 + lane;
+    } else {  // ===== softmax: two threads per query row, 64 key columns each =====
+        tc::setmaxnreg_inc<104>();
+        const int qd = warp & 3, hf = (warp - 4) >> 2;       // TMEM lane quarter, column half
+        const int r = qd * 32 + lane;
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        float m_run = -INFINITY, l_run = 0.f;   // m_run: exponent reference (exp2 domain), <= row max + 8
-        float o[HD];
+        const uint32_t tS_h = tS + lane_off + hf * 64, tO_h = tO + lane_off + hf * 32, tX_q = tX + lane_off;
+        const int pair_bar = 2 + qd;                          // named barrier of the two warps sharing these rows
+        float m_run = -INFINITY, l_part = 0.f;                // m_run: exponent reference (exp2 domain)
+        const uint32_t p_row_u32 = tc::smem_u32(sP) + (uint32_t)hf * TILE_BYTES + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+        uint32_t p_off[8];                                    // swizzled 16-byte chunk offsets of this row
 #pragma unroll
-        for (int i = 0; i < HD; ++i) o[i] = 0.f;
-        uint8_t *p_row = sP + (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128;
-        const int sw = r & 7;
-
-        uint32_t p_off[8];                       // swizzled 16-byte chunk offsets of this row
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) p_off[ch] = (uint32_t)((ch ^ sw) << 4);
-        const uint32_t p_row_u32 = tc::smem_u32(p_row);
+        for (int ch = 0; ch < 8; ++ch) p_off[ch] = (uint32_t)((ch ^ (r & 7)) << 4);
         const float2 c2 = make_float2(scale_log2e, scale_log2e);
 
         for (int j = 0; j < nkv; ++j) {
-            uint32_t s[128];
+            uint32_t s[64];
             tc::mbar_wait(s_full, j & 1);
             tc::tc_fence_after();
             {
                 uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
                 uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
-                uint32_t(&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
-                uint32_t(&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
-                tc::tmem_ld32(tS + lane_off + 0, s0);
-                tc::tmem_ld32(tS + lane_off + 32, s1);
-                tc::tmem_ld32(tS + lane_off + 64, s2);
-                tc::tmem_ld32(tS + lane_off + 96, s3);
+                tc::tmem_ld32(tS_h, s0);
+                tc::tmem_ld32(tS_h + 32, s1);
             }
             tc::tmem_wait_ld();
             tc::tc_fence_before();
             tc::mbar_arrive(s_empty);
 
-            const int valid = n - j * BKV;               // keys of this tile inside the video
-            if (valid < BKV) {
+            const int valid = n - j * BKV - hf * 64;      // keys of this half-tile inside the video
+            if (valid < 64) {
 #pragma unroll
-                for (int c = 0; c < BKV; ++c)
+                for (int c = 0; c < 64; ++c)
                     if (c >= valid) s[c] = 0xff800000u;   // -inf
             }
-            // 8 independent chains (a single 128-long fmax / fadd chain costs 128 x 4 cycles of latency)
             float mx8[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) mx8[e] = __uint_as_float(s[e]);
 #pragma unroll
-            for (int c = 8; c < BKV; c += 8)
+            for (int c = 8; c < 64; c += 8)
 #pragma unroll
                 for (int e = 0; e < 8; ++e) mx8[e] = fmaxf(mx8[e], __uint_as_float(s[c + e]));
-            const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
-                                   fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]))) * scale_log2e;
-            // Lazy rescale: the exponent reference m_run only moves when the row max grew by more
-            // than 2^8, so P stays <= 256 (exact in the fp32/bf16 exponent range) and the O / l
-            // correction is skipped on almost every tile.  The branch is warp-uniform.
+            const float mxl = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
+                                    fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]))) * scale_log2e;
+            // row max across the two halves: through two spare TMEM columns (parity double-buffered)
+            const uint32_t xcol = tX_q + (uint32_t)((j & 1) * 2);
+            tc::tmem_st1(xcol + hf, __float_as_uint(mxl));
+            tc::tmem_wait_st();
+            tc::tc_fence_before();
+            tc::bar_sync(pair_bar, 64);
+            tc::tc_fence_after();
+            const float mx = fmaxf(mxl, __uint_as_float(tc::tmem_ld1(xcol + (hf ^ 1))));
+            tc::tmem_wait_ld();
             float alpha = 1.0f;
-            const bool bump = mx > m_run + 8.0f;
+            const bool bump = mx > m_run + 8.0f;              // identical decision in both threads of the row
             if (__any_sync(0xffffffffu, bump)) {
                 if (bump) { alpha = ex2(m_run - mx); m_run = mx; }      // alpha = 0 on the first tile
             }
+            tc::mbar_wait(p_empty, (j & 1) ^ 1);              // PV(j-1) done: P is free, O is stable
+            if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {   // rare: rescale my 32 columns of O
+                tc::tc_fence_after();
+                uint32_t t[32];
+                tc::tmem_ld32(tO_h, t);
+                tc::tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+                tc::tmem_st32(tO_h, t);
+                tc::tmem_wait_st();
+            }
             const float2 nm2 = make_float2(-m_run, -m_run);
             float2 ps[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-            tc::mbar_wait(p_empty, (j & 1) ^ 1);                      // PV(j-1) has consumed P
 #pragma unroll
-            for (int c = 0; c < BKV; c += 8) {
+            for (int c = 0; c < 64; c += 8) {
                 float2 pv[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -231,72 +231,39 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
                     pv[e] = make_float2(ex2(x.x), ex2(x.y));
                     ps[e] = fadd2(ps[e], pv[e]);
                 }
-                const uint32_t addr = p_row_u32 + (uint32_t)(c >> 6) * TILE_BYTES + p_off[(c >> 3) & 7];
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack2(pv[0].x, pv[0].y)),
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row_u32 + p_off[c >> 3]), "r"(pack2(pv[0].x, pv[0].y)),
                              "r"(pack2(pv[1].x, pv[1].y)), "r"(pack2(pv[2].x, pv[2].y)), "r"(pack2(pv[3].x, pv[3].y))
                              : "memory");
             }
             tc::fence_proxy_async_smem();
+            tc::tc_fence_before();
             tc::mbar_arrive(p_full);
             const float2 pq = fadd2(fadd2(ps[0], ps[1]), fadd2(ps[2], ps[3]));
-            const float psum = pq.x + pq.y;
-
-            if (j > 0) {    // fold in O_{j-1} = P_{j-1} V_{j-1}; rescale only when the reference max moved
-                const int b = (j - 1) & 1;
-                tc::mbar_wait(o_full + b, ((j - 1) >> 1) & 1);
-                tc::tc_fence_after();
-                uint32_t t0[32], t1[32];
-                tc::tmem_ld32(tO + lane_off + b * HD, t0);
-                tc::tmem_ld32(tO + lane_off + b * HD + 32, t1);
-                tc::tmem_wait_ld();
-                tc::tc_fence_before();
-                tc::mbar_arrive(o_empty + b);
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float2 a0 = fadd2(make_float2(o[i], o[i + 1]), make_float2(__uint_as_float(t0[i]), __uint_as_float(t0[i + 1])));
-                    float2 a1 = fadd2(make_float2(o[i + 32], o[i + 33]), make_float2(__uint_as_float(t1[i]), __uint_as_float(t1[i + 1])));
-                    o[i] = a0.x; o[i + 1] = a0.y; o[i + 32] = a1.x; o[i + 33] = a1.y;
-                }
-                if (__any_sync(0xffffffffu, alpha != 1.0f)) {
-                    const float2 al2 = make_float2(alpha, alpha);
-#pragma unroll
-                    for (int i = 0; i < HD; i += 2) {
-                        const float2 a = fmul2(make_float2(o[i], o[i + 1]), al2);
-                        o[i] = a.x; o[i + 1] = a.y;
-                    }
-                }
-            }
-            l_run = fmaf(l_run, alpha, psum);
+            l_part = fmaf(l_part, alpha, pq.x + pq.y);
         }
-        {
-            const int b = (nkv - 1) & 1;
-            tc::mbar_wait(o_full + b, ((nkv - 1) >> 1) & 1);
-            tc::tc_fence_after();
-            uint32_t t0[32], t1[32];
-            tc::tmem_ld32(tO + lane_off + b * HD, t0);
-            tc::tmem_ld32(tO + lane_off + b * HD + 32, t1);
-            tc::tmem_wait_ld();
-            const float inv = 1.0f / l_run;
-            if (q0 + r < n) {
-                __nv_bfloat16 *dst = out + (int64_t)(base + q0 + r) * DM + h * HD;
+        // epilogue: O / l for my 32 head-dim columns of this row
+        tc::mbar_wait(p_empty, (nkv - 1) & 1);                // last PV done
+        tc::tc_fence_after();
+        tc::tmem_st1(tX_q + 4 + hf, __float_as_uint(l_part));
+        tc::tmem_wait_st();
+        tc::tc_fence_before();
+        tc::bar_sync(pair_bar, 64);
+        tc::tc_fence_after();
+        const float l_tot = l_part + __uint_as_float(tc::tmem_ld1(tX_q + 4 + (hf ^ 1)));
+        uint32_t t[32];
+        tc::tmem_ld32(tO_h, t);
+        tc::tmem_wait_ld();
+        const float inv = 1.0f / l_tot;
+        if (q0 + r < n) {
+            __nv_bfloat16 *dst = out + (int64_t)(base + q0 + r) * DM + h_idx * HD + hf * 32;
 #pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    uint4 pk;
-                    pk.x = pack2((o[i + 0] + __uint_as_float(t0[i + 0])) * inv, (o[i + 1] + __uint_as_float(t0[i + 1])) * inv);
-                    pk.y = pack2((o[i + 2] + __uint_as_float(t0[i + 2])) * inv, (o[i + 3] + __uint_as_float(t0[i + 3])) * inv);
-                    pk.z = pack2((o[i + 4] + __uint_as_float(t0[i + 4])) * inv, (o[i + 5] + __uint_as_float(t0[i + 5])) * inv);
-                    pk.w = pack2((o[i + 6] + __uint_as_float(t0[i + 6])) * inv, (o[i + 7] + __uint_as_float(t0[i + 7])) * inv);
-                    *reinterpret_cast<uint4 *>(dst + i) = pk;
-                }
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    uint4 pk;
-                    pk.x = pack2((o[32 + i + 0] + __uint_as_float(t1[i + 0])) * inv, (o[32 + i + 1] + __uint_as_float(t1[i + 1])) * inv);
-                    pk.y = pack2((o[32 + i + 2] + __uint_as_float(t1[i + 2])) * inv, (o[32 + i + 3] + __uint_as_float(t1[i + 3])) * inv);
-                    pk.z = pack2((o[32 + i + 4] + __uint_as_float(t1[i + 4])) * inv, (o[32 + i + 5] + __uint_as_float(t1[i + 5])) * inv);
-                    pk.w = pack2((o[32 + i + 6] + __uint_as_float(t1[i + 6])) * inv, (o[32 + i + 7] + __uint_as_float(t1[i + 7])) * inv);
-                    *reinterpret_cast<uint4 *>(dst + 32 + i) = pk;
-                }
+            for (int i = 0; i < 32; i += 8) {
+                uint4 pk;
+                pk.x = pack2(__uint_as_float(t[i + 0]) * inv, __uint_as_float(t[i + 1]) * inv);
+                pk.y = pack2(__uint_as_float(t[i + 2]) * inv, __uint_as_float(t[i + 3]) * inv);
+                pk.z = pack2(__uint_as_float(t[i + 4]) * inv, __uint_as_float(t[i + 5]) * inv);
+                pk.w = pack2(__uint_as_float(t[i + 6]) * inv, __uint_as_float(t[i + 7]) * inv);
+                *reinterpret_cast<uint4 *>(dst + i) = pk;
             }
         }
     }
