@@ -66,17 +66,23 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__restrict__ cu,
                  const int32_t *__restrict__ tile_video, const int32_t *__restrict__ tile_q0,
                  const int32_t *__restrict__ n_tiles_ptr, __nv_bfloat16 *__restrict__ out,
-                 float scale_log2e, uint32_t v_lbo, uint32_t v_sbo, uint32_t v_kstep) {
+                 float scale_log2e, uint32_t v_lbo, uint32_t v_sbo, uint32_t v_kstep
+#ifdef VSUM_ATTN_TIMING
+                 , unsigned long long *timing
+#endif
+                 ) {
     if ((int)blockIdx.x >= __ldg(n_tiles_ptr)) return;
     extern __shared__ __align__(1024) uint8_t smem[];    // no alignment slack: it would cost the 2nd CTA / SM
     if ((tc::smem_u32(smem) & 1023u) != 0) __trap();     // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t *sQ = smem;
-    uint8_t *sKV = smem + TILE_BYTES;                 // stage s: K at 2s, V at 2s+1 (tiles)
-    uint8_t *sP = smem + 5 * (size_t)TILE_BYTES;      // two 64-key halves, 16 KB each
+    // K and V are single-buffered (each is free again long before its successor is needed); the 32 KB
+    // this saves double-buffers P, so the exponentials of tile j+1 never wait for the MMAs of tile j.
+    uint8_t *sK = smem + TILE_BYTES, *sV = smem + 2 * (size_t)TILE_BYTES;
+    uint8_t *sP = smem + 3 * (size_t)TILE_BYTES;      // 2 buffers x two 64-key halves of 16 KB
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 7 * (size_t)TILE_BYTES);
-    uint64_t *q_full = bars, *kv_full = bars + 1, *kv_empty = bars + 3, *s_full = bars + 5,
-             *s_empty = bars + 6, *p_full = bars + 7, *p_empty = bars + 8;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 9);
+    uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3, *v_empty = bars + 4,
+             *s_full = bars + 5, *s_empty = bars + 6, *p_full = bars + 7, *p_empty = bars + 9;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 11);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int vid = __ldg(tile_video + blockIdx.x), q0 = __ldg(tile_q0 + blockIdx.x);
@@ -87,9 +93,9 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
     if (warp == 0 && lane == 0) tc::tma_prefetch_desc(&tmQKV);
     if (warp == 1 && lane == 0) {
         tc::mbar_init(q_full, 1);
-        for (int s = 0; s < 2; ++s) { tc::mbar_init(kv_full + s, 1); tc::mbar_init(kv_empty + s, 1); }
+        tc::mbar_init(k_full, 1); tc::mbar_init(k_empty, 1); tc::mbar_init(v_full, 1); tc::mbar_init(v_empty, 1);
         tc::mbar_init(s_full, 1); tc::mbar_init(s_empty, 256);
-        tc::mbar_init(p_full, 256); tc::mbar_init(p_empty, 1);
+        for (int b = 0; b < 2; ++b) { tc::mbar_init(p_full + b, 256); tc::mbar_init(p_empty + b, 1); }
         tc::fence_barrier_init();
     }
     if (warp == 2) {
@@ -104,42 +110,48 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
 
     if (warp < 4) {
         tc::setmaxnreg_dec<32>();
-        if (warp == 0 && lane == 0) {  // ===== TMA producer =====
+        if (warp == 0 && lane == 0) {  // ===== TMA producer: Q, then the K tiles =====
             tc::mbar_arrive_expect_tx(q_full, TILE_BYTES);
             tc::tma_load_2d(sQ, &tmQKV, q_full, h_idx * HD, base + q0);
             for (int j = 0; j < nkv; ++j) {
-                const int s = j & 1;
-                tc::mbar_wait(kv_empty + s, ((j >> 1) & 1) ^ 1);
-                tc::mbar_arrive_expect_tx(kv_full + s, 2 * TILE_BYTES);
-                tc::tma_load_2d(sKV + (size_t)(2 * s) * TILE_BYTES, &tmQKV, kv_full + s, DM + h_idx * HD, base + j * BKV);
-                tc::tma_load_2d(sKV + (size_t)(2 * s + 1) * TILE_BYTES, &tmQKV, kv_full + s, 2 * DM + h_idx * HD, base + j * BKV);
+                tc::mbar_wait(k_empty, (j & 1) ^ 1);                 // QK(j-1) has consumed K
+                tc::mbar_arrive_expect_tx(k_full, TILE_BYTES);
+                tc::tma_load_2d(sK, &tmQKV, k_full, DM + h_idx * HD, base + j * BKV);
+            }
+        } else if (warp == 3 && lane == 0) {  // ===== TMA producer: the V tiles =====
+            for (int j = 0; j < nkv; ++j) {
+                tc::mbar_wait(v_empty, (j & 1) ^ 1);                 // PV(j-1) has consumed V
+                tc::mbar_arrive_expect_tx(v_full, TILE_BYTES);
+                tc::tma_load_2d(sV, &tmQKV, v_full, 2 * DM + h_idx * HD, base + j * BKV);
             }
         } else if (warp == 1 && lane == 0) {  // ===== MMA issuer =====
             constexpr uint32_t IDESC_QK = tc::make_idesc(1, BQ, BKV, 0, 0);   // S[128x128], both K-major
             constexpr uint32_t IDESC_PV = tc::make_idesc(1, BQ, HD, 0, 1);    // O[128x64], B (=V) MN-major
-            const uint32_t q_addr = tc::smem_u32(sQ), p_addr = tc::smem_u32(sP);
-            auto issue_qk = [&](int j) {
-                const uint32_t k_addr = tc::smem_u32(sKV + (size_t)(2 * (j & 1)) * TILE_BYTES);
+            const uint32_t q_addr = tc::smem_u32(sQ), p_base = tc::smem_u32(sP), k_addr = tc::smem_u32(sK),
+                           v_addr = tc::smem_u32(sV);
+            auto issue_qk = [&]() {
 #pragma unroll
                 for (int k = 0; k < HD / 16; ++k)
                     tc::mma_f16_ss(tS, tc::make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
                                    tc::make_smem_desc_sw128(k_addr + k * 32, 16, 1024), IDESC_QK, k != 0);
                 tc::mma_commit(s_full);
+                tc::mma_commit(k_empty);
             };
             tc::mbar_wait(q_full, 0);
-            tc::mbar_wait(kv_full + 0, 0);
+            tc::mbar_wait(k_full, 0);
             tc::tc_fence_after();
-            issue_qk(0);
+            issue_qk();
             for (int j = 0; j < nkv; ++j) {
                 if (j + 1 < nkv) {   // S(j+1) as soon as the softmax warps have S(j) in registers
-                    tc::mbar_wait(kv_full + ((j + 1) & 1), ((j + 1) >> 1) & 1);
+                    tc::mbar_wait(k_full, (j + 1) & 1);
                     tc::mbar_wait(s_empty, j & 1);
                     tc::tc_fence_after();
-                    issue_qk(j + 1);
+                    issue_qk();
                 }
-                tc::mbar_wait(p_full, j & 1);          // P(j) written and O rescaled where needed
+                tc::mbar_wait(p_full + (j & 1), (j >> 1) & 1);   // P(j) written and O rescaled where needed
+                tc::mbar_wait(v_full, j & 1);
                 tc::tc_fence_after();
-                const uint32_t v_addr = tc::smem_u32(sKV + (size_t)(2 * (j & 1) + 1) * TILE_BYTES);
+                const uint32_t p_addr = p_base + (uint32_t)(j & 1) * 2 * TILE_BYTES;
 #pragma unroll
                 for (int k = 0; k < BKV / 16; ++k) {
                     // A: P half (k/4), 32-byte step inside the 128-byte swizzled row
@@ -148,8 +160,8 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
                     const uint64_t bd = tc::make_smem_desc_sw128(v_addr + k * v_kstep, v_lbo, v_sbo);
                     tc::mma_f16_ss(tO, ad, bd, IDESC_PV, (j | k) != 0);     // O accumulates over all KV tiles
                 }
-                tc::mma_commit(kv_empty + (j & 1));
-                tc::mma_commit(p_empty);
+                tc::mma_commit(v_empty);
+                tc::mma_commit(p_empty + (j & 1));           // also means "PV(j) done"
             }
         }
     } else {  // ===== softmax: two threads per query row, 64 key columns each =====
@@ -166,9 +178,18 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
         for (int ch = 0; ch < 8; ++ch) p_off[ch] = (uint32_t)((ch ^ (r & 7)) << 4);
         const float2 c2 = make_float2(scale_log2e, scale_log2e);
 
+#ifdef VSUM_ATTN_TIMING
+        long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define TSTAMP(k) { const long long _t = clock64(); tacc[k] += _t - tprev; tprev = _t; }
+        long long tprev = clock64();
+#else
+#define TSTAMP(k)
+#endif
         for (int j = 0; j < nkv; ++j) {
             uint32_t s[64];
+            TSTAMP(0)
             tc::mbar_wait(s_full, j & 1);
+            TSTAMP(1)
             tc::tc_fence_after();
             {
                 uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
@@ -179,6 +200,7 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
             tc::tmem_wait_ld();
             tc::tc_fence_before();
             tc::mbar_arrive(s_empty);
+            TSTAMP(2)
 
             const int valid = n - j * BKV - hf * 64;      // keys of this half-tile inside the video
             if (valid < 64) {
@@ -195,6 +217,7 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
                 for (int e = 0; e < 8; ++e) mx8[e] = fmaxf(mx8[e], __uint_as_float(s[c + e]));
             const float mxl = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
                                     fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]))) * scale_log2e;
+            TSTAMP(3)
             // row max across the two halves: through two spare TMEM columns (parity double-buffered)
             const uint32_t xcol = tX_q + (uint32_t)((j & 1) * 2);
             tc::tmem_st1(xcol + hf, __float_as_uint(mxl));
@@ -204,13 +227,15 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
             tc::tc_fence_after();
             const float mx = fmaxf(mxl, __uint_as_float(tc::tmem_ld1(xcol + (hf ^ 1))));
             tc::tmem_wait_ld();
+            TSTAMP(4)
             float alpha = 1.0f;
             const bool bump = mx > m_run + 8.0f;              // identical decision in both threads of the row
             if (__any_sync(0xffffffffu, bump)) {
                 if (bump) { alpha = ex2(m_run - mx); m_run = mx; }      // alpha = 0 on the first tile
             }
-            tc::mbar_wait(p_empty, (j & 1) ^ 1);              // PV(j-1) done: P is free, O is stable
+            tc::mbar_wait(p_empty + (j & 1), ((j >> 1) & 1) ^ 1);    // PV(j-2) done: this P buffer is free
             if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {   // rare: rescale my 32 columns of O
+                tc::mbar_wait(p_empty + ((j - 1) & 1), ((j - 1) >> 1) & 1);   // PV(j-1) done: O is stable
                 tc::tc_fence_after();
                 uint32_t t[32];
                 tc::tmem_ld32(tO_h, t);
@@ -220,7 +245,9 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
                 tc::tmem_st32(tO_h, t);
                 tc::tmem_wait_st();
             }
+            TSTAMP(5)
             const float2 nm2 = make_float2(-m_run, -m_run);
+            const uint32_t p_buf = p_row_u32 + (uint32_t)(j & 1) * 2 * TILE_BYTES;
             float2 ps[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
             for (int c = 0; c < 64; c += 8) {
@@ -231,18 +258,26 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
                     pv[e] = make_float2(ex2(x.x), ex2(x.y));
                     ps[e] = fadd2(ps[e], pv[e]);
                 }
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row_u32 + p_off[c >> 3]), "r"(pack2(pv[0].x, pv[0].y)),
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_buf + p_off[c >> 3]), "r"(pack2(pv[0].x, pv[0].y)),
                              "r"(pack2(pv[1].x, pv[1].y)), "r"(pack2(pv[2].x, pv[2].y)), "r"(pack2(pv[3].x, pv[3].y))
                              : "memory");
             }
+            TSTAMP(6)
             tc::fence_proxy_async_smem();
             tc::tc_fence_before();
-            tc::mbar_arrive(p_full);
+            tc::mbar_arrive(p_full + (j & 1));
+            TSTAMP(7)
             const float2 pq = fadd2(fadd2(ps[0], ps[1]), fadd2(ps[2], ps[3]));
             l_part = fmaf(l_part, alpha, pq.x + pq.y);
         }
+#ifdef VSUM_ATTN_TIMING
+        if (timing && lane == 0 && warp == 4) {
+            for (int k = 0; k < 8; ++k) atomicAdd(timing + k, (unsigned long long)tacc[k]);
+            atomicAdd(timing + 8, (unsigned long long)nkv);
+        }
+#endif
         // epilogue: O / l for my 32 head-dim columns of this row
-        tc::mbar_wait(p_empty, (nkv - 1) & 1);                // last PV done
+        tc::mbar_wait(p_empty + ((nkv - 1) & 1), ((nkv - 1) >> 1) & 1);   // last PV done
         tc::tc_fence_after();
         tc::tmem_st1(tX_q + 4 + hf, __float_as_uint(l_part));
         tc::tmem_wait_st();
@@ -325,7 +360,7 @@ int launch_attention_tc05(const __nv_bfloat16 *qkv, const int32_t *cu_seqlens, c
     if (rc) return rc;
     static bool configured = false;
     if (!configured) {
-        VSUM_CUDA_OK(cudaFuncSetAttribute(attn_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+        VSUM_CUDA_OK(cudaFuncSetAttribute(attn_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(120 * 1024)));
         configured = true;
     }
     // V operand descriptor (MN-major, 128B swizzle): 8-key groups are 1024 bytes apart (SBO); the
@@ -336,9 +371,30 @@ int launch_attention_tc05(const __nv_bfloat16 *qkv, const int32_t *cu_seqlens, c
         if (sscanf(e, "%u,%u,%u", &a, &b, &c) == 3) { v_lbo = a; v_sbo = b; v_kstep = c; }
     }
     dim3 grid((unsigned)max_tiles, NH);
+    size_t smem_bytes = ATT_SMEM;
+    if (const char *e = getenv("VSUM_ATTN_ONE_CTA")) {   // experiment: force 1 CTA / SM
+        if (atoi(e)) smem_bytes = 120 * 1024;
+    }
     ProfScope prof(PROF_ATTN, s);
-    attn_tc05_kernel<<<grid, ATT_THREADS, ATT_SMEM, s>>>(tm, cu_seqlens, tile_video, tile_q0, n_tiles_ptr, out,
+#ifdef VSUM_ATTN_TIMING
+    static unsigned long long *d_timing = nullptr;
+    if (!d_timing) { cudaMalloc(&d_timing, 9 * sizeof(unsigned long long)); }
+    cudaMemsetAsync(d_timing, 0, 9 * sizeof(unsigned long long), s);
+    attn_tc05_kernel<<<grid, ATT_THREADS, smem_bytes, s>>>(tm, cu_seqlens, tile_video, tile_q0, n_tiles_ptr, out,
+                                                         scale * 1.4426950408889634f, v_lbo, v_sbo, v_kstep, d_timing);
+    {
+        unsigned long long h[9];
+        cudaMemcpy(h, d_timing, sizeof(h), cudaMemcpyDeviceToHost);
+        const char *names[8] = {"loop/top", "wait s_full", "S load", "mask+max", "row-max exchange", "bump/p_empty/rescale", "exp+P store", "fence+arrive"};
+        double tot = 0; for (int k = 0; k < 8; ++k) tot += (double)h[k];
+        fprintf(stderr, "[attn timing] tiles(warp4)=%llu cycles/tile=%.0f :", h[8], tot / (double)h[8]);
+        for (int k = 0; k < 8; ++k) fprintf(stderr, " %s=%.0f", names[k], (double)h[k] / (double)h[8]);
+        fprintf(stderr, "\n");
+    }
+#else
+    attn_tc05_kernel<<<grid, ATT_THREADS, smem_bytes, s>>>(tm, cu_seqlens, tile_video, tile_q0, n_tiles_ptr, out,
                                                          scale * 1.4426950408889634f, v_lbo, v_sbo, v_kstep);
+#endif
     VSUM_LAUNCH_OK("attn_tc05_kernel");
     return VSUM_OK;
 }

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvsum_b200.so")
+LIB_PATH = os.environ.get("VSUM_LIB", os.path.join(_HERE, "libvsum_b200.so"))   # VSUM_LIB: debug builds only
 
 VSUM_MAX_LAYERS = 16
 MODE_FP32, MODE_BF16 = 0, 1
