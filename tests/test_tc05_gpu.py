@@ -76,8 +76,9 @@ def attention_ref(qkv, lens):
     return out
 
 
-@pytest.mark.parametrize("lens", [[128], [1], [37], [129], [256, 64], [300, 1, 127, 128, 513], [2048], [1000, 3000]])
-def test_attention(lens):
+@pytest.mark.parametrize("lens", [[128], [1], [37], [129], [256, 64], [300, 1, 127, 128, 513], [2048], [1000, 3000],
+                                  [300] * 150, [8192, 4000, 77], [1] * 700, [129, 128, 127] * 60])
+def test_attention(lens):   # the last four have more work items than resident CTAs (persistent loop)
     T = sum(lens)
     g = torch.Generator(device="cuda").manual_seed(T)
     qkv = torch.randn((T, 768), device="cuda", generator=g).bfloat16()
