@@ -57,66 +57,41 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
-// Persistent CTAs (2 / SM), each walking work items (video, head, 128 queries) idx = blockIdx.x,
-// += gridDim.x.  Each query row is shared by TWO softmax threads (64 key columns each, warps q+4
-// and q+8 of the same TMEM lane quarter).  O accumulates in TMEM across KV tiles; the exponent
-// reference only moves when the row max grew by more than 2^8 (lazy rescale).  K and V are
-// single-buffered, P is double-buffered, and the loads + first QK^T of the NEXT work item are
-// issued while the softmax of the current one is still running, so a CTA never drains.
-struct AttnItem {
-    int base, n, nkv, q0, head;
-};
-__device__ __forceinline__ AttnItem attn_item(int idx, const int32_t *__restrict__ cu,
-                                              const int32_t *__restrict__ tile_video,
-                                              const int32_t *__restrict__ tile_q0) {
-    AttnItem it;
-    const int tile = idx >> 2;
-    it.head = idx & 3;
-    const int vid = __ldg(tile_video + tile);
-    it.q0 = __ldg(tile_q0 + tile);
-    it.base = __ldg(cu + vid);
-    it.n = __ldg(cu + vid + 1) - it.base;
-    it.nkv = (it.n + BKV - 1) / BKV;
-    return it;
-}
-
+// One CTA = (video, head, 128 queries); 2 CTAs / SM.  Each query row is shared by TWO softmax
+// threads (64 key columns each, warps q+4 and q+8 of the same TMEM lane quarter), which puts four
+// softmax warps on every SM sub-partition -- the MUFU pipe, not issue latency, becomes the limit.
+// O accumulates in TMEM across KV tiles; the exponent reference only moves when the row max grew
+// by more than 2^8 (lazy rescale), so the read-modify-write of O is rare.
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__restrict__ cu,
                  const int32_t *__restrict__ tile_video, const int32_t *__restrict__ tile_q0,
                  const int32_t *__restrict__ n_tiles_ptr, __nv_bfloat16 *__restrict__ out,
-                 float scale_log2e, uint32_t v_lbo, uint32_t v_sbo, uint32_t v_kstep
-#ifdef VSUM_ATTN_TIMING
-                 , unsigned long long *timing
-#endif
-                 ) {
-#ifdef VSUM_ATTN_TIMING
-#define TWAIT(k, stmt) { const long long _t0 = clock64(); stmt; tacc[k] += clock64() - _t0; }
-#else
-#define TWAIT(k, stmt) stmt;
-#endif
-    const int total = __ldg(n_tiles_ptr) * NH;
-    const int first = blockIdx.x, stride = gridDim.x;
-    if (first >= total) return;
+                 float scale_log2e, uint32_t v_lbo, uint32_t v_sbo, uint32_t v_kstep) {
+    if ((int)blockIdx.x >= __ldg(n_tiles_ptr)) return;
     extern __shared__ __align__(1024) uint8_t smem[];    // no alignment slack: it would cost the 2nd CTA / SM
     if ((tc::smem_u32(smem) & 1023u) != 0) __trap();     // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t *sQ = smem;
+    // K and V are single-buffered (each is free again long before its successor is needed); the 32 KB
+    // this saves double-buffers P, so the exponentials of tile j+1 never wait for the MMAs of tile j.
     uint8_t *sK = smem + TILE_BYTES, *sV = smem + 2 * (size_t)TILE_BYTES;
     uint8_t *sP = smem + 3 * (size_t)TILE_BYTES;      // 2 buffers x two 64-key halves of 16 KB
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 7 * (size_t)TILE_BYTES);
-    uint64_t *q_full = bars, *q_empty = bars + 1, *k_full = bars + 2, *k_empty = bars + 3, *v_full = bars + 4,
-             *v_empty = bars + 5, *s_full = bars + 6, *s_empty = bars + 7, *p_full = bars + 8, *p_empty = bars + 10,
-             *o_free = bars + 12;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 13);
+    uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3, *v_empty = bars + 4,
+             *s_full = bars + 5, *s_empty = bars + 6, *p_full = bars + 7, *p_empty = bars + 9;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 11);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int vid = __ldg(tile_video + blockIdx.x), q0 = __ldg(tile_q0 + blockIdx.x);
+    const int h_idx = blockIdx.y;
+    const int base = __ldg(cu + vid), n = __ldg(cu + vid + 1) - base;
+    const int nkv = (n + BKV - 1) / BKV;
 
     if (warp == 0 && lane == 0) tc::tma_prefetch_desc(&tmQKV);
     if (warp == 1 && lane == 0) {
-        tc::mbar_init(q_full, 1); tc::mbar_init(q_empty, 1);
+        tc::mbar_init(q_full, 1);
         tc::mbar_init(k_full, 1); tc::mbar_init(k_empty, 1); tc::mbar_init(v_full, 1); tc::mbar_init(v_empty, 1);
         tc::mbar_init(s_full, 1); tc::mbar_init(s_empty, 256);
         for (int b = 0; b < 2; ++b) { tc::mbar_init(p_full + b, 256); tc::mbar_init(p_empty + b, 1); }
-        tc::mbar_init(o_free, 256);
         tc::fence_barrier_init();
     }
     if (warp == 2) {
@@ -129,104 +104,70 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tS = tmem_base, tO = tmem_base + 128, tX = tmem_base + 192;
 
-    // Phase bookkeeping: `g` counts KV tiles and `it` work items over the CTA's whole lifetime.
     if (warp < 4) {
         tc::setmaxnreg_dec<32>();
-        if (warp == 0 && lane == 0) {  // ===== TMA producer: Q and the K tiles =====
-            uint32_t g = 0, it = 0;
-            for (int idx = first; idx < total; idx += stride, ++it) {
-                const AttnItem w = attn_item(idx, cu, tile_video, tile_q0);
-                tc::mbar_wait(q_empty, (it & 1) ^ 1);                    // last QK of the previous item is done
-                tc::mbar_arrive_expect_tx(q_full, TILE_BYTES);
-                tc::tma_load_2d(sQ, &tmQKV, q_full, w.head * HD, w.base + w.q0);
-                for (int j = 0; j < w.nkv; ++j, ++g) {
-                    tc::mbar_wait(k_empty, (g & 1) ^ 1);                 // QK(g-1) has consumed K
-                    tc::mbar_arrive_expect_tx(k_full, TILE_BYTES);
-                    tc::tma_load_2d(sK, &tmQKV, k_full, DM + w.head * HD, w.base + j * BKV);
-                }
+        if (warp == 0 && lane == 0) {  // ===== TMA producer: Q, then the K tiles =====
+            tc::mbar_arrive_expect_tx(q_full, TILE_BYTES);
+            tc::tma_load_2d(sQ, &tmQKV, q_full, h_idx * HD, base + q0);
+            for (int j = 0; j < nkv; ++j) {
+                tc::mbar_wait(k_empty, (j & 1) ^ 1);                 // QK(j-1) has consumed K
+                tc::mbar_arrive_expect_tx(k_full, TILE_BYTES);
+                tc::tma_load_2d(sK, &tmQKV, k_full, DM + h_idx * HD, base + j * BKV);
             }
         } else if (warp == 3 && lane == 0) {  // ===== TMA producer: the V tiles =====
-            uint32_t g = 0;
-            for (int idx = first; idx < total; idx += stride) {
-                const AttnItem w = attn_item(idx, cu, tile_video, tile_q0);
-                for (int j = 0; j < w.nkv; ++j, ++g) {
-                    tc::mbar_wait(v_empty, (g & 1) ^ 1);                 // PV(g-1) has consumed V
-                    tc::mbar_arrive_expect_tx(v_full, TILE_BYTES);
-                    tc::tma_load_2d(sV, &tmQKV, v_full, 2 * DM + w.head * HD, w.base + j * BKV);
-                }
+            for (int j = 0; j < nkv; ++j) {
+                tc::mbar_wait(v_empty, (j & 1) ^ 1);                 // PV(j-1) has consumed V
+                tc::mbar_arrive_expect_tx(v_full, TILE_BYTES);
+                tc::tma_load_2d(sV, &tmQKV, v_full, 2 * DM + h_idx * HD, base + j * BKV);
             }
         } else if (warp == 1) {  // ===== MMA issuer =====
             // The WHOLE warp runs this role with warp-uniform control flow and one elected lane issuing
-            // the tcgen05 instructions: descriptors then live in uniform registers.  (Running it under
-            // `lane == 0` costs ~160 cycles of R2UR / spill traffic per MMA, which made this thread --
-            // not the tensor pipe or the MUFU -- the limiter of the whole kernel.)
+            // the tcgen05 instructions, so descriptors live in uniform registers.  (Under `lane == 0`
+            // every MMA cost ~160 cycles of R2UR / spill traffic: measured with clock64 stamps, the
+            // issuing thread -- not the tensor pipe or the MUFU -- was the limiter.)
             constexpr uint32_t IDESC_QK = tc::make_idesc(1, BQ, BKV, 0, 0);   // S[128x128], both K-major
             constexpr uint32_t IDESC_PV = tc::make_idesc(1, BQ, HD, 0, 1);    // O[128x64], B (=V) MN-major
-            const uint32_t q_addr = tc::smem_u32(sQ), p_base = tc::smem_u32(sP), k_addr = tc::smem_u32(sK),
-                           v_addr = tc::smem_u32(sV);
-            const uint64_t q_desc = tc::make_smem_desc_sw128(q_addr, 16, 1024);      // + 2 per 32-byte K step
-            const uint64_t k_desc = tc::make_smem_desc_sw128(k_addr, 16, 1024);
-            const uint64_t v_desc = tc::make_smem_desc_sw128(v_addr, v_lbo, v_sbo);  // + v_kstep/16 per 16 keys
-            const uint64_t p_desc0 = tc::make_smem_desc_sw128(p_base, 16, 1024);
+            const uint64_t q_desc = tc::make_smem_desc_sw128(tc::smem_u32(sQ), 16, 1024);   // + 2 per 32-byte K step
+            const uint64_t k_desc = tc::make_smem_desc_sw128(tc::smem_u32(sK), 16, 1024);
+            const uint64_t v_desc = tc::make_smem_desc_sw128(tc::smem_u32(sV), v_lbo, v_sbo);   // + v_kstep/16 per 16 keys
+            const uint64_t p_desc0 = tc::make_smem_desc_sw128(tc::smem_u32(sP), 16, 1024);
             const uint32_t v_step = v_kstep >> 4;
-#ifdef VSUM_ATTN_TIMING
-            long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            const long long t_begin = clock64();
-#endif
-            // S(g1) = Q K^T for KV tile g1 (K must have landed, S(g1-1) must have been read)
-            auto issue_qk = [&](uint32_t g1, bool last_of_item) {
-                TWAIT(0, tc::mbar_wait(k_full, g1 & 1))
-                if (g1 > 0) TWAIT(1, tc::mbar_wait(s_empty, (g1 - 1) & 1))
-                tc::tc_fence_after();
+            auto issue_qk = [&]() {
                 if (tc::elect_one()) {
 #pragma unroll
                     for (int k = 0; k < HD / 16; ++k)
                         tc::mma_f16_ss(tS, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), IDESC_QK, k != 0);
                     tc::mma_commit(s_full);
                     tc::mma_commit(k_empty);
-                    if (last_of_item) tc::mma_commit(q_empty);           // Q may be replaced by the next item's
                 }
                 __syncwarp();
             };
-            uint32_t g = 0, it = 0;
-            int nkv = attn_item(first, cu, tile_video, tile_q0).nkv;
             tc::mbar_wait(q_full, 0);
-            issue_qk(0, nkv == 1);
-            for (int idx = first; idx < total; idx += stride, ++it) {
-                const bool has_next = idx + stride < total;
-                const int nkv_next = has_next ? attn_item(idx + stride, cu, tile_video, tile_q0).nkv : 0;
-                for (int j = 0; j < nkv; ++j, ++g) {
-                    if (j + 1 < nkv) {
-                        issue_qk(g + 1, j + 1 == nkv - 1);               // next tile of this item
-                    } else if (has_next) {
-                        TWAIT(2, tc::mbar_wait(q_full, (it + 1) & 1))    // first tile of the NEXT item
-                        issue_qk(g + 1, nkv_next == 1);
-                    }
-                    TWAIT(3, tc::mbar_wait(p_full + (g & 1), (g >> 1) & 1))   // P(g) written and O rescaled where needed
-                    TWAIT(4, tc::mbar_wait(v_full, g & 1))
-                    if (j == 0) TWAIT(5, tc::mbar_wait(o_free, (it & 1) ^ 1))   // previous item's O has been read out
+            tc::mbar_wait(k_full, 0);
+            tc::tc_fence_after();
+            issue_qk();
+            for (int j = 0; j < nkv; ++j) {
+                if (j + 1 < nkv) {   // S(j+1) as soon as the softmax warps have S(j) in registers
+                    tc::mbar_wait(k_full, (j + 1) & 1);
+                    tc::mbar_wait(s_empty, j & 1);
                     tc::tc_fence_after();
-                    // A: P buffer (g&1): half k/4 (16 KB apart), 32-byte step inside the 128-byte swizzled row
-                    const uint64_t p_desc = p_desc0 + (uint64_t)((g & 1) * (2 * TILE_BYTES >> 4));
-                    if (tc::elect_one()) {
-#pragma unroll
-                        for (int k = 0; k < BKV / 16; ++k)
-                            tc::mma_f16_ss(tO, p_desc + (uint64_t)((k >> 2) * (TILE_BYTES >> 4) + (k & 3) * 2),
-                                           v_desc + (uint64_t)(k * v_step), IDESC_PV, (j | k) != 0);   // O accumulates over the item
-                        tc::mma_commit(v_empty);
-                        tc::mma_commit(p_empty + (g & 1));               // also means "PV(g) done"
-                    }
-                    __syncwarp();
+                    issue_qk();
                 }
-                nkv = nkv_next;
+                tc::mbar_wait(p_full + (j & 1), (j >> 1) & 1);   // P(j) written and O rescaled where needed
+                tc::mbar_wait(v_full, j & 1);
+                tc::tc_fence_after();
+                // A: P buffer (j&1): half k/4 (16 KB apart), 32-byte step inside the 128-byte swizzled row
+                const uint64_t p_desc = p_desc0 + (uint64_t)((j & 1) * (2 * TILE_BYTES >> 4));
+                if (tc::elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < BKV / 16; ++k)
+                        tc::mma_f16_ss(tO, p_desc + (uint64_t)((k >> 2) * (TILE_BYTES >> 4) + (k & 3) * 2),
+                                       v_desc + (uint64_t)(k * v_step), IDESC_PV, (j | k) != 0);   // O accumulates over all KV tiles
+                    tc::mma_commit(v_empty);
+                    tc::mma_commit(p_empty + (j & 1));           // also means "PV(j) done"
+                }
+                __syncwarp();
             }
-#ifdef VSUM_ATTN_TIMING
-            if (timing && lane == 0) {
-                for (int k = 0; k < 6; ++k) atomicAdd(timing + k, (unsigned long long)tacc[k]);
-                atomicAdd(timing + 6, (unsigned long long)(clock64() - t_begin));
-                atomicAdd(timing + 7, (unsigned long long)g);
-            }
-#endif
         }
     } else {  // ===== softmax: two threads per query row, 64 key columns each =====
         tc::setmaxnreg_inc<104>();
@@ -235,119 +176,113 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
         const uint32_t tS_h = tS + lane_off + hf * 64, tO_h = tO + lane_off + hf * 32, tX_q = tX + lane_off;
         const int pair_bar = 2 + qd;                          // named barrier of the two warps sharing these rows
+        float m_run = -INFINITY, l_part = 0.f;                // m_run: exponent reference (exp2 domain)
         const uint32_t p_row_u32 = tc::smem_u32(sP) + (uint32_t)hf * TILE_BYTES + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
         uint32_t p_off[8];                                    // swizzled 16-byte chunk offsets of this row
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) p_off[ch] = (uint32_t)((ch ^ (r & 7)) << 4);
         const float2 c2 = make_float2(scale_log2e, scale_log2e);
-        uint32_t g = 0;
 
-        for (int idx = first; idx < total; idx += stride) {
-            const AttnItem w = attn_item(idx, cu, tile_video, tile_q0);
-            float m_run = -INFINITY, l_part = 0.f;            // m_run: exponent reference (exp2 domain)
-            for (int j = 0; j < w.nkv; ++j, ++g) {
-                uint32_t s[64];
-                tc::mbar_wait(s_full, g & 1);
-                tc::tc_fence_after();
-                {
-                    uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
-                    uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
-                    tc::tmem_ld32(tS_h, s0);
-                    tc::tmem_ld32(tS_h + 32, s1);
-                }
-                tc::tmem_wait_ld();
-                tc::tc_fence_before();
-                tc::mbar_arrive(s_empty);
-
-                const int valid = w.n - j * BKV - hf * 64;    // keys of this half-tile inside the video
-                if (valid < 64) {
-#pragma unroll
-                    for (int c = 0; c < 64; ++c)
-                        if (c >= valid) s[c] = 0xff800000u;   // -inf
-                }
-                float mx8[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) mx8[e] = __uint_as_float(s[e]);
-#pragma unroll
-                for (int c = 8; c < 64; c += 8)
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) mx8[e] = fmaxf(mx8[e], __uint_as_float(s[c + e]));
-                const float mxl = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
-                                        fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]))) * scale_log2e;
-                // row max across the two halves: through two spare TMEM columns (parity double-buffered)
-                const uint32_t xcol = tX_q + (uint32_t)((g & 1) * 2);
-                tc::tmem_st1(xcol + hf, __float_as_uint(mxl));
-                tc::tmem_wait_st();
-                tc::tc_fence_before();
-                tc::bar_sync(pair_bar, 64);
-                tc::tc_fence_after();
-                const float mx = fmaxf(mxl, __uint_as_float(tc::tmem_ld1(xcol + (hf ^ 1))));
-                tc::tmem_wait_ld();
-                float alpha = 1.0f;
-                const bool bump = mx > m_run + 8.0f;          // identical decision in both threads of the row
-                if (__any_sync(0xffffffffu, bump)) {
-                    if (bump) { alpha = ex2(m_run - mx); m_run = mx; }      // alpha = 0 on the item's first tile
-                }
-                tc::mbar_wait(p_empty + (g & 1), ((g >> 1) & 1) ^ 1);       // PV(g-2) done: this P buffer is free
-                if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {      // rare: rescale my 32 columns of O
-                    tc::mbar_wait(p_empty + ((g - 1) & 1), ((g - 1) >> 1) & 1);   // PV(g-1) done: O is stable
-                    tc::tc_fence_after();
-                    uint32_t t[32];
-                    tc::tmem_ld32(tO_h, t);
-                    tc::tmem_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
-                    tc::tmem_st32(tO_h, t);
-                    tc::tmem_wait_st();
-                }
-                const float2 nm2 = make_float2(-m_run, -m_run);
-                const uint32_t p_buf = p_row_u32 + (uint32_t)(g & 1) * 2 * TILE_BYTES;
-                float2 ps[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-#pragma unroll
-                for (int c = 0; c < 64; c += 8) {
-                    float2 pv[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 x = ffma2(make_float2(__uint_as_float(s[c + 2 * e]), __uint_as_float(s[c + 2 * e + 1])), c2, nm2);
-                        pv[e] = make_float2(ex2(x.x), ex2(x.y));
-                        ps[e] = fadd2(ps[e], pv[e]);
-                    }
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_buf + p_off[c >> 3]), "r"(pack2(pv[0].x, pv[0].y)),
-                                 "r"(pack2(pv[1].x, pv[1].y)), "r"(pack2(pv[2].x, pv[2].y)), "r"(pack2(pv[3].x, pv[3].y))
-                                 : "memory");
-                }
-                tc::fence_proxy_async_smem();
-                tc::tc_fence_before();
-                tc::mbar_arrive(p_full + (g & 1));
-                const float2 pq = fadd2(fadd2(ps[0], ps[1]), fadd2(ps[2], ps[3]));
-                l_part = fmaf(l_part, alpha, pq.x + pq.y);
-            }
-            // item epilogue: O / l for my 32 head-dim columns of this row
-            tc::mbar_wait(p_empty + ((g - 1) & 1), ((g - 1) >> 1) & 1);   // last PV of the item done
+        for (int j = 0; j < nkv; ++j) {
+            uint32_t s[64];
+            tc::mbar_wait(s_full, j & 1);
             tc::tc_fence_after();
-            tc::tmem_st1(tX_q + 4 + hf, __float_as_uint(l_part));
+            {
+                uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+                uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+                tc::tmem_ld32(tS_h, s0);
+                tc::tmem_ld32(tS_h + 32, s1);
+            }
+            tc::tmem_wait_ld();
+            tc::tc_fence_before();
+            tc::mbar_arrive(s_empty);
+
+            const int valid = n - j * BKV - hf * 64;      // keys of this half-tile inside the video
+            if (valid < 64) {
+#pragma unroll
+                for (int c = 0; c < 64; ++c)
+                    if (c >= valid) s[c] = 0xff800000u;   // -inf
+            }
+            float mx8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) mx8[e] = __uint_as_float(s[e]);
+#pragma unroll
+            for (int c = 8; c < 64; c += 8)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) mx8[e] = fmaxf(mx8[e], __uint_as_float(s[c + e]));
+            const float mxl = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
+                                    fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]))) * scale_log2e;
+            // row max across the two halves: through two spare TMEM columns (parity double-buffered)
+            const uint32_t xcol = tX_q + (uint32_t)((j & 1) * 2);
+            tc::tmem_st1(xcol + hf, __float_as_uint(mxl));
             tc::tmem_wait_st();
             tc::tc_fence_before();
             tc::bar_sync(pair_bar, 64);
             tc::tc_fence_after();
-            const float l_tot = l_part + __uint_as_float(tc::tmem_ld1(tX_q + 4 + (hf ^ 1)));
-            uint32_t t[32];
-            tc::tmem_ld32(tO_h, t);
+            const float mx = fmaxf(mxl, __uint_as_float(tc::tmem_ld1(xcol + (hf ^ 1))));
             tc::tmem_wait_ld();
-            tc::tc_fence_before();
-            tc::mbar_arrive(o_free);                              // the next item's first PV may overwrite O
-            const float inv = 1.0f / l_tot;
-            if (w.q0 + r < w.n) {
-                __nv_bfloat16 *dst = out + (int64_t)(w.base + w.q0 + r) * DM + w.head * HD + hf * 32;
+            float alpha = 1.0f;
+            const bool bump = mx > m_run + 8.0f;              // identical decision in both threads of the row
+            if (__any_sync(0xffffffffu, bump)) {
+                if (bump) { alpha = ex2(m_run - mx); m_run = mx; }      // alpha = 0 on the first tile
+            }
+            tc::mbar_wait(p_empty + (j & 1), ((j >> 1) & 1) ^ 1);    // PV(j-2) done: this P buffer is free
+            if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {   // rare: rescale my 32 columns of O
+                tc::mbar_wait(p_empty + ((j - 1) & 1), ((j - 1) >> 1) & 1);   // PV(j-1) done: O is stable
+                tc::tc_fence_after();
+                uint32_t t[32];
+                tc::tmem_ld32(tO_h, t);
+                tc::tmem_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    uint4 pk;
-                    pk.x = pack2(__uint_as_float(t[i + 0]) * inv, __uint_as_float(t[i + 1]) * inv);
-                    pk.y = pack2(__uint_as_float(t[i + 2]) * inv, __uint_as_float(t[i + 3]) * inv);
-                    pk.z = pack2(__uint_as_float(t[i + 4]) * inv, __uint_as_float(t[i + 5]) * inv);
-                    pk.w = pack2(__uint_as_float(t[i + 6]) * inv, __uint_as_float(t[i + 7]) * inv);
-                    *reinterpret_cast<uint4 *>(dst + i) = pk;
+                for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+                tc::tmem_st32(tO_h, t);
+                tc::tmem_wait_st();
+            }
+            const float2 nm2 = make_float2(-m_run, -m_run);
+            const uint32_t p_buf = p_row_u32 + (uint32_t)(j & 1) * 2 * TILE_BYTES;
+            float2 ps[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+            for (int c = 0; c < 64; c += 8) {
+                float2 pv[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 x = ffma2(make_float2(__uint_as_float(s[c + 2 * e]), __uint_as_float(s[c + 2 * e + 1])), c2, nm2);
+                    pv[e] = make_float2(ex2(x.x), ex2(x.y));
+                    ps[e] = fadd2(ps[e], pv[e]);
                 }
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_buf + p_off[c >> 3]), "r"(pack2(pv[0].x, pv[0].y)),
+                             "r"(pack2(pv[1].x, pv[1].y)), "r"(pack2(pv[2].x, pv[2].y)), "r"(pack2(pv[3].x, pv[3].y))
+                             : "memory");
+            }
+            tc::fence_proxy_async_smem();
+            tc::tc_fence_before();
+            tc::mbar_arrive(p_full + (j & 1));
+            const float2 pq = fadd2(fadd2(ps[0], ps[1]), fadd2(ps[2], ps[3]));
+            l_part = fmaf(l_part, alpha, pq.x + pq.y);
+        }
+        // epilogue: O / l for my 32 head-dim columns of this row
+        tc::mbar_wait(p_empty + ((nkv - 1) & 1), ((nkv - 1) >> 1) & 1);   // last PV done
+        tc::tc_fence_after();
+        tc::tmem_st1(tX_q + 4 + hf, __float_as_uint(l_part));
+        tc::tmem_wait_st();
+        tc::tc_fence_before();
+        tc::bar_sync(pair_bar, 64);
+        tc::tc_fence_after();
+        const float l_tot = l_part + __uint_as_float(tc::tmem_ld1(tX_q + 4 + (hf ^ 1)));
+        uint32_t t[32];
+        tc::tmem_ld32(tO_h, t);
+        tc::tmem_wait_ld();
+        const float inv = 1.0f / l_tot;
+        if (q0 + r < n) {
+            __nv_bfloat16 *dst = out + (int64_t)(base + q0 + r) * DM + h_idx * HD + hf * 32;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+                uint4 pk;
+                pk.x = pack2(__uint_as_float(t[i + 0]) * inv, __uint_as_float(t[i + 1]) * inv);
+                pk.y = pack2(__uint_as_float(t[i + 2]) * inv, __uint_as_float(t[i + 3]) * inv);
+                pk.z = pack2(__uint_as_float(t[i + 4]) * inv, __uint_as_float(t[i + 5]) * inv);
+                pk.w = pack2(__uint_as_float(t[i + 6]) * inv, __uint_as_float(t[i + 7]) * inv);
+                *reinterpret_cast<uint4 *>(dst + i) = pk;
             }
         }
     }
@@ -419,30 +354,10 @@ int launch_attention_tc05(const __nv_bfloat16 *qkv, const int32_t *cu_seqlens, c
         unsigned a, b, c;
         if (sscanf(e, "%u,%u,%u", &a, &b, &c) == 3) { v_lbo = a; v_sbo = b; v_kstep = c; }
     }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // persistent: 2 CTAs per SM walk the (tile, head) work items; CTAs beyond the real item count exit
-    dim3 grid((unsigned)min((int64_t)max_tiles * NH, (int64_t)2 * sms));
+    dim3 grid((unsigned)max_tiles, NH);
     ProfScope prof(PROF_ATTN, s);
-#ifdef VSUM_ATTN_TIMING
-    static unsigned long long *d_timing = nullptr;
-    if (!d_timing) cudaMalloc(&d_timing, 8 * sizeof(unsigned long long));
-    cudaMemsetAsync(d_timing, 0, 8 * sizeof(unsigned long long), s);
-    attn_tc05_kernel<<<grid, ATT_THREADS, ATT_SMEM, s>>>(tm, cu_seqlens, tile_video, tile_q0, n_tiles_ptr, out,
-                                                         scale * 1.4426950408889634f, v_lbo, v_sbo, v_kstep, d_timing);
-    {
-        unsigned long long h[8];
-        cudaMemcpy(h, d_timing, sizeof(h), cudaMemcpyDeviceToHost);
-        const char *names[6] = {"k_full", "s_empty", "q_full(next)", "p_full", "v_full", "o_free"};
-        fprintf(stderr, "[attn MMA-thread waits, cycles per KV tile] tiles=%llu total=%.0f :", h[7], (double)h[6] / (double)h[7]);
-        for (int k = 0; k < 6; ++k) fprintf(stderr, " %s=%.0f", names[k], (double)h[k] / (double)h[7]);
-        fprintf(stderr, "\n");
-    }
-#else
     attn_tc05_kernel<<<grid, ATT_THREADS, ATT_SMEM, s>>>(tm, cu_seqlens, tile_video, tile_q0, n_tiles_ptr, out,
                                                          scale * 1.4426950408889634f, v_lbo, v_sbo, v_kstep);
-#endif
     VSUM_LAUNCH_OK("attn_tc05_kernel");
     return VSUM_OK;
 }

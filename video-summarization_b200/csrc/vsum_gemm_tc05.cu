@@ -170,31 +170,37 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {  // ===== MMA issuer =====
-            if (WRES) { tc::mbar_wait(wfull, 0); }
-            uint32_t it = 0, tl = 0;
-            for (int64_t t = first; t < total; t += step, ++tl) {
-                const int acc = tl & 1;
-                tc::mbar_wait(tempty + acc, ((tl >> 1) & 1) ^ 1);
+    } else if (warp == 1) {  // ===== MMA issuer =====
+        // Whole warp, warp-uniform control flow, one elected lane issues: the smem descriptors stay in
+        // uniform registers (issuing under `lane == 0` costs ~160 cycles of R2UR traffic per MMA, more
+        // than the 128 cycles an M128 N256 K16 MMA takes to execute).
+        if (WRES) { tc::mbar_wait(wfull, 0); }
+        const uint64_t ring_desc = tc::make_smem_desc_sw128(tc::smem_u32(ring), 16, 1024);
+        uint32_t it = 0, tl = 0;
+        for (int64_t t = first; t < total; t += step, ++tl) {
+            const int acc = tl & 1;
+            tc::mbar_wait(tempty + acc, ((tl >> 1) & 1) ^ 1);
+            tc::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+                const int s = it % STAGES;
+                tc::mbar_wait(full + s, (it / STAGES) & 1);
                 tc::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    tc::mbar_wait(full + s, (it / STAGES) & 1);
-                    tc::tc_fence_after();
-                    const uint32_t a_addr = tc::smem_u32(a_stage(s));
-                    const uint32_t b_addr = WRES ? tc::smem_u32(ring + (size_t)kb * B_STAGE) : tc::smem_u32(b_stage(s));
+                // descriptor start-address field is in 16-byte units
+                const uint32_t a_off = (uint32_t)(a_stage(s) - ring) >> 4;
+                const uint32_t b_off = (uint32_t)((WRES ? ring + (size_t)kb * B_STAGE : b_stage(s)) - ring) >> 4;
+                if (tc::elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {   // 4 x (32 bytes of K) per 128-byte k-block
-                        const uint64_t ad = tc::make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-                        const uint64_t bd = tc::make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                        const uint64_t ad = ring_desc + (uint64_t)(a_off + k * 2);
+                        const uint64_t bd = ring_desc + (uint64_t)(b_off + k * 2);
                         if (TF32) tc::mma_tf32_ss(d_tmem, ad, bd, IDESC, (kb | k) != 0);
                         else tc::mma_f16_ss(d_tmem, ad, bd, IDESC, (kb | k) != 0);
                     }
                     tc::mma_commit(empty + s);
+                    if (kb == p.num_kb - 1) tc::mma_commit(tfull + acc);
                 }
-                tc::mma_commit(tfull + acc);
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {  // ===== epilogue: thread <-> one output row =====
