@@ -117,11 +117,15 @@ VSUM_API int vsum_shot_mean(const float *scores, const int32_t *cu_steps, const 
  * 0/1 knapsack: replaces knapSack (src/evaluation/knapsack_implementation.py:1-30) for B videos
  * at once, one video per CTA.  fp64 DP row in shared memory, strict-greater decision bits,
  * back-track from w = capacity; ties go to the lower-indexed shot exactly as line 26 does.
- *   take_bits: scratch of vsum_knapsack_scratch_words() 32-bit words; bit_offsets int64[B+1]
- *   are word offsets of each video's S x ceil((cap+1)/32) decision matrix.
+ *   take_bits: scratch of sum(vsum_knapsack_scratch_words(S_v, cap_v)) 32-bit words; bit_offsets
+ *   int64[B+1] are word offsets of each video's S x (class width / 32) decision matrix.
  *   order int32[B] (optional, may be NULL): video processing order (heaviest first).
  *   selected_out uint8[S_total]: 1 iff the shot is in the summary.
  * ------------------------------------------------------------------------------------------ */
+/* Width (in capacities) of the kernel class that solves a video of this capacity, or -1 when the
+ * fp64 row would not fit shared memory.  All videos of ONE vsum_knapsack call must belong to the
+ * class of `max_cap`; decision-bit rows are padded to the class width. */
+VSUM_API int32_t vsum_knapsack_class_width(int32_t capacity);
 VSUM_API int64_t vsum_knapsack_scratch_words(int32_t n_shots, int32_t capacity);
 VSUM_API int vsum_knapsack(const double *val, const int32_t *wt, const int32_t *cu_shots,
                   const int32_t *cap, const int64_t *bit_offsets, const int32_t *order, int32_t B,

@@ -33,8 +33,13 @@ def test_every_declared_symbol_is_exported():
 def test_abi_version_and_error_text():
     L = _cabi.load()
     assert L.vsum_abi_version() == 1
-    assert L.vsum_knapsack_scratch_words(3, 64) == 3 * 3       # 65 capacities -> 3 words per shot
+    assert L.vsum_knapsack_scratch_words(3, 64) == 3 * 8       # 65 capacities -> class width 256 -> 8 words per shot
     assert L.vsum_knapsack_scratch_words(0, 10) == 0
+    import numpy as np
+    from vsum_b200.evaluation import _engine
+    caps = np.array([0, 1, 254, 255, 256, 1023, 1024, 4095, 4096, 9727, 9728, 18432, 18943, 18944, 28671])
+    assert [L.vsum_knapsack_class_width(int(c)) for c in caps] == _engine.knapsack_class_width(caps).tolist()
+    assert L.vsum_knapsack_class_width(28672) == -1
 
 
 def test_no_cpu_fallback_without_cuda():

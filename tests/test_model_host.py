@@ -93,9 +93,11 @@ def test_host_eval_batch_packing():
     assert hb.cu_users.tolist() == [0, 2, 22, 23]
     caps = [int(v.n_frames * 0.15) for v in vids]
     assert hb.max_cap == max(caps)
-    words = [len(v.change_points) * ((c + 32) // 32) for v, c in zip(vids, caps)]
+    widths = _engine.knapsack_class_width(np.array(caps))
+    words = [len(v.change_points) * int(w // 32) for v, w in zip(vids, widths)]
     assert hb.bit_offsets.tolist() == np.cumsum([0] + words).tolist()
-    assert hb.order[0] == 1                                              # heaviest knapsack first
+    assert hb.order[0] == 1                                              # largest capacity first
+    assert sum(c for _, c, _ in hb.launches) == 3 and hb.launches[0] == (0, 1, caps[1])
 
 
 def test_partition_is_balanced_and_complete():

@@ -130,56 +130,72 @@ shot_mean_kernel(const float *__restrict__ scores, const int32_t *__restrict__ c
 // ---------------------------------------------------------------------------------------------
 // K11  0/1 knapsack  (reference: src/evaluation/knapsack_implementation.py:11-28)
 // ---------------------------------------------------------------------------------------------
-// One video per CTA.  The fp64 DP row K[i-1][0..W] lives in shared memory; every thread owns
-// EPT capacities, computes K[i][w] for them from the old row into registers, then the row is
-// overwritten (two barriers per shot).  take[i][w] = (K[i][w] != K[i-1][w]) -- the reference's
-// own back-track test -- is packed with a warp ballot into a bit matrix in global memory (it
-// stays in L2), and warp 0 walks it back from w = W, 32 rows per probe.
+// One video per CTA.  Thread t owns the capacities w = t + k*THREADS and keeps K[i][w] for them in
+// REGISTERS across shots; shared memory holds a copy of the previous row only so that other threads
+// can read K[i-1][w - wt].  Per shot and capacity that is one 8-byte shared load and, only where the
+// value changed, one 8-byte shared store (two barriers per shot).  Capacities below the shot's
+// weight cannot change and are skipped.  take[i][w] = (K[i][w] != K[i-1][w]) -- the reference's own
+// back-track test -- is packed with a warp ballot into a bit matrix in global memory (it stays in
+// L2); words whose capacities are all below the weight are never written and never read, because
+// the back-track (warp 0, 32 rows per probe) only probes rows with wt <= w.
 template <int THREADS, int EPT>
 __global__ void __launch_bounds__(THREADS, 1)
 knapsack_kernel(const double *__restrict__ val, const int32_t *__restrict__ wt,
                 const int32_t *__restrict__ cu_shots, const int32_t *__restrict__ cap,
                 const int64_t *__restrict__ bit_offsets, const int32_t *__restrict__ order,
                 uint32_t *__restrict__ take_bits, uint8_t *__restrict__ selected_out) {
-    extern __shared__ double row[];
-    const int tid = threadIdx.x, lane = tid & 31;
+    extern __shared__ double row[];                       // THREADS * EPT capacities
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int v = order ? __ldg(order + blockIdx.x) : (int)blockIdx.x;
     const int s0 = __ldg(cu_shots + v), S = __ldg(cu_shots + v + 1) - s0;
     const int W = __ldg(cap + v);
     for (int i = tid; i < S; i += THREADS) selected_out[s0 + i] = 0;
     if (W < 0 || S <= 0) return;
-    const int width = W + 1;
-    const int words = (width + 31) >> 5;
+    {   // every video of a launch must belong to this kernel's class (its bit rows are padded to it)
+        constexpr int kW[] = {256, 1024, 4096, 9728, 18944, 28672};
+        int own = -1;
+#pragma unroll
+        for (int c = 5; c >= 0; --c) if (W + 1 <= kW[c]) own = kW[c];
+        if (own != THREADS * EPT) __trap();
+    }
+    // The row is padded to this kernel's full width (shared memory and bit matrix alike): padding
+    // cells are computed like real ones -- the recurrence only looks at lower capacities, so they
+    // cannot influence K[i][w] for w <= W -- which removes every bounds test from the inner loop.
+    constexpr int WORDS = THREADS * EPT / 32;
     uint32_t *bits = take_bits + __ldg(bit_offsets + v);
-    if (width > THREADS * EPT) return;                    // host guarantees this never happens
-    for (int w = tid; w < width; w += THREADS) row[w] = 0.0;            // K[0][*] = 0
+    double cur[EPT];                                      // K[i][w] for my capacities
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) { cur[k] = 0.0; row[k * THREADS + tid] = 0.0; }   // K[0][*] = 0
     __syncthreads();
 
+    int wi_next = __ldg(wt + s0);
+    double vi_next = __ldg(val + s0);
     for (int i = 0; i < S; ++i) {
-        const int wi = __ldg(wt + s0 + i);
-        const double vi = __ldg(val + s0 + i);
-        double nv[EPT];
+        const int wi = wi_next;
+        const double vi = vi_next;
+        if (i + 1 < S) {                                  // next shot's (weight, value): hide the L2 round trip
+            wi_next = __ldg(wt + s0 + i + 1);
+            vi_next = __ldg(val + s0 + i + 1);
+        }
+        if (wi < 0 || wi > W) continue;                   // line 16: no capacity can hold it (block-uniform)
+        const int w_min = wi > 1 ? wi : 1;                // K[i][0] stays 0 (line 14)
+        const double *rd = row + tid - wi;                // rd[k*THREADS] = K[i-1][w - wt]
+        uint32_t *bw = bits + (int64_t)i * WORDS + warp;  // this warp's ballot word of chunk k: bw[k*THREADS/32]
 #pragma unroll
         for (int k = 0; k < EPT; ++k) {
-            if (k * THREADS >= width) break;                            // block-uniform
-            const int w = k * THREADS + tid;
-            const bool in = w < width;
-            const double b = in ? row[w] : 0.0;                         // K[i-1][w]
-            const bool can = in && w >= 1 && wi >= 0 && wi <= w;        // line 16-18
-            const double a = can ? vi + row[w - wi] : b;
-            const double m = can ? ((b > a) ? b : a) : b;               // Python max(a, b)
-            const bool take = can && (m != b);                          // line 26
-            nv[k] = m;
+            const bool can = k * THREADS + tid >= w_min;
+            const double b = cur[k];                      // K[i-1][w]
+            const double a = vi + (can ? rd[k * THREADS] : 0.0);
+            // Python: m = max(a, b) keeps a unless b > a; take = (m != b).  With take = !(b >= a)
+            // and m = take ? a : b this is identical for every input incl. NaN (values equal when a == b).
+            const bool take = can && !(b >= a);
+            cur[k] = take ? a : b;
             const unsigned word = __ballot_sync(0xffffffffu, take);
-            if (lane == 0 && (w - lane) < width) bits[(int64_t)i * words + (w >> 5)] = word;
+            if (lane == 0) bw[k * (THREADS / 32)] = word;
         }
-        __syncthreads();
+        __syncthreads();                                  // everyone has read the old row
 #pragma unroll
-        for (int k = 0; k < EPT; ++k) {
-            if (k * THREADS >= width) break;
-            const int w = k * THREADS + tid;
-            if (w < width) row[w] = nv[k];
-        }
+        for (int k = 0; k < EPT; ++k) row[k * THREADS + tid] = cur[k];
         __syncthreads();
     }
 
@@ -188,7 +204,12 @@ knapsack_kernel(const double *__restrict__ val, const int32_t *__restrict__ wt,
         while (i > 0) {
             const int r = i - 1 - lane;
             bool bit = false;
-            if (r >= 0) bit = (__ldcg(bits + (int64_t)r * words + (w >> 5)) >> (w & 31)) & 1u;
+            if (r >= 0) {
+                const int wr = __ldg(wt + s0 + r);
+                // rows whose weight exceeds w never wrote (or could set) their bit
+                if (wr >= 0 && wr <= w)
+                    bit = (__ldcg(bits + (int64_t)r * WORDS + (w >> 5)) >> (w & 31)) & 1u;
+            }
             const unsigned m = __ballot_sync(0xffffffffu, bit);
             if (m == 0) { i -= 32; continue; }
             const int rsel = i - 1 - (__ffs(m) - 1);                    // highest row that took
@@ -345,9 +366,19 @@ extern "C" int vsum_shot_mean(const float *scores, const int32_t *cu_steps, cons
     return VSUM_OK;
 }
 
+// Kernel classes: a video of capacity W runs in the smallest class whose width holds W + 1 cells.
+static const int kKnapsackClassWidth[] = {256, 1024, 4096, 9728, 18944, 28672};
+
+extern "C" int32_t vsum_knapsack_class_width(int32_t capacity) {
+    for (int w : kKnapsackClassWidth)
+        if (capacity + 1 <= w) return w;
+    return -1;
+}
+
 extern "C" int64_t vsum_knapsack_scratch_words(int32_t n_shots, int32_t capacity) {
     if (n_shots <= 0 || capacity < 0) return 0;
-    return (int64_t)n_shots * (((int64_t)capacity + 1 + 31) >> 5);
+    const int64_t padded = vsum_knapsack_class_width(capacity);             // rows padded to the kernel class width
+    return padded < 0 ? -1 : (int64_t)n_shots * (padded / 32);
 }
 
 template <int THREADS, int EPT>
@@ -355,7 +386,7 @@ static int launch_knapsack(const double *val, const int32_t *wt, const int32_t *
                            const int32_t *cap, const int64_t *bit_offsets, const int32_t *order,
                            int32_t B, int32_t max_cap, uint32_t *take_bits, uint8_t *selected_out,
                            cudaStream_t stream) {
-    const size_t smem = (size_t)(max_cap + 1) * sizeof(double);
+    const size_t smem = (size_t)THREADS * EPT * sizeof(double);
     auto kern = knapsack_kernel<THREADS, EPT>;
     if (smem > 48 * 1024)
         VSUM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -376,11 +407,11 @@ extern "C" int vsum_knapsack(const double *val, const int32_t *wt, const int32_t
     const int width = max_cap + 1;
     cudaStream_t s = (cudaStream_t)stream;
 #define VSUM_KS(T, E) return launch_knapsack<T, E>(val, wt, cu_shots, cap, bit_offsets, order, B, max_cap, take_bits, selected_out, s)
-    if (width <= 256) VSUM_KS(256, 1);
-    if (width <= 1024) VSUM_KS(512, 2);
-    if (width <= 4096) VSUM_KS(1024, 4);
-    if (width <= 8192) VSUM_KS(1024, 8);
-    if (width <= 14336) VSUM_KS(1024, 14);
+    if (width <= 256) VSUM_KS(128, 2);
+    if (width <= 1024) VSUM_KS(256, 4);
+    if (width <= 4096) VSUM_KS(512, 8);
+    if (width <= 9728) VSUM_KS(512, 19);
+    if (width <= 18944) VSUM_KS(512, 37);
     if (width <= 28672) VSUM_KS(512, 56);
 #undef VSUM_KS
     return set_error(VSUM_EUNSUPPORTED,

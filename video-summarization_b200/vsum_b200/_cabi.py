@@ -21,7 +21,7 @@ EXPORTS = (
     "vsum_abi_version", "vsum_last_error", "vsum_launch_count",
     "vsum_scorer_create", "vsum_scorer_destroy", "vsum_scorer_load_weights",
     "vsum_scorer_workspace_bytes", "vsum_scorer_forward",
-    "vsum_shot_mean", "vsum_knapsack_scratch_words", "vsum_knapsack", "vsum_summary_fscore",
+    "vsum_shot_mean", "vsum_knapsack_class_width", "vsum_knapsack_scratch_words", "vsum_knapsack", "vsum_summary_fscore",
     "vsum_debug_gemm_tc05", "vsum_debug_attention_tc05",
     "vsum_profile_begin", "vsum_profile_end", "vsum_profile_num_categories", "vsum_profile_category_name",
 )
@@ -75,6 +75,8 @@ def load():
     L.vsum_scorer_workspace_bytes.argtypes = [vp, i64, i32, i32]
     L.vsum_scorer_forward.argtypes = [vp, vp, vp, i32, i64, i32, i32, i32, vp, vp, vp, C.c_size_t, vp]
     L.vsum_shot_mean.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]
+    L.vsum_knapsack_class_width.restype = i32
+    L.vsum_knapsack_class_width.argtypes = [i32]
     L.vsum_knapsack_scratch_words.restype = i64
     L.vsum_knapsack_scratch_words.argtypes = [i32, i32]
     L.vsum_knapsack.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp]

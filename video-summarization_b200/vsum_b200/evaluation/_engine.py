@@ -32,6 +32,21 @@ def _cu(counts) -> np.ndarray:
     return out
 
 
+# Knapsack kernel classes (vsum_knapsack_class_width): a video runs in the smallest class whose width
+# holds capacity + 1 cells; one launch per class, so short videos never pin a whole SM's shared
+# memory while the scorer of the next batch is running.  Mirrors kKnapsackClassWidth in vsum_eval.cu
+# (tests/test_cabi_symbols.py checks the two tables agree).
+KNAPSACK_CLASS_WIDTHS = np.array([256, 1024, 4096, 9728, 18944, 28672], dtype=np.int64)
+
+
+def knapsack_class_width(caps: np.ndarray) -> np.ndarray:
+    idx = np.searchsorted(KNAPSACK_CLASS_WIDTHS, np.asarray(caps, dtype=np.int64) + 1, side="left")
+    if np.any(idx >= len(KNAPSACK_CLASS_WIDTHS)):
+        raise _cabi.VsumError(f"knapsack capacity {int(np.max(caps))} exceeds the largest kernel class "
+                              f"({int(KNAPSACK_CLASS_WIDTHS[-1])} cells: n_frames <= 191146)")
+    return KNAPSACK_CLASS_WIDTHS[idx]
+
+
 def capacity_of(last_end: int) -> int:
     """Buffer sizing only (the kernel computes the capacity itself, generate_summary.py:45-46)."""
     return int((int(last_end) + 1) * 0.15)
@@ -47,8 +62,9 @@ class HostEvalBatch:
     cps: np.ndarray              # int32[S_total,2]
     cu_shots: np.ndarray         # int32[B+1]
     bit_offsets: np.ndarray      # int64[B+1]  word offsets of each video's decision-bit matrix
-    order: np.ndarray            # int32[B]    heaviest knapsack first
+    order: np.ndarray            # int32[B]    largest capacity first
     max_cap: int
+    launches: list               # [(first index into order, count, max capacity)] one per kernel class
     sum_offsets: np.ndarray      # int64[B+1]  summary v occupies [sum_offsets[v], sum_offsets[v+1])
     user_summary: Optional[np.ndarray]   # float32 flat
     us_offsets: Optional[np.ndarray]     # int64[B+1]
@@ -67,8 +83,18 @@ class HostEvalBatch:
         n_shots = [len(c) for c in cps_list]
         last_end = [int(c[-1, 1]) if len(c) else -1 for c in cps_list]
         caps = [capacity_of(e) if e >= 0 else 0 for e in last_end]
-        words = [s * ((c + 1 + 31) // 32) for s, c in zip(n_shots, caps)]
-        work = np.asarray([s * (c + 1) for s, c in zip(n_shots, caps)], dtype=np.int64)
+        caps_np = np.asarray(caps, dtype=np.int64)
+        widths = knapsack_class_width(caps_np) if B else np.zeros(0, np.int64)
+        words = [int(s) * int(w // 32) for s, w in zip(n_shots, widths)]
+        order = np.argsort(-caps_np, kind="stable").astype(np.int32)
+        launches, pos = [], 0
+        while pos < B:
+            w = widths[order[pos]]
+            end = pos
+            while end < B and widths[order[end]] == w:
+                end += 1
+            launches.append((pos, end - pos, int(caps_np[order[pos]])))
+            pos = end
         us = us_off = cu_users = us_cols = None
         if user_summaries is not None:
             mats = [np.ascontiguousarray(np.asarray(u), dtype=np.float32).reshape(len(u), -1) for u in user_summaries]
@@ -84,8 +110,9 @@ class HostEvalBatch:
             cps=np.concatenate(cps_list) if B else np.zeros((0, 2), np.int32),
             cu_shots=_cu(n_shots).astype(np.int32),
             bit_offsets=_cu(words),
-            order=np.argsort(-work, kind="stable").astype(np.int32),
+            order=order,
             max_cap=max(caps) if B else 0,
+            launches=launches,
             sum_offsets=_cu([e + 1 for e in last_end]),
             user_summary=us, us_offsets=us_off, cu_users=cu_users, us_cols=us_cols)
 
@@ -162,9 +189,11 @@ def summarize(db: DeviceEvalBatch, scores: torch.Tensor, cu_steps: torch.Tensor,
                                      db.cu_shots.data_ptr(), B, S, val.data_ptr(), wt.data_ptr(),
                                      cap.data_ptr(), stream), "vsum_shot_mean")
         bits = _scratch_buf("bits", int(hb.bit_offsets[-1]) * 4, dev)
-        _cabi.check(L.vsum_knapsack(val.data_ptr(), wt.data_ptr(), db.cu_shots.data_ptr(), cap.data_ptr(),
-                                    db.bit_offsets.data_ptr(), db.order.data_ptr(), B, hb.max_cap,
-                                    bits.data_ptr(), selected.data_ptr(), stream), "vsum_knapsack")
+        for first, count, max_cap in hb.launches:
+            if count > 0:
+                _cabi.check(L.vsum_knapsack(val.data_ptr(), wt.data_ptr(), db.cu_shots.data_ptr(), cap.data_ptr(),
+                                            db.bit_offsets.data_ptr(), db.order.data_ptr() + 4 * first, count, max_cap,
+                                            bits.data_ptr(), selected.data_ptr(), stream), "vsum_knapsack")
         f = per_user = counts = None
         total_users = 0
         if want_f:

@@ -24,6 +24,8 @@ def knapSack(W, wt, val, n):
         d_cu = torch.tensor([0, n], dtype=torch.int32, device=dev)
         d_cap = torch.tensor([W], dtype=torch.int32, device=dev)
         words = int(L.vsum_knapsack_scratch_words(n, W))
+        if words < 0:
+            raise _cabi.VsumError(f"knapSack: capacity {W} exceeds the largest sm_100a kernel class (28671)")
         d_off = torch.tensor([0, words], dtype=torch.int64, device=dev)
         bits = torch.empty(max(words, 1), dtype=torch.int32, device=dev)
         sel = torch.empty(n, dtype=torch.uint8, device=dev)
