@@ -252,6 +252,13 @@ def main_b200(args):
             pass
         peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))       # kernel timed inside a long step
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+        traffic, traffic_src = None, None
+        try:   # dram bytes per launch from the committed ncu --set full capture of this same workload
+            rec = json.load(open(os.path.join(ROOT, "profiles", "r01_attn_ncu_full_default_workload.json")))
+            if rec["frames_per_gpu_per_step"] == hb.n_steps:
+                traffic, traffic_src = rec["dram_bytes_total"] / 1e9, "profiles/r01_attn_ncu_full_default_workload.json"
+        except Exception:
+            pass
         att_ms, att_n = prof.get("attention", (0.0, 0))
         att_flops = attention_flops(hb.seqlens)                            # per launch (one layer, whole batch)
         achieved = att_flops / (att_ms / max(att_n, 1) * 1e-3) / 1e12 if att_ms > 0 else None
@@ -271,7 +278,10 @@ def main_b200(args):
             "gpu_launches": launches,
             "roofline": {"kernel": "attn_tc05_kernel (varlen QK^T/softmax/PV, tcgen05)", "bound": "tensor",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
+                         "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch_gb": hb.n_steps * (768 + 256) * 2 / 1e9,
                          "peak_source": peak_src,
                          "flops_per_launch": att_flops, "launch_ms": att_ms / max(att_n, 1),
                          "share_of_step": (att_ms / args.steps) / gpu_ms if gpu_ms else None},

@@ -120,3 +120,23 @@ def test_eval_metrics_golden():
     assert abs(tau - g["result"][1]) < 1e-12 and abs(rho - g["result"][2]) < 1e-12   # scipy on host, as the reference
     per_video = eval_fscores(data, users)
     assert bits_equal(np.float64(np.mean(per_video)), np.float64(f))
+
+
+def test_knapsack_properties_hypothesis():
+    """Random small instances (duplicated values force ties): GPU == oracle, selection is feasible,
+    ascending, and no single swap-in of an unselected shot that still fits improves the value."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.tuples(st.integers(1, 40), st.sampled_from([0.125, 0.25, 0.5, 0.75, 0.3, 0.7])), min_size=1, max_size=30),
+           st.integers(0, 300))
+    def check(items, W):
+        wt = [w for w, _ in items]
+        val = [v for _, v in items]
+        got = knapSack(W, wt, val, len(items))
+        assert got == c_oracle.knapsack(W, wt, val)
+        assert got == sorted(got) and sum(wt[i] for i in got) <= W
+        used = sum(wt[i] for i in got)
+        for j in range(len(items)):        # values are positive: an optimal selection leaves no room for another shot
+            assert j in got or used + wt[j] > W
+    check()

@@ -62,3 +62,32 @@ def test_deterministic(models):
         a, _ = bf(x)
         b, _ = bf(x)
     assert torch.equal(a, b)
+
+
+def test_full_size_video_bf16_vs_fp32(models):
+    """BASELINE config 5 upper end: one N = 8192 video (64 query tiles x 64 key tiles per head)."""
+    bf, fp = models
+    v = make_video(710, 8192)
+    x = torch.from_numpy(v.features).cuda()
+    cu = torch.tensor([0, 8192], dtype=torch.int32).cuda()
+    a, _ = bf.forward_packed(x, cu, [8192], apply_sigmoid=True, want_feats=False)
+    b, _ = fp.forward_packed(x, cu, [8192], apply_sigmoid=True, want_feats=False)
+    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=TOL, atol=0)
+
+
+def test_packing_order_invariance(models):
+    """Scores of a video do not depend on which other videos share the batch or on their order."""
+    bf, _ = models
+    vids = [make_video(720 + i, n) for i, n in enumerate([333, 1200, 90, 128])]
+    def run(order):
+        feats = torch.from_numpy(np.concatenate([vids[i].features for i in order])).cuda()
+        lens = [vids[i].n_steps for i in order]
+        cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32).cuda()
+        s, _ = bf.forward_packed(feats, cu, lens, want_feats=False)
+        out, off = {}, 0
+        for i, n in zip(order, lens):
+            out[i] = s[off:off + n, 0].cpu().numpy(); off += n
+        return out
+    a, b = run([0, 1, 2, 3]), run([3, 1, 0, 2])
+    for i in range(4):
+        assert np.array_equal(a[i], b[i]), i
