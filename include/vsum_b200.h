@@ -102,6 +102,39 @@ VSUM_API int vsum_scorer_forward(vsum_scorer_t h, const float *features, const i
                         size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Training step of the scorer (fp32 kernels): replaces autograd through SimNet.forward as used by
+ * src/train.py:111-131 and src/pretrain.py:49-86, including the four dropout sites of
+ * simnet.py:107,110,159,181 (counter-based masks recomputed from `seed` in the backward pass).
+ *   forward_train keeps every activation the backward needs in `tape` (vsum_scorer_tape_bytes);
+ *   backward writes d(loss)/d(parameter) for each tensor named in the vsum_scorer_grads struct [same fields
+ *   as vsum_scorer_weights, fp32 device arrays of the parameter's shape; they are overwritten].
+ *   d_feats [T,d_model] may be NULL (gradient w.r.t. the second forward output).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *o_w, *o_b, *ln1_g, *ln1_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b,
+          *ln2_g, *ln2_b;
+} vsum_layer_grads;
+typedef struct {
+    float *embed_w, *embed_b, *final_w, *final_b;
+    vsum_layer_grads layers[VSUM_MAX_LAYERS];
+} vsum_scorer_grads;
+
+VSUM_API size_t vsum_scorer_tape_bytes(vsum_scorer_t h, int64_t T);
+VSUM_API size_t vsum_scorer_train_workspace_bytes(vsum_scorer_t h, int64_t T, int32_t B);
+VSUM_API int vsum_scorer_forward_train(vsum_scorer_t h, const float *features, const int32_t *cu_seqlens,
+                              int32_t B, int64_t T, int32_t max_len, float dropout_p, uint64_t seed,
+                              float *scores_out, float *feats_out, void *tape, size_t tape_bytes,
+                              void *workspace, size_t workspace_bytes, void *stream);
+VSUM_API int vsum_scorer_backward(vsum_scorer_t h, const float *features, const int32_t *cu_seqlens, int32_t B,
+                         int64_t T, int32_t max_len, float dropout_p, uint64_t seed, const float *d_scores,
+                         const float *d_feats, const void *tape, const vsum_scorer_grads *grads_host,
+                         void *workspace, size_t workspace_bytes, void *stream);
+/* Masked MSE of src/utils/utils.py:45-56 over n = bs*Nmax entries: *loss_out (device, pre-zeroed) +=
+ * sum(((out - tgt) * !pad)^2) / denom; d_out (optional) = grad_scale * d(loss)/d(out). */
+VSUM_API int vsum_masked_mse(const float *out, const float *tgt, const uint8_t *pad_mask, int64_t n, float denom,
+                    float *loss_out, float grad_scale, float *d_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Shot pooling: replaces generate_summary.py:25-46 (upsample by picks, per-shot float32 mean in
  * numpy's pairwise order widened to fp64, shot lengths, 15 % capacity).
  *   scores int32-indexed by cu_steps[B+1]; picks by cu_picks[B+1]; change points cps[S_total][2]

@@ -33,8 +33,7 @@ def _lin(x, sd, prefix):
     return F.linear(x, sd[prefix + ".weight"], sd[prefix + ".bias"])
 
 
-@torch.no_grad()
-def scorer_forward(sd: dict, x: torch.Tensor, num_heads: int, key_padding_mask=None):
+def _scorer_forward(sd: dict, x: torch.Tensor, num_heads: int, key_padding_mask=None):
     """x [bs,N,1024] fp32 -> (logits [bs,N,C], feats [bs,N,d]).  `key_padding_mask` bool [bs,N],
     True = padded key (src/model/simnet.py:47-56,156-157)."""
     bs, n, _ = x.shape
@@ -60,6 +59,10 @@ def scorer_forward(sd: dict, x: torch.Tensor, num_heads: int, key_padding_mask=N
         m = _lin(F.relu(_lin(h, sd, p + ".mlp.fc1")), sd, p + ".mlp.fc2")  # simnet.py:181-182
         h = F.layer_norm(m + h, (d,), sd[p + ".norm2.weight"], sd[p + ".norm2.bias"])   # simnet.py:110
     return _lin(h, sd, "final_layer"), h                                   # simnet.py:42-45
+
+
+scorer_forward = torch.no_grad()(_scorer_forward)
+scorer_forward.__wrapped__ = _scorer_forward          # differentiable version for the gradient tests
 
 
 def masked_mse(output, targets, mask):

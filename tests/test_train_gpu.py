@@ -1,0 +1,125 @@
+"""GPU parity of the native training path (fp32 kernels): loss and EVERY parameter gradient of
+SimNet + masked MSE against PyTorch autograd through the fp32 CPU oracle (oracle/scorer_ref.py),
+on padded batches exactly as src/train.py:111-131 builds them."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import scorer_ref
+from vsum_b200.model import SimNet
+from vsum_b200.synthetic import make_video
+from vsum_b200.utils import mse_with_mask_loss
+
+pytestmark = pytest.mark.gpu
+
+
+def padded_batch(lens, first_id=1200):
+    nmax = max(lens)
+    x = torch.full((len(lens), nmax, 1024), 1000.0)
+    tgt = torch.full((len(lens), nmax), 1000.0)
+    for b, n in enumerate(lens):
+        v = make_video(first_id + b, n)
+        x[b, :n] = torch.from_numpy(v.features)
+        tgt[b, :n] = torch.from_numpy(v.gtscore)
+    return x, tgt, x[:, :, 0] == 1000                       # collate_fn_train + train.py:118
+
+
+def oracle_grads(sd, x, tgt, mask, num_heads):
+    params = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "pos_embedding" not in k) for k, v in sd.items()}
+    with torch.enable_grad():
+        logits, feats = scorer_ref.scorer_forward.__wrapped__(params, x, num_heads, mask)
+        loss = scorer_ref.masked_mse(logits, tgt, mask)
+    loss.backward()
+    return loss.item(), {k: p.grad for k, p in params.items() if p.requires_grad}
+
+
+@pytest.mark.parametrize("kw,lens", [
+    (dict(num_heads=4, d_model=256, num_layers=2, dropout=0.3), (150, 97, 64, 130)),
+    (dict(num_heads=4, d_model=64, num_layers=3, dropout=0.1), (70, 33)),
+    (dict(num_heads=4, d_model=256, num_layers=4, dropout=0.0), (300,)),
+])
+def test_gradients_match_autograd_oracle(kw, lens):
+    torch.manual_seed(11)
+    model = SimNet(sparsity=0., use_cls=False, num_classes=1, use_pos=True, **kw).cuda()
+    with torch.no_grad():
+        for p in model.parameters():                        # non-trivial LayerNorm affine / biases
+            p.add_(0.05 * torch.randn_like(p))
+    model.eval()                                            # dropout off: deterministic comparison
+    x, tgt, mask = padded_batch(lens)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    want_loss, want = oracle_grads(sd, x, tgt, mask, kw["num_heads"])
+
+    pred, feats = model(x.cuda(), mask.cuda())
+    assert pred.requires_grad and pred.shape == (len(lens), max(lens), 1)
+    loss = mse_with_mask_loss(pred, tgt.cuda(), mask.cuda())
+    loss.backward()
+    assert abs(loss.item() - want_loss) <= 1e-5 * max(1.0, abs(want_loss))
+    named = dict(model.named_parameters())
+    assert set(named) == set(want)
+    for k, g in want.items():
+        got = named[k].grad
+        assert got is not None, k
+        scale = max(g.abs().max().item(), 1e-6)
+        err = (got.cpu() - g).abs().max().item()
+        assert err <= 2e-4 * scale + 1e-7, f"{k}: max err {err:.3e} vs scale {scale:.3e}"
+
+
+def test_dropout_is_active_and_consistent():
+    torch.manual_seed(3)
+    model = SimNet(num_heads=4, d_model=256, num_layers=2, sparsity=0., dropout=0.3).cuda().train()
+    x, tgt, mask = padded_batch((120, 60))
+    x, tgt, mask = x.cuda(), tgt.cuda(), mask.cuda()
+    torch.manual_seed(5)
+    a, _ = model(x, mask)
+    torch.manual_seed(5)
+    b, _ = model(x, mask)
+    torch.manual_seed(6)
+    c, _ = model(x, mask)
+    assert torch.equal(a, b)                                # same seed -> same masks
+    assert not torch.equal(a, c)                            # different seed -> different masks
+    model.eval()
+    with torch.no_grad():
+        e, _ = model(x, mask)
+    assert not torch.allclose(a, e)
+    # finite-difference check of the dropout backward along a random direction (fixed masks)
+    model.train()
+    p = model.encoder.module_list[0].mlp.fc1.weight
+    direction = torch.randn_like(p)
+    def loss_at(eps):
+        with torch.no_grad():
+            p.add_(eps * direction)
+        torch.manual_seed(9)
+        pred, _ = model(x, mask)
+        val = mse_with_mask_loss(pred, tgt, mask)
+        with torch.no_grad():
+            p.sub_(eps * direction)
+        return val
+    torch.manual_seed(9)
+    pred, _ = model(x, mask)
+    model.zero_grad()
+    mse_with_mask_loss(pred, tgt, mask).backward()
+    analytic = (p.grad * direction).sum().item()
+    h = 1e-2
+    numeric = (loss_at(h).item() - loss_at(-h).item()) / (2 * h)
+    assert abs(analytic - numeric) <= 5e-2 * max(abs(numeric), 1e-3), (analytic, numeric)
+
+
+def test_adam_step_reduces_loss():
+    """train.py:124-127 with GradScaler: a few optimiser steps on one batch must reduce the loss."""
+    torch.manual_seed(0)
+    model = SimNet(num_heads=4, d_model=256, num_layers=2, sparsity=0., dropout=0.0).cuda().train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    scaler = torch.amp.GradScaler("cuda")
+    x, tgt, mask = padded_batch((100, 80, 40))
+    x, tgt, mask = x.cuda(), tgt.cuda(), mask.cuda()
+    losses = []
+    for _ in range(12):
+        with torch.autocast("cuda"):
+            pred, _ = model(x, mask)
+            loss = mse_with_mask_loss(pred, tgt, mask)
+        opt.zero_grad()
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+        losses.append(loss.item())
+    assert max(losses[-3:]) < losses[0] * 0.9, losses

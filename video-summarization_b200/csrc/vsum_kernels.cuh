@@ -20,7 +20,53 @@ int launch_add_layernorm_f32(const float *a, const float *res, const float *gamm
                              float *out, int64_t M, int d, cudaStream_t s);
 // qkv [T, 3d] (q | k | v, head h = columns [h*hd, (h+1)*hd) of each third) -> out [T, d]
 int launch_attention_f32(const float *qkv, const int32_t *cu_seqlens, int B, int max_len, int d,
-                         int num_heads, float scale, float *out, cudaStream_t s);
+                         int num_heads, float scale, float *out, cudaStream_t s, float *lse = nullptr,
+                         float drop_p = 0.f, unsigned long long seed = 0);
+
+// ---- fp32 training path (vsum_train_fp32.cu) --------------------------------------------------
+// Counter-based dropout: the keep decision is a pure function of (seed, element index), so the
+// backward pass recomputes the forward's masks instead of storing them.
+__host__ __device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned long long idx, float p) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (idx + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    return (float)(z >> 40) * (1.0f / 16777216.0f) >= p;      // 24 uniform bits
+}
+__host__ __device__ __forceinline__ unsigned long long attn_drop_index(long long q_row, int h, int H, int key) {
+    return ((unsigned long long)(q_row * H + h) << 20) ^ (unsigned long long)key ^ 0xA5A5000000000000ULL;
+}
+__host__ __device__ __forceinline__ unsigned long long site_seed(unsigned long long seed, int site, int layer) {
+    return seed ^ ((unsigned long long)(site + 1) << 56) ^ ((unsigned long long)(layer + 1) << 48);
+}
+enum DropSite { SITE_ATTN = 0, SITE_PROJ = 1, SITE_HIDDEN = 2, SITE_MLP = 3 };
+
+// s = dropout(a) + res (written to s_out), out = LayerNorm(s)
+int launch_add_dropout_layernorm_f32(const float *a, const float *res, const float *gamma, const float *beta,
+                                     float *s_out, float *out, int64_t M, int d, float drop_p,
+                                     unsigned long long seed, cudaStream_t s);
+int launch_dropout_inplace_f32(float *x, int64_t n, float drop_p, unsigned long long seed, cudaStream_t s);
+// y = LayerNorm(s): (dy, s, gamma) -> ds, d_a = dropout_bwd(ds) (optional), dgamma += , dbeta +=
+int launch_layernorm_bwd_f32(const float *dy, const float *s_in, const float *gamma, float *ds, float *d_a,
+                             float *dgamma, float *dbeta, int64_t M, int d, float drop_p,
+                             unsigned long long seed, cudaStream_t s);
+// dW[N,K] += dY[M,N]^T X[M,K];  db[N] += colsum(dY)   (dW, db must be zeroed by the caller)
+int launch_linear_wgrad_f32(const float *dY, const float *X, float *dW, float *db, int64_t M, int N, int K,
+                            cudaStream_t s);
+// dX[M,K] = dY[M,N] W[N,K]  (+= when accumulate)
+int launch_linear_dgrad_f32(const float *dY, const float *W, float *dX, int64_t M, int N, int K, int accumulate,
+                            cudaStream_t s);
+// dh = (hid > 0) ? dhid * keep_scale : 0   (hid is the saved post-ReLU, post-dropout activation)
+int launch_relu_dropout_bwd_f32(const float *hid, float *dhid, int64_t n, float drop_p, cudaStream_t s);
+int launch_attention_bwd_f32(const float *qkv, const float *o, const float *d_o, const float *lse,
+                             const int32_t *cu_seqlens, int B, int max_len, int64_t T, int d, int num_heads,
+                             float scale, float drop_p, unsigned long long seed, float *delta_ws, float *dqkv,
+                             cudaStream_t s);
+int launch_head_bwd_f32(const float *x, const float *w, const float *d_scores, const float *d_feats, float *dx,
+                        float *dw, float *db, int64_t M, int d, int C, cudaStream_t s);
+// masked MSE (src/utils/utils.py:45-56): loss = sum(((out - tgt) * keep)^2) / denom; d_out optional
+int launch_masked_mse_f32(const float *out, const float *tgt, const uint8_t *pad_mask, int64_t n, float denom,
+                          float *loss, float grad_scale, float *d_out, cudaStream_t s);
 // scores[m, c] = x[m,:] . w[c,:] + b[c], optional sigmoid
 int launch_head_f32(const float *x, const float *w, const float *b, float *scores, int64_t M, int d,
                     int num_classes, int apply_sigmoid, cudaStream_t s);

@@ -269,6 +269,152 @@ extern "C" int vsum_scorer_forward(vsum_scorer_t h, const float *features, const
     return forward_bf16(h, features, cu_seqlens, B, T, apply_sigmoid, scores_out, feats_out, workspace, s);
 }
 
+// ---- training (fp32) ---------------------------------------------------------------------------
+namespace {
+struct TapeLayer { float *qkv, *lse, *att, *s1, *xmid, *hid, *s2, *xout; };
+struct Tape { float *x0; TapeLayer L[VSUM_MAX_LAYERS]; };
+size_t carve_tape(const vsum_scorer_config &c, int64_t T, void *base, Tape &t) {
+    Carver k{(uint8_t *)base};
+    const size_t n = (size_t)T, d = c.d_model;
+    t.x0 = k.get<float>(n * d);
+    for (int l = 0; l < c.num_layers; ++l) {
+        TapeLayer &L = t.L[l];
+        L.qkv = k.get<float>(n * 3 * d); L.lse = k.get<float>(n * c.num_heads); L.att = k.get<float>(n * d);
+        L.s1 = k.get<float>(n * d); L.xmid = k.get<float>(n * d); L.hid = k.get<float>(n * c.d_ff);
+        L.s2 = k.get<float>(n * d); L.xout = k.get<float>(n * d);
+    }
+    return align_up(k.off, 1024);
+}
+struct TrainWs { int32_t *row_pos; float *a, *b, *c, *dd, *dhid, *dqkv, *delta, *dwqkv, *dbqkv; };
+size_t carve_train_ws(const vsum_scorer_config &c, int64_t T, void *base, TrainWs &w) {
+    Carver k{(uint8_t *)base};
+    const size_t n = (size_t)T, d = c.d_model;
+    w.row_pos = k.get<int32_t>(n);
+    w.a = k.get<float>(n * d); w.b = k.get<float>(n * d); w.c = k.get<float>(n * d); w.dd = k.get<float>(n * d);
+    w.dhid = k.get<float>(n * c.d_ff); w.dqkv = k.get<float>(n * 3 * d); w.delta = k.get<float>(n * c.num_heads);
+    w.dwqkv = k.get<float>(3 * d * d); w.dbqkv = k.get<float>(3 * d);
+    return align_up(k.off, 1024);
+}
+}  // namespace
+
+extern "C" size_t vsum_scorer_tape_bytes(vsum_scorer_t h, int64_t T) {
+    if (!h || T <= 0) return 0;
+    Tape t;
+    return carve_tape(h->cfg, T, nullptr, t);
+}
+extern "C" size_t vsum_scorer_train_workspace_bytes(vsum_scorer_t h, int64_t T, int32_t B) {
+    if (!h || T <= 0 || B <= 0) return 0;
+    TrainWs w;
+    return carve_train_ws(h->cfg, T, nullptr, w);
+}
+
+#define RUN(call) do { if ((rc = (call))) return rc; } while (0)
+extern "C" int vsum_scorer_forward_train(vsum_scorer_t h, const float *x, const int32_t *cu, int32_t B, int64_t T,
+                                         int32_t max_len, float p, uint64_t seed, float *scores, float *feats,
+                                         void *tape_mem, size_t tape_bytes, void *ws_mem, size_t ws_bytes, void *stream) {
+    VSUM_REQUIRE(h && h->loaded, VSUM_EINVAL, "vsum_scorer_forward_train: handle without weights");
+    VSUM_REQUIRE(B > 0 && T > 0 && x && cu && scores && tape_mem && ws_mem, VSUM_EINVAL, "vsum_scorer_forward_train: bad argument");
+    VSUM_REQUIRE(p >= 0.f && p < 1.f, VSUM_EINVAL, "vsum_scorer_forward_train: dropout %f", p);
+    VSUM_REQUIRE(!h->cfg.use_pos || max_len <= h->pos_rows, VSUM_EINVAL, "vsum_scorer_forward_train: positional table too short");
+    VSUM_REQUIRE(tape_bytes >= vsum_scorer_tape_bytes(h, T) && ws_bytes >= vsum_scorer_train_workspace_bytes(h, T, B),
+                 VSUM_ENOMEM, "vsum_scorer_forward_train: tape or workspace too small");
+    const vsum_scorer_config &c = h->cfg;
+    const int d = c.d_model;
+    cudaStream_t s = (cudaStream_t)stream;
+    Tape t; TrainWs w;
+    carve_tape(c, T, tape_mem, t);
+    carve_train_ws(c, T, ws_mem, w);
+    int rc;
+    RUN(launch_row_positions(cu, B, T, w.row_pos, nullptr, s));
+    RUN(launch_linear_f32(x, h->w32 + h->embed_w, h->w32 + h->embed_b, t.x0, T, d, c.in_features,
+                          c.use_pos ? EPI_BIAS_POS : EPI_BIAS, h->pos_table, w.row_pos, h->pos_rows, s));
+    const float scale = 1.0f / sqrtf((float)d);
+    const float *xin = t.x0;
+    for (int l = 0; l < c.num_layers; ++l) {
+        const LayerOffsets &o = h->L[l];
+        TapeLayer &L = t.L[l];
+        RUN(launch_linear_f32(xin, h->w32 + o.wqkv, h->w32 + o.bqkv, L.qkv, T, 3 * d, d, EPI_BIAS, nullptr, nullptr, 0, s));
+        RUN(launch_attention_f32(L.qkv, cu, B, max_len, d, c.num_heads, scale, L.att, s, L.lse, p, site_seed(seed, SITE_ATTN, l)));
+        RUN(launch_linear_f32(L.att, h->w32 + o.wo, h->w32 + o.bo, w.a, T, d, d, EPI_BIAS, nullptr, nullptr, 0, s));
+        RUN(launch_add_dropout_layernorm_f32(w.a, xin, h->w32 + o.ln1g, h->w32 + o.ln1b, L.s1, L.xmid, T, d, p, site_seed(seed, SITE_PROJ, l), s));
+        RUN(launch_linear_f32(L.xmid, h->w32 + o.fc1w, h->w32 + o.fc1b, L.hid, T, c.d_ff, d, EPI_BIAS_RELU, nullptr, nullptr, 0, s));
+        RUN(launch_dropout_inplace_f32(L.hid, (int64_t)T * c.d_ff, p, site_seed(seed, SITE_HIDDEN, l), s));
+        RUN(launch_linear_f32(L.hid, h->w32 + o.fc2w, h->w32 + o.fc2b, w.a, T, d, c.d_ff, EPI_BIAS, nullptr, nullptr, 0, s));
+        RUN(launch_add_dropout_layernorm_f32(w.a, L.xmid, h->w32 + o.ln2g, h->w32 + o.ln2b, L.s2, L.xout, T, d, p, site_seed(seed, SITE_MLP, l), s));
+        xin = L.xout;
+    }
+    RUN(launch_head_f32(xin, h->w32 + h->final_w, h->w32 + h->final_b, scores, T, d, c.num_classes, 0, s));
+    if (feats) VSUM_CUDA_OK(cudaMemcpyAsync(feats, xin, (size_t)T * d * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return VSUM_OK;
+}
+
+extern "C" int vsum_scorer_backward(vsum_scorer_t h, const float *x, const int32_t *cu, int32_t B, int64_t T,
+                                    int32_t max_len, float p, uint64_t seed, const float *d_scores, const float *d_feats,
+                                    const void *tape_mem, const vsum_scorer_grads *g, void *ws_mem, size_t ws_bytes,
+                                    void *stream) {
+    VSUM_REQUIRE(h && h->loaded && g, VSUM_EINVAL, "vsum_scorer_backward: bad handle / grads");
+    VSUM_REQUIRE(B > 0 && T > 0 && x && cu && d_scores && tape_mem && ws_mem, VSUM_EINVAL, "vsum_scorer_backward: bad argument");
+    VSUM_REQUIRE(ws_bytes >= vsum_scorer_train_workspace_bytes(h, T, B), VSUM_ENOMEM, "vsum_scorer_backward: workspace too small");
+    const vsum_scorer_config &c = h->cfg;
+    const size_t d = c.d_model, ff = c.d_ff, C = c.num_classes;
+    cudaStream_t s = (cudaStream_t)stream;
+    Tape t; TrainWs w;
+    carve_tape(c, T, const_cast<void *>(tape_mem), t);
+    carve_train_ws(c, T, ws_mem, w);
+    int rc;
+#define ZERO(ptr, n) do { VSUM_REQUIRE((ptr) != nullptr, VSUM_EINVAL, "vsum_scorer_backward: null gradient " #ptr); \
+                          VSUM_CUDA_OK(cudaMemsetAsync((ptr), 0, (n) * sizeof(float), s)); } while (0)
+    ZERO(g->embed_w, d * c.in_features); ZERO(g->embed_b, d); ZERO(g->final_w, C * d); ZERO(g->final_b, C);
+    const float scale = 1.0f / sqrtf((float)d);
+    const float *x_last = t.L[c.num_layers - 1].xout;
+    RUN(launch_head_bwd_f32(x_last, h->w32 + h->final_w, d_scores, d_feats, w.a, g->final_w, g->final_b, T, (int)d, (int)C, s));
+    for (int l = c.num_layers - 1; l >= 0; --l) {
+        const LayerOffsets &o = h->L[l];
+        const TapeLayer &L = t.L[l];
+        const vsum_layer_grads &gl = g->layers[l];
+        const float *xin = l == 0 ? t.x0 : t.L[l - 1].xout;
+        ZERO(gl.ln2_g, d); ZERO(gl.ln2_b, d); ZERO(gl.fc2_w, d * ff); ZERO(gl.fc2_b, d); ZERO(gl.fc1_w, ff * d); ZERO(gl.fc1_b, ff);
+        ZERO(gl.ln1_g, d); ZERO(gl.ln1_b, d); ZERO(gl.o_w, d * d); ZERO(gl.o_b, d);
+        ZERO(w.dwqkv, 3 * d * d); ZERO(w.dbqkv, 3 * d);
+        VSUM_REQUIRE(gl.q_w && gl.q_b && gl.k_w && gl.k_b && gl.v_w && gl.v_b, VSUM_EINVAL, "vsum_scorer_backward: null q/k/v gradient");
+        // xout = LN2(s2), s2 = dropout(mlp) + xmid          a: d_xout -> b: d_s2 (residual path), c: d_mlp
+        RUN(launch_layernorm_bwd_f32(w.a, L.s2, h->w32 + o.ln2g, w.b, w.c, gl.ln2_g, gl.ln2_b, T, (int)d, p, site_seed(seed, SITE_MLP, l), s));
+        // mlp = hid W2^T + b2
+        RUN(launch_linear_wgrad_f32(w.c, L.hid, gl.fc2_w, gl.fc2_b, T, (int)d, (int)ff, s));
+        RUN(launch_linear_dgrad_f32(w.c, h->w32 + o.fc2w, w.dhid, T, (int)d, (int)ff, 0, s));
+        RUN(launch_relu_dropout_bwd_f32(L.hid, w.dhid, (int64_t)T * ff, p, s));
+        // h1 = xmid W1^T + b1                               b: d_xmid += dh1 W1
+        RUN(launch_linear_wgrad_f32(w.dhid, L.xmid, gl.fc1_w, gl.fc1_b, T, (int)ff, (int)d, s));
+        RUN(launch_linear_dgrad_f32(w.dhid, h->w32 + o.fc1w, w.b, T, (int)ff, (int)d, 1, s));
+        // xmid = LN1(s1), s1 = dropout(proj) + xin          b: d_xmid -> a: d_s1 (residual path), c: d_proj
+        RUN(launch_layernorm_bwd_f32(w.b, L.s1, h->w32 + o.ln1g, w.a, w.c, gl.ln1_g, gl.ln1_b, T, (int)d, p, site_seed(seed, SITE_PROJ, l), s));
+        // proj = att Wo^T + bo                              dd: d_att
+        RUN(launch_linear_wgrad_f32(w.c, L.att, gl.o_w, gl.o_b, T, (int)d, (int)d, s));
+        RUN(launch_linear_dgrad_f32(w.c, h->w32 + o.wo, w.dd, T, (int)d, (int)d, 0, s));
+        RUN(launch_attention_bwd_f32(L.qkv, L.att, w.dd, L.lse, cu, B, max_len, T, (int)d, c.num_heads, scale, p,
+                                     site_seed(seed, SITE_ATTN, l), w.delta, w.dqkv, s));
+        // qkv = xin Wqkv^T + bqkv                           a: d_xin += dqkv Wqkv
+        RUN(launch_linear_wgrad_f32(w.dqkv, xin, w.dwqkv, w.dbqkv, T, (int)(3 * d), (int)d, s));
+        RUN(launch_linear_dgrad_f32(w.dqkv, h->w32 + o.wqkv, w.a, T, (int)(3 * d), (int)d, 1, s));
+        float *wdst[3] = {gl.q_w, gl.k_w, gl.v_w}, *bdst[3] = {gl.q_b, gl.k_b, gl.v_b};
+        for (int i = 0; i < 3; ++i) {
+            VSUM_CUDA_OK(cudaMemcpyAsync(wdst[i], w.dwqkv + i * d * d, d * d * sizeof(float), cudaMemcpyDeviceToDevice, s));
+            VSUM_CUDA_OK(cudaMemcpyAsync(bdst[i], w.dbqkv + i * d, d * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        }
+    }
+    // x0 = features We^T + be (+ positions)
+    RUN(launch_linear_wgrad_f32(w.a, x, g->embed_w, g->embed_b, T, (int)d, c.in_features, s));
+#undef ZERO
+    return VSUM_OK;
+}
+#undef RUN
+
+extern "C" int vsum_masked_mse(const float *out, const float *tgt, const uint8_t *pad_mask, int64_t n, float denom,
+                               float *loss_out, float grad_scale, float *d_out, void *stream) {
+    VSUM_REQUIRE(out && tgt && n >= 0 && denom > 0.f, VSUM_EINVAL, "vsum_masked_mse: bad argument");
+    return launch_masked_mse_f32(out, tgt, pad_mask, n, denom, loss_out, grad_scale, d_out, (cudaStream_t)stream);
+}
+
 // ---- diagnostics -----------------------------------------------------------------------------
 extern "C" int vsum_debug_gemm_tc05(const void *A, const void *W, const float *bias, const void *residual,
                                     const float *gamma, const float *beta, void *out, int64_t M, int32_t N,

@@ -152,7 +152,8 @@ int launch_add_layernorm_f32(const float *a, const float *res, const float *gamm
 template <int HD>
 __global__ void __launch_bounds__(256)
 attention_f32_kernel(const float *__restrict__ qkv, const int32_t *__restrict__ cu, int d,
-                     float scale, float *__restrict__ out) {
+                     float scale, float *__restrict__ out, float *__restrict__ lse, float drop_p,
+                     unsigned long long seed) {
     extern __shared__ __align__(16) float smem[];
     float *Qt = smem;                 // [HD][64]   Qt[k][r]
     float *Kt = Qt + HD * 64;         // [HD][64]   Kt[k][c]
@@ -172,6 +173,8 @@ attention_f32_kernel(const float *__restrict__ qkv, const int32_t *__restrict__ 
         const int r = idx / HD, k = idx % HD;
         Qt[k * 64 + r] = (q0 + r < n) ? qp[(int64_t)(q0 + r) * ld + k] : 0.f;
     }
+    const int H = gridDim.y;
+    const float keep_scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
     float m_run[4], l_run[4], o[4][OC];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -215,8 +218,11 @@ attention_f32_kernel(const float *__restrict__ qkv, const int32_t *__restrict__ 
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float p = expf(sacc[i][j] - m_new);
-                Ps[(ty * 4 + i) * 65 + tx * 4 + j] = p;
-                ps += p;
+                ps += p;                                          // the softmax normaliser ignores dropout
+                float pd = p;
+                if (drop_p > 0.f)                                 // simnet.py:159: dropout on the attention weights
+                    pd = dropout_keep(seed, attn_drop_index(base + q0 + ty * 4 + i, h, H, k0 + tx * 4 + j), drop_p) ? p * keep_scale : 0.f;
+                Ps[(ty * 4 + i) * 65 + tx * 4 + j] = pd;
             }
 #pragma unroll
             for (int off = 8; off > 0; off >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
@@ -247,11 +253,13 @@ attention_f32_kernel(const float *__restrict__ qkv, const int32_t *__restrict__ 
 #pragma unroll
         for (int j = 0; j < OC; ++j)
             out[(int64_t)(base + r) * d + h * HD + tx + 16 * j] = o[i][j] * inv;
+        if (lse && tx == 0) lse[(int64_t)(base + r) * H + h] = m_run[i] + logf(l_run[i]);
     }
 }
 
 int launch_attention_f32(const float *qkv, const int32_t *cu_seqlens, int B, int max_len, int d,
-                         int num_heads, float scale, float *out, cudaStream_t s) {
+                         int num_heads, float scale, float *out, cudaStream_t s, float *lse, float drop_p,
+                         unsigned long long seed) {
     if (B == 0 || max_len == 0) return VSUM_OK;
     const int hd = d / num_heads;
     VSUM_REQUIRE(hd * num_heads == d, VSUM_EINVAL, "attention: d_model %d not divisible by %d heads", d, num_heads);
@@ -263,7 +271,7 @@ int launch_attention_f32(const float *qkv, const int32_t *cu_seqlens, int B, int
         auto kern = attention_f32_kernel<HD>;                                                          \
         if (smem > 48 * 1024)                                                                          \
             VSUM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        kern<<<grid, 256, smem, s>>>(qkv, cu_seqlens, d, scale, out);                                  \
+        kern<<<grid, 256, smem, s>>>(qkv, cu_seqlens, d, scale, out, lse, drop_p, seed);               \
     }
     if (hd == 16) VSUM_ATT(16)
     else if (hd == 32) VSUM_ATT(32)

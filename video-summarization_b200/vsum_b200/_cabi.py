@@ -22,6 +22,8 @@ EXPORTS = (
     "vsum_scorer_create", "vsum_scorer_destroy", "vsum_scorer_load_weights",
     "vsum_scorer_workspace_bytes", "vsum_scorer_forward",
     "vsum_shot_mean", "vsum_knapsack_class_width", "vsum_knapsack_scratch_words", "vsum_knapsack", "vsum_summary_fscore",
+    "vsum_scorer_tape_bytes", "vsum_scorer_train_workspace_bytes", "vsum_scorer_forward_train",
+    "vsum_scorer_backward", "vsum_masked_mse",
     "vsum_debug_gemm_tc05", "vsum_debug_attention_tc05",
     "vsum_profile_begin", "vsum_profile_end", "vsum_profile_num_categories", "vsum_profile_category_name",
 )
@@ -51,6 +53,15 @@ class ScorerWeights(C.Structure):
                 ("layers", LayerWeights * VSUM_MAX_LAYERS)]
 
 
+class LayerGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _LAYER_FIELDS]
+
+
+class ScorerGrads(C.Structure):
+    _fields_ = [("embed_w", C.c_void_p), ("embed_b", C.c_void_p), ("final_w", C.c_void_p), ("final_b", C.c_void_p),
+                ("layers", LayerGrads * VSUM_MAX_LAYERS)]
+
+
 _lib = None
 
 
@@ -74,6 +85,15 @@ def load():
     L.vsum_scorer_workspace_bytes.restype = C.c_size_t
     L.vsum_scorer_workspace_bytes.argtypes = [vp, i64, i32, i32]
     L.vsum_scorer_forward.argtypes = [vp, vp, vp, i32, i64, i32, i32, i32, vp, vp, vp, C.c_size_t, vp]
+    L.vsum_scorer_tape_bytes.restype = C.c_size_t
+    L.vsum_scorer_tape_bytes.argtypes = [vp, i64]
+    L.vsum_scorer_train_workspace_bytes.restype = C.c_size_t
+    L.vsum_scorer_train_workspace_bytes.argtypes = [vp, i64, i32]
+    L.vsum_scorer_forward_train.argtypes = [vp, vp, vp, i32, i64, i32, C.c_float, C.c_uint64, vp, vp, vp, C.c_size_t,
+                                            vp, C.c_size_t, vp]
+    L.vsum_scorer_backward.argtypes = [vp, vp, vp, i32, i64, i32, C.c_float, C.c_uint64, vp, vp, vp,
+                                       C.POINTER(ScorerGrads), vp, C.c_size_t, vp]
+    L.vsum_masked_mse.argtypes = [vp, vp, vp, i64, C.c_float, vp, C.c_float, vp, vp]
     L.vsum_shot_mean.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]
     L.vsum_knapsack_class_width.restype = i32
     L.vsum_knapsack_class_width.argtypes = [i32]

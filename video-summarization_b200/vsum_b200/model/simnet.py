@@ -85,6 +85,74 @@ class _Encoder(nn.Module):
         self.module_score = nn.ModuleList([])
 
 
+def _layer_tensors(blk):
+    """Parameters of one encoder block in the field order of vsum_layer_weights / vsum_layer_grads."""
+    return (blk.sa.q.weight, blk.sa.q.bias, blk.sa.k.weight, blk.sa.k.bias, blk.sa.v.weight, blk.sa.v.bias,
+            blk.sa.feature_projection.weight, blk.sa.feature_projection.bias, blk.norm1.weight, blk.norm1.bias,
+            blk.mlp.fc1.weight, blk.mlp.fc1.bias, blk.mlp.fc2.weight, blk.mlp.fc2.bias, blk.norm2.weight, blk.norm2.bias)
+
+
+class _ScorerTrainFn(torch.autograd.Function):
+    """Autograd bridge to vsum_scorer_forward_train / vsum_scorer_backward (fp32 kernels)."""
+
+    @staticmethod
+    def forward(ctx, model, features, cu_seqlens, seqlens_host, drop_p, seed, *params):
+        dev = features.device
+        T, B = features.shape[0], len(seqlens_host)
+        max_len = max(seqlens_host)
+        L = _cabi.load()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            model._sync_weights(max_len, dev, stream)
+            h = model._handle
+            tape = torch.empty(L.vsum_scorer_tape_bytes(h, T) + 1024, dtype=torch.uint8, device=dev)
+            ws = model._workspace_for(L.vsum_scorer_train_workspace_bytes(h, T, B), dev)
+            scores = torch.empty((T, model.num_classes), dtype=torch.float32, device=dev)
+            feats = torch.empty((T, model.d_model), dtype=torch.float32, device=dev)
+            tp, wp = _al(tape), _al(ws)
+            _cabi.check(L.vsum_scorer_forward_train(h, features.data_ptr(), cu_seqlens.data_ptr(), B, T, max_len,
+                                                    float(drop_p), int(seed), scores.data_ptr(), feats.data_ptr(),
+                                                    tp, tape.numel() - (tp - tape.data_ptr()), wp,
+                                                    ws.numel() - (wp - ws.data_ptr()), stream), "vsum_scorer_forward_train")
+        ctx.model, ctx.tape, ctx.args = model, tape, (features, cu_seqlens, B, T, max_len, float(drop_p), int(seed))
+        ctx.set_materialize_grads(False)
+        return scores, feats
+
+    @staticmethod
+    def backward(ctx, d_scores, d_feats):
+        model, tape = ctx.model, ctx.tape
+        features, cu_seqlens, B, T, max_len, drop_p, seed = ctx.args
+        dev = features.device
+        L = _cabi.load()
+        params = list(model._train_params())
+        grads = [torch.empty_like(p) for p in params]
+        if d_scores is None:
+            d_scores = torch.zeros((T, model.num_classes), dtype=torch.float32, device=dev)
+        d_scores = d_scores.contiguous().float()
+        d_feats = None if d_feats is None else d_feats.contiguous().float()
+        g = _cabi.ScorerGrads()
+        it = iter(grads)
+        g.embed_w, g.embed_b = next(it).data_ptr(), next(it).data_ptr()
+        for i in range(model.num_layers):
+            for name in _cabi._LAYER_FIELDS:
+                setattr(g.layers[i], name, next(it).data_ptr())
+        g.final_w, g.final_b = next(it).data_ptr(), next(it).data_ptr()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            model._sync_weights(max_len, dev, stream)          # the optimiser may not have stepped yet: no-op
+            ws = model._workspace_for(L.vsum_scorer_train_workspace_bytes(model._handle, T, B), dev)
+            wp = _al(ws)
+            _cabi.check(L.vsum_scorer_backward(model._handle, features.data_ptr(), cu_seqlens.data_ptr(), B, T, max_len,
+                                               drop_p, seed, d_scores.data_ptr(), None if d_feats is None else d_feats.data_ptr(),
+                                               _al(tape), C.byref(g), wp, ws.numel() - (wp - ws.data_ptr()), stream),
+                        "vsum_scorer_backward")
+        return (None, None, None, None, None, None, *grads)
+
+
+def _al(t: Tensor) -> int:
+    return (t.data_ptr() + 1023) // 1024 * 1024
+
+
 class SimNet(nn.Module):
     """Drop-in for the reference `SimNet`.  Extra, optional attribute: `precision` ("bf16" uses
     the tcgen05 kernels and needs d_model=256, heads=4; "fp32" uses the fp32 SIMT kernels)."""
@@ -185,6 +253,26 @@ class SimNet(nn.Module):
             self._workspace = ws
         return ws
 
+    def _train_params(self):
+        """Parameters in the order _ScorerTrainFn returns their gradients."""
+        emb = self.embedding_layer.feature_transform
+        yield emb.weight
+        yield emb.bias
+        for blk in self.encoder.module_list:
+            yield from _layer_tensors(blk)
+        yield self.final_layer.weight
+        yield self.final_layer.bias
+
+    def forward_packed_train(self, features: Tensor, cu_seqlens: Tensor, seqlens_host: Sequence[int]):
+        """Differentiable packed forward (fp32 kernels + native backward).  Dropout follows
+        `self.training` / `self.dropout` like nn.Dropout in the reference (simnet.py:107,110,159,181)."""
+        if not features.is_cuda:
+            raise _cabi.VsumError("vsum_b200 runs on CUDA devices only (no CPU fallback)")
+        drop_p = float(self.dropout) if self.training else 0.0
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if drop_p > 0 else 0
+        return _ScorerTrainFn.apply(self, features.contiguous().float(), cu_seqlens, list(seqlens_host), drop_p, seed,
+                                    *self._train_params())
+
     # ------------------------------------------------------------------ packed entry point
     @torch.no_grad()
     def forward_packed(self, features: Tensor, cu_seqlens: Tensor, seqlens_host: Sequence[int],
@@ -229,12 +317,11 @@ class SimNet(nn.Module):
         mask is ignored like the reference does (simnet.py:38, train.py:162).  Returns
         (scores [bs,n,num_classes], feats [bs,n,d_model]); with `model_score=True` the second
         element is the same tensor because the reference's score stack is empty (simnet.py:80-83)."""
-        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "vsum_b200 round 1 ships the scorer forward only; call under torch.no_grad() / model.eval(). "
-                "The backward kernels (SURVEY.md section 8 row a1/K7) are the next row.")
         bs, n, _ = x.shape
         dev = x.device
+        # autograd on (train_step, train.py:111-131): fp32 kernels with the native backward
+        differentiable = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        run = self.forward_packed_train if differentiable else self.forward_packed
         if isinstance(mask, Tensor):
             keep = ~mask
             lens = keep.sum(dim=1)
@@ -245,11 +332,11 @@ class SimNet(nn.Module):
             packed = x[keep]                                       # [T,1024] gather of the valid frames
             cu = torch.zeros(bs + 1, dtype=torch.int32, device=dev)
             cu[1:] = lens.cumsum(0).to(torch.int32)
-            s, f = self.forward_packed(packed, cu, lens_host)
-            scores = torch.zeros((bs, n, self.num_classes), dtype=torch.float32, device=dev)
-            feats = torch.zeros((bs, n, self.d_model), dtype=torch.float32, device=dev)
-            scores[keep], feats[keep] = s, f                       # padded rows stay 0 (the loss masks them)
-            return scores, feats
+            s, f = run(packed, cu, lens_host)
+            idx = keep.reshape(-1).nonzero().squeeze(1)            # padded rows stay 0 (the loss masks them)
+            scores = torch.zeros((bs * n, self.num_classes), dtype=torch.float32, device=dev).index_copy(0, idx, s)
+            feats = torch.zeros((bs * n, self.d_model), dtype=torch.float32, device=dev).index_copy(0, idx, f)
+            return scores.view(bs, n, self.num_classes), feats.view(bs, n, self.d_model)
         cu = torch.arange(0, (bs + 1) * n, n, dtype=torch.int32, device=dev)
-        s, f = self.forward_packed(x.reshape(bs * n, -1), cu, [n] * bs)
+        s, f = run(x.reshape(bs * n, -1), cu, [n] * bs)
         return s.view(bs, n, self.num_classes), f.view(bs, n, self.d_model)

@@ -1,7 +1,7 @@
 """Host helpers with the reference's names (`src/utils/utils.py`).  Only `mse_with_mask_loss`
-(lines 45-56) touches the hot path; in round 1 it is thin PyTorch glue over tensors the CUDA
-scorer produced (the native fwd/bwd loss kernel is SURVEY.md section 8 row a9, scheduled with
-the backward pass)."""
+(lines 45-56) touches the hot path: on CUDA tensors it runs the native fwd+bwd kernel behind
+`vsum_masked_mse`; the CPU expression below exists for host-side
+unit tests of the normalisation only."""
 from __future__ import annotations
 
 import json
@@ -40,8 +40,37 @@ def load_json(path):
         return json.load(f)
 
 
+class _MaskedMSE(torch.autograd.Function):
+    """vsum_masked_mse: loss and d(loss)/d(output) in one kernel pass."""
+
+    @staticmethod
+    def forward(ctx, output, targets, mask, denom):
+        from .. import _cabi
+        out = output.contiguous().float()
+        tgt = targets.contiguous().float()
+        pad = mask.contiguous().to(torch.uint8)
+        loss = torch.zeros((), dtype=torch.float32, device=out.device)
+        d_out = torch.empty_like(out)
+        with torch.cuda.device(out.device):
+            _cabi.check(_cabi.load().vsum_masked_mse(out.data_ptr(), tgt.data_ptr(), pad.data_ptr(), out.numel(), float(denom),
+                                                     loss.data_ptr(), 1.0, d_out.data_ptr(),
+                                                     torch.cuda.current_stream(out.device).cuda_stream), "vsum_masked_mse")
+        ctx.save_for_backward(d_out)
+        ctx.shape = output.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (d_out,) = ctx.saved_tensors
+        return (d_out * g).view(ctx.shape), None, None, None
+
+
 def mse_with_mask_loss(output, targets, mask, reduction="avg"):
-    """Masked MSE normalised by the PADDED size bs*Nmax, not by the valid frames (utils.py:55)."""
+    """Masked MSE normalised by the PADDED size bs*Nmax, not by the valid frames (utils.py:55).
+    On CUDA tensors this is the native kernel behind `vsum_masked_mse` (forward and backward)."""
+    if output.is_cuda:
+        squeezed = output.squeeze(2)
+        return _MaskedMSE.apply(squeezed, targets, mask, float(squeezed.numel()) if reduction == "avg" else 1.0)
     keep = (~mask).to(output.dtype)
     err = ((output.squeeze(2) - targets) * keep) ** 2
     return err.mean() if reduction == "avg" else err.sum()
