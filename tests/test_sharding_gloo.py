@@ -43,3 +43,30 @@ def test_gather_fscores_two_ranks():
 def test_single_process_path():
     f = gather_fscores([2, 0], np.array([5.0, 7.0]), 3)
     assert f[0] == 7.0 and f[2] == 5.0 and np.isnan(f[1])
+
+
+def _grad_worker(rank, world, port, ret):
+    import torch
+    from vsum_b200.sharding import allreduce_gradients, global_loss_denominator
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(6, 3)
+    for i, p in enumerate(lin.parameters()):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    allreduce_gradients(lin.parameters())
+    denom = global_loss_denominator(local_batch=4 - rank, local_nmax=100 + 50 * rank)
+    ret[rank] = ([p.grad.flatten()[0].item() for p in lin.parameters()], denom)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_and_global_denominator_two_ranks():
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_grad_worker, args=(2, port, ret), nprocs=2, join=True)
+    for rank in (0, 1):
+        grads, denom = ret[rank]
+        assert grads == [3.0, 6.0]                      # (1 + 2) * (i + 1): summed over the two ranks
+        assert denom == float((4 + 3) * 150)            # sum of batch sizes x max padded length

@@ -123,3 +123,28 @@ def test_adam_step_reduces_loss():
         scaler.update()
         losses.append(loss.item())
     assert max(losses[-3:]) < losses[0] * 0.9, losses
+
+
+def test_pretrain_losses_match_reference_and_backprop():
+    """PretrainModel (src/model/simnet_pretrain.py:71-100): the three losses against the reference's
+    own values (golden fixture), and gradients reach the encoder through the native backward."""
+    import os
+    from conftest import GOLDEN
+    from vsum_b200.model import PretrainModel
+    g = np.load(os.path.join(GOLDEN, "pretrain_golden.npz"))["losses"]
+    torch.manual_seed(1234)
+    import random; random.seed(1234); np.random.seed(1234)
+    net = PretrainModel(feature_dim=256, sparsity=0.0, num_heads=4, num_layers=4, dropout=0.2, use_pos=True).cuda().eval()
+    lens = (120, 77)
+    x = torch.full((2, 120, 1024), 1000.0)
+    for b, n in enumerate(lens):
+        x[b, :n] = torch.from_numpy(make_video(130 + b, n).features)
+    vid_rep = torch.from_numpy(np.random.default_rng(4321).random((2, 512), dtype=np.float32)).cuda()
+    x = x.cuda()
+    mask = x[:, :, 0] == 1000
+    loss, center, repel = net(x, vid_rep, mask)
+    np.testing.assert_allclose([loss.item(), center.item(), repel.item()], g, rtol=2e-4, atol=1e-6)
+    (loss + 0.5 * center + 1.0 * repel).backward()                      # pretrain.py:63
+    grads = [p.grad for p in net.encoder.parameters()]
+    assert all(gr is not None and torch.isfinite(gr).all() for gr in grads)
+    assert sum(gr.abs().sum().item() for gr in grads) > 0

@@ -3,10 +3,11 @@
 a `Linear(feature_dim, 512)`, `forward(x, video_representation, mask)` returns
 `(loss, center_loss, repel_loss)`.
 
-Round-1 status: the encoder (the hot part) runs on the sm_100a kernels; the three thin losses
-on top of it are PyTorch glue evaluated without autograd.  `repelling_loss` uses the O(N*d)
-algebraic form of the reference's N x N cosine matrix.  Native
-loss/backward kernels are section 8 row a10, after the scorer backward.
+Round-1 status: the encoder (the hot part) runs on the CUDA kernels, forward AND backward (autograd
+goes through `vsum_scorer_backward`, including the gradient w.r.t. the frame features it returns);
+the three thin losses on top of it are PyTorch glue.  `repelling_loss` uses the O(N*d) algebraic
+form of the reference's N x N cosine matrix, so no [bs,N,N] tensor exists.
+Native loss kernels are section 8 row a10.
 """
 from __future__ import annotations
 
@@ -46,7 +47,6 @@ class PretrainModel(nn.Module):
         total = xh.sum(dim=1).pow(2).sum(dim=1) - xh.pow(2).sum(dim=(1, 2))
         return (total / (n * n)).mean()
 
-    @torch.no_grad()
     def forward(self, x, video_representation, mask=None, visualize_attention=None, pen_met="entropy"):
         scores, frame_features = self.encoder(x, mask, model_score=True)
         frame_features = self.video_transform(frame_features)

@@ -60,3 +60,42 @@ def gather_fscores(local_idx: Sequence[int], local_f: np.ndarray, n_total: int, 
         keep = i_np >= 0
         out[i_np[keep]] = v_np[keep]
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# data-parallel training (BASELINE config 3): one process per GPU, NCCL gradient all-reduce
+# ---------------------------------------------------------------------------------------------
+def global_loss_denominator(local_batch: int, local_nmax: int, group=None, device=None) -> float:
+    """`mse_with_mask_loss` divides by the PADDED size bs * Nmax (src/utils/utils.py:55).  For the
+    data-parallel step to equal the single-process step on the concatenated batch the denominator
+    must be (sum of bs over ranks) * (max Nmax over ranks)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return float(local_batch * local_nmax)
+    dev = device or (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu"))
+    bs = torch.tensor([local_batch], dtype=torch.int64, device=dev)
+    nm = torch.tensor([local_nmax], dtype=torch.int64, device=dev)
+    dist.all_reduce(bs, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(nm, op=dist.ReduceOp.MAX, group=group)
+    return float(int(bs.item()) * int(nm.item()))
+
+
+def allreduce_gradients(params, group=None, average: bool = False) -> None:
+    """One flat all-reduce (sum) over every gradient: 3.4 M fp32 values = 13.7 MB for the benchmark
+    model, i.e. latency-bound on NVLink -- a single bucket is the right size.  With the loss
+    normalised by `global_loss_denominator` the sum IS the gradient of the global batch; pass
+    `average=True` when every rank normalised by its own local size instead."""
+    params = [p for p in params if p.grad is not None]
+    if not params or not (dist.is_available() and dist.is_initialized()):
+        return
+    world = dist.get_world_size(group)
+    if world == 1:
+        return
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat.div_(world)
+    off = 0
+    for p in params:
+        n = p.grad.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n

@@ -65,12 +65,14 @@ class _MaskedMSE(torch.autograd.Function):
         return (d_out * g).view(ctx.shape), None, None, None
 
 
-def mse_with_mask_loss(output, targets, mask, reduction="avg"):
+def mse_with_mask_loss(output, targets, mask, reduction="avg", denom=None):
     """Masked MSE normalised by the PADDED size bs*Nmax, not by the valid frames (utils.py:55).
     On CUDA tensors this is the native kernel behind `vsum_masked_mse` (forward and backward)."""
     if output.is_cuda:
         squeezed = output.squeeze(2)
-        return _MaskedMSE.apply(squeezed, targets, mask, float(squeezed.numel()) if reduction == "avg" else 1.0)
+        if denom is None:       # data-parallel callers pass sharding.global_loss_denominator(...)
+            denom = float(squeezed.numel()) if reduction == "avg" else 1.0
+        return _MaskedMSE.apply(squeezed, targets, mask, float(denom))
     keep = (~mask).to(output.dtype)
     err = ((output.squeeze(2) - targets) * keep) ** 2
     return err.mean() if reduction == "avg" else err.sum()
