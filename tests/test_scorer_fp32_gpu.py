@@ -102,11 +102,10 @@ def test_against_torch_oracle_random_weights():
 
 
 def test_error_paths(model):
-    with pytest.raises(NotImplementedError):
-        model.train()
-        try:
-            model(torch.zeros(1, 4, 1024, device="cuda"))
-        finally:
-            model.eval()
     with pytest.raises(Exception):
         model(torch.zeros(1, 4, 1024))                                   # CPU tensor: no fallback
+    with torch.no_grad():
+        model.precision = "int8"
+        with pytest.raises(ValueError):
+            model(torch.zeros(1, 4, 1024, device="cuda"))
+        model.precision = "fp32"
