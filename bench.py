@@ -39,8 +39,9 @@ METRIC, UNIT = "summarized_videos_per_sec", "videos/s"
 REF_SAMPLE_N = (256, 1024, 4096)        # one video per third of the log-uniform length range
 
 
-def workload_name(videos):
-    return (f"config5 throughput sweep: {videos} synthetic videos/GPU/step, N log-uniform [{N_LO},{N_HI}], "
+def workload_name(videos, lo=None, hi=None):
+    lo, hi = lo or N_LO, hi or N_HI
+    return (f"config5 throughput sweep: {videos} synthetic videos/GPU/step, N log-uniform [{lo},{hi}], "
             f"1024-d fp32 features, {N_USERS} users, scorer d256/h4/L4 + knapsack 15% + F-score(avg)")
 
 
@@ -57,22 +58,55 @@ def scorer_flops(seqlens, d=256, layers=4, in_features=1024):
 # clocks: sampled DURING the timed region
 # --------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled every ~20 ms through NVML (nvidia-smi as a fallback)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.index, self.sm, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop, self._t, self._nvml = threading.Event(), None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES remaps indices: resolve through the UUID torch reports when possible
+            try:
+                import torch
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+                self._h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if isinstance(uuid, str) else uuid)
+            except Exception:
+                self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        c = [x.strip() for x in out.split(",")]
+        if len(c) >= 6:
+            self.sm.append(float(c[0]))
+            self.max_mhz = float(c[1])
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[2:6]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                self._sample_nvml() if self._nvml else self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.02 if self._nvml else 0.2)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -84,12 +118,9 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -170,12 +201,13 @@ def main_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- workload: weak scaling, rank r owns videos [r*V, (r+1)*V) of the global id space
     V = args.videos
     ids = [rank * V + i for i in range(V)]
-    videos = [make_video(v, video_length(v, N_LO, N_HI), n_users=N_USERS, with_features=False) for v in ids]
+    videos = [make_video(v, video_length(v, args.len_lo, args.len_hi), n_users=N_USERS, with_features=False) for v in ids]
     hb = pack_videos(videos, pin=True, with_features=False)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     feats_dev = torch.rand((hb.n_steps, 1024), device=dev, generator=g)        # rng.random-like features in [0,1)
@@ -268,7 +300,7 @@ def main_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(V), "videos_per_gpu_per_step": V, "frames_per_gpu_per_step": hb.n_steps,
+            "config": {"workload": workload_name(V, args.len_lo, args.len_hi), "videos_per_gpu_per_step": V, "frames_per_gpu_per_step": hb.n_steps,
                        "l2": "inputs (fp32 features, %.2f GB/GPU) are larger than L2; no flush needed" % (hb.n_steps * 4096 / 1e9),
                        "parallelism": f"videos sharded over {world} GPU(s), F-score all-gather",
                        "pipelining": "scorer(batch i+1) overlaps pooling/knapsack/F-score(batch i) on a side stream; e2e adds a copy stream"},
@@ -306,6 +338,8 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--videos", type=int, default=256, help="videos per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--len-lo", type=int, default=N_LO, help="shortest video (frames); default = BASELINE config 5")
+    ap.add_argument("--len-hi", type=int, default=N_HI, help="longest video (frames)")
     a = ap.parse_args()
     if a.impl == "reference":
         main_reference(a)
