@@ -140,3 +140,19 @@ def test_knapsack_properties_hypothesis():
         for j in range(len(items)):        # values are positive: an optimal selection leaves no room for another shot
             assert j in got or used + wt[j] > W
     check()
+
+
+def test_empty_and_maximum_sizes():
+    # empty inputs
+    assert generate_summary([], [], [], []) == []
+    assert len(eval_fscores({}, {})) == 0
+    # the largest knapsack class: capacity 28 671 frames (n_frames = 191 146 -> N ~ 12 743 sub-sampled frames)
+    v = make_video(4000, 12700, n_users=3, with_features=False)
+    assert 18944 < int(v.n_frames * 0.15) + 1 <= 28672
+    check_against_oracle([v], [make_scores(4000, 12700)], "avg")
+    # one frame more than the fp64 DP row can hold in shared memory must fail loudly, not silently
+    from vsum_b200 import _cabi
+    too_long = make_video(4001, 12800, n_users=1, with_features=False)
+    assert int(too_long.n_frames * 0.15) + 1 > 28672
+    with pytest.raises(_cabi.VsumError):
+        run_batch([too_long], [make_scores(4001, 12800)])
