@@ -214,7 +214,7 @@ def main_b200(args):
     hb.features.copy_(feats_dev)                                                # pinned host copy for the e2e leg
     torch.manual_seed(1234)
     model = SimNet(**MODEL_KW).to(dev).eval()
-    summ = Summarizer(model, "avg")
+    summ = Summarizer(model, "avg", eval_sms=args.eval_sms)
     db = DeviceBatch(hb, dev, features=feats_dev)
     f_all = torch.empty(world * V, dtype=torch.float64, device=dev) if world > 1 else None
 
@@ -338,6 +338,7 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--videos", type=int, default=256, help="videos per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eval-sms", type=int, default=0, help="SMs left to the evaluation stream in pipelined mode (0 = no partition)")
     ap.add_argument("--len-lo", type=int, default=N_LO, help="shortest video (frames); default = BASELINE config 5")
     ap.add_argument("--len-hi", type=int, default=N_HI, help="longest video (frames)")
     a = ap.parse_args()

@@ -181,6 +181,14 @@ VSUM_API int vsum_summary_fscore(const uint8_t *selected, const int32_t *cps, co
                         double *f_out, double *per_user_out, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * SM partition for pipelined execution (scorer of batch i+1 on one stream, evaluation of batch i
+ * on another): the knapsack / overlap kernels run as at most `eval_sms` SMs' worth of persistent
+ * CTAs, and the persistent scorer GEMMs launch on (SM count - scorer_reserved_sms) CTAs, so that
+ * neither stage waits for an SM the other holds.  0 / 0 (the default) removes both limits.
+ * ------------------------------------------------------------------------------------------ */
+VSUM_API int vsum_set_sm_partition(int32_t eval_sms, int32_t scorer_reserved_sms);
+
+/* ------------------------------------------------------------------------------------------
  * Per-kernel timing (bench.py's roofline leg): between begin and end every kernel launch of
  * this library is bracketed by CUDA events on its own stream; end() synchronises those events
  * and returns summed milliseconds and launch counts per category.

@@ -18,6 +18,8 @@ namespace vsum {
 char *error_buffer();
 int set_error(int code, const char *fmt, ...);
 void count_launch(int n = 1);
+int eval_sm_budget();       // 0 = unlimited; else the evaluation kernels keep at most this many SMs busy
+int scorer_sm_reserve();    // persistent scorer GEMMs leave this many SMs free
 
 #define VSUM_CUDA_OK(expr)                                                                      \
     do {                                                                                        \

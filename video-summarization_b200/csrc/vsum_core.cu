@@ -23,6 +23,11 @@ int set_error(int code, const char *fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// SM partition between the evaluation stage and the scorer when they overlap on two streams.
+static std::atomic<int> g_eval_sm_budget{0}, g_scorer_sm_reserve{0};
+int eval_sm_budget() { return g_eval_sm_budget.load(std::memory_order_relaxed); }
+int scorer_sm_reserve() { return g_scorer_sm_reserve.load(std::memory_order_relaxed); }
+
 // ---- profiling -------------------------------------------------------------------------------
 struct ProfRecord { int cat; cudaEvent_t a, b; };
 static std::mutex g_prof_mu;
@@ -75,6 +80,14 @@ extern "C" int vsum_profile_end(float *ms_out, int32_t *count_out, int32_t ncat)
 extern "C" int32_t vsum_profile_num_categories(void) { return vsum::PROF_NUM; }
 extern "C" const char *vsum_profile_category_name(int32_t i) {
     return (i >= 0 && i < vsum::PROF_NUM) ? vsum::kProfNames[i] : "";
+}
+
+extern "C" int vsum_set_sm_partition(int32_t eval_sms, int32_t scorer_reserved_sms) {
+    VSUM_REQUIRE(eval_sms >= 0 && scorer_reserved_sms >= 0 && scorer_reserved_sms < 128, VSUM_EINVAL,
+                 "vsum_set_sm_partition: eval_sms=%d scorer_reserved_sms=%d", eval_sms, scorer_reserved_sms);
+    vsum::g_eval_sm_budget.store(eval_sms);
+    vsum::g_scorer_sm_reserve.store(scorer_reserved_sms);
+    return VSUM_OK;
 }
 
 extern "C" int vsum_abi_version(void) { return 1; }

@@ -143,14 +143,17 @@ __global__ void __launch_bounds__(THREADS, 1)
 knapsack_kernel(const double *__restrict__ val, const int32_t *__restrict__ wt,
                 const int32_t *__restrict__ cu_shots, const int32_t *__restrict__ cap,
                 const int64_t *__restrict__ bit_offsets, const int32_t *__restrict__ order,
-                uint32_t *__restrict__ take_bits, uint8_t *__restrict__ selected_out) {
+                uint32_t *__restrict__ take_bits, uint8_t *__restrict__ selected_out, int n_videos) {
     extern __shared__ double row[];                       // THREADS * EPT capacities
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int v = order ? __ldg(order + blockIdx.x) : (int)blockIdx.x;
+    constexpr int WORDS = THREADS * EPT / 32;
+  for (int slot = blockIdx.x; slot < n_videos; slot += gridDim.x) {      // persistent: a bounded number of CTAs walks the list
+    const int v = order ? __ldg(order + slot) : slot;
     const int s0 = __ldg(cu_shots + v), S = __ldg(cu_shots + v + 1) - s0;
     const int W = __ldg(cap + v);
+    __syncthreads();                                      // previous video's back-track is done with row / bits
     for (int i = tid; i < S; i += THREADS) selected_out[s0 + i] = 0;
-    if (W < 0 || S <= 0) return;
+    if (W < 0 || S <= 0) continue;
     {   // every video of a launch must belong to this kernel's class (its bit rows are padded to it)
         constexpr int kW[] = {256, 1024, 4096, 9728, 18944, 28672};
         int own = -1;
@@ -161,7 +164,6 @@ knapsack_kernel(const double *__restrict__ val, const int32_t *__restrict__ wt,
     // The row is padded to this kernel's full width (shared memory and bit matrix alike): padding
     // cells are computed like real ones -- the recurrence only looks at lower capacities, so they
     // cannot influence K[i][w] for w <= W -- which removes every bounds test from the inner loop.
-    constexpr int WORDS = THREADS * EPT / 32;
     uint32_t *bits = take_bits + __ldg(bit_offsets + v);
     double cur[EPT];                                      // K[i][w] for my capacities
 #pragma unroll
@@ -218,6 +220,7 @@ knapsack_kernel(const double *__restrict__ val, const int32_t *__restrict__ wt,
             i = rsel;
         }
     }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -264,9 +267,9 @@ __global__ void __launch_bounds__(256)
 overlap_kernel(const int8_t *__restrict__ summary, const int64_t *__restrict__ sum_offsets,
                const float *__restrict__ user_summary, const int64_t *__restrict__ us_offsets,
                const int32_t *__restrict__ cu_users, const int32_t *__restrict__ us_cols, int B,
-               long long *__restrict__ counts) {
+               long long *__restrict__ counts, int total_rows) {
     __shared__ long long red[32];
-    const int rowid = blockIdx.x;
+  for (int rowid = blockIdx.x; rowid < total_rows; rowid += gridDim.x) {
     const int v = find_segment(cu_users, B, rowid);
     const int u = rowid - __ldg(cu_users + v);
     const int cols = __ldg(us_cols + v);
@@ -315,6 +318,7 @@ overlap_kernel(const int8_t *__restrict__ summary, const int64_t *__restrict__ s
         counts[3 * (int64_t)rowid + 1] = g_cnt;
         counts[3 * (int64_t)rowid + 2] = s_cnt;
     }
+  }
 }
 
 // fp64 ratios in the reference's evaluation order (evaluation_metrics.py:23-33).
@@ -390,8 +394,13 @@ static int launch_knapsack(const double *val, const int32_t *wt, const int32_t *
     auto kern = knapsack_kernel<THREADS, EPT>;
     if (smem > 48 * 1024)
         VSUM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = B;
+    if (const int budget = eval_sm_budget()) {             // CTAs of this kernel that fit one SM (smem / threads)
+        const int per_sm = (int)max((size_t)1, min((size_t)(2048 / THREADS), (size_t)(227 * 1024) / (smem + 1024)));
+        grid = min(B, budget * per_sm);
+    }
     ProfScope prof(PROF_KNAPSACK, stream);
-    kern<<<B, THREADS, smem, stream>>>(val, wt, cu_shots, cap, bit_offsets, order, take_bits, selected_out);
+    kern<<<grid, THREADS, smem, stream>>>(val, wt, cu_shots, cap, bit_offsets, order, take_bits, selected_out, B);
     VSUM_LAUNCH_OK("knapsack_kernel");
     return VSUM_OK;
 }
@@ -446,9 +455,11 @@ extern "C" int vsum_summary_fscore(const uint8_t *selected, const int32_t *cps,
                  "vsum_summary_fscore: null pointer");
     if (total_users > 0) {
         ProfScope prof(PROF_OVERLAP, s);
-        overlap_kernel<<<total_users, 256, 0, s>>>(summary_out, sum_offsets, user_summary,
-                                                   us_offsets, cu_users, us_cols, B,
-                                                   reinterpret_cast<long long *>(counts_ws));
+        int grid = total_users;
+        if (const int budget = eval_sm_budget()) grid = min(total_users, budget * 8);
+        overlap_kernel<<<grid, 256, 0, s>>>(summary_out, sum_offsets, user_summary,
+                                            us_offsets, cu_users, us_cols, B,
+                                            reinterpret_cast<long long *>(counts_ws), total_users);
         VSUM_LAUNCH_OK("overlap_kernel");
     }
     ProfScope prof(PROF_FSCORE, s);

@@ -390,6 +390,7 @@ int launch_variant(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtenso
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    sms = max(8, sms - scorer_sm_reserve());               // SM partition with the evaluation stream
     dim3 grid;
     if (WRES) grid = dim3((unsigned)max((int64_t)1, min(p.m_tiles, (int64_t)(sms / p.n_tiles))), (unsigned)p.n_tiles);
     else grid = dim3((unsigned)min(p.m_tiles * p.n_tiles, (int64_t)sms));

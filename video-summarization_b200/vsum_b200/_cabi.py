@@ -18,7 +18,7 @@ FSCORE_AVG, FSCORE_MAX = 0, 1
 
 # every symbol include/vsum_b200.h declares (checked by tests/test_cabi_symbols.py)
 EXPORTS = (
-    "vsum_abi_version", "vsum_last_error", "vsum_launch_count",
+    "vsum_abi_version", "vsum_last_error", "vsum_launch_count", "vsum_set_sm_partition",
     "vsum_scorer_create", "vsum_scorer_destroy", "vsum_scorer_load_weights",
     "vsum_scorer_workspace_bytes", "vsum_scorer_forward",
     "vsum_shot_mean", "vsum_knapsack_class_width", "vsum_knapsack_scratch_words", "vsum_knapsack", "vsum_summary_fscore",
@@ -79,6 +79,7 @@ def load():
     L.vsum_abi_version.restype = C.c_int
     L.vsum_last_error.restype = C.c_char_p
     L.vsum_launch_count.restype = i64
+    L.vsum_set_sm_partition.argtypes = [i32, i32]
     L.vsum_scorer_create.argtypes = [C.POINTER(vp), C.POINTER(ScorerConfig)]
     L.vsum_scorer_destroy.argtypes = [vp]
     L.vsum_scorer_load_weights.argtypes = [vp, C.POINTER(ScorerWeights), vp]

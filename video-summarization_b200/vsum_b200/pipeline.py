@@ -16,6 +16,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 import torch
 
+from . import _cabi
 from .evaluation import _engine
 from .model.simnet import SimNet
 from .synthetic import SyntheticVideo
@@ -93,9 +94,13 @@ class Summarizer:
       for host batches, the H2D copy of batch k+1 runs on a copy stream.
     """
 
-    def __init__(self, model: SimNet, eval_method: str = "avg"):
+    def __init__(self, model: SimNet, eval_method: str = "avg", eval_sms: int = 0):
         self.model = model
         self.eval_method = eval_method
+        # optional SM partition for pipelined mode (0 = off, the measured optimum on the bench workload):
+        # pooling / knapsack / F-score keep at most `eval_sms` SMs busy and the scorer's
+        # persistent GEMMs leave as many free, so neither stream waits for an SM the other holds
+        self.eval_sms = eval_sms
         self._side = None
         self._copy = None
         self._slots = {}
@@ -104,6 +109,7 @@ class Summarizer:
     def run_device(self, db: DeviceBatch, want_intermediates: bool = False):
         """Inputs already in HBM.  Returns the per-video F tensor (fp64, packed order) or the
         full dict of intermediates."""
+        _cabi.check(_cabi.load().vsum_set_sm_partition(0, 0), "vsum_set_sm_partition")   # one stream: no partition
         scores, _ = self.model.forward_packed(db.features, db.cu_steps, db.host.seqlens,
                                               apply_sigmoid=True, want_feats=False)   # train.py:143-144
         out = _engine.summarize(db.meta, scores.view(-1), db.cu_steps, self.eval_method)
@@ -143,6 +149,7 @@ class Summarizer:
         dev = db.features.device
         main, side, _ = self._streams(dev)
         st = self._slot(slot, db)
+        _cabi.check(_cabi.load().vsum_set_sm_partition(self.eval_sms, self.eval_sms), "vsum_set_sm_partition")
         if st.done is not None:
             main.wait_event(st.done)                      # the score buffer of this slot is free again
         if st.copied is not None:
