@@ -52,6 +52,45 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
         : "l"(*reinterpret_cast<const uint64_t *>(&a)), "l"(*reinterpret_cast<const uint64_t *>(&b)));
     return d;
 }
+// exp2 on the FMA pipe for a share of the elements (the MUFU pipe is the limiter at head_dim 64:
+// 16 ex2 / clk / SM, profiles/r01_microbench_mufu_ex2.txt).  Round-to-nearest split x = n + f with the
+// 1.5 * 2^23 trick, degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5,
+// 50x below the bf16 rounding of P), then n is added into the exponent field with one IMAD.
+#ifndef VSUM_ATTN_POLY_EVERY
+#define VSUM_ATTN_POLY_EVERY 5      // every k-th pair of exponentials goes to the FMA pipe (0 = none); swept 2..9 on B200, 5 is best
+#endif
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+    const float2 magic = make_float2(12582912.0f, 12582912.0f);
+    x.x = fmaxf(x.x, -126.0f);
+    x.y = fmaxf(x.y, -126.0f);
+    float2 t, r, f, p;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<uint64_t *>(&t))
+        : "l"(*reinterpret_cast<const uint64_t *>(&x)), "l"(*reinterpret_cast<const uint64_t *>(&magic)));
+    const float2 nmagic = make_float2(-12582912.0f, -12582912.0f);
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<uint64_t *>(&r))
+        : "l"(*reinterpret_cast<const uint64_t *>(&t)), "l"(*reinterpret_cast<const uint64_t *>(&nmagic)));
+    const float2 mone = make_float2(-1.0f, -1.0f);
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(*reinterpret_cast<uint64_t *>(&f))        // f = x - r
+        : "l"(*reinterpret_cast<const uint64_t *>(&r)), "l"(*reinterpret_cast<const uint64_t *>(&mone)),
+          "l"(*reinterpret_cast<const uint64_t *>(&x)));
+    const float2 c3 = make_float2(0.05517147481441498f, 0.05517147481441498f);
+    const float2 c2 = make_float2(0.242610901594162f, 0.242610901594162f);
+    const float2 c1 = make_float2(0.6932609677314758f, 0.6932609677314758f);
+    const float2 c0 = make_float2(0.9999281167984009f, 0.9999281167984009f);
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(*reinterpret_cast<uint64_t *>(&p))
+        : "l"(*reinterpret_cast<const uint64_t *>(&c3)), "l"(*reinterpret_cast<const uint64_t *>(&f)),
+          "l"(*reinterpret_cast<const uint64_t *>(&c2)));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "+l"(*reinterpret_cast<uint64_t *>(&p))
+        : "l"(*reinterpret_cast<const uint64_t *>(&p)), "l"(*reinterpret_cast<const uint64_t *>(&f)),
+          "l"(*reinterpret_cast<const uint64_t *>(&c1)));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "+l"(*reinterpret_cast<uint64_t *>(&p))
+        : "l"(*reinterpret_cast<const uint64_t *>(&p)), "l"(*reinterpret_cast<const uint64_t *>(&f)),
+          "l"(*reinterpret_cast<const uint64_t *>(&c0)));
+    // 2^n: (bits(t) << 23) is n << 23 modulo 2^32 (the magic constant's own bits shift out)
+    p.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23));
+    p.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23));
+    return p;
+}
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&h);
@@ -247,7 +286,10 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float2 x = ffma2(make_float2(__uint_as_float(s[c + 2 * e]), __uint_as_float(s[c + 2 * e + 1])), c2, nm2);
-                    pv[e] = make_float2(ex2(x.x), ex2(x.y));
+                    if (VSUM_ATTN_POLY_EVERY > 0 && (((c >> 1) + e) % (VSUM_ATTN_POLY_EVERY > 0 ? VSUM_ATTN_POLY_EVERY : 1)) == (VSUM_ATTN_POLY_EVERY - 1))
+                        pv[e] = exp2_poly2(x);
+                    else
+                        pv[e] = make_float2(ex2(x.x), ex2(x.y));
                     ps[e] = fadd2(ps[e], pv[e]);
                 }
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_buf + p_off[c >> 3]), "r"(pack2(pv[0].x, pv[0].y)),
