@@ -119,6 +119,10 @@ typedef struct {
     vsum_layer_grads layers[VSUM_MAX_LAYERS];
 } vsum_scorer_grads;
 
+/* Linear layers of the training path: mode 0 = fp32 SIMT kernels (reference accuracy), mode 1 =
+ * tcgen05 kernels: tf32 MMA for forward and dgrad, bf16 MMA (fp32 accumulation) for wgrad; needs
+ * d_model and d_ff multiples of 256. */
+VSUM_API int vsum_scorer_set_train_mode(vsum_scorer_t h, int32_t mode);
 VSUM_API size_t vsum_scorer_tape_bytes(vsum_scorer_t h, int64_t T);
 VSUM_API size_t vsum_scorer_train_workspace_bytes(vsum_scorer_t h, int64_t T, int32_t B);
 VSUM_API int vsum_scorer_forward_train(vsum_scorer_t h, const float *features, const int32_t *cu_seqlens,
@@ -201,13 +205,18 @@ VSUM_API const char *vsum_profile_category_name(int32_t i);
 /* ------------------------------------------------------------------------------------------
  * Diagnostics: the two tcgen05 kernels on their own, so tests can pin them individually.
  *   vsum_debug_gemm_tc05: out[M,N] bf16 = epi(A[M,K] W[N,K]^T + bias); A/W bf16, or fp32 when
- *     a_is_f32 (tf32 MMA).  epi: 0 bias, 1 bias+ReLU, 3 bias+residual+LayerNorm (N == 256).
+ *     a_is_f32 (tf32 MMA).  epi: 0 bias, 1 bias+ReLU, 3 bias+residual+LayerNorm (N == 256),
+ *     5 / 6: bias (+ReLU) with an fp32 output (tf32 operands only).
  *   vsum_debug_attention_tc05: qkv [T,768] bf16 -> out [T,256] bf16 (4 heads of 64, scale 1/16);
  *     scratch_i32 holds 2*(T/128+B)+1 int32.
  * ------------------------------------------------------------------------------------------ */
 VSUM_API int vsum_debug_gemm_tc05(const void *A, const void *W, const float *bias, const void *residual_bf16,
                          const float *gamma, const float *beta, void *out_bf16, int64_t M, int32_t N,
                          int32_t K, int32_t a_is_f32, int32_t epi, void *stream);
+/* dW[N,K] += dY[M,N]^T X[M,K] on tcgen05 (operands rounded to bf16 into scratch_bf16, M*(N+K) elements,
+ * both MN-major; fp32 accumulation), db[N] += colsum(dY) or NULL. */
+VSUM_API int vsum_debug_wgrad_tc05(const float *dY, const float *X, float *dW, float *db, int64_t M, int32_t N,
+                          int32_t K, void *scratch_bf16, void *stream);
 VSUM_API int vsum_debug_attention_tc05(const void *qkv_bf16, const int32_t *cu_seqlens, int32_t B, int64_t T,
                               void *out_bf16, int32_t *scratch_i32, void *stream);
 

@@ -89,3 +89,41 @@ def test_attention(lens):   # the last four have more work items than resident C
                                                        scratch.data_ptr(), _stream()), "vsum_debug_attention_tc05")
     torch.cuda.synchronize()
     torch.testing.assert_close(out.float(), attention_ref(qkv, lens), rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(300, 256, 1024, 5), (5000, 768, 256, 5), (777, 1024, 256, 6), (40000, 256, 256, 5)])
+def test_gemm_tf32_fp32_output(M, N, K, epi):
+    """Training-path linear: fp32 in memory, tf32 MMA, fp32 output."""
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    A = torch.randn((M, K), device="cuda", generator=g)
+    W = torch.randn((N, K), device="cuda", generator=g) / K ** 0.5
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = torch.empty((M, N), dtype=torch.float32, device="cuda")
+    _cabi.check(_cabi.load().vsum_debug_gemm_tc05(A.data_ptr(), W.data_ptr(), bias.data_ptr(), None, None, None, out.data_ptr(),
+                                                  M, N, K, 1, epi, _stream()), "vsum_debug_gemm_tc05")
+    torch.cuda.synchronize()
+    want = A.double() @ W.double().t() + bias.double()
+    if epi == 6:
+        want = want.relu()
+    torch.testing.assert_close(out.double(), want, rtol=3e-3, atol=3e-3)
+
+
+@pytest.mark.parametrize("bf16", [True])
+@pytest.mark.parametrize("M,N,K", [(32, 128, 256), (300, 256, 256), (5000, 768, 256), (4097, 256, 1024), (70000, 1024, 256)])
+def test_wgrad_tc05(M, N, K, bf16):
+    """dW = dY^T X with both operands MN-major (contraction over frames), split over frames + atomics."""
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    dY = torch.randn((M, N), device="cuda", generator=g)
+    X = torch.randn((M, K), device="cuda", generator=g)
+    dW = torch.zeros((N, K), device="cuda")
+    db = torch.zeros(N, device="cuda")
+    scratch = torch.empty(M * (N + K), dtype=torch.bfloat16, device="cuda") if bf16 else None
+    _cabi.check(_cabi.load().vsum_debug_wgrad_tc05(dY.data_ptr(), X.data_ptr(), dW.data_ptr(), db.data_ptr(), M, N, K,
+                                                   None if scratch is None else scratch.data_ptr(), _stream()),
+                "vsum_debug_wgrad_tc05")
+    torch.cuda.synchronize()
+    want = dY.double().t() @ X.double()
+    scale = want.abs().max().item()
+    err = (dW.double() - want).abs().max().item()
+    assert err <= (1.5e-2 if bf16 else 3e-3) * scale, f"max err {err:.3e} of scale {scale:.3e}; dW[0,:4]={dW[0,:4].tolist()} want {want[0,:4].tolist()}"
+    torch.testing.assert_close(db.double(), dY.double().sum(0), rtol=1e-4, atol=1e-3 * M ** 0.5)

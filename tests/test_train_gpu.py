@@ -33,18 +33,22 @@ def oracle_grads(sd, x, tgt, mask, num_heads):
     return loss.item(), {k: p.grad for k, p in params.items() if p.requires_grad}
 
 
-@pytest.mark.parametrize("kw,lens", [
-    (dict(num_heads=4, d_model=256, num_layers=2, dropout=0.3), (150, 97, 64, 130)),
-    (dict(num_heads=4, d_model=64, num_layers=3, dropout=0.1), (70, 33)),
-    (dict(num_heads=4, d_model=256, num_layers=4, dropout=0.0), (300,)),
+@pytest.mark.parametrize("kw,lens,train_precision,tol", [
+    (dict(num_heads=4, d_model=256, num_layers=2, dropout=0.3), (150, 97, 64, 130), "fp32", 2e-4),
+    (dict(num_heads=4, d_model=64, num_layers=3, dropout=0.1), (70, 33), "fp32", 2e-4),
+    (dict(num_heads=4, d_model=256, num_layers=4, dropout=0.0), (300,), "fp32", 2e-4),
+    # linear layers on the tensor cores: tf32 forward / dgrad, bf16 wgrad (8-bit mantissa operands)
+    (dict(num_heads=4, d_model=256, num_layers=2, dropout=0.3), (150, 97, 64, 130), "tf32", 2e-2),
+    (dict(num_heads=4, d_model=256, num_layers=4, dropout=0.0), (300,), "tf32", 2e-2),
 ])
-def test_gradients_match_autograd_oracle(kw, lens):
+def test_gradients_match_autograd_oracle(kw, lens, train_precision, tol):
     torch.manual_seed(11)
     model = SimNet(sparsity=0., use_cls=False, num_classes=1, use_pos=True, **kw).cuda()
     with torch.no_grad():
         for p in model.parameters():                        # non-trivial LayerNorm affine / biases
             p.add_(0.05 * torch.randn_like(p))
     model.eval()                                            # dropout off: deterministic comparison
+    model.train_precision = train_precision
     x, tgt, mask = padded_batch(lens)
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     want_loss, want = oracle_grads(sd, x, tgt, mask, kw["num_heads"])
@@ -53,7 +57,7 @@ def test_gradients_match_autograd_oracle(kw, lens):
     assert pred.requires_grad and pred.shape == (len(lens), max(lens), 1)
     loss = mse_with_mask_loss(pred, tgt.cuda(), mask.cuda())
     loss.backward()
-    assert abs(loss.item() - want_loss) <= 1e-5 * max(1.0, abs(want_loss))
+    assert abs(loss.item() - want_loss) <= (1e-5 if train_precision == "fp32" else 6e-3) * max(1.0, abs(want_loss))
     named = dict(model.named_parameters())
     assert set(named) == set(want)
     for k, g in want.items():
@@ -61,12 +65,13 @@ def test_gradients_match_autograd_oracle(kw, lens):
         assert got is not None, k
         scale = max(g.abs().max().item(), 1e-6)
         err = (got.cpu() - g).abs().max().item()
-        assert err <= 2e-4 * scale + 1e-7, f"{k}: max err {err:.3e} vs scale {scale:.3e}"
+        assert err <= tol * scale + 1e-7, f"{k}: max err {err:.3e} vs scale {scale:.3e}"
 
 
 def test_dropout_is_active_and_consistent():
     torch.manual_seed(3)
     model = SimNet(num_heads=4, d_model=256, num_layers=2, sparsity=0., dropout=0.3).cuda().train()
+    model.train_precision = "fp32"                          # the finite-difference check below needs fp32 linears
     x, tgt, mask = padded_batch((120, 60))
     x, tgt, mask = x.cuda(), tgt.cuda(), mask.cuda()
     torch.manual_seed(5)
@@ -135,6 +140,7 @@ def test_pretrain_losses_match_reference_and_backprop():
     torch.manual_seed(1234)
     import random; random.seed(1234); np.random.seed(1234)
     net = PretrainModel(feature_dim=256, sparsity=0.0, num_heads=4, num_layers=4, dropout=0.2, use_pos=True).cuda().eval()
+    net.encoder.train_precision = "fp32"                     # exact mode for the comparison with the reference values
     lens = (120, 77)
     x = torch.full((2, 120, 1024), 1000.0)
     for b, n in enumerate(lens):

@@ -118,6 +118,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int KELTS = TF32 ? 32 : 64;          // elements per 128-byte k-block
     constexpr uint32_t IDESC = tc::make_idesc(TF32 ? 2 : 1, BM, BN, 0, 0);
     constexpr bool IS_LN = EPI == TC_EPI_BIAS_RES_LN || EPI == TC_EPI_BIAS_RES_LN_HEAD;
+    constexpr bool OUT_F32 = EPI >= TC_EPI_BIAS_F32;
 
     auto a_stage = [&](int s) -> uint8_t * {
         return WRES ? ring + (size_t)WRES_MAX_KB * B_STAGE + (size_t)s * A_STAGE : ring + (size_t)s * (A_STAGE + B_STAGE);
@@ -232,7 +233,41 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
             uint32_t ra[32], rb[32];
 
-            if (!IS_LN) {
+            if (OUT_F32) {   // fp32 output: 32 columns (= one 128-byte swizzled row of fp32) per pass
+                const float *pos = nullptr;
+                if (EPI == TC_EPI_BIAS_POS_F32 && valid)
+                    pos = p.pos_table + (int64_t)min(__ldg(p.row_pos + row), p.pos_rows - 1) * BN;
+#pragma unroll 1
+                for (int cc = 0; cc < 8; ++cc) {
+                    tc::tmem_ld32(taddr + cc * 32, ra);
+                    tc::tmem_wait_ld();
+                    if (cc == 7) { tc::tc_fence_before(); tc::mbar_arrive(tempty + acc); }
+                    if (leader) tc::bulk_wait_read<1>();
+                    tc::bar_sync(EPI_BAR, 128);
+                    const uint32_t dst = stg_row + (uint32_t)(cc & 1) * STG_BYTES;
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch) {         // 4 columns -> one 16-byte chunk
+                        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + cc * 32 + ch * 4));
+                        float v[4] = {__uint_as_float(ra[ch * 4 + 0]) + b4.x, __uint_as_float(ra[ch * 4 + 1]) + b4.y,
+                                      __uint_as_float(ra[ch * 4 + 2]) + b4.z, __uint_as_float(ra[ch * 4 + 3]) + b4.w};
+                        if (EPI == TC_EPI_BIAS_POS_F32 && valid) {
+                            const float4 p4 = __ldg(reinterpret_cast<const float4 *>(pos + cc * 32 + ch * 4));
+                            v[0] += p4.x; v[1] += p4.y; v[2] += p4.z; v[3] += p4.w;
+                        }
+                        if (EPI == TC_EPI_BIAS_RELU_F32) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+                        }
+                        sts128(dst + sw_off[ch], __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+                    }
+                    tc::fence_proxy_async_smem();
+                    tc::bar_sync(EPI_BAR, 128);
+                    if (leader) {
+                        tc::tma_store_2d(stg + (cc & 1) * STG_BYTES, &tmOut, n0 + cc * 32, (int)(m_blk * BM));
+                        tc::bulk_commit();
+                    }
+                }
+            } else if (!IS_LN) {
                 const float *pos = nullptr;
                 if (EPI == TC_EPI_BIAS_POS && valid)
                     pos = p.pos_table + (int64_t)min(__ldg(p.row_pos + row), p.pos_rows - 1) * BN;
@@ -409,7 +444,9 @@ int launch_gemm_tc05(const Tc05GemmArgs &a, cudaStream_t s) {
     VSUM_REQUIRE(a.N % BN == 0 && a.K % kelts == 0, VSUM_EUNSUPPORTED,
                  "gemm_tc05: N=%d must be a multiple of 256 and K=%d of %d", a.N, a.K, kelts);
     VSUM_REQUIRE(a.M < ((int64_t)1 << 31), VSUM_EUNSUPPORTED, "gemm_tc05: M=%lld exceeds the TMA coordinate range", (long long)a.M);
-    const bool full_row = a.epi == TC_EPI_BIAS_POS || a.epi == TC_EPI_BIAS_RES_LN || a.epi == TC_EPI_BIAS_RES_LN_HEAD;
+    const bool full_row = a.epi == TC_EPI_BIAS_POS || a.epi == TC_EPI_BIAS_RES_LN || a.epi == TC_EPI_BIAS_RES_LN_HEAD ||
+                          a.epi == TC_EPI_BIAS_POS_F32;
+    const bool out_f32 = a.epi >= TC_EPI_BIAS_F32;
     VSUM_REQUIRE(!full_row || a.N == BN, VSUM_EUNSUPPORTED, "gemm_tc05: epilogue %d needs N == 256", a.epi);
     CUtensorMap tmA, tmB;
     int rc = make_tensor_map_2d(&tmA, a.A, elt, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.K * elt, kelts, BM);
@@ -417,16 +454,20 @@ int launch_gemm_tc05(const Tc05GemmArgs &a, cudaStream_t s) {
     rc = make_tensor_map_2d(&tmB, a.W, elt, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.K * elt, kelts, BN);
     if (rc) return rc;
     CUtensorMap tmOut = tmA, tmRes = tmA;                    // unused maps alias a valid one
-    if (a.out) {
+    if (out_f32) {
+        VSUM_REQUIRE(a.out_f32 && a.a_is_f32, VSUM_EINVAL, "gemm_tc05: fp32-output epilogues need out_f32 and fp32 (tf32) operands");
+        rc = make_tensor_map_2d(&tmOut, a.out_f32, 4, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.N * 4, 32, BM);
+        if (rc) return rc;
+    } else if (a.out) {
         rc = make_tensor_map_2d(&tmOut, a.out, 2, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.N * 2, 64, BM);
         if (rc) return rc;
     }
-    if (full_row && a.epi != TC_EPI_BIAS_POS) {
+    if (full_row && a.epi != TC_EPI_BIAS_POS && a.epi != TC_EPI_BIAS_POS_F32) {
         VSUM_REQUIRE(a.residual && a.gamma && a.beta, VSUM_EINVAL, "gemm_tc05: LayerNorm epilogue needs residual, gamma, beta");
         rc = make_tensor_map_2d(&tmRes, a.residual, 2, (uint64_t)BN, (uint64_t)a.M, (uint64_t)BN * 2, 64, BM);
         if (rc) return rc;
     }
-    VSUM_REQUIRE(a.out || a.epi == TC_EPI_BIAS_RES_LN_HEAD, VSUM_EINVAL, "gemm_tc05: epilogue %d needs an output", a.epi);
+    VSUM_REQUIRE(a.out || out_f32 || a.epi == TC_EPI_BIAS_RES_LN_HEAD, VSUM_EINVAL, "gemm_tc05: epilogue %d needs an output", a.epi);
     GemmParams p{};
     p.M = a.M; p.N = a.N; p.num_kb = a.K / kelts; p.n_tiles = a.N / BN; p.m_tiles = ceil_div(a.M, BM);
     p.bias = a.bias; p.gamma = a.gamma; p.beta = a.beta;
@@ -435,9 +476,14 @@ int launch_gemm_tc05(const Tc05GemmArgs &a, cudaStream_t s) {
     p.store_out = a.out != nullptr;
     const bool wres = !a.a_is_f32 && p.num_kb <= WRES_MAX_KB && p.m_tiles >= 2 * (148 / p.n_tiles);
     if (a.a_is_f32) {
-        VSUM_REQUIRE(a.epi == TC_EPI_BIAS_POS || a.epi == TC_EPI_BIAS, VSUM_EUNSUPPORTED, "gemm_tc05: tf32 path supports BIAS / BIAS_POS only");
-        if (a.epi == TC_EPI_BIAS_POS) return launch_variant<true, TC_EPI_BIAS_POS, false>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat);
-        return launch_variant<true, TC_EPI_BIAS, false>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat);
+        switch (a.epi) {
+            case TC_EPI_BIAS_POS: return launch_variant<true, TC_EPI_BIAS_POS, false>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat);
+            case TC_EPI_BIAS: return launch_variant<true, TC_EPI_BIAS, false>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat);
+            case TC_EPI_BIAS_F32: return launch_variant<true, TC_EPI_BIAS_F32, false>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat);
+            case TC_EPI_BIAS_RELU_F32: return launch_variant<true, TC_EPI_BIAS_RELU_F32, false>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat);
+            case TC_EPI_BIAS_POS_F32: return launch_variant<true, TC_EPI_BIAS_POS_F32, false>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat);
+            default: return set_error(VSUM_EUNSUPPORTED, "gemm_tc05: the tf32 path has no epilogue %d", a.epi);
+        }
     }
     switch (a.epi) {
         case TC_EPI_BIAS:

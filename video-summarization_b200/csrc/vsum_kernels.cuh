@@ -88,7 +88,10 @@ enum Tc05Epilogue {
     TC_EPI_BIAS_RELU = 1,    // out bf16 = relu(acc + bias)
     TC_EPI_BIAS_POS = 2,     // out bf16 = acc + bias + pos_table[row_pos[m]]       (N == 256)
     TC_EPI_BIAS_RES_LN = 3,  // out bf16 = LN(acc + bias + residual) * g + b        (N == 256)
-    TC_EPI_BIAS_RES_LN_HEAD = 4  // ... plus feats fp32 and score = sigmoid?(y . w_head + b_head)
+    TC_EPI_BIAS_RES_LN_HEAD = 4, // ... plus feats fp32 and score = sigmoid?(y . w_head + b_head)
+    TC_EPI_BIAS_F32 = 5,         // fp32 output variants (training path, tf32 operands): out_f32 = acc + bias
+    TC_EPI_BIAS_RELU_F32 = 6,
+    TC_EPI_BIAS_POS_F32 = 7
 };
 
 struct Tc05GemmArgs {
@@ -100,6 +103,7 @@ struct Tc05GemmArgs {
     int epi;
     const float *bias;        // [N]
     __nv_bfloat16 *out;       // [M,N] bf16 (may be NULL for the HEAD epilogue)
+    float *out_f32;           // [M,N] fp32 for the *_F32 epilogues
     const __nv_bfloat16 *residual;   // [M,256]
     const float *gamma, *beta;       // [256]
     const float *pos_table;   // [pos_rows,256]
@@ -120,6 +124,12 @@ int launch_attention_tc05(const __nv_bfloat16 *qkv, const int32_t *cu_seqlens, c
                           float scale, __nv_bfloat16 *out, cudaStream_t s);
 int launch_attn_schedule(const int32_t *cu_seqlens, int B, int32_t *tile_video, int32_t *tile_q0,
                          int32_t *n_tiles_out, int max_tiles, cudaStream_t s);
+
+// dW[N,K] += dY[M,N]^T X[M,K] on tcgen05 (tf32), db[N] += colsum(dY)   (vsum_wgrad_tc05.cu)
+int launch_linear_wgrad_tc05(const float *dY, const float *X, float *dW, float *db, int64_t M, int N, int K,
+                             cudaStream_t s, __nv_bfloat16 *dY16 = nullptr, __nv_bfloat16 *X16 = nullptr);
+int launch_transpose_f32(const float *in, float *out, int rows, int cols, cudaStream_t s);   // out[c][r] = in[r][c]
+int launch_add_inplace_f32(float *dst, const float *src, int64_t n, cudaStream_t s);         // dst += src
 
 int launch_f32_to_bf16(const float *in, __nv_bfloat16 *out, int64_t n, cudaStream_t s);
 

@@ -5,6 +5,7 @@
 // every valid row (padded keys are masked, simnet.py:156-157).
 #include "vsum_kernels.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <new>
 
@@ -13,6 +14,7 @@ using namespace vsum;
 struct LayerOffsets {
     size_t wqkv, bqkv, wo, bo, ln1g, ln1b, fc1w, fc1b, fc2w, fc2b, ln2g, ln2b;   // fp32 blob (floats)
     size_t h_wqkv, h_wo, h_fc1, h_fc2;                                              // bf16 blob (elements)
+    size_t t_wqkv, t_wo, t_fc1, t_fc2;                                              // fp32 transposes [in,out] (floats)
 };
 
 struct vsum_scorer {
@@ -25,6 +27,8 @@ struct vsum_scorer {
     LayerOffsets L[VSUM_MAX_LAYERS];
     bool loaded = false;
     bool tc05_shape = false;
+    int train_mode = 0;            // 0: fp32 SIMT linears; 1: tf32 tcgen05 linears (forward, dgrad, wgrad)
+    float *zeros = nullptr;        // zero bias for the dgrad GEMMs
 };
 
 static size_t take(size_t &cursor, size_t n) {
@@ -62,12 +66,16 @@ extern "C" int vsum_scorer_create(vsum_scorer_t *out, const vsum_scorer_config *
         o.ln2g = take(c32, d); o.ln2b = take(c32, d);
         o.h_wqkv = take(c16, 3 * d * d); o.h_wo = take(c16, d * d);
         o.h_fc1 = take(c16, ff * d); o.h_fc2 = take(c16, d * ff);
+        o.t_wqkv = take(c32, 3 * d * d); o.t_wo = take(c32, d * d);
+        o.t_fc1 = take(c32, ff * d); o.t_fc2 = take(c32, d * ff);
     }
     h->n32 = c32; h->n16 = c16;
     h->tc05_shape = cfg->d_model == 256 && cfg->num_heads == 4 && cfg->d_ff == 1024 && cfg->num_classes == 1 &&
                     cfg->in_features % 32 == 0;
     cudaError_t e = cudaMalloc(&h->w32, c32 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&h->w16, c16 * sizeof(__nv_bfloat16));
+    if (e == cudaSuccess) e = cudaMalloc(&h->zeros, 4096 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(h->zeros, 0, 4096 * sizeof(float));
     if (e != cudaSuccess) {
         cudaFree(h->w32); cudaFree(h->w16); delete h;
         return set_error(VSUM_ENOMEM, "vsum_scorer_create: cudaMalloc failed: %s", cudaGetErrorString(e));
@@ -78,7 +86,7 @@ extern "C" int vsum_scorer_create(vsum_scorer_t *out, const vsum_scorer_config *
 
 extern "C" int vsum_scorer_destroy(vsum_scorer_t h) {
     if (!h) return VSUM_OK;
-    cudaFree(h->w32); cudaFree(h->w16); cudaFree(h->pos_table);
+    cudaFree(h->w32); cudaFree(h->w16); cudaFree(h->pos_table); cudaFree(h->zeros);
     delete h;
     return VSUM_OK;
 }
@@ -120,6 +128,11 @@ extern "C" int vsum_scorer_load_weights(vsum_scorer_t h, const vsum_scorer_weigh
         if ((rc = launch_f32_to_bf16(h->w32 + o.wo, h->w16 + o.h_wo, d * d, s))) return rc;
         if ((rc = launch_f32_to_bf16(h->w32 + o.fc1w, h->w16 + o.h_fc1, ff * d, s))) return rc;
         if ((rc = launch_f32_to_bf16(h->w32 + o.fc2w, h->w16 + o.h_fc2, d * ff, s))) return rc;
+        // [out,in] -> [in,out] copies: the dgrad GEMMs dX = dY W run as dY (W^T)^T on the K-major kernel
+        if ((rc = launch_transpose_f32(h->w32 + o.wqkv, h->w32 + o.t_wqkv, (int)(3 * d), (int)d, s))) return rc;
+        if ((rc = launch_transpose_f32(h->w32 + o.wo, h->w32 + o.t_wo, (int)d, (int)d, s))) return rc;
+        if ((rc = launch_transpose_f32(h->w32 + o.fc1w, h->w32 + o.t_fc1, (int)ff, (int)d, s))) return rc;
+        if ((rc = launch_transpose_f32(h->w32 + o.fc2w, h->w32 + o.t_fc2, (int)d, (int)ff, s))) return rc;
     }
 #undef CP
     h->loaded = true;
@@ -285,7 +298,7 @@ size_t carve_tape(const vsum_scorer_config &c, int64_t T, void *base, Tape &t) {
     }
     return align_up(k.off, 1024);
 }
-struct TrainWs { int32_t *row_pos; float *a, *b, *c, *dd, *dhid, *dqkv, *delta, *dwqkv, *dbqkv; };
+struct TrainWs { int32_t *row_pos; float *a, *b, *c, *dd, *dhid, *dqkv, *delta, *dwqkv, *dbqkv; __nv_bfloat16 *y16, *x16; };
 size_t carve_train_ws(const vsum_scorer_config &c, int64_t T, void *base, TrainWs &w) {
     Carver k{(uint8_t *)base};
     const size_t n = (size_t)T, d = c.d_model;
@@ -293,6 +306,8 @@ size_t carve_train_ws(const vsum_scorer_config &c, int64_t T, void *base, TrainW
     w.a = k.get<float>(n * d); w.b = k.get<float>(n * d); w.c = k.get<float>(n * d); w.dd = k.get<float>(n * d);
     w.dhid = k.get<float>(n * c.d_ff); w.dqkv = k.get<float>(n * 3 * d); w.delta = k.get<float>(n * c.num_heads);
     w.dwqkv = k.get<float>(3 * d * d); w.dbqkv = k.get<float>(3 * d);
+    const size_t widest = std::max<size_t>(std::max<size_t>(c.d_ff, 3 * d), c.in_features);
+    w.y16 = k.get<__nv_bfloat16>(n * widest); w.x16 = k.get<__nv_bfloat16>(n * widest);   // bf16 operands of the tcgen05 wgrad
     return align_up(k.off, 1024);
 }
 }  // namespace
@@ -306,6 +321,41 @@ extern "C" size_t vsum_scorer_train_workspace_bytes(vsum_scorer_t h, int64_t T, 
     if (!h || T <= 0 || B <= 0) return 0;
     TrainWs w;
     return carve_train_ws(h->cfg, T, nullptr, w);
+}
+
+// Linear layers of the training path: fp32 SIMT (mode 0) or tf32 tcgen05 (mode 1).
+static int lin_fwd(vsum_scorer_t h, const float *A, const float *W, const float *bias, float *C, int64_t M, int N, int K,
+                   int epi, const int32_t *row_pos, cudaStream_t s) {
+    if (h->train_mode == 0 || N % 256 != 0 || K % 32 != 0)
+        return launch_linear_f32(A, W, bias, C, M, N, K, epi, h->pos_table, row_pos, h->pos_rows, s);
+    Tc05GemmArgs g{};
+    g.A = A; g.W = W; g.M = M; g.N = N; g.K = K; g.a_is_f32 = 1; g.bias = bias; g.out_f32 = C; g.prof_cat = PROF_OTHER;
+    g.epi = epi == EPI_BIAS_RELU ? TC_EPI_BIAS_RELU_F32 : (epi == EPI_BIAS_POS ? TC_EPI_BIAS_POS_F32 : TC_EPI_BIAS_F32);
+    g.pos_table = h->pos_table; g.row_pos = row_pos; g.pos_rows = h->pos_rows;
+    return launch_gemm_tc05(g, s);
+}
+// dX[M,K] (+)= dY[M,N] W[N,K];  WT is W transposed ([K,N]); tmp [M,K] is scratch for the accumulating form
+static int lin_dgrad(vsum_scorer_t h, const float *dY, const float *W, const float *WT, float *dX, float *tmp, int64_t M,
+                     int N, int K, int accumulate, cudaStream_t s) {
+    if (h->train_mode == 0 || K % 256 != 0 || N % 32 != 0 || K > 4096)
+        return launch_linear_dgrad_f32(dY, W, dX, M, N, K, accumulate, s);
+    Tc05GemmArgs g{};
+    g.A = dY; g.W = WT; g.M = M; g.N = K; g.K = N; g.a_is_f32 = 1; g.bias = h->zeros; g.epi = TC_EPI_BIAS_F32;
+    g.out_f32 = accumulate ? tmp : dX; g.prof_cat = PROF_OTHER;
+    int rc = launch_gemm_tc05(g, s);
+    if (rc || !accumulate) return rc;
+    return launch_add_inplace_f32(dX, tmp, M * K, s);
+}
+static int lin_wgrad(vsum_scorer_t h, const float *dY, const float *X, float *dW, float *db, int64_t M, int N, int K,
+                     __nv_bfloat16 *y16, __nv_bfloat16 *x16, cudaStream_t s) {
+    if (h->train_mode == 0 || N % 128 != 0 || K % 256 != 0) return launch_linear_wgrad_f32(dY, X, dW, db, M, N, K, s);
+    return launch_linear_wgrad_tc05(dY, X, dW, db, M, N, K, s, y16, x16);
+}
+
+extern "C" int vsum_scorer_set_train_mode(vsum_scorer_t h, int32_t mode) {
+    VSUM_REQUIRE(h && (mode == 0 || mode == 1), VSUM_EINVAL, "vsum_scorer_set_train_mode: mode %d", mode);
+    h->train_mode = mode;
+    return VSUM_OK;
 }
 
 #define RUN(call) do { if ((rc = (call))) return rc; } while (0)
@@ -326,20 +376,20 @@ extern "C" int vsum_scorer_forward_train(vsum_scorer_t h, const float *x, const 
     carve_train_ws(c, T, ws_mem, w);
     int rc;
     RUN(launch_row_positions(cu, B, T, w.row_pos, nullptr, s));
-    RUN(launch_linear_f32(x, h->w32 + h->embed_w, h->w32 + h->embed_b, t.x0, T, d, c.in_features,
-                          c.use_pos ? EPI_BIAS_POS : EPI_BIAS, h->pos_table, w.row_pos, h->pos_rows, s));
+    RUN(lin_fwd(h, x, h->w32 + h->embed_w, h->w32 + h->embed_b, t.x0, T, d, c.in_features,
+                c.use_pos ? EPI_BIAS_POS : EPI_BIAS, w.row_pos, s));
     const float scale = 1.0f / sqrtf((float)d);
     const float *xin = t.x0;
     for (int l = 0; l < c.num_layers; ++l) {
         const LayerOffsets &o = h->L[l];
         TapeLayer &L = t.L[l];
-        RUN(launch_linear_f32(xin, h->w32 + o.wqkv, h->w32 + o.bqkv, L.qkv, T, 3 * d, d, EPI_BIAS, nullptr, nullptr, 0, s));
+        RUN(lin_fwd(h, xin, h->w32 + o.wqkv, h->w32 + o.bqkv, L.qkv, T, 3 * d, d, EPI_BIAS, nullptr, s));
         RUN(launch_attention_f32(L.qkv, cu, B, max_len, d, c.num_heads, scale, L.att, s, L.lse, p, site_seed(seed, SITE_ATTN, l)));
-        RUN(launch_linear_f32(L.att, h->w32 + o.wo, h->w32 + o.bo, w.a, T, d, d, EPI_BIAS, nullptr, nullptr, 0, s));
+        RUN(lin_fwd(h, L.att, h->w32 + o.wo, h->w32 + o.bo, w.a, T, d, d, EPI_BIAS, nullptr, s));
         RUN(launch_add_dropout_layernorm_f32(w.a, xin, h->w32 + o.ln1g, h->w32 + o.ln1b, L.s1, L.xmid, T, d, p, site_seed(seed, SITE_PROJ, l), s));
-        RUN(launch_linear_f32(L.xmid, h->w32 + o.fc1w, h->w32 + o.fc1b, L.hid, T, c.d_ff, d, EPI_BIAS_RELU, nullptr, nullptr, 0, s));
+        RUN(lin_fwd(h, L.xmid, h->w32 + o.fc1w, h->w32 + o.fc1b, L.hid, T, c.d_ff, d, EPI_BIAS_RELU, nullptr, s));
         RUN(launch_dropout_inplace_f32(L.hid, (int64_t)T * c.d_ff, p, site_seed(seed, SITE_HIDDEN, l), s));
-        RUN(launch_linear_f32(L.hid, h->w32 + o.fc2w, h->w32 + o.fc2b, w.a, T, d, c.d_ff, EPI_BIAS, nullptr, nullptr, 0, s));
+        RUN(lin_fwd(h, L.hid, h->w32 + o.fc2w, h->w32 + o.fc2b, w.a, T, d, c.d_ff, EPI_BIAS, nullptr, s));
         RUN(launch_add_dropout_layernorm_f32(w.a, L.xmid, h->w32 + o.ln2g, h->w32 + o.ln2b, L.s2, L.xout, T, d, p, site_seed(seed, SITE_MLP, l), s));
         xin = L.xout;
     }
@@ -380,22 +430,22 @@ extern "C" int vsum_scorer_backward(vsum_scorer_t h, const float *x, const int32
         // xout = LN2(s2), s2 = dropout(mlp) + xmid          a: d_xout -> b: d_s2 (residual path), c: d_mlp
         RUN(launch_layernorm_bwd_f32(w.a, L.s2, h->w32 + o.ln2g, w.b, w.c, gl.ln2_g, gl.ln2_b, T, (int)d, p, site_seed(seed, SITE_MLP, l), s));
         // mlp = hid W2^T + b2
-        RUN(launch_linear_wgrad_f32(w.c, L.hid, gl.fc2_w, gl.fc2_b, T, (int)d, (int)ff, s));
-        RUN(launch_linear_dgrad_f32(w.c, h->w32 + o.fc2w, w.dhid, T, (int)d, (int)ff, 0, s));
+        RUN(lin_wgrad(h, w.c, L.hid, gl.fc2_w, gl.fc2_b, T, (int)d, (int)ff, w.y16, w.x16, s));
+        RUN(lin_dgrad(h, w.c, h->w32 + o.fc2w, h->w32 + o.t_fc2, w.dhid, nullptr, T, (int)d, (int)ff, 0, s));
         RUN(launch_relu_dropout_bwd_f32(L.hid, w.dhid, (int64_t)T * ff, p, s));
         // h1 = xmid W1^T + b1                               b: d_xmid += dh1 W1
-        RUN(launch_linear_wgrad_f32(w.dhid, L.xmid, gl.fc1_w, gl.fc1_b, T, (int)ff, (int)d, s));
-        RUN(launch_linear_dgrad_f32(w.dhid, h->w32 + o.fc1w, w.b, T, (int)ff, (int)d, 1, s));
+        RUN(lin_wgrad(h, w.dhid, L.xmid, gl.fc1_w, gl.fc1_b, T, (int)ff, (int)d, w.y16, w.x16, s));
+        RUN(lin_dgrad(h, w.dhid, h->w32 + o.fc1w, h->w32 + o.t_fc1, w.b, w.dd, T, (int)ff, (int)d, 1, s));
         // xmid = LN1(s1), s1 = dropout(proj) + xin          b: d_xmid -> a: d_s1 (residual path), c: d_proj
         RUN(launch_layernorm_bwd_f32(w.b, L.s1, h->w32 + o.ln1g, w.a, w.c, gl.ln1_g, gl.ln1_b, T, (int)d, p, site_seed(seed, SITE_PROJ, l), s));
         // proj = att Wo^T + bo                              dd: d_att
-        RUN(launch_linear_wgrad_f32(w.c, L.att, gl.o_w, gl.o_b, T, (int)d, (int)d, s));
-        RUN(launch_linear_dgrad_f32(w.c, h->w32 + o.wo, w.dd, T, (int)d, (int)d, 0, s));
+        RUN(lin_wgrad(h, w.c, L.att, gl.o_w, gl.o_b, T, (int)d, (int)d, w.y16, w.x16, s));
+        RUN(lin_dgrad(h, w.c, h->w32 + o.wo, h->w32 + o.t_wo, w.dd, nullptr, T, (int)d, (int)d, 0, s));
         RUN(launch_attention_bwd_f32(L.qkv, L.att, w.dd, L.lse, cu, B, max_len, T, (int)d, c.num_heads, scale, p,
                                      site_seed(seed, SITE_ATTN, l), w.delta, w.dqkv, s));
         // qkv = xin Wqkv^T + bqkv                           a: d_xin += dqkv Wqkv
-        RUN(launch_linear_wgrad_f32(w.dqkv, xin, w.dwqkv, w.dbqkv, T, (int)(3 * d), (int)d, s));
-        RUN(launch_linear_dgrad_f32(w.dqkv, h->w32 + o.wqkv, w.a, T, (int)(3 * d), (int)d, 1, s));
+        RUN(lin_wgrad(h, w.dqkv, xin, w.dwqkv, w.dbqkv, T, (int)(3 * d), (int)d, w.y16, w.x16, s));
+        RUN(lin_dgrad(h, w.dqkv, h->w32 + o.wqkv, h->w32 + o.t_wqkv, w.a, w.dd, T, (int)(3 * d), (int)d, 1, s));
         float *wdst[3] = {gl.q_w, gl.k_w, gl.v_w}, *bdst[3] = {gl.q_b, gl.k_b, gl.v_b};
         for (int i = 0; i < 3; ++i) {
             VSUM_CUDA_OK(cudaMemcpyAsync(wdst[i], w.dwqkv + i * d * d, d * d * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -403,7 +453,7 @@ extern "C" int vsum_scorer_backward(vsum_scorer_t h, const float *x, const int32
         }
     }
     // x0 = features We^T + be (+ positions)
-    RUN(launch_linear_wgrad_f32(w.a, x, g->embed_w, g->embed_b, T, (int)d, c.in_features, s));
+    RUN(lin_wgrad(h, w.a, x, g->embed_w, g->embed_b, T, (int)d, c.in_features, w.y16, w.x16, s));
 #undef ZERO
     return VSUM_OK;
 }
@@ -420,13 +470,21 @@ extern "C" int vsum_debug_gemm_tc05(const void *A, const void *W, const float *b
                                     const float *gamma, const float *beta, void *out, int64_t M, int32_t N,
                                     int32_t K, int32_t a_is_f32, int32_t epi, void *stream) {
     VSUM_REQUIRE(A && W && bias && out, VSUM_EINVAL, "vsum_debug_gemm_tc05: null pointer");
-    VSUM_REQUIRE(epi == TC_EPI_BIAS || epi == TC_EPI_BIAS_RELU || epi == TC_EPI_BIAS_RES_LN, VSUM_EINVAL,
-                 "vsum_debug_gemm_tc05: epi %d", epi);
+    VSUM_REQUIRE(epi == TC_EPI_BIAS || epi == TC_EPI_BIAS_RELU || epi == TC_EPI_BIAS_RES_LN || epi == TC_EPI_BIAS_F32 ||
+                 epi == TC_EPI_BIAS_RELU_F32, VSUM_EINVAL, "vsum_debug_gemm_tc05: epi %d", epi);
     Tc05GemmArgs g{};
     g.A = A; g.W = W; g.M = M; g.N = N; g.K = K; g.a_is_f32 = a_is_f32; g.epi = epi; g.bias = bias;
     g.prof_cat = PROF_OTHER;
+    if (epi >= TC_EPI_BIAS_F32) g.out_f32 = (float *)out; else
     g.out = (__nv_bfloat16 *)out; g.residual = (const __nv_bfloat16 *)residual; g.gamma = gamma; g.beta = beta;
     return launch_gemm_tc05(g, (cudaStream_t)stream);
+}
+
+extern "C" int vsum_debug_wgrad_tc05(const float *dY, const float *X, float *dW, float *db, int64_t M, int32_t N,
+                                     int32_t K, void *scratch_bf16, void *stream) {
+    VSUM_REQUIRE(dY && X && dW, VSUM_EINVAL, "vsum_debug_wgrad_tc05: null pointer");
+    __nv_bfloat16 *y16 = (__nv_bfloat16 *)scratch_bf16, *x16 = y16 ? y16 + (size_t)M * N : nullptr;
+    return launch_linear_wgrad_tc05(dY, X, dW, db, M, N, K, (cudaStream_t)stream, y16, x16);
 }
 
 extern "C" int vsum_debug_attention_tc05(const void *qkv, const int32_t *cu_seqlens, int32_t B, int64_t T,

@@ -530,4 +530,42 @@ int launch_masked_mse_f32(const float *out, const float *tgt, const uint8_t *pad
     return VSUM_OK;
 }
 
+__global__ void __launch_bounds__(256)
+transpose_f32_kernel(const float *__restrict__ in, float *__restrict__ out, int rows, int cols) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8)
+        if (r0 + i < rows && c0 + threadIdx.x < cols) tile[i][threadIdx.x] = in[(int64_t)(r0 + i) * cols + c0 + threadIdx.x];
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8)
+        if (c0 + i < cols && r0 + threadIdx.x < rows) out[(int64_t)(c0 + i) * rows + r0 + threadIdx.x] = tile[threadIdx.x][i];
+}
+
+int launch_transpose_f32(const float *in, float *out, int rows, int cols, cudaStream_t s) {
+    dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32)), block(32, 8);
+    transpose_f32_kernel<<<grid, block, 0, s>>>(in, out, rows, cols);
+    VSUM_LAUNCH_OK("transpose_f32_kernel");
+    return VSUM_OK;
+}
+
+__global__ void __launch_bounds__(256)
+add_inplace_f32_kernel(float *__restrict__ dst, const float *__restrict__ src, int64_t n) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        float4 a = *reinterpret_cast<float4 *>(dst + i);
+        const float4 b = *reinterpret_cast<const float4 *>(src + i);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        *reinterpret_cast<float4 *>(dst + i) = a;
+    } else {
+        for (int64_t j = i; j < n; ++j) dst[j] += src[j];
+    }
+}
+
+int launch_add_inplace_f32(float *dst, const float *src, int64_t n, cudaStream_t s) {
+    if (n == 0) return VSUM_OK;
+    add_inplace_f32_kernel<<<(unsigned)ceil_div(ceil_div(n, 4), 256), 256, 0, s>>>(dst, src, n);
+    VSUM_LAUNCH_OK("add_inplace_f32_kernel");
+    return VSUM_OK;
+}
+
 }  // namespace vsum

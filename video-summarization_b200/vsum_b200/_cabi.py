@@ -22,9 +22,9 @@ EXPORTS = (
     "vsum_scorer_create", "vsum_scorer_destroy", "vsum_scorer_load_weights",
     "vsum_scorer_workspace_bytes", "vsum_scorer_forward",
     "vsum_shot_mean", "vsum_knapsack_class_width", "vsum_knapsack_scratch_words", "vsum_knapsack", "vsum_summary_fscore",
-    "vsum_scorer_tape_bytes", "vsum_scorer_train_workspace_bytes", "vsum_scorer_forward_train",
+    "vsum_scorer_set_train_mode", "vsum_scorer_tape_bytes", "vsum_scorer_train_workspace_bytes", "vsum_scorer_forward_train",
     "vsum_scorer_backward", "vsum_masked_mse",
-    "vsum_debug_gemm_tc05", "vsum_debug_attention_tc05",
+    "vsum_debug_gemm_tc05", "vsum_debug_wgrad_tc05", "vsum_debug_attention_tc05",
     "vsum_profile_begin", "vsum_profile_end", "vsum_profile_num_categories", "vsum_profile_category_name",
 )
 
@@ -86,6 +86,8 @@ def load():
     L.vsum_scorer_workspace_bytes.restype = C.c_size_t
     L.vsum_scorer_workspace_bytes.argtypes = [vp, i64, i32, i32]
     L.vsum_scorer_forward.argtypes = [vp, vp, vp, i32, i64, i32, i32, i32, vp, vp, vp, C.c_size_t, vp]
+    L.vsum_scorer_set_train_mode.argtypes = [vp, i32]
+    L.vsum_debug_wgrad_tc05.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, vp]
     L.vsum_scorer_tape_bytes.restype = C.c_size_t
     L.vsum_scorer_tape_bytes.argtypes = [vp, i64]
     L.vsum_scorer_train_workspace_bytes.restype = C.c_size_t

@@ -105,6 +105,7 @@ class _ScorerTrainFn(torch.autograd.Function):
             stream = torch.cuda.current_stream(dev).cuda_stream
             model._sync_weights(max_len, dev, stream)
             h = model._handle
+            _cabi.check(L.vsum_scorer_set_train_mode(h, model._train_mode()), "vsum_scorer_set_train_mode")
             tape = torch.empty(L.vsum_scorer_tape_bytes(h, T) + 1024, dtype=torch.uint8, device=dev)
             ws = model._workspace_for(L.vsum_scorer_train_workspace_bytes(h, T, B), dev)
             scores = torch.empty((T, model.num_classes), dtype=torch.float32, device=dev)
@@ -140,6 +141,7 @@ class _ScorerTrainFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             model._sync_weights(max_len, dev, stream)          # the optimiser may not have stepped yet: no-op
+            _cabi.check(L.vsum_scorer_set_train_mode(model._handle, model._train_mode()), "vsum_scorer_set_train_mode")
             ws = model._workspace_for(L.vsum_scorer_train_workspace_bytes(model._handle, T, B), dev)
             wp = _al(ws)
             _cabi.check(L.vsum_scorer_backward(model._handle, features.data_ptr(), cu_seqlens.data_ptr(), B, T, max_len,
@@ -175,6 +177,8 @@ class SimNet(nn.Module):
 
         tc05 = d_model == 256 and num_heads == 4 and num_classes == 1
         self.precision = os.environ.get("VSUM_PRECISION", "bf16" if tc05 else "fp32")
+        # linear layers of the TRAINING path: "tf32" = tcgen05 kernels (forward, dgrad, wgrad), "fp32" = SIMT
+        self.train_precision = os.environ.get("VSUM_TRAIN_PRECISION", "tf32" if tc05 else "fp32")
         self._handle = None
         self._weights_key = None
         self._table: Optional[Tensor] = None
@@ -252,6 +256,11 @@ class SimNet(nn.Module):
             ws = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
             self._workspace = ws
         return ws
+
+    def _train_mode(self) -> int:
+        if self.train_precision not in ("tf32", "fp32"):
+            raise ValueError(f"train_precision must be 'tf32' or 'fp32', got {self.train_precision!r}")
+        return 1 if self.train_precision == "tf32" else 0
 
     def _train_params(self):
         """Parameters in the order _ScorerTrainFn returns their gradients."""
