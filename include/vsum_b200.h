@@ -119,9 +119,10 @@ typedef struct {
     vsum_layer_grads layers[VSUM_MAX_LAYERS];
 } vsum_scorer_grads;
 
-/* Linear layers of the training path: mode 0 = fp32 SIMT kernels (reference accuracy), mode 1 =
- * tcgen05 kernels: tf32 MMA for forward and dgrad, bf16 MMA (fp32 accumulation) for wgrad; needs
- * d_model and d_ff multiples of 256. */
+/* Training path arithmetic: mode 0 = fp32 SIMT kernels (reference accuracy); mode 1 = linear layers on
+ * tcgen05 (tf32 MMA for forward and dgrad, bf16 MMA with fp32 accumulation for wgrad; needs d_model and
+ * d_ff multiples of 256); mode 2 = mode 1 plus attention forward and backward on tcgen05 with bf16
+ * operands (d_model 256, 4 heads) -- the counterpart of the reference's autocast (src/train.py:120). */
 VSUM_API int vsum_scorer_set_train_mode(vsum_scorer_t h, int32_t mode);
 VSUM_API size_t vsum_scorer_tape_bytes(vsum_scorer_t h, int64_t T);
 VSUM_API size_t vsum_scorer_train_workspace_bytes(vsum_scorer_t h, int64_t T, int32_t B);
@@ -217,6 +218,15 @@ VSUM_API int vsum_debug_gemm_tc05(const void *A, const void *W, const float *bia
  * both MN-major; fp32 accumulation), db[N] += colsum(dY) or NULL. */
 VSUM_API int vsum_debug_wgrad_tc05(const float *dY, const float *X, float *dW, float *db, int64_t M, int32_t N,
                           int32_t K, void *scratch_bf16, void *stream);
+/* Training variant of the tcgen05 attention: FP32 output [T,256], also writes the log2-domain
+ * log-sum-exp [T,4] and applies dropout to P; and its backward (qkv, d_out bf16; lse2, delta [T,4] fp32;
+ * delta = rowsum per head of out * d_out) -> dqkv [T,768] fp32. */
+VSUM_API int vsum_debug_attention_train_tc05(const void *qkv_bf16, const int32_t *cu_seqlens, int32_t B, int64_t T,
+                                             float *out_f32, float *lse2, float drop_p, uint64_t seed,
+                                             int32_t *scratch, void *stream);
+VSUM_API int vsum_debug_attention_bwd_tc05(const void *qkv_bf16, const void *d_out_bf16, const float *lse2,
+                                           const float *delta, const int32_t *cu_seqlens, int32_t B, int64_t T,
+                                           float drop_p, uint64_t seed, float *dqkv, int32_t *scratch, void *stream);
 VSUM_API int vsum_debug_attention_tc05(const void *qkv_bf16, const int32_t *cu_seqlens, int32_t B, int64_t T,
                               void *out_bf16, int32_t *scratch_i32, void *stream);
 

@@ -127,3 +127,69 @@ def test_wgrad_tc05(M, N, K, bf16):
     err = (dW.double() - want).abs().max().item()
     assert err <= (1.5e-2 if bf16 else 3e-3) * scale, f"max err {err:.3e} of scale {scale:.3e}; dW[0,:4]={dW[0,:4].tolist()} want {want[0,:4].tolist()}"
     torch.testing.assert_close(db.double(), dY.double().sum(0), rtol=1e-4, atol=1e-3 * M ** 0.5)
+
+
+def _drop_keep(seed, q_rows, h, keys, thresh):
+    """numpy restatement of the grouped dropout hash (vsum_kernels.cuh: dropout_bits64 / attn_drop_group_index)."""
+    with np.errstate(over="ignore"):
+        idx = ((q_rows.astype(np.uint64)[:, None] * np.uint64(4) + np.uint64(h)) << np.uint64(20)) \
+            ^ (keys.astype(np.uint64)[None, :] >> np.uint64(2)) ^ np.uint64(0x5A5A000000000000)
+        z = np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * (idx + np.uint64(1))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+        lane = (keys.astype(np.uint64)[None, :] & np.uint64(3)) * np.uint64(16)
+        return ((z >> lane) & np.uint64(0xFFFF)) >= np.uint64(thresh)
+
+
+@pytest.mark.parametrize("lens,p", [([128], 0.0), ([37], 0.0), ([129, 300], 0.0), ([300, 1, 127, 513], 0.3), ([1000, 2100], 0.0),
+                                    ([700, 260], 0.1)])
+def test_attention_train_and_backward(lens, p):
+    """tcgen05 attention with log-sum-exp + dropout, and its tcgen05 backward, against torch autograd (fp32
+    math on the same bf16-rounded operands, the same dropout mask)."""
+    T, B, seed = sum(lens), len(lens), 0x1234567 + sum(lens)
+    g = torch.Generator(device="cuda").manual_seed(T + 5)
+    qkv = torch.randn((T, 768), device="cuda", generator=g).bfloat16()
+    d_out = torch.randn((T, 256), device="cuda", generator=g).bfloat16()
+    cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device="cuda")
+    out = torch.zeros((T, 256), device="cuda")                      # the training variant writes fp32
+    lse2 = torch.zeros((T, 4), device="cuda")
+    scratch = torch.zeros(2 * (T // 128 + B) + 1, dtype=torch.int32, device="cuda")
+    L = _cabi.load()
+    _cabi.check(L.vsum_debug_attention_train_tc05(qkv.data_ptr(), cu.data_ptr(), B, T, out.data_ptr(), lse2.data_ptr(), p, seed,
+                                                  scratch.data_ptr(), _stream()), "vsum_debug_attention_train_tc05")
+    torch.cuda.synchronize()
+    thresh = 0 if p <= 0 else int(p * 65536 + 0.5)
+    ks = 65536.0 / (65536 - thresh)
+    x = qkv.float().requires_grad_(True)
+    want_out, want_lse, off = [], [], 0
+    for n in lens:
+        heads, lses = [], []
+        for h in range(4):
+            q, k, v = (x[off:off + n, i * 256 + h * 64: i * 256 + (h + 1) * 64] for i in range(3))
+            s = (q @ k.t()) / 16.0
+            lses.append(torch.logsumexp(s, dim=1) * 1.4426950408889634)
+            pr = torch.softmax(s, dim=1)
+            if thresh:
+                keep = _drop_keep(seed, np.arange(off, off + n), h, np.arange(n), thresh)
+                pr = pr * torch.from_numpy(keep).to(pr) * ks
+            heads.append(pr @ v)
+        want_out.append(torch.cat(heads, dim=1))
+        want_lse.append(torch.stack(lses, dim=1))
+        off += n
+    want_out, want_lse = torch.cat(want_out), torch.cat(want_lse)
+    torch.testing.assert_close(lse2, want_lse.detach(), rtol=1e-3, atol=2e-3)
+    torch.testing.assert_close(out, want_out.detach(), rtol=2e-2, atol=2e-2)
+
+    want_out.backward(d_out.float())
+    delta = (out * d_out.float()).view(T, 4, 64).sum(-1).contiguous()
+    dqkv = torch.full((T, 768), float("nan"), device="cuda")
+    _cabi.check(L.vsum_debug_attention_bwd_tc05(qkv.data_ptr(), d_out.data_ptr(), lse2.data_ptr(), delta.data_ptr(), cu.data_ptr(),
+                                                B, T, p, seed, dqkv.data_ptr(), scratch.data_ptr(), _stream()),
+                "vsum_debug_attention_bwd_tc05")
+    torch.cuda.synchronize()
+    for i, name in enumerate(("dq", "dk", "dv")):
+        got, want = dqkv[:, i * 256:(i + 1) * 256], x.grad[:, i * 256:(i + 1) * 256]
+        scale = want.abs().max().item()
+        err = (got - want).abs().max().item()
+        assert err <= 2e-2 * scale, f"{name}: max err {err:.3e} vs scale {scale:.3e}"

@@ -40,6 +40,11 @@ def oracle_grads(sd, x, tgt, mask, num_heads):
     # linear layers on the tensor cores: tf32 forward / dgrad, bf16 wgrad (8-bit mantissa operands)
     (dict(num_heads=4, d_model=256, num_layers=2, dropout=0.3), (150, 97, 64, 130), "tf32", 2e-2),
     (dict(num_heads=4, d_model=256, num_layers=4, dropout=0.0), (300,), "tf32", 2e-2),
+    # + attention forward / backward on the tensor cores with bf16 operands (delta is taken from the same
+    # rounded dO the MMAs see, so dS rows sum to zero and the small q/k gradients stay accurate:
+    # profiles/r01_train_grad_error_yardstick.txt, 2x closer to fp32 than torch's own bf16 autocast)
+    (dict(num_heads=4, d_model=256, num_layers=2, dropout=0.3), (150, 97, 64, 130), "bf16", 3e-2),
+    (dict(num_heads=4, d_model=256, num_layers=4, dropout=0.0), (300, 513), "bf16", 3e-2),
 ])
 def test_gradients_match_autograd_oracle(kw, lens, train_precision, tol):
     torch.manual_seed(11)
@@ -60,12 +65,18 @@ def test_gradients_match_autograd_oracle(kw, lens, train_precision, tol):
     assert abs(loss.item() - want_loss) <= (1e-5 if train_precision == "fp32" else 6e-3) * max(1.0, abs(want_loss))
     named = dict(model.named_parameters())
     assert set(named) == set(want)
+    # k.bias has a mathematically zero gradient (softmax is invariant to it): in the reduced-precision modes
+    # its rounding noise is judged against the q/k/v bias gradients' scale instead of against ~0
+    floor = 1e-6 if train_precision == "fp32" else 1e-2 * max(g.abs().max().item() for k, g in want.items() if ".sa." in k and "bias" in k)
     for k, g in want.items():
         got = named[k].grad
         assert got is not None, k
-        scale = max(g.abs().max().item(), 1e-6)
+        scale = max(g.abs().max().item(), floor)
         err = (got.cpu() - g).abs().max().item()
         assert err <= tol * scale + 1e-7, f"{k}: max err {err:.3e} vs scale {scale:.3e}"
+        if train_precision != "fp32" and g.abs().max().item() > floor:
+            rel = ((got.cpu() - g).norm() / g.norm()).item()
+            assert rel <= 1e-2, f"{k}: relative Frobenius error {rel:.3e}"
 
 
 def test_dropout_is_active_and_consistent():

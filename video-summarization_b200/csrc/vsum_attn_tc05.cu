@@ -101,11 +101,15 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // softmax warps on every SM sub-partition -- the MUFU pipe, not issue latency, becomes the limit.
 // O accumulates in TMEM across KV tiles; the exponent reference only moves when the row max grew
 // by more than 2^8 (lazy rescale), so the read-modify-write of O is rare.
+// TRAIN: additionally writes the log-sum-exp of every (row, head) in the exp2 domain for the backward
+// kernel (vsum_attn_bwd_tc05.cu) and applies dropout to P (simnet.py:159); the row sum stays un-dropped.
+template <bool TRAIN>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__restrict__ cu,
                  const int32_t *__restrict__ tile_video, const int32_t *__restrict__ tile_q0,
                  const int32_t *__restrict__ n_tiles_ptr, __nv_bfloat16 *__restrict__ out,
-                 float scale_log2e, uint32_t v_lbo, uint32_t v_sbo, uint32_t v_kstep) {
+                 float scale_log2e, uint32_t v_lbo, uint32_t v_sbo, uint32_t v_kstep,
+                 float *__restrict__ lse2, float keep_scale, uint32_t drop_thresh16, unsigned long long seed) {
     if ((int)blockIdx.x >= __ldg(n_tiles_ptr)) return;
     extern __shared__ __align__(1024) uint8_t smem[];    // no alignment slack: it would cost the 2nd CTA / SM
     if ((tc::smem_u32(smem) & 1023u) != 0) __trap();     // SWIZZLE_128B tiles need 1024-byte alignment
@@ -292,6 +296,17 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
                         pv[e] = make_float2(ex2(x.x), ex2(x.y));
                     ps[e] = fadd2(ps[e], pv[e]);
                 }
+                if (TRAIN && drop_thresh16 != 0) {            // two 4-key groups per 8 columns
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        const int key = j * BKV + hf * 64 + c + 4 * g;
+                        const unsigned long long z = dropout_bits64(seed, attn_drop_group_index(base + q0 + r, h_idx, NH, key >> 2));
+                        if ((uint32_t)(z & 0xffffu) < drop_thresh16) pv[2 * g].x = 0.f;
+                        if ((uint32_t)((z >> 16) & 0xffffu) < drop_thresh16) pv[2 * g].y = 0.f;
+                        if ((uint32_t)((z >> 32) & 0xffffu) < drop_thresh16) pv[2 * g + 1].x = 0.f;
+                        if ((uint32_t)(z >> 48) < drop_thresh16) pv[2 * g + 1].y = 0.f;
+                    }
+                }
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_buf + p_off[c >> 3]), "r"(pack2(pv[0].x, pv[0].y)),
                              "r"(pack2(pv[1].x, pv[1].y)), "r"(pack2(pv[2].x, pv[2].y)), "r"(pack2(pv[3].x, pv[3].y))
                              : "memory");
@@ -314,8 +329,17 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
         uint32_t t[32];
         tc::tmem_ld32(tO_h, t);
         tc::tmem_wait_ld();
-        const float inv = 1.0f / l_tot;
-        if (q0 + r < n) {
+        const float inv = (TRAIN ? keep_scale : 1.0f) / l_tot;
+        if (TRAIN && hf == 0 && q0 + r < n) lse2[(int64_t)(base + q0 + r) * NH + h_idx] = m_run + log2f(l_tot);
+        if (TRAIN) {   // fp32 output: the backward's delta = rowsum(dO o O) must not see a rounded O
+            if (q0 + r < n) {
+                float *dst = reinterpret_cast<float *>(out) + (int64_t)(base + q0 + r) * DM + h_idx * HD + hf * 32;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4 *>(dst + i) = make_float4(__uint_as_float(t[i]) * inv, __uint_as_float(t[i + 1]) * inv,
+                                                                       __uint_as_float(t[i + 2]) * inv, __uint_as_float(t[i + 3]) * inv);
+            }
+        } else if (q0 + r < n) {
             __nv_bfloat16 *dst = out + (int64_t)(base + q0 + r) * DM + h_idx * HD + hf * 32;
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
@@ -377,16 +401,21 @@ int launch_attn_schedule(const int32_t *cu_seqlens, int B, int32_t *tile_video, 
     return VSUM_OK;
 }
 
+// lse2 != NULL selects the training variant: lse2 [T, 4] receives log2-domain log-sum-exps, P is dropped
+// with probability drop_p (16-bit resolution), the output is scaled by 1 / (1 - drop_p) and `out` is an
+// FP32 [T,256] buffer.
 int launch_attention_tc05(const __nv_bfloat16 *qkv, const int32_t *cu_seqlens, const int32_t *tile_video,
                           const int32_t *tile_q0, const int32_t *n_tiles_ptr, int max_tiles, int64_t T,
-                          float scale, __nv_bfloat16 *out, cudaStream_t s) {
+                          float scale, void *out, cudaStream_t s, float *lse2, float drop_p,
+                          unsigned long long seed) {
     if (T == 0 || max_tiles == 0) return VSUM_OK;
     CUtensorMap tm;
     int rc = make_tensor_map_2d(&tm, qkv, 2, 3 * DM, (uint64_t)T, (uint64_t)3 * DM * 2, 64, 128);
     if (rc) return rc;
     static bool configured = false;
     if (!configured) {
-        VSUM_CUDA_OK(cudaFuncSetAttribute(attn_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+        VSUM_CUDA_OK(cudaFuncSetAttribute(attn_tc05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+        VSUM_CUDA_OK(cudaFuncSetAttribute(attn_tc05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
         configured = true;
     }
     // V operand descriptor (MN-major, 128B swizzle): 8-key groups are 1024 bytes apart (SBO); the
@@ -398,8 +427,15 @@ int launch_attention_tc05(const __nv_bfloat16 *qkv, const int32_t *cu_seqlens, c
     }
     dim3 grid((unsigned)max_tiles, NH);
     ProfScope prof(PROF_ATTN, s);
-    attn_tc05_kernel<<<grid, ATT_THREADS, ATT_SMEM, s>>>(tm, cu_seqlens, tile_video, tile_q0, n_tiles_ptr, out,
-                                                         scale * 1.4426950408889634f, v_lbo, v_sbo, v_kstep);
+    const float sl2 = scale * 1.4426950408889634f;
+    if (lse2) {
+        const uint32_t thresh = attn_drop_thresh16(drop_p);
+        attn_tc05_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, s>>>(tm, cu_seqlens, tile_video, tile_q0, n_tiles_ptr, (__nv_bfloat16 *)out, sl2, v_lbo,
+                                                                   v_sbo, v_kstep, lse2, 65536.0f / (float)(65536u - thresh), thresh, seed);
+    } else {
+        attn_tc05_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, s>>>(tm, cu_seqlens, tile_video, tile_q0, n_tiles_ptr, (__nv_bfloat16 *)out, sl2, v_lbo,
+                                                                    v_sbo, v_kstep, nullptr, 1.0f, 0u, 0ull);
+    }
     VSUM_LAUNCH_OK("attn_tc05_kernel");
     return VSUM_OK;
 }

@@ -36,6 +36,17 @@ __host__ __device__ __forceinline__ bool dropout_keep(unsigned long long seed, u
 __host__ __device__ __forceinline__ unsigned long long attn_drop_index(long long q_row, int h, int H, int key) {
     return ((unsigned long long)(q_row * H + h) << 20) ^ (unsigned long long)key ^ 0xA5A5000000000000ULL;
 }
+// Tensor-core attention (training): one 64-bit draw decides FOUR consecutive keys of a query row, 16 bits
+// each (drop iff bits < thresh16 = round(p * 65536)), so forward and backward hash once per 4 elements.
+__host__ __device__ __forceinline__ unsigned long long dropout_bits64(unsigned long long seed, unsigned long long idx) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (idx + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ unsigned long long attn_drop_group_index(long long q_row, int h, int H, int key_group) {
+    return ((unsigned long long)(q_row * H + h) << 20) ^ (unsigned long long)key_group ^ 0x5A5A000000000000ULL;
+}
 __host__ __device__ __forceinline__ unsigned long long site_seed(unsigned long long seed, int site, int layer) {
     return seed ^ ((unsigned long long)(site + 1) << 56) ^ ((unsigned long long)(layer + 1) << 48);
 }
@@ -119,13 +130,26 @@ struct Tc05GemmArgs {
 int launch_gemm_tc05(const Tc05GemmArgs &a, cudaStream_t s);
 
 // qkv [T,768] bf16 -> out [T,256] bf16, d_model 256, 4 heads of 64, scale = 1/16
+// lse2 != NULL: training variant (log2-domain log-sum-exp [T,4] out, dropout on P with the grouped hash,
+// `out` is then fp32 [T,256] instead of bf16)
 int launch_attention_tc05(const __nv_bfloat16 *qkv, const int32_t *cu_seqlens, const int32_t *tile_video,
                           const int32_t *tile_q0, const int32_t *n_tiles_ptr, int max_tiles, int64_t T,
-                          float scale, __nv_bfloat16 *out, cudaStream_t s);
+                          float scale, void *out, cudaStream_t s, float *lse2 = nullptr, float drop_p = 0.f,
+                          unsigned long long seed = 0);
+inline uint32_t attn_drop_thresh16(float p) { return p <= 0.f ? 0u : (uint32_t)(p * 65536.0f + 0.5f); }
+// Backward of the above on tcgen05 (vsum_attn_bwd_tc05.cu): qkv16 [T,768], dO16 [T,256] bf16, lse2 / delta [T,4]
+// fp32 -> dqkv [T,768] fp32 (overwritten).  Tiles = the forward's schedule (video, first key row).
+int launch_attention_bwd_tc05(const __nv_bfloat16 *qkv16, const __nv_bfloat16 *dO16, const float *lse2, const float *delta,
+                              const int32_t *cu_seqlens, const int32_t *tile_video, const int32_t *tile_k0,
+                              const int32_t *n_tiles_ptr, int max_tiles, int64_t T, float scale, float drop_p,
+                              unsigned long long seed, float *dqkv, cudaStream_t s);
+// delta[t, h] = sum_c o[t, h*64 + c] * dO16[t, h*64 + c]: the SAME rounded dO the backward MMAs consume, so
+// that every row of dS sums to zero up to fp32 rounding (d_model 256, 4 heads)
+int launch_attn_delta_bf16(const float *o, const __nv_bfloat16 *dO16, float *delta, int64_t T, cudaStream_t s);
 int launch_attn_schedule(const int32_t *cu_seqlens, int B, int32_t *tile_video, int32_t *tile_q0,
                          int32_t *n_tiles_out, int max_tiles, cudaStream_t s);
 
-// dW[N,K] += dY[M,N]^T X[M,K] on tcgen05 (tf32), db[N] += colsum(dY)   (vsum_wgrad_tc05.cu)
+// dW[N,K] += dY[M,N]^T X[M,K] on tcgen05 (bf16 operands), db[N] += colsum(dY)   (vsum_wgrad_tc05.cu)
 int launch_linear_wgrad_tc05(const float *dY, const float *X, float *dW, float *db, int64_t M, int N, int K,
                              cudaStream_t s, __nv_bfloat16 *dY16 = nullptr, __nv_bfloat16 *X16 = nullptr);
 int launch_transpose_f32(const float *in, float *out, int rows, int cols, cudaStream_t s);   // out[c][r] = in[r][c]

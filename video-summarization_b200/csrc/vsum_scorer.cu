@@ -298,8 +298,11 @@ size_t carve_tape(const vsum_scorer_config &c, int64_t T, void *base, Tape &t) {
     }
     return align_up(k.off, 1024);
 }
-struct TrainWs { int32_t *row_pos; float *a, *b, *c, *dd, *dhid, *dqkv, *delta, *dwqkv, *dbqkv; __nv_bfloat16 *y16, *x16; };
-size_t carve_train_ws(const vsum_scorer_config &c, int64_t T, void *base, TrainWs &w) {
+struct TrainWs {
+    int32_t *row_pos; float *a, *b, *c, *dd, *dhid, *dqkv, *delta, *dwqkv, *dbqkv; __nv_bfloat16 *y16, *x16;
+    int32_t *tile_video, *tile_q0, *n_tiles; int max_tiles;       // tile list of the tcgen05 attention kernels
+};
+size_t carve_train_ws(const vsum_scorer_config &c, int64_t T, int32_t B, void *base, TrainWs &w) {
     Carver k{(uint8_t *)base};
     const size_t n = (size_t)T, d = c.d_model;
     w.row_pos = k.get<int32_t>(n);
@@ -307,7 +310,9 @@ size_t carve_train_ws(const vsum_scorer_config &c, int64_t T, void *base, TrainW
     w.dhid = k.get<float>(n * c.d_ff); w.dqkv = k.get<float>(n * 3 * d); w.delta = k.get<float>(n * c.num_heads);
     w.dwqkv = k.get<float>(3 * d * d); w.dbqkv = k.get<float>(3 * d);
     const size_t widest = std::max<size_t>(std::max<size_t>(c.d_ff, 3 * d), c.in_features);
-    w.y16 = k.get<__nv_bfloat16>(n * widest); w.x16 = k.get<__nv_bfloat16>(n * widest);   // bf16 operands of the tcgen05 wgrad
+    w.y16 = k.get<__nv_bfloat16>(n * widest); w.x16 = k.get<__nv_bfloat16>(n * widest);   // bf16 operands of the tcgen05 wgrad / attention
+    w.max_tiles = (int)(T / 128 + B);
+    w.tile_video = k.get<int32_t>(w.max_tiles); w.tile_q0 = k.get<int32_t>(w.max_tiles); w.n_tiles = k.get<int32_t>(1);
     return align_up(k.off, 1024);
 }
 }  // namespace
@@ -320,7 +325,7 @@ extern "C" size_t vsum_scorer_tape_bytes(vsum_scorer_t h, int64_t T) {
 extern "C" size_t vsum_scorer_train_workspace_bytes(vsum_scorer_t h, int64_t T, int32_t B) {
     if (!h || T <= 0 || B <= 0) return 0;
     TrainWs w;
-    return carve_train_ws(h->cfg, T, nullptr, w);
+    return carve_train_ws(h->cfg, T, B, nullptr, w);
 }
 
 // Linear layers of the training path: fp32 SIMT (mode 0) or tf32 tcgen05 (mode 1).
@@ -353,7 +358,9 @@ static int lin_wgrad(vsum_scorer_t h, const float *dY, const float *X, float *dW
 }
 
 extern "C" int vsum_scorer_set_train_mode(vsum_scorer_t h, int32_t mode) {
-    VSUM_REQUIRE(h && (mode == 0 || mode == 1), VSUM_EINVAL, "vsum_scorer_set_train_mode: mode %d", mode);
+    VSUM_REQUIRE(h && mode >= 0 && mode <= 2, VSUM_EINVAL, "vsum_scorer_set_train_mode: mode %d", mode);
+    VSUM_REQUIRE(mode < 2 || (h->cfg.d_model == 256 && h->cfg.num_heads == 4), VSUM_EUNSUPPORTED,
+                 "vsum_scorer_set_train_mode: the tcgen05 attention needs d_model 256 with 4 heads");
     h->train_mode = mode;
     return VSUM_OK;
 }
@@ -373,17 +380,24 @@ extern "C" int vsum_scorer_forward_train(vsum_scorer_t h, const float *x, const 
     cudaStream_t s = (cudaStream_t)stream;
     Tape t; TrainWs w;
     carve_tape(c, T, tape_mem, t);
-    carve_train_ws(c, T, ws_mem, w);
+    carve_train_ws(c, T, B, ws_mem, w);
     int rc;
     RUN(launch_row_positions(cu, B, T, w.row_pos, nullptr, s));
     RUN(lin_fwd(h, x, h->w32 + h->embed_w, h->w32 + h->embed_b, t.x0, T, d, c.in_features,
                 c.use_pos ? EPI_BIAS_POS : EPI_BIAS, w.row_pos, s));
     const float scale = 1.0f / sqrtf((float)d);
     const float *xin = t.x0;
+    const bool tc_attn = h->train_mode == 2;
+    if (tc_attn) RUN(launch_attn_schedule(cu, B, w.tile_video, w.tile_q0, w.n_tiles, w.max_tiles, s));
     for (int l = 0; l < c.num_layers; ++l) {
         const LayerOffsets &o = h->L[l];
         TapeLayer &L = t.L[l];
         RUN(lin_fwd(h, xin, h->w32 + o.wqkv, h->w32 + o.bqkv, L.qkv, T, 3 * d, d, EPI_BIAS, nullptr, s));
+        if (tc_attn) {   // bf16 operands on tcgen05; L.lse holds log2-domain values in this mode
+            RUN(launch_f32_to_bf16(L.qkv, w.x16, (int64_t)T * 3 * d, s));
+            RUN(launch_attention_tc05(w.x16, cu, w.tile_video, w.tile_q0, w.n_tiles, w.max_tiles, T, scale, L.att, s, L.lse, p,
+                                      site_seed(seed, SITE_ATTN, l)));
+        } else
         RUN(launch_attention_f32(L.qkv, cu, B, max_len, d, c.num_heads, scale, L.att, s, L.lse, p, site_seed(seed, SITE_ATTN, l)));
         RUN(lin_fwd(h, L.att, h->w32 + o.wo, h->w32 + o.bo, w.a, T, d, d, EPI_BIAS, nullptr, s));
         RUN(launch_add_dropout_layernorm_f32(w.a, xin, h->w32 + o.ln1g, h->w32 + o.ln1b, L.s1, L.xmid, T, d, p, site_seed(seed, SITE_PROJ, l), s));
@@ -410,13 +424,15 @@ extern "C" int vsum_scorer_backward(vsum_scorer_t h, const float *x, const int32
     cudaStream_t s = (cudaStream_t)stream;
     Tape t; TrainWs w;
     carve_tape(c, T, const_cast<void *>(tape_mem), t);
-    carve_train_ws(c, T, ws_mem, w);
+    carve_train_ws(c, T, B, ws_mem, w);
     int rc;
 #define ZERO(ptr, n) do { VSUM_REQUIRE((ptr) != nullptr, VSUM_EINVAL, "vsum_scorer_backward: null gradient " #ptr); \
                           VSUM_CUDA_OK(cudaMemsetAsync((ptr), 0, (n) * sizeof(float), s)); } while (0)
     ZERO(g->embed_w, d * c.in_features); ZERO(g->embed_b, d); ZERO(g->final_w, C * d); ZERO(g->final_b, C);
     const float scale = 1.0f / sqrtf((float)d);
     const float *x_last = t.L[c.num_layers - 1].xout;
+    const bool tc_attn = h->train_mode == 2;
+    if (tc_attn) RUN(launch_attn_schedule(cu, B, w.tile_video, w.tile_q0, w.n_tiles, w.max_tiles, s));
     RUN(launch_head_bwd_f32(x_last, h->w32 + h->final_w, d_scores, d_feats, w.a, g->final_w, g->final_b, T, (int)d, (int)C, s));
     for (int l = c.num_layers - 1; l >= 0; --l) {
         const LayerOffsets &o = h->L[l];
@@ -441,6 +457,13 @@ extern "C" int vsum_scorer_backward(vsum_scorer_t h, const float *x, const int32
         // proj = att Wo^T + bo                              dd: d_att
         RUN(lin_wgrad(h, w.c, L.att, gl.o_w, gl.o_b, T, (int)d, (int)d, w.y16, w.x16, s));
         RUN(lin_dgrad(h, w.c, h->w32 + o.wo, h->w32 + o.t_wo, w.dd, nullptr, T, (int)d, (int)d, 0, s));
+        if (tc_attn) {
+            RUN(launch_f32_to_bf16(L.qkv, w.x16, (int64_t)T * 3 * d, s));
+            RUN(launch_f32_to_bf16(w.dd, w.y16, (int64_t)T * d, s));
+            RUN(launch_attn_delta_bf16(L.att, w.y16, w.delta, T, s));
+            RUN(launch_attention_bwd_tc05(w.x16, w.y16, L.lse, w.delta, cu, w.tile_video, w.tile_q0, w.n_tiles, w.max_tiles, T,
+                                          scale, p, site_seed(seed, SITE_ATTN, l), w.dqkv, s));
+        } else
         RUN(launch_attention_bwd_f32(L.qkv, L.att, w.dd, L.lse, cu, B, max_len, T, (int)d, c.num_heads, scale, p,
                                      site_seed(seed, SITE_ATTN, l), w.delta, w.dqkv, s));
         // qkv = xin Wqkv^T + bqkv                           a: d_xin += dqkv Wqkv
@@ -485,6 +508,30 @@ extern "C" int vsum_debug_wgrad_tc05(const float *dY, const float *X, float *dW,
     VSUM_REQUIRE(dY && X && dW, VSUM_EINVAL, "vsum_debug_wgrad_tc05: null pointer");
     __nv_bfloat16 *y16 = (__nv_bfloat16 *)scratch_bf16, *x16 = y16 ? y16 + (size_t)M * N : nullptr;
     return launch_linear_wgrad_tc05(dY, X, dW, db, M, N, K, (cudaStream_t)stream, y16, x16);
+}
+
+extern "C" int vsum_debug_attention_train_tc05(const void *qkv, const int32_t *cu_seqlens, int32_t B, int64_t T, float *out,
+                                               float *lse2, float drop_p, uint64_t seed, int32_t *scratch, void *stream) {
+    VSUM_REQUIRE(qkv && cu_seqlens && out && lse2 && scratch, VSUM_EINVAL, "vsum_debug_attention_train_tc05: null pointer");
+    const int max_tiles = (int)(T / 128 + B);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = launch_attn_schedule(cu_seqlens, B, scratch, scratch + max_tiles, scratch + 2 * max_tiles, max_tiles, s);
+    if (rc) return rc;
+    return launch_attention_tc05((const __nv_bfloat16 *)qkv, cu_seqlens, scratch, scratch + max_tiles, scratch + 2 * max_tiles,
+                                 max_tiles, T, 1.0f / 16.0f, out, s, lse2, drop_p, seed);
+}
+
+extern "C" int vsum_debug_attention_bwd_tc05(const void *qkv, const void *d_out, const float *lse2, const float *delta,
+                                             const int32_t *cu_seqlens, int32_t B, int64_t T, float drop_p, uint64_t seed,
+                                             float *dqkv, int32_t *scratch, void *stream) {
+    VSUM_REQUIRE(qkv && d_out && lse2 && delta && cu_seqlens && dqkv && scratch, VSUM_EINVAL,
+                 "vsum_debug_attention_bwd_tc05: null pointer");
+    const int max_tiles = (int)(T / 128 + B);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = launch_attn_schedule(cu_seqlens, B, scratch, scratch + max_tiles, scratch + 2 * max_tiles, max_tiles, s);
+    if (rc) return rc;
+    return launch_attention_bwd_tc05((const __nv_bfloat16 *)qkv, (const __nv_bfloat16 *)d_out, lse2, delta, cu_seqlens, scratch,
+                                     scratch + max_tiles, scratch + 2 * max_tiles, max_tiles, T, 1.0f / 16.0f, drop_p, seed, dqkv, s);
 }
 
 extern "C" int vsum_debug_attention_tc05(const void *qkv, const int32_t *cu_seqlens, int32_t B, int64_t T,

@@ -25,6 +25,7 @@ EXPORTS = (
     "vsum_scorer_set_train_mode", "vsum_scorer_tape_bytes", "vsum_scorer_train_workspace_bytes", "vsum_scorer_forward_train",
     "vsum_scorer_backward", "vsum_masked_mse",
     "vsum_debug_gemm_tc05", "vsum_debug_wgrad_tc05", "vsum_debug_attention_tc05",
+    "vsum_debug_attention_train_tc05", "vsum_debug_attention_bwd_tc05",
     "vsum_profile_begin", "vsum_profile_end", "vsum_profile_num_categories", "vsum_profile_category_name",
 )
 
@@ -106,6 +107,8 @@ def load():
     L.vsum_summary_fscore.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, i64, vp, vp, vp, vp]
     L.vsum_debug_gemm_tc05.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]
     L.vsum_debug_attention_tc05.argtypes = [vp, vp, i32, i64, vp, vp, vp]
+    L.vsum_debug_attention_train_tc05.argtypes = [vp, vp, i32, i64, vp, vp, C.c_float, C.c_uint64, vp, vp]
+    L.vsum_debug_attention_bwd_tc05.argtypes = [vp, vp, vp, vp, vp, i32, i64, C.c_float, C.c_uint64, vp, vp, vp]
     L.vsum_profile_end.argtypes = [vp, vp, i32]
     L.vsum_profile_num_categories.restype = i32
     L.vsum_profile_category_name.restype = C.c_char_p

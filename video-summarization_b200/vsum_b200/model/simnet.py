@@ -177,8 +177,10 @@ class SimNet(nn.Module):
 
         tc05 = d_model == 256 and num_heads == 4 and num_classes == 1
         self.precision = os.environ.get("VSUM_PRECISION", "bf16" if tc05 else "fp32")
-        # linear layers of the TRAINING path: "tf32" = tcgen05 kernels (forward, dgrad, wgrad), "fp32" = SIMT
-        self.train_precision = os.environ.get("VSUM_TRAIN_PRECISION", "tf32" if tc05 else "fp32")
+        # TRAINING path: "bf16" = every contraction on tcgen05 (tf32 linears, bf16 wgrad and attention -- the
+        # counterpart of the reference's autocast, train.py:120), "tf32" = tensor-core linears with fp32
+        # attention, "fp32" = SIMT kernels at reference accuracy
+        self.train_precision = os.environ.get("VSUM_TRAIN_PRECISION", "bf16" if tc05 else "fp32")
         self._handle = None
         self._weights_key = None
         self._table: Optional[Tensor] = None
@@ -258,9 +260,9 @@ class SimNet(nn.Module):
         return ws
 
     def _train_mode(self) -> int:
-        if self.train_precision not in ("tf32", "fp32"):
-            raise ValueError(f"train_precision must be 'tf32' or 'fp32', got {self.train_precision!r}")
-        return 1 if self.train_precision == "tf32" else 0
+        if self.train_precision not in ("bf16", "tf32", "fp32"):
+            raise ValueError(f"train_precision must be 'bf16', 'tf32' or 'fp32', got {self.train_precision!r}")
+        return {"fp32": 0, "tf32": 1, "bf16": 2}[self.train_precision]
 
     def _train_params(self):
         """Parameters in the order _ScorerTrainFn returns their gradients."""
