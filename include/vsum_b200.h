@@ -204,6 +204,40 @@ VSUM_API int32_t vsum_profile_num_categories(void);
 VSUM_API const char *vsum_profile_category_name(int32_t i);
 
 /* ------------------------------------------------------------------------------------------
+ * Pretraining head (src/model/simnet_pretrain.py:33, 35-100; src/pretrain.py:59-67).
+ *
+ * vsum_linear_*: a stand-alone Linear layer on packed rows (PretrainModel.video_transform,
+ *   simnet_pretrain.py:33,80): y[M,N] = x[M,K] w[N,K]^T + bias; backward overwrites dw, db and, when
+ *   non-NULL, dx.  mode 0 = fp32 SIMT, mode 1 = tcgen05 (tf32 forward / dgrad, bf16 wgrad; N, K
+ *   multiples of 256, else it falls back to mode 0).  The backward workspace (1024-byte aligned,
+ *   the bytes vsum_linear_workspace_bytes returns) is only needed in mode 1.
+ *
+ * vsum_pretrain_losses_*: the three losses of PretrainModel.forward (simnet_pretrain.py:82-100) and
+ *   their gradients on the packed layout.  scores [T] = encoder logits, x512 [T,512] = video_transform
+ *   output, video_rep [B,512] = the target representation (no gradient), n_pad = padded length Nmax of
+ *   the reference's batch (its means divide by it), pen_entropy 1 = "entropy" centering (line 90), 0 =
+ *   the norm variant (line 94).  losses3 (device) = {distillation, center, repel}.  `saved` keeps the
+ *   mixture weights and per-video sums for the backward, which takes d_losses3 (device, the three
+ *   upstream gradients) and writes d_scores [T] and d_x512 [T,512].  Reductions are order-fixed
+ *   (no atomics); the repel term uses |sum xh|^2 - sum |xh|^2, so no [N,N] tensor exists.
+ * ------------------------------------------------------------------------------------------ */
+VSUM_API size_t vsum_linear_workspace_bytes(int64_t M, int32_t N, int32_t K);
+VSUM_API int vsum_linear_forward(const float *x, const float *w, const float *bias, float *y, int64_t M, int32_t N,
+                                 int32_t K, int32_t mode, void *stream);
+VSUM_API int vsum_linear_backward(const float *dy, const float *x, const float *w, float *dx, float *dw, float *db,
+                                  int64_t M, int32_t N, int32_t K, int32_t mode, void *workspace,
+                                  size_t workspace_bytes, void *stream);
+VSUM_API size_t vsum_pretrain_saved_bytes(int64_t T, int32_t B, int32_t max_len);
+VSUM_API int vsum_pretrain_losses_forward(const float *scores, const float *x512, const int32_t *cu_seqlens,
+                                          int32_t B, int64_t T, int32_t max_len, int32_t n_pad, float sharpening_t,
+                                          const float *video_rep, int32_t pen_entropy, float *losses3,
+                                          void *saved, size_t saved_bytes, void *stream);
+VSUM_API int vsum_pretrain_losses_backward(const float *x512, const int32_t *cu_seqlens, int32_t B, int64_t T,
+                                           int32_t max_len, int32_t n_pad, float sharpening_t, int32_t pen_entropy,
+                                           const float *d_losses3, void *saved, float *d_scores, float *d_x512,
+                                           void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Diagnostics: the two tcgen05 kernels on their own, so tests can pin them individually.
  *   vsum_debug_gemm_tc05: out[M,N] bf16 = epi(A[M,K] W[N,K]^T + bias); A/W bf16, or fp32 when
  *     a_is_f32 (tf32 MMA).  epi: 0 bias, 1 bias+ReLU, 3 bias+residual+LayerNorm (N == 256),

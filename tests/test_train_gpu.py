@@ -165,3 +165,70 @@ def test_pretrain_losses_match_reference_and_backprop():
     grads = [p.grad for p in net.encoder.parameters()]
     assert all(gr is not None and torch.isfinite(gr).all() for gr in grads)
     assert sum(gr.abs().sum().item() for gr in grads) > 0
+
+
+def _reference_losses(scores, x512, mask, video_rep, t, pen_met):
+    """torch restatement of simnet_pretrain.py:35-100 on padded tensors, [N,N] matrix and all (the checker)."""
+    import torch.nn.functional as F
+    n = x512.shape[1]
+    xm = x512 * (~mask).unsqueeze(2)
+    xh = xm / (xm.norm(dim=2, keepdim=True) + 1e-9)
+    sim = torch.matmul(xh, xh.transpose(1, 2)) * (torch.eye(n, device=x512.device) == 0).float().unsqueeze(0)
+    repel = sim.mean(dim=1).mean()
+    m3 = mask.unsqueeze(2)
+    mix = F.softmax(scores.masked_fill(m3, float("-inf")) / t, dim=1)
+    if pen_met == "entropy":
+        e = (mix + 1e-9) * torch.log(mix + 1e-9)
+        center = e.masked_fill(m3, 0.).mean(dim=1).mean()
+    else:
+        center = torch.norm(mix, dim=1).mean()
+    pooled = torch.matmul(mix.transpose(1, 2), x512).squeeze(1)
+    loss = (-F.softmax(video_rep, dim=1) * torch.log(F.softmax(pooled, dim=1))).mean()
+    return loss, center, repel
+
+
+@pytest.mark.parametrize("lens,pen_met", [((120, 77), "entropy"), ((300, 513, 1), "entropy"), ((64, 200), "norm")])
+def test_pretrain_loss_kernels_forward_backward(lens, pen_met):
+    """vsum_pretrain_losses_* and vsum_linear_* (fp32 mode) against autograd through the restated reference formulas."""
+    from vsum_b200.model.simnet_pretrain import _LinearFn, _PretrainLossFn
+    torch.manual_seed(17)
+    B, n = len(lens), max(lens)
+    T = sum(lens)
+    cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device="cuda")
+    feats = torch.randn(T, 256, device="cuda", dtype=torch.float64)
+    scores = torch.randn(T, 1, device="cuda", dtype=torch.float64)
+    w = (torch.randn(512, 256, device="cuda", dtype=torch.float64) / 16)
+    b = torch.randn(512, device="cuda", dtype=torch.float64) * 0.1
+    vid_rep = torch.rand(B, 512, device="cuda")
+    coef = torch.tensor([1.0, 0.5, 1.0], device="cuda")                    # pretrain.py:63
+    # checker: fp64 autograd on the padded layout
+    ref_in = [v.clone().requires_grad_(True) for v in (feats, scores, w, b)]
+    pf = torch.zeros(B, n, 256, device="cuda", dtype=torch.float64)
+    ps = torch.zeros(B, n, 1, device="cuda", dtype=torch.float64)
+    mask = torch.ones(B, n, dtype=torch.bool, device="cuda")
+    for v, ln in enumerate(lens):
+        mask[v, :ln] = False
+    idx = (~mask).reshape(-1).nonzero().squeeze(1)
+    pf = pf.reshape(B * n, 256).index_copy(0, idx, ref_in[0]).reshape(B, n, 256)
+    ps = ps.reshape(B * n, 1).index_copy(0, idx, ref_in[1]).reshape(B, n, 1)
+    want = torch.stack(_reference_losses(ps, pf @ ref_in[2].t() + ref_in[3], mask, vid_rep.double(), 0.4, pen_met))
+    (want * coef.double()).sum().backward()
+    # native kernels, fp32
+    got_in = [v.float().clone().requires_grad_(True) for v in (feats, scores, w, b)]
+    x512 = _LinearFn.apply(got_in[0], got_in[2], got_in[3], 0)
+    got = _PretrainLossFn.apply(got_in[1], x512, cu, list(lens), n, 0.4, vid_rep, pen_met == "entropy")
+    (got * coef).sum().backward()
+    np.testing.assert_allclose(got.detach().cpu().numpy(), want.detach().cpu().numpy(), rtol=2e-5, atol=1e-7)
+    for name, a, r in zip(("d_feats", "d_scores", "d_w", "d_b"), got_in, ref_in):
+        scale = r.grad.abs().max().item()
+        err = (a.grad.double() - r.grad).abs().max().item()
+        assert err <= 2e-4 * scale + 1e-10, f"{name}: max err {err:.3e} vs scale {scale:.3e}"
+    # tensor-core mode of the linear layer
+    tc_in = [v.float().clone().requires_grad_(True) for v in (feats, w, b)]
+    y = _LinearFn.apply(tc_in[0], tc_in[1], tc_in[2], 1)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    ref_y = feats @ w.t() + b
+    assert (y.double() - ref_y).abs().max().item() <= 5e-3 * ref_y.abs().max().item()
+    for a, r in zip(tc_in, (gy.double() @ w, gy.double().t() @ feats, gy.double().sum(0))):
+        assert (a.grad.double() - r).abs().max().item() <= 2e-2 * r.abs().max().item()

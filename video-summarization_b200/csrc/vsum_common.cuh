@@ -59,6 +59,19 @@ struct ProfScope {
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Carves 1024-byte aligned sub-buffers out of one caller-provided allocation (base == nullptr: size only).
+struct Carver {
+    uint8_t *base;
+    size_t off = 0;
+    template <class T>
+    T *get(size_t n) {
+        off = align_up(off, 1024);
+        T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
 // Largest v in [0, n) with cu[v] <= x (cu ascending, cu[0] = 0, x < cu[n]).
 __device__ __forceinline__ int find_segment(const int32_t *__restrict__ cu, int n, int x) {
     int lo = 0, hi = n;            // invariant: cu[lo] <= x < cu[hi]

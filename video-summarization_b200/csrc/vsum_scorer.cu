@@ -140,17 +140,7 @@ extern "C" int vsum_scorer_load_weights(vsum_scorer_t h, const vsum_scorer_weigh
 }
 
 namespace {
-struct Carver {
-    uint8_t *base;
-    size_t off = 0;
-    template <class T>
-    T *get(size_t n) {
-        off = align_up(off, 1024);
-        T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
-        off += n * sizeof(T);
-        return p;
-    }
-};
+
 struct Ws32 { int32_t *row_pos; float *xa, *xb, *qkv, *att, *tmp, *hid; };
 struct Ws16 { int32_t *row_pos, *tile_video, *tile_q0, *n_tiles; __nv_bfloat16 *xa, *xb, *qkv, *att, *hid; };
 
@@ -481,6 +471,63 @@ extern "C" int vsum_scorer_backward(vsum_scorer_t h, const float *x, const int32
     return VSUM_OK;
 }
 #undef RUN
+
+// ---- stand-alone Linear layer (PretrainModel.video_transform, simnet_pretrain.py:33,80) ---------------
+namespace {
+struct LinWs { float *wt, *zeros; __nv_bfloat16 *y16, *x16; };
+size_t carve_lin_ws(int64_t M, int N, int K, void *base, LinWs &w) {
+    Carver k{(uint8_t *)base};
+    w.wt = k.get<float>((size_t)N * K); w.zeros = k.get<float>(K);
+    w.y16 = k.get<__nv_bfloat16>((size_t)M * N); w.x16 = k.get<__nv_bfloat16>((size_t)M * K);
+    return align_up(k.off, 1024);
+}
+bool lin_tc_ok(int N, int K) { return N % 256 == 0 && K % 256 == 0 && N <= 4096 && K <= 4096; }
+}  // namespace
+
+extern "C" size_t vsum_linear_workspace_bytes(int64_t M, int32_t N, int32_t K) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    LinWs w;
+    return carve_lin_ws(M, N, K, nullptr, w);
+}
+
+extern "C" int vsum_linear_forward(const float *x, const float *w, const float *bias, float *y, int64_t M, int32_t N,
+                                   int32_t K, int32_t mode, void *stream) {
+    VSUM_REQUIRE(x && w && bias && y && M >= 0 && N > 0 && K > 0 && (mode == 0 || mode == 1), VSUM_EINVAL, "vsum_linear_forward: bad argument");
+    if (M == 0) return VSUM_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (mode == 0 || !lin_tc_ok(N, K)) return launch_linear_f32(x, w, bias, y, M, N, K, EPI_BIAS, nullptr, nullptr, 0, s);
+    Tc05GemmArgs g{};
+    g.A = x; g.W = w; g.M = M; g.N = N; g.K = K; g.a_is_f32 = 1; g.bias = bias; g.out_f32 = y; g.epi = TC_EPI_BIAS_F32;
+    g.prof_cat = PROF_OTHER;
+    return launch_gemm_tc05(g, s);
+}
+
+// dx [M,K] = dy W (dx may be NULL);  dw [N,K] = dy^T x;  db [N] = colsum(dy)   (dw, db overwritten)
+extern "C" int vsum_linear_backward(const float *dy, const float *x, const float *w, float *dx, float *dw, float *db,
+                                    int64_t M, int32_t N, int32_t K, int32_t mode, void *ws_mem, size_t ws_bytes, void *stream) {
+    VSUM_REQUIRE(dy && x && w && dw && db && M >= 0 && N > 0 && K > 0 && (mode == 0 || mode == 1), VSUM_EINVAL, "vsum_linear_backward: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    VSUM_CUDA_OK(cudaMemsetAsync(dw, 0, (size_t)N * K * sizeof(float), s));
+    VSUM_CUDA_OK(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), s));
+    if (M == 0) return VSUM_OK;
+    int rc;
+    if (mode == 0 || !lin_tc_ok(N, K)) {
+        if ((rc = launch_linear_wgrad_f32(dy, x, dw, db, M, N, K, s))) return rc;
+        return dx ? launch_linear_dgrad_f32(dy, w, dx, M, N, K, 0, s) : VSUM_OK;
+    }
+    VSUM_REQUIRE(ws_mem && ((uintptr_t)ws_mem & 1023) == 0 && ws_bytes >= vsum_linear_workspace_bytes(M, N, K), VSUM_ENOMEM,
+                 "vsum_linear_backward: workspace missing, unaligned or too small");
+    LinWs k;
+    carve_lin_ws(M, N, K, ws_mem, k);
+    if ((rc = launch_linear_wgrad_tc05(dy, x, dw, db, M, N, K, s, k.y16, k.x16))) return rc;
+    if (!dx) return VSUM_OK;
+    if ((rc = launch_transpose_f32(w, k.wt, N, K, s))) return rc;
+    VSUM_CUDA_OK(cudaMemsetAsync(k.zeros, 0, (size_t)K * sizeof(float), s));
+    Tc05GemmArgs g{};
+    g.A = dy; g.W = k.wt; g.M = M; g.N = K; g.K = N; g.a_is_f32 = 1; g.bias = k.zeros; g.out_f32 = dx; g.epi = TC_EPI_BIAS_F32;
+    g.prof_cat = PROF_OTHER;
+    return launch_gemm_tc05(g, s);
+}
 
 extern "C" int vsum_masked_mse(const float *out, const float *tgt, const uint8_t *pad_mask, int64_t n, float denom,
                                float *loss_out, float grad_scale, float *d_out, void *stream) {

@@ -151,6 +151,23 @@ class _ScorerTrainFn(torch.autograd.Function):
         return (None, None, None, None, None, None, *grads)
 
 
+def pack_padded(x: Tensor, mask: Tensor):
+    """Padded batch [bs,n,F] + bool mask [bs,n] (True = padded frame, src/train.py:118) -> packed rows [T,F],
+    cu_seqlens int32[bs+1] on the device, host lengths, and the keep mask."""
+    bs, n = mask.shape
+    dev = x.device
+    keep = ~mask
+    lens = keep.sum(dim=1)
+    ramp = torch.arange(n, device=dev).unsqueeze(0) < lens.unsqueeze(1)
+    lens_host = [int(v) for v in lens.tolist()]
+    if not bool((ramp == keep).all()):
+        raise _cabi.VsumError("only suffix padding (pad_sequence layout, dataset.py:157-161) is supported")
+    packed = x[keep]                                               # [T,F] gather of the valid frames
+    cu = torch.zeros(bs + 1, dtype=torch.int32, device=dev)
+    cu[1:] = lens.cumsum(0).to(torch.int32)
+    return packed, cu, lens_host, keep
+
+
 def _al(t: Tensor) -> int:
     return (t.data_ptr() + 1023) // 1024 * 1024
 
@@ -334,15 +351,7 @@ class SimNet(nn.Module):
         differentiable = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         run = self.forward_packed_train if differentiable else self.forward_packed
         if isinstance(mask, Tensor):
-            keep = ~mask
-            lens = keep.sum(dim=1)
-            ramp = torch.arange(n, device=dev).unsqueeze(0) < lens.unsqueeze(1)
-            lens_host = [int(v) for v in lens.tolist()]
-            if not bool((ramp == keep).all()):
-                raise _cabi.VsumError("only suffix padding (pad_sequence layout, dataset.py:157-161) is supported")
-            packed = x[keep]                                       # [T,1024] gather of the valid frames
-            cu = torch.zeros(bs + 1, dtype=torch.int32, device=dev)
-            cu[1:] = lens.cumsum(0).to(torch.int32)
+            packed, cu, lens_host, keep = pack_padded(x, mask)
             s, f = run(packed, cu, lens_host)
             idx = keep.reshape(-1).nonzero().squeeze(1)            # padded rows stay 0 (the loss masks them)
             scores = torch.zeros((bs * n, self.num_classes), dtype=torch.float32, device=dev).index_copy(0, idx, s)
