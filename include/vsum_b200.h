@@ -204,6 +204,29 @@ VSUM_API int32_t vsum_profile_num_categories(void);
 VSUM_API const char *vsum_profile_category_name(int32_t i);
 
 /* ------------------------------------------------------------------------------------------
+ * Rank correlations (src/evaluation/compute_correlation.py:4-15, called from compute_metrics.py:82-85):
+ * per video the mean over users of Kendall tau-b and Spearman rho between the predicted frame scores
+ * (the sub-sampled scores repeated up to the next pick, compute_metrics.py:19-39 -- never materialised)
+ * and each user's frame scores, with scipy's tie handling.  tau is bit-exact with scipy.stats.kendalltau
+ * (exact integer pair counts, scipy's expression order); rho comes from exact integer rank sums and
+ * agrees with scipy.stats.spearmanr to ~1e-15.  Constant inputs give NaN like scipy.
+ *   scores float32[T] packed, cu_steps int32[B+1]; picks int32 (one per step), n_frames int32[B];
+ *   user_scores float32: video v holds n_users[v] rows of us_cols[v] (== n_frames[v]) columns starting at
+ *   element us_offsets[v] (int64[B+1]); cu_users int32[B+1].  At most 8191 steps per video.
+ *   kendall_out / spearman_out fp64[B]; per_user_* fp64[sum(n_users)] or NULL.
+ *   workspace: 1024-byte aligned device memory of vsum_rank_correlation_workspace_bytes() bytes
+ *   (16 bytes per user-score element).
+ * ------------------------------------------------------------------------------------------ */
+VSUM_API size_t vsum_rank_correlation_workspace_bytes(int64_t total_user_elems, int64_t T, int32_t B,
+                                                      int32_t total_users);
+VSUM_API int vsum_rank_correlation(const float *scores, const int32_t *cu_steps, const int32_t *picks,
+                                   const int32_t *n_frames, const float *user_scores, const int64_t *us_offsets,
+                                   const int32_t *cu_users, const int32_t *us_cols, int32_t B, int64_t T,
+                                   int32_t max_steps, int32_t total_users, int64_t total_user_elems,
+                                   void *workspace, size_t workspace_bytes, double *kendall_out,
+                                   double *spearman_out, double *per_user_tau, double *per_user_rho, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Pretraining head (src/model/simnet_pretrain.py:33, 35-100; src/pretrain.py:59-67).
  *
  * vsum_linear_*: a stand-alone Linear layer on packed rows (PretrainModel.video_transform,

@@ -117,7 +117,8 @@ def test_eval_metrics_golden():
         data[v.name], users[v.name] = make_scores(int(vid), int(n)), v.as_user()
     f, tau, rho = eval_metrics(data, users)
     assert bits_equal(np.float64(f), np.float64(g["result"][0]))          # F: bit-exact
-    assert abs(tau - g["result"][1]) < 1e-12 and abs(rho - g["result"][2]) < 1e-12   # scipy on host, as the reference
+    assert bits_equal(np.float64(tau), np.float64(g["result"][1]))        # Kendall tau on the GPU: bit-exact with the reference
+    assert abs(rho - g["result"][2]) < 1e-12                              # Spearman rho: exact rank sums vs np.corrcoef
     per_video = eval_fscores(data, users)
     assert bits_equal(np.float64(np.mean(per_video)), np.float64(f))
 
@@ -156,3 +157,81 @@ def test_empty_and_maximum_sizes():
     assert int(too_long.n_frames * 0.15) + 1 > 28672
     with pytest.raises(_cabi.VsumError):
         run_batch([too_long], [make_scores(4001, 12800)])
+
+
+def _scipy_correlations(frame_scores, user_scores):
+    """The reference's evaluate_scores (compute_correlation.py:4-15), per user, on fp64 copies so that scipy
+    returns its fp64 statistic (with float32 inputs it rounds tau to float32, see _engine.rank_correlations)."""
+    from scipy import stats
+    taus, rhos = [], []
+    pr = stats.rankdata(-frame_scores.astype(np.float64))
+    for row in user_scores:
+        ur = stats.rankdata(-row.astype(np.float64))
+        rhos.append(stats.spearmanr(pr, ur)[0])
+        taus.append(stats.kendalltau(pr, ur)[0])
+    return np.asarray(taus, np.float64), np.asarray(rhos, np.float64)
+
+
+def _corr_case(kind, n_steps, n_users, seed):
+    from vsum_b200.evaluation.compute_metrics import upsample
+    rng = np.random.default_rng(seed)
+    n_frames = 15 * (n_steps - 1) + 1 + int(rng.integers(0, 15))
+    picks = np.arange(0, n_frames, 15, dtype=np.int32)[:n_steps]
+    scores = rng.random(n_steps, dtype=np.float32)
+    users = rng.random((n_users, n_frames), dtype=np.float32)
+    if kind == "levels":                                   # TVSum-like annotations 1..5 held for 2 s: heavy ties
+        users = np.repeat(rng.integers(1, 6, (n_users, n_frames // 30 + 1)), 30, axis=1)[:, :n_frames].astype(np.float32)
+    elif kind == "pred_ties":                              # equal scores in different segments, signed zeros
+        scores = rng.choice(np.asarray([0.25, 0.5, 0.75, 0.0, -0.0], np.float32), n_steps)
+        users[:, ::3] = 0.5
+    elif kind == "constant_user":
+        users[0] = 2.0                                     # scipy: nan for that user -> nan mean
+    elif kind == "head":                                   # frames before the first pick keep np.zeros' 0
+        picks = picks + 7
+        picks[-1] = min(picks[-1], n_frames - 1)
+    elif kind == "perfect":
+        users[0] = upsample(scores, n_frames, picks)       # tau = rho = 1 for user 0
+        users[1] = -users[0]
+    return scores, picks, n_frames, users
+
+
+@pytest.mark.parametrize("kind,n_steps,n_users", [
+    ("random", 40, 3), ("random", 300, 20), ("levels", 300, 20), ("pred_ties", 257, 5), ("constant_user", 64, 4),
+    ("head", 90, 3), ("perfect", 120, 3), ("random", 1, 2), ("random", 2, 2), ("levels", 2100, 4), ("random", 8000, 2)])
+def test_rank_correlations_match_scipy(kind, n_steps, n_users):
+    """vsum_rank_correlation against scipy (the reference's implementation): tau bit-exact per user, rho to 1e-13."""
+    from vsum_b200.evaluation import _engine
+    from vsum_b200.evaluation.compute_metrics import upsample
+    scores, picks, n_frames, users = _corr_case(kind, n_steps, n_users, seed=n_steps * 7 + n_users)
+    want_tau, want_rho = _scipy_correlations(upsample(scores, n_frames, picks), users)
+    tau, rho, pu_tau, pu_rho = _engine.rank_correlations([scores], [picks], [n_frames], [users], per_user=True)
+    assert np.array_equal(np.isnan(pu_tau), np.isnan(want_tau)) and np.array_equal(np.isnan(pu_rho), np.isnan(want_rho))
+    ok = ~np.isnan(want_tau)
+    assert (pu_tau[ok].view(np.int64) == want_tau[ok].view(np.int64)).all(), (pu_tau, want_tau)
+    ok = ~np.isnan(want_rho)
+    np.testing.assert_allclose(pu_rho[ok], want_rho[ok], rtol=0, atol=1e-13)
+    want32 = list(want_tau.astype(np.float32))            # float32 user scores: scipy rounds each tau to float32
+    assert bits_equal(np.float64(tau[0]), np.float64(sum(want32) / len(want32)))          # compute_correlation.py:15
+    t64, _ = _engine.rank_correlations([scores], [picks], [n_frames], [users.astype(np.float64)])
+    assert bits_equal(np.float64(t64[0]), np.float64(sum(list(want_tau)) / len(want_tau)))
+    if kind == "perfect":
+        assert pu_tau[0] == 1.0 and pu_tau[1] == -1.0 and abs(pu_rho[0] - 1.0) < 1e-15
+
+
+def test_rank_correlations_batched_and_dropin():
+    """Several videos of different lengths in one call == one call per video; the drop-in evaluate_scores
+    (frame-level prediction in, compute_correlation.py:4) gives the same numbers."""
+    from vsum_b200.evaluation import _engine
+    from vsum_b200.evaluation.compute_correlation import evaluate_scores
+    from vsum_b200.evaluation.compute_metrics import upsample
+    cases = [_corr_case(k, n, u, seed=5 + i) for i, (k, n, u) in enumerate([("random", 33, 2), ("levels", 700, 20), ("pred_ties", 129, 7),
+                                                                             ("random", 1500, 1)])]
+    tau, rho = _engine.rank_correlations([c[0] for c in cases], [c[1] for c in cases], [c[2] for c in cases], [c[3] for c in cases])
+    for i, (scores, picks, n_frames, users) in enumerate(cases):
+        t1, r1 = _engine.rank_correlations([scores], [picks], [n_frames], [users])
+        assert bits_equal(np.float64(tau[i]), np.float64(t1[0])) and bits_equal(np.float64(rho[i]), np.float64(r1[0]))
+        t2, r2 = evaluate_scores(upsample(scores, n_frames, picks), users)
+        assert bits_equal(np.float64(t2), np.float64(tau[i])) and bits_equal(np.float64(r2), np.float64(rho[i]))
+        wt, wr = _scipy_correlations(upsample(scores, n_frames, picks), users)
+        wt32 = list(wt.astype(np.float32))
+        assert bits_equal(np.float64(tau[i]), np.float64(sum(wt32) / len(wt32))) and abs(rho[i] - sum(wr) / len(wr)) < 1e-13

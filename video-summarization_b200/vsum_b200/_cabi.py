@@ -27,6 +27,7 @@ EXPORTS = (
     "vsum_debug_gemm_tc05", "vsum_debug_wgrad_tc05", "vsum_debug_attention_tc05",
     "vsum_debug_attention_train_tc05", "vsum_debug_attention_bwd_tc05",
     "vsum_linear_workspace_bytes", "vsum_linear_forward", "vsum_linear_backward",
+    "vsum_rank_correlation_workspace_bytes", "vsum_rank_correlation",
     "vsum_pretrain_saved_bytes", "vsum_pretrain_losses_forward", "vsum_pretrain_losses_backward",
     "vsum_profile_begin", "vsum_profile_end", "vsum_profile_num_categories", "vsum_profile_category_name",
 )
@@ -119,6 +120,9 @@ def load():
     L.vsum_pretrain_saved_bytes.argtypes = [i64, i32, i32]
     L.vsum_pretrain_losses_forward.argtypes = [vp, vp, vp, i32, i64, i32, i32, C.c_float, vp, i32, vp, vp, C.c_size_t, vp]
     L.vsum_pretrain_losses_backward.argtypes = [vp, vp, i32, i64, i32, i32, C.c_float, i32, vp, vp, vp, vp, vp]
+    L.vsum_rank_correlation_workspace_bytes.restype = C.c_size_t
+    L.vsum_rank_correlation_workspace_bytes.argtypes = [i64, i64, i32, i32]
+    L.vsum_rank_correlation.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, i64, vp, C.c_size_t, vp, vp, vp, vp, vp]
     L.vsum_profile_end.argtypes = [vp, vp, i32]
     L.vsum_profile_num_categories.restype = i32
     L.vsum_profile_category_name.restype = C.c_char_p

@@ -242,3 +242,68 @@ def fscore_of_masks(summaries: Sequence[np.ndarray], user_summaries: Sequence[np
             d_mask.data_ptr(), d_sum_off.data_ptr(), int(sum_off[-1]), counts.data_ptr(), f.data_ptr(), None,
             stream), "vsum_summary_fscore")
         return f.cpu().numpy()
+
+
+def rank_correlations(scores: Sequence[np.ndarray], picks: Sequence[np.ndarray], n_frames: Sequence,
+                      user_scores: Sequence[np.ndarray], device=None, per_user: bool = False):
+    """Kendall tau-b / Spearman rho of every video's predicted frame scores against each user's frame
+    scores (compute_correlation.py:4-15) in one batched GPU pass.  `scores[v]` are the sub-sampled
+    scores (float32[N_v]); the upsampling of compute_metrics.py:19-39 happens inside the kernels.
+    Returns (kendall[B], spearman[B]) -- the per-video `sum(x) / len(x)` over users (line 15) -- and,
+    with `per_user`, also the two flat fp64 per-user arrays.
+
+    Result dtype follows scipy's: with float32 user scores the rank arrays are float32, so
+    `stats.kendalltau` hands back its fp64 statistic rounded to float32 and line 15 sums float32
+    scalars; any other dtype keeps fp64.  `stats.spearmanr` is fp64 either way.  The kernels always
+    produce the fp64 statistic (tau bit-exact with scipy's internal value); the rounding and the
+    per-video mean over a handful of users are applied here."""
+    dev = _device(device)
+    B = len(scores)
+    if B == 0:
+        z = np.zeros(0, np.float64)
+        return (z, z, z, z) if per_user else (z, z)
+    sc = [np.ascontiguousarray(np.asarray(s), dtype=np.float32).reshape(-1) for s in scores]
+    pk = [np.asarray(p).astype(np.int32, copy=False).reshape(-1) for p in picks]
+    for s_, p_ in zip(sc, pk):
+        if len(s_) != len(p_):
+            raise ValueError("every video needs one pick per score")
+    raw = [np.asarray(u) for u in user_scores]
+    tau_dtypes = [np.float32 if r.dtype in (np.float32, np.float16) else np.float64 for r in raw]
+    mats = [np.ascontiguousarray(r, dtype=np.float32).reshape(len(r), -1) for r in raw]
+    cu_steps = _cu([len(s_) for s_ in sc]).astype(np.int32)
+    us_off = _cu([m.size for m in mats])
+    cu_users = _cu([m.shape[0] for m in mats]).astype(np.int32)
+    us_cols = np.asarray([m.shape[1] for m in mats], dtype=np.int32)
+    nfr = np.asarray([int(np.asarray(n)) for n in n_frames], dtype=np.int32)
+    T, total_users, total_elems = int(cu_steps[-1]), int(cu_users[-1]), int(us_off[-1])
+    max_steps = max(len(s_) for s_ in sc)
+    with torch.cuda.device(dev):
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        d_sc = t(np.concatenate(sc)) if T else torch.zeros(1, device=dev)
+        d_pk = t(np.concatenate(pk)) if T else torch.zeros(1, dtype=torch.int32, device=dev)
+        d_us = t(np.concatenate([m.reshape(-1) for m in mats])) if total_elems else torch.zeros(1, device=dev)
+        d_cu, d_nf, d_off, d_cuu, d_cols = t(cu_steps), t(nfr), t(us_off), t(cu_users), t(us_cols)
+        L = _cabi.load()
+        need = L.vsum_rank_correlation_workspace_bytes(total_elems, T, B, total_users)
+        ws = _scratch_buf("corr", need + 1024, dev)
+        wp = (ws.data_ptr() + 1023) // 1024 * 1024
+        out = torch.empty(2 * B + 2 * max(total_users, 1), dtype=torch.float64, device=dev)
+        tau, rho, pu_t, pu_r = out[:B], out[B:2 * B], out[2 * B:2 * B + max(total_users, 1)], out[2 * B + max(total_users, 1):]
+        _cabi.check(L.vsum_rank_correlation(
+            d_sc.data_ptr(), d_cu.data_ptr(), d_pk.data_ptr(), d_nf.data_ptr(), d_us.data_ptr(), d_off.data_ptr(),
+            d_cuu.data_ptr(), d_cols.data_ptr(), B, T, max_steps, total_users, total_elems, wp,
+            ws.numel() - (wp - ws.data_ptr()), tau.data_ptr(), rho.data_ptr(), pu_t.data_ptr(), pu_r.data_ptr(),
+            torch.cuda.current_stream(dev).cuda_stream), "vsum_rank_correlation")
+        host = out.cpu().numpy()
+    pu_tau, pu_rho = host[2 * B:2 * B + total_users], host[2 * B + max(total_users, 1):2 * B + max(total_users, 1) + total_users]
+    taus, rhos = [], []
+    for v in range(B):                                   # line 15: sum(kendal) / len(kendal), in scipy's result dtype
+        u0, u1 = int(cu_users[v]), int(cu_users[v + 1])
+        if u1 == u0:
+            raise ZeroDivisionError("division by zero")  # what line 15 does for a video without users
+        taus.append(sum(list(pu_tau[u0:u1].astype(tau_dtypes[v]))) / (u1 - u0))
+        rhos.append(sum(list(pu_rho[u0:u1])) / (u1 - u0))
+    res = (taus, rhos)
+    if per_user:
+        res += (pu_tau.copy(), pu_rho.copy())
+    return res

@@ -1,14 +1,17 @@
-"""Rank correlations against each user's frame scores.  Out of the GPU scope of this round
-(SURVEY.md section 8(f) rank 1): like the reference (`src/evaluation/compute_correlation.py:4-15`)
-this calls scipy on the host, so `eval_metrics` keeps returning its 3-tuple."""
-from scipy import stats
+"""Rank correlations against each user's frame scores with the reference signature
+(`src/evaluation/compute_correlation.py:4-15`), computed by `vsum_rank_correlation` on the GPU
+(SURVEY.md section 8(f) rank 1).  Kendall's tau is bit-exact with scipy; Spearman's rho agrees to ~1e-15."""
+import numpy as np
+
+from . import _engine
 
 
 def evaluate_scores(predicted_summary, user_scores):
-    taus, rhos = [], []
-    pred_rank = stats.rankdata(-predicted_summary)
-    for row in user_scores:
-        user_rank = stats.rankdata(-row)
-        rhos.append(stats.spearmanr(pred_rank, user_rank)[0])
-        taus.append(stats.kendalltau(pred_rank, user_rank)[0])
-    return sum(taus) / len(taus), sum(rhos) / len(rhos)
+    """predicted_summary: float32[n_frames] (upsampled frame scores); user_scores [U, n_frames].
+    Returns (mean Kendall tau-b, mean Spearman rho) over the users."""
+    pred = np.ascontiguousarray(np.asarray(predicted_summary), dtype=np.float32).reshape(-1)
+    n = len(pred)
+    # the kernels take the piecewise-constant form: run starts are the picks, run values the scores
+    starts = np.concatenate([[0], np.flatnonzero(pred[1:] != pred[:-1]) + 1]).astype(np.int32) if n else np.zeros(0, np.int32)
+    tau, rho = _engine.rank_correlations([pred[starts]], [starts], [n], [np.asarray(user_scores)])
+    return tau[0], rho[0]

@@ -20,8 +20,8 @@ from .compute_correlation import evaluate_scores
 
 
 def upsample(scores, n_frames, positions):
-    """Repeat each sub-sampled score up to the next pick (host helper for the scipy correlations;
-    the GPU path never materialises this array -- see vsum_shot_mean)."""
+    """Repeat each sub-sampled score up to the next pick (host helper with the reference signature;
+    the GPU kernels never materialise this array -- see vsum_shot_mean / vsum_rank_correlation)."""
     n_frames = int(n_frames)
     pos = np.asarray(positions)
     if pos.dtype != int:
@@ -59,15 +59,12 @@ def eval_metrics(data, user_dict, with_correlation: bool = True):
     keys = list(data.keys())
     f_scores = eval_fscores(data, user_dict, eval_method)
     taus, rhos = [], []
-    if with_correlation:
-        for k in keys:
-            u = user_dict[k]
-            frame_scores = upsample(data[k], u.n_frames, u.picks)
-            tau, rho = evaluate_scores(frame_scores, u.user_scores)
-            taus.append(tau)
-            rhos.append(rho)
+    if with_correlation and keys:               # all videos in one batched GPU pass (compute_metrics.py:80-85)
+        users = [user_dict[k] for k in keys]
+        taus, rhos = _engine.rank_correlations([data[k] for k in keys], [u.picks for u in users],
+                                               [u.n_frames for u in users], [u.user_scores for u in users])
     mean_f = np.mean(f_scores)
-    mean_tau = np.mean(taus) if taus else float("nan")
-    mean_rho = np.mean(rhos) if rhos else float("nan")
+    mean_tau = np.mean(taus) if len(taus) else float("nan")
+    mean_rho = np.mean(rhos) if len(rhos) else float("nan")
     logging.info(f" [f_score: {mean_f:.4f}, kenadall_tau: {mean_tau:.4f}, spearsman_r: {mean_rho:.4f}]")
     return mean_f, mean_tau, mean_rho
