@@ -107,7 +107,9 @@ VSUM_API int vsum_scorer_forward(vsum_scorer_t h, const float *features, const i
  * simnet.py:107,110,159,181 (counter-based masks recomputed from `seed` in the backward pass).
  *   forward_train keeps every activation the backward needs in `tape` (vsum_scorer_tape_bytes);
  *   backward writes d(loss)/d(parameter) for each tensor named in the vsum_scorer_grads struct [same fields
- *   as vsum_scorer_weights, fp32 device arrays of the parameter's shape; they are overwritten].
+ *   as vsum_scorer_weights, fp32 device arrays of the parameter's shape; they are overwritten].  When
+ *   q_w|k_w|v_w (and q_b|k_b|v_b) of a layer are adjacent in memory the fused QKV weight gradient is
+ *   written in place, otherwise it goes through a scratch copy.
  *   d_feats [T,d_model] may be NULL (gradient w.r.t. the second forward output).
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
@@ -117,6 +119,7 @@ typedef struct {
 typedef struct {
     float *embed_w, *embed_b, *final_w, *final_b;
     vsum_layer_grads layers[VSUM_MAX_LAYERS];
+    int32_t pre_zeroed;   /* non-zero: the caller has already zeroed every array (e.g. one memset of a flat buffer) */
 } vsum_scorer_grads;
 
 /* Training path arithmetic: mode 0 = fp32 SIMT kernels (reference accuracy); mode 1 = linear layers on

@@ -417,7 +417,8 @@ extern "C" int vsum_scorer_backward(vsum_scorer_t h, const float *x, const int32
     carve_train_ws(c, T, B, ws_mem, w);
     int rc;
 #define ZERO(ptr, n) do { VSUM_REQUIRE((ptr) != nullptr, VSUM_EINVAL, "vsum_scorer_backward: null gradient " #ptr); \
-                          VSUM_CUDA_OK(cudaMemsetAsync((ptr), 0, (n) * sizeof(float), s)); } while (0)
+                          if (!pre_zeroed) VSUM_CUDA_OK(cudaMemsetAsync((ptr), 0, (n) * sizeof(float), s)); } while (0)
+    const bool pre_zeroed = g->pre_zeroed != 0;
     ZERO(g->embed_w, d * c.in_features); ZERO(g->embed_b, d); ZERO(g->final_w, C * d); ZERO(g->final_b, C);
     const float scale = 1.0f / sqrtf((float)d);
     const float *x_last = t.L[c.num_layers - 1].xout;
@@ -431,8 +432,11 @@ extern "C" int vsum_scorer_backward(vsum_scorer_t h, const float *x, const int32
         const float *xin = l == 0 ? t.x0 : t.L[l - 1].xout;
         ZERO(gl.ln2_g, d); ZERO(gl.ln2_b, d); ZERO(gl.fc2_w, d * ff); ZERO(gl.fc2_b, d); ZERO(gl.fc1_w, ff * d); ZERO(gl.fc1_b, ff);
         ZERO(gl.ln1_g, d); ZERO(gl.ln1_b, d); ZERO(gl.o_w, d * d); ZERO(gl.o_b, d);
-        ZERO(w.dwqkv, 3 * d * d); ZERO(w.dbqkv, 3 * d);
         VSUM_REQUIRE(gl.q_w && gl.q_b && gl.k_w && gl.k_b && gl.v_w && gl.v_b, VSUM_EINVAL, "vsum_scorer_backward: null q/k/v gradient");
+        // q|k|v gradients adjacent in memory (flat gradient buffer): the fused [3d,d] wgrad lands in place
+        const bool qkv_in_place = gl.k_w == gl.q_w + d * d && gl.v_w == gl.k_w + d * d && gl.k_b == gl.q_b + d && gl.v_b == gl.k_b + d;
+        if (qkv_in_place) { ZERO(gl.q_w, 3 * d * d); ZERO(gl.q_b, 3 * d); }
+        else { VSUM_CUDA_OK(cudaMemsetAsync(w.dwqkv, 0, 3 * d * d * sizeof(float), s)); VSUM_CUDA_OK(cudaMemsetAsync(w.dbqkv, 0, 3 * d * sizeof(float), s)); }
         // xout = LN2(s2), s2 = dropout(mlp) + xmid          a: d_xout -> b: d_s2 (residual path), c: d_mlp
         RUN(launch_layernorm_bwd_f32(w.a, L.s2, h->w32 + o.ln2g, w.b, w.c, gl.ln2_g, gl.ln2_b, T, (int)d, p, site_seed(seed, SITE_MLP, l), s));
         // mlp = hid W2^T + b2
@@ -457,10 +461,11 @@ extern "C" int vsum_scorer_backward(vsum_scorer_t h, const float *x, const int32
         RUN(launch_attention_bwd_f32(L.qkv, L.att, w.dd, L.lse, cu, B, max_len, T, (int)d, c.num_heads, scale, p,
                                      site_seed(seed, SITE_ATTN, l), w.delta, w.dqkv, s));
         // qkv = xin Wqkv^T + bqkv                           a: d_xin += dqkv Wqkv
-        RUN(lin_wgrad(h, w.dqkv, xin, w.dwqkv, w.dbqkv, T, (int)(3 * d), (int)d, w.y16, w.x16, s));
+        RUN(lin_wgrad(h, w.dqkv, xin, qkv_in_place ? gl.q_w : w.dwqkv, qkv_in_place ? gl.q_b : w.dbqkv, T, (int)(3 * d), (int)d,
+                      w.y16, w.x16, s));
         RUN(lin_dgrad(h, w.dqkv, h->w32 + o.wqkv, h->w32 + o.t_wqkv, w.a, w.dd, T, (int)(3 * d), (int)d, 1, s));
         float *wdst[3] = {gl.q_w, gl.k_w, gl.v_w}, *bdst[3] = {gl.q_b, gl.k_b, gl.v_b};
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < 3 && !qkv_in_place; ++i) {
             VSUM_CUDA_OK(cudaMemcpyAsync(wdst[i], w.dwqkv + i * d * d, d * d * sizeof(float), cudaMemcpyDeviceToDevice, s));
             VSUM_CUDA_OK(cudaMemcpyAsync(bdst[i], w.dbqkv + i * d, d * sizeof(float), cudaMemcpyDeviceToDevice, s));
         }

@@ -63,7 +63,7 @@ class LayerGrads(C.Structure):
 
 class ScorerGrads(C.Structure):
     _fields_ = [("embed_w", C.c_void_p), ("embed_b", C.c_void_p), ("final_w", C.c_void_p), ("final_b", C.c_void_p),
-                ("layers", LayerGrads * VSUM_MAX_LAYERS)]
+                ("layers", LayerGrads * VSUM_MAX_LAYERS), ("pre_zeroed", C.c_int32)]
 
 
 _lib = None

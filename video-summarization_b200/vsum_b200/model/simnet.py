@@ -126,7 +126,21 @@ class _ScorerTrainFn(torch.autograd.Function):
         dev = features.device
         L = _cabi.load()
         params = list(model._train_params())
-        grads = [torch.empty_like(p) for p in params]
+        # one flat, zeroed gradient buffer; every .grad is a view of it (sharding.allreduce_gradients reduces it
+        # in place) and q|k|v of a layer are adjacent so the fused QKV weight gradient is written in place
+        names = ["embed_w", "embed_b"] + [f"{i}.{f}" for i in range(model.num_layers) for f in _cabi._LAYER_FIELDS] + ["final_w", "final_b"]
+        sizes = dict(zip(names, (p.numel() for p in params)))
+        order = ["embed_w", "embed_b"]
+        for i in range(model.num_layers):
+            first = [f"{i}.{f}" for f in ("q_w", "k_w", "v_w", "q_b", "k_b", "v_b")]
+            order += first + [f"{i}.{f}" for f in _cabi._LAYER_FIELDS if f"{i}.{f}" not in first]
+        order += ["final_w", "final_b"]
+        flat = torch.zeros(sum(sizes.values()), dtype=torch.float32, device=dev)
+        views, off = {}, 0
+        for k in order:
+            views[k] = flat[off:off + sizes[k]]
+            off += sizes[k]
+        grads = [views[k].view_as(p) for k, p in zip(names, params)]
         if d_scores is None:
             d_scores = torch.zeros((T, model.num_classes), dtype=torch.float32, device=dev)
         d_scores = d_scores.contiguous().float()
@@ -138,6 +152,7 @@ class _ScorerTrainFn(torch.autograd.Function):
             for name in _cabi._LAYER_FIELDS:
                 setattr(g.layers[i], name, next(it).data_ptr())
         g.final_w, g.final_b = next(it).data_ptr(), next(it).data_ptr()
+        g.pre_zeroed = 1
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             model._sync_weights(max_len, dev, stream)          # the optimiser may not have stepped yet: no-op

@@ -90,6 +90,18 @@ def allreduce_gradients(params, group=None, average: bool = False) -> None:
     world = dist.get_world_size(group)
     if world == 1:
         return
+    # The native backward hands out views of ONE flat buffer: when every gradient still lives in that storage
+    # (and fills it), reduce the storage in place -- no concatenation, no copy back.
+    st = params[0].grad.untyped_storage()
+    total = sum(p.grad.numel() for p in params)
+    if (all(p.grad.dtype == torch.float32 and p.grad.is_contiguous() and p.grad.untyped_storage().data_ptr() == st.data_ptr()
+            for p in params) and st.nbytes() == 4 * total
+            and len({p.grad.data_ptr() for p in params}) == len(params)):
+        base = torch.empty(0, dtype=torch.float32, device=params[0].grad.device).set_(st, 0, (total,))
+        dist.all_reduce(base, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            base.div_(world)
+        return
     flat = torch.cat([p.grad.reshape(-1) for p in params])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     if average:
