@@ -206,6 +206,14 @@ VSUM_API int vsum_profile_end(float *ms_out_host, int32_t *count_out_host, int32
 VSUM_API int32_t vsum_profile_num_categories(void);
 VSUM_API const char *vsum_profile_category_name(int32_t i);
 
+/* Frame numbers of the summary (src/generate_summary_image.py:74-76, the lists written to summary.json):
+ * ascending indices of the frames inside selected shots.  frames_out holds video v at
+ * [out_offsets[v], out_offsets[v+1]) (int64[B+1]; the knapsack capacity of the video is always enough
+ * room), counts_out[v] = how many were written. */
+VSUM_API int vsum_summary_frames(const uint8_t *selected, const int32_t *change_points, const int32_t *cu_shots,
+                                 const int64_t *out_offsets, int32_t B, int32_t *frames_out, int32_t *counts_out,
+                                 void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Rank correlations (src/evaluation/compute_correlation.py:4-15, called from compute_metrics.py:82-85):
  * per video the mean over users of Kendall tau-b and Spearman rho between the predicted frame scores
@@ -262,6 +270,32 @@ VSUM_API int vsum_pretrain_losses_backward(const float *x512, const int32_t *cu_
                                            int32_t max_len, int32_t n_pad, float sharpening_t, int32_t pen_entropy,
                                            const float *d_losses3, void *saved, float *d_scores, float *d_x512,
                                            void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Data layer (host side; replaces the h5py / pad_sequence input path of src/data/dataset.py:64-168 and
+ * src/train.py:115-118): a packed, memory-mapped dataset file (written by vsum_b200/data/packed.py) and a
+ * multi-threaded padding-free collate that gathers a batch straight into one caller buffer (pinned
+ * host memory) as packed rows + cu_seqlens -- the layout vsum_scorer_forward consumes.
+ *   vsum_pack_array returns a zero-copy view into the mapping (NULL / 0 bytes when the array is absent).
+ *   vsum_pack_collate: features_out [sum N, feature_dim] fp32, gtscore_out [sum N] or NULL,
+ *   cu_seqlens_out int32[n+1]; `threads` host threads split the bytes evenly.
+ * ------------------------------------------------------------------------------------------ */
+enum { VSUM_PACK_FEATURES = 0, VSUM_PACK_GTSCORE, VSUM_PACK_PICKS, VSUM_PACK_CHANGE_POINTS, VSUM_PACK_USER_SUMMARY,
+       VSUM_PACK_USER_SCORES, VSUM_PACK_VIDEO_REP, VSUM_PACK_NUM_ARRAYS };
+typedef struct vsum_pack *vsum_pack_t;
+typedef struct {
+    char name[96];
+    int32_t n_steps, n_frames, n_shots, n_users, rep_dim, has_user_scores;
+    int32_t user_summary_dtype;   /* 0 = float32 (as in the h5 files), 1 = uint8 */
+} vsum_pack_info;
+VSUM_API int vsum_pack_open(const char *path, vsum_pack_t *out);
+VSUM_API void vsum_pack_close(vsum_pack_t pack);
+VSUM_API int32_t vsum_pack_num_videos(vsum_pack_t pack);
+VSUM_API int32_t vsum_pack_feature_dim(vsum_pack_t pack);
+VSUM_API int vsum_pack_video_info(vsum_pack_t pack, int32_t video, vsum_pack_info *out);
+VSUM_API int vsum_pack_array(vsum_pack_t pack, int32_t video, int32_t kind, const void **ptr, uint64_t *bytes);
+VSUM_API int vsum_pack_collate(vsum_pack_t pack, const int32_t *videos, int32_t n, int32_t threads,
+                               float *features_out, float *gtscore_out, int32_t *cu_seqlens_out);
 
 /* ------------------------------------------------------------------------------------------
  * Diagnostics: the two tcgen05 kernels on their own, so tests can pin them individually.

@@ -1,0 +1,79 @@
+"""CPU: the packed dataset file, the native memory-mapped reader and the padding-free collate
+(vsum_pack_*, vsum_b200/data) against the arrays they were written from -- the records mirror
+src/data/dataset.py:64-168."""
+import numpy as np
+import pytest
+import torch
+
+from vsum_b200 import _cabi
+from vsum_b200.data import PackedDataset, PackedLoader, write_pack
+from vsum_b200.synthetic import make_video
+
+
+def _videos(ns, first=700):
+    out = []
+    for i, n in enumerate(ns):
+        v = make_video(first + i, n, n_users=3, with_features=True, with_user_scores=True)
+        out.append(dict(name=v.name, features=v.features, gtscore=v.gtscore, picks=v.picks, change_points=v.change_points,
+                        n_frames=v.n_frames, user_summary=v.user_summary, user_scores=v.user_scores,
+                        video_rep=np.random.default_rng(i).random(512, dtype=np.float32)))
+    return out
+
+
+@pytest.mark.parametrize("u8", [False, True])
+def test_roundtrip_and_records(tmp_path, u8):
+    vids = _videos((60, 7, 131, 300))
+    path = str(tmp_path / "d.vspack")
+    write_pack(path, vids, user_summary_u8=u8)
+    ds = PackedDataset(path, split="val")
+    assert len(ds) == 4 and ds.feature_dim == 1024 and ds.names == [v["name"] for v in vids]
+    for i, v in enumerate(vids):
+        feats, tgt, user = ds[i]
+        assert torch.equal(feats, torch.from_numpy(v["features"])) and torch.equal(tgt, torch.from_numpy(v["gtscore"]))
+        assert np.array_equal(user.picks, v["picks"]) and np.array_equal(user.change_points, v["change_points"])
+        assert int(user.n_frames) == v["n_frames"] and user.name == v["name"]
+        assert np.array_equal(np.asarray(user.user_summary, np.float32), v["user_summary"].astype(np.float32))
+        assert user.user_summary.dtype == (np.uint8 if u8 else np.float32)
+        assert np.array_equal(user.user_scores, v["user_scores"])
+    tr = PackedDataset(path, split="train", min_steps=50)            # dataset.py:121 keeps videos with > 50 steps
+    assert tr.names == [vids[0]["name"], vids[2]["name"], vids[3]["name"]] and len(tr[0]) == 2
+    sel = PackedDataset(path, split="val", keys=["some/dir/" + vids[1]["name"], vids[3]["name"]])     # split keys, dataset.py:137-140
+    assert sel.names == [vids[1]["name"], vids[3]["name"]]
+    pre = PackedDataset(path, split="pretrain")
+    f, rep = pre[2]
+    assert rep.shape == (512,) and np.array_equal(rep.numpy(), vids[2]["video_rep"])
+
+
+@pytest.mark.parametrize("threads", [1, 5])
+def test_collate_is_packed_and_ordered(tmp_path, threads):
+    vids = _videos((60, 7, 131, 300, 1, 2000), first=720)
+    path = str(tmp_path / "d.vspack")
+    write_pack(path, vids)
+    ds = PackedDataset(path, split="train")
+    loader = PackedLoader(ds, batch_size=4, device="cpu", collate_threads=threads)
+    batches = list(loader)
+    assert len(loader) == 2 and [b.ids for b in batches] == [[0, 1, 2, 3], [4, 5]]
+    for b in batches:
+        want = np.concatenate([vids[i]["features"] for i in b.ids])
+        assert np.array_equal(b.features.numpy(), want)
+        assert np.array_equal(b.targets.numpy(), np.concatenate([vids[i]["gtscore"] for i in b.ids]))
+        assert b.cu_seqlens.tolist() == np.concatenate([[0], np.cumsum(b.seqlens)]).tolist()
+    sh = PackedLoader(ds, batch_size=4, shuffle=True, seed=3, device="cpu", drop_last=True)
+    got = [b.ids for b in sh]
+    assert len(got) == 1 and len(set(got[0])) == 4
+
+
+def test_open_errors(tmp_path):
+    bad = tmp_path / "bad.vspack"
+    bad.write_bytes(b"not a pack file" * 10)
+    with pytest.raises(_cabi.VsumError):
+        PackedDataset(str(bad))
+    with pytest.raises(_cabi.VsumError):
+        PackedDataset(str(tmp_path / "missing.vspack"))
+    vids = _videos((20,))
+    path = tmp_path / "t.vspack"
+    write_pack(str(path), vids)
+    data = path.read_bytes()
+    (tmp_path / "trunc.vspack").write_bytes(data[: len(data) // 2])
+    with pytest.raises(_cabi.VsumError):
+        PackedDataset(str(tmp_path / "trunc.vspack"))

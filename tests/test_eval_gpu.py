@@ -235,3 +235,16 @@ def test_rank_correlations_batched_and_dropin():
         wt, wr = _scipy_correlations(upsample(scores, n_frames, picks), users)
         wt32 = list(wt.astype(np.float32))
         assert bits_equal(np.float64(tau[i]), np.float64(sum(wt32) / len(wt32))) and abs(rho[i] - sum(wr) / len(wr)) < 1e-13
+
+
+def test_summary_frames_match_mask():
+    """vsum_summary_frames == [i for i, is_in in enumerate(summary) if is_in == 1] (generate_summary_image.py:74-76)."""
+    from vsum_b200.evaluation.generate_summary import summary_frames
+    vids = [make_video(900 + i, n, n_users=2, with_features=False) for i, n in enumerate((5, 64, 300, 1333, 4000))]
+    scores = [make_scores(900 + i, v.n_steps) for i, v in enumerate(vids)]
+    args = ([v.change_points for v in vids], scores, [v.n_frames for v in vids], [v.picks for v in vids])
+    masks = generate_summary(*args)
+    frames = summary_frames(*args)
+    for m, f in zip(masks, frames):
+        assert f == [i for i, is_in in enumerate(m) if is_in == 1]
+    assert any(len(f) > 0 for f in frames)

@@ -56,3 +56,37 @@ def test_pipelined_submission_matches_single_stream(seeded_model_kwargs):
     summ.drain()
     torch.cuda.synchronize()
     assert bits_equal(hosts[-1].numpy(), want) and bits_equal(hosts[-2].numpy(), want)
+
+
+def test_packed_loader_feeds_the_scorer(tmp_path):
+    """Data layer end to end: pack file -> native collate into pinned staging -> async copy -> packed forward.
+    Same scores as SimNet.forward on the padded batch the reference's collate_fn_train builds (dataset.py:157-161)."""
+    import numpy as np
+    import torch
+    from vsum_b200.data import PackedDataset, PackedLoader, write_pack
+    from vsum_b200.model import SimNet
+    from vsum_b200.synthetic import make_video
+    vids = [make_video(1500 + i, n, n_users=2) for i, n in enumerate((120, 64, 257, 90, 33))]
+    path = str(tmp_path / "d.vspack")
+    write_pack(path, [dict(name=v.name, features=v.features, gtscore=v.gtscore) for v in vids])
+    torch.manual_seed(5)
+    model = SimNet(num_heads=4, d_model=256, num_layers=2, sparsity=0., dropout=0.).cuda().eval()
+    loader = PackedLoader(PackedDataset(path, split="train"), batch_size=3, collate_threads=4)
+    seen = 0
+    for b in loader:
+        assert b.features.is_cuda and b.cu_seqlens.is_cuda and b.features.shape[0] == sum(b.seqlens)
+        scores, _ = model.forward_packed(b.features, b.cu_seqlens, b.seqlens)
+        nmax = max(b.seqlens)
+        x = torch.full((len(b.ids), nmax, 1024), 1000.0)
+        for k, i in enumerate(b.ids):
+            x[k, :b.seqlens[k]] = torch.from_numpy(vids[i].features)
+        x = x.cuda()
+        mask = x[:, :, 0] == 1000
+        with torch.no_grad():                                   # same (inference) kernels as forward_packed
+            padded, _ = model(x, mask)
+        want = torch.cat([padded[k, :n, 0] for k, n in enumerate(b.seqlens)])
+        assert torch.equal(scores[:, 0], want)
+        tgt = np.concatenate([vids[i].gtscore for i in b.ids])
+        assert np.array_equal(b.targets.cpu().numpy(), tgt)
+        seen += len(b.ids)
+    assert seen == 5

@@ -248,6 +248,45 @@ summary_mask_kernel(const uint8_t *__restrict__ selected, const int32_t *__restr
     }
 }
 
+// Frame indices of the keyshot summary in ascending order -- what generate_summary_image.py:74-76 builds with
+// `[i for i, is_in in enumerate(summary) if is_in == 1]` -- straight from the selected shots (they are
+// ascending and disjoint), one CTA per video.  frames_out holds video v at [out_offsets[v], out_offsets[v+1]).
+__global__ void __launch_bounds__(256)
+summary_frames_kernel(const uint8_t *__restrict__ selected, const int32_t *__restrict__ cps, const int32_t *__restrict__ cu_shots,
+                      const int64_t *__restrict__ out_offsets, int32_t *__restrict__ frames_out, int32_t *__restrict__ counts_out) {
+    __shared__ int s_off[256], s_warp[8], s_carry;
+    const int v = blockIdx.x, s0 = __ldg(cu_shots + v), S = __ldg(cu_shots + v + 1) - s0;
+    int32_t *out = frames_out + __ldg(out_offsets + v);
+    const int64_t room = __ldg(out_offsets + v + 1) - __ldg(out_offsets + v);
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < S; c0 += 256) {
+        const int k = c0 + threadIdx.x;
+        int len = 0;
+        if (k < S && selected[s0 + k]) len = max(__ldg(cps + 2 * (s0 + k) + 1) - __ldg(cps + 2 * (s0 + k)) + 1, 0);
+        int inc = len;                                   // inclusive scan over the chunk
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, inc, o); if ((threadIdx.x & 31) >= o) inc += y; }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        int wbase = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += s_warp[w];
+        const int carry = s_carry;
+        s_off[threadIdx.x] = carry + wbase + inc - len;
+        __syncthreads();
+        for (int i = 0; i < min(256, S - c0); ++i) {     // all threads write one shot's frames at a time
+            if (!selected[s0 + c0 + i]) continue;
+            const int start = __ldg(cps + 2 * (s0 + c0 + i)), n = __ldg(cps + 2 * (s0 + c0 + i) + 1) - start + 1, o = s_off[i];
+            for (int f = threadIdx.x; f < n; f += 256)
+                if (o + f < room) out[o + f] = start + f;
+        }
+        __syncthreads();
+        if (threadIdx.x == 255) s_carry = carry + wbase + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counts_out[v] = s_carry;
+}
+
 __device__ __forceinline__ long long block_sum_i64(long long x, long long *smem) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
@@ -466,5 +505,16 @@ extern "C" int vsum_summary_fscore(const uint8_t *selected, const int32_t *cps,
     fscore_finalize_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, s>>>(
         reinterpret_cast<const long long *>(counts_ws), cu_users, B, method, f_out, per_user_out);
     VSUM_LAUNCH_OK("fscore_finalize_kernel");
+    return VSUM_OK;
+}
+
+extern "C" int vsum_summary_frames(const uint8_t *selected, const int32_t *cps, const int32_t *cu_shots,
+                                   const int64_t *out_offsets, int32_t B, int32_t *frames_out, int32_t *counts_out,
+                                   void *stream) {
+    VSUM_REQUIRE(B >= 0, VSUM_EINVAL, "vsum_summary_frames: negative batch");
+    if (B == 0) return VSUM_OK;
+    VSUM_REQUIRE(selected && cps && cu_shots && out_offsets && frames_out && counts_out, VSUM_EINVAL, "vsum_summary_frames: null pointer");
+    vsum::summary_frames_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(selected, cps, cu_shots, out_offsets, frames_out, counts_out);
+    VSUM_LAUNCH_OK("summary_frames_kernel");
     return VSUM_OK;
 }

@@ -27,7 +27,8 @@ EXPORTS = (
     "vsum_debug_gemm_tc05", "vsum_debug_wgrad_tc05", "vsum_debug_attention_tc05",
     "vsum_debug_attention_train_tc05", "vsum_debug_attention_bwd_tc05",
     "vsum_linear_workspace_bytes", "vsum_linear_forward", "vsum_linear_backward",
-    "vsum_rank_correlation_workspace_bytes", "vsum_rank_correlation",
+    "vsum_pack_open", "vsum_pack_close", "vsum_pack_num_videos", "vsum_pack_feature_dim", "vsum_pack_video_info",
+    "vsum_pack_array", "vsum_pack_collate", "vsum_summary_frames", "vsum_rank_correlation_workspace_bytes", "vsum_rank_correlation",
     "vsum_pretrain_saved_bytes", "vsum_pretrain_losses_forward", "vsum_pretrain_losses_backward",
     "vsum_profile_begin", "vsum_profile_end", "vsum_profile_num_categories", "vsum_profile_category_name",
 )
@@ -65,6 +66,13 @@ class ScorerGrads(C.Structure):
     _fields_ = [("embed_w", C.c_void_p), ("embed_b", C.c_void_p), ("final_w", C.c_void_p), ("final_b", C.c_void_p),
                 ("layers", LayerGrads * VSUM_MAX_LAYERS), ("pre_zeroed", C.c_int32)]
 
+
+class PackInfo(C.Structure):
+    _fields_ = [("name", C.c_char * 96), ("n_steps", C.c_int32), ("n_frames", C.c_int32), ("n_shots", C.c_int32),
+                ("n_users", C.c_int32), ("rep_dim", C.c_int32), ("has_user_scores", C.c_int32), ("user_summary_dtype", C.c_int32)]
+
+
+PACK_FEATURES, PACK_GTSCORE, PACK_PICKS, PACK_CHANGE_POINTS, PACK_USER_SUMMARY, PACK_USER_SCORES, PACK_VIDEO_REP = range(7)
 
 _lib = None
 
@@ -120,6 +128,17 @@ def load():
     L.vsum_pretrain_saved_bytes.argtypes = [i64, i32, i32]
     L.vsum_pretrain_losses_forward.argtypes = [vp, vp, vp, i32, i64, i32, i32, C.c_float, vp, i32, vp, vp, C.c_size_t, vp]
     L.vsum_pretrain_losses_backward.argtypes = [vp, vp, i32, i64, i32, i32, C.c_float, i32, vp, vp, vp, vp, vp]
+    L.vsum_pack_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.vsum_pack_close.argtypes = [vp]
+    L.vsum_pack_close.restype = None
+    L.vsum_pack_num_videos.argtypes = [vp]
+    L.vsum_pack_num_videos.restype = i32
+    L.vsum_pack_feature_dim.argtypes = [vp]
+    L.vsum_pack_feature_dim.restype = i32
+    L.vsum_pack_video_info.argtypes = [vp, i32, C.POINTER(PackInfo)]
+    L.vsum_pack_array.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_uint64)]
+    L.vsum_pack_collate.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+    L.vsum_summary_frames.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp]
     L.vsum_rank_correlation_workspace_bytes.restype = C.c_size_t
     L.vsum_rank_correlation_workspace_bytes.argtypes = [i64, i64, i32, i32]
     L.vsum_rank_correlation.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, i64, vp, C.c_size_t, vp, vp, vp, vp, vp]
