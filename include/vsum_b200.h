@@ -272,6 +272,20 @@ VSUM_API int vsum_pretrain_losses_backward(const float *x512, const int32_t *cu_
                                            void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Kernel temporal segmentation (src/data/preprocess/segmentations/kts/cpd_nonlin.py:5-91, cpd_auto.py:5-44):
+ * the change-point detection that produces the shot boundaries.  vsum_kts_gram: K = X X^T in fp32
+ * (create_segments.py:44; zeros_n = n floats of scratch).  vsum_kts_dp: scatters + dynamic programme for
+ * 0..m change points; scores_out fp64[m+1] = I[:, n], prev_out int32[(m+1)(n+1)] = the back-pointer table p
+ * (both on the device).  Given the same K, scores and back-pointers are bit-identical to the reference
+ * (float32 cumulative sums, fp64 scatters in its expression order, first-minimum rule); the host wrapper
+ * applies the penalty of cpd_auto.py:30-36 and back-tracks.
+ * ------------------------------------------------------------------------------------------ */
+VSUM_API size_t vsum_kts_workspace_bytes(int32_t n, int32_t m);
+VSUM_API int vsum_kts_gram(const float *features, int32_t n, int32_t dim, float *zeros_n, float *K_out, void *stream);
+VSUM_API int vsum_kts_dp(const float *K, int32_t n, int32_t m, int32_t lmin, int32_t lmax, void *workspace,
+                         size_t workspace_bytes, double *scores_out, int32_t *prev_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Data layer (host side; replaces the h5py / pad_sequence input path of src/data/dataset.py:64-168 and
  * src/train.py:115-118): a packed, memory-mapped dataset file (written by vsum_b200/data/packed.py) and a
  * multi-threaded padding-free collate that gathers a batch straight into one caller buffer (pinned

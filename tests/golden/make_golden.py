@@ -137,6 +137,40 @@ def scorer_goldens(mods):
     np.savez_compressed(os.path.join(HERE, "scorer_golden.npz"), **out)
 
 
+KTS_CASES = [(0, 80, 32, 10, 1, 100000), (1, 150, 64, 20, 1, 100000), (2, 60, 16, 5, 3, 20), (3, 40, 8, 39, 1, 100000),
+             (4, 33, 4, 0, 1, 100000), (5, 300, 128, 40, 2, 100000)]       # (seed, n, dim, ncp, lmin, lmax)
+
+
+def kts_features(seed, n, dim):
+    """Frame features with a few plateaus (so change points exist); float32 like the h5 features."""
+    rng = np.random.default_rng(seed)
+    x = rng.random((n, dim), dtype=np.float32)
+    for c in np.sort(rng.choice(np.arange(1, n), size=min(6, n - 1), replace=False)):
+        x[c:] += rng.random(dim, dtype=np.float32)
+    return x
+
+
+def kts_golden():
+    """Runs the reference's kts_segmentation (src/data/preprocess/segmentations/kts) on seeded kernels."""
+    import contextlib, importlib.util, io
+    d = os.path.join(REF, "data/preprocess/segmentations/kts")          # loaded as its own package: `data` needs h5py
+    spec = importlib.util.spec_from_file_location("ref_kts", os.path.join(d, "__init__.py"), submodule_search_locations=[d])
+    ref = importlib.util.module_from_spec(spec)
+    sys.modules["ref_kts"] = ref
+    spec.loader.exec_module(ref)
+    out = {"versions": versions(), "cases": np.array(KTS_CASES, dtype=np.int64)}
+    for seed, n, dim, ncp, lmin, lmax in KTS_CASES:
+        x = kts_features(seed, n, dim)
+        K = np.dot(x, x.T)
+        with contextlib.redirect_stdout(io.StringIO()):
+            cps, costs = ref.kts_segmentation(K, ncp, 1.0, lmin=lmin, lmax=lmax)
+            cps_fixed, scores = ref.cpd_nonlin(K, ncp, lmin=lmin, lmax=lmax, verbose=False)
+        out[f"K_{seed}"], out[f"cps_{seed}"], out[f"costs_{seed}"] = K, cps, costs
+        out[f"cpsfixed_{seed}"], out[f"scores_{seed}"] = cps_fixed, scores
+    np.savez_compressed(os.path.join(HERE, "kts_golden.npz"), **out)
+    print("kts_golden.npz written")
+
+
 @torch.no_grad()
 def pretrain_golden(mods):
     sp = importlib.import_module("model.simnet_pretrain")
@@ -162,6 +196,7 @@ if __name__ == "__main__":
     eval_metrics_golden(mods["evaluation"])
     scorer_goldens(mods)
     pretrain_golden(mods)
+    kts_golden()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -76,3 +76,20 @@ def test_scorer_restatement_matches_reference(scorer_golden, seeded_model_kwargs
     logits, feats = scorer_ref.scorer_forward(sd, x, num_heads=4)
     np.testing.assert_allclose(logits.view(-1).numpy(), scorer_golden[f"logits_{vid}"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(feats[0, :4].numpy(), scorer_golden[f"feats_head_{vid}"], rtol=1e-5, atol=1e-5)
+
+
+def test_kts_restatement_matches_reference_golden():
+    """oracle/kts_ref.py against the reference's own kts_segmentation / cpd_nonlin outputs (tests/golden/kts_golden.npz,
+    written by make_golden.py from src/data/preprocess/segmentations/kts): bit-exact costs, same change points."""
+    import os
+    from conftest import GOLDEN
+    from oracle import kts_ref
+    g = np.load(os.path.join(GOLDEN, "kts_golden.npz"))
+    for seed, n, dim, ncp, lmin, lmax in g["cases"]:
+        K = g[f"K_{seed}"]
+        cps, costs = kts_ref.kts_segmentation(K, int(ncp), 1.0, lmin=int(lmin), lmax=int(lmax))
+        assert np.array_equal(cps, g[f"cps_{seed}"])
+        assert np.array_equal(costs.view(np.int64), g[f"costs_{seed}"].view(np.int64))
+        cps2, scores = kts_ref.cpd_nonlin(K, int(ncp), lmin=int(lmin), lmax=int(lmax))
+        assert np.array_equal(cps2, g[f"cpsfixed_{seed}"])
+        assert np.array_equal(scores.view(np.int64), g[f"scores_{seed}"].view(np.int64))

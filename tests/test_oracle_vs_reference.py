@@ -77,3 +77,23 @@ def test_upsample_host_helper(ref_eval):
         sc = make_scores(v_id, n)
         assert bits_equal(ref_eval["cm"].upsample(sc, v.n_frames, v.picks), upsample(sc, v.n_frames, v.picks))
         assert bits_equal(ref_eval["cm"].upsample(sc, v.n_frames, v.picks), ref_port.upsample_scores(sc, v.n_frames, v.picks))
+
+
+def test_kts_port_against_live_reference():
+    """oracle/kts_ref.py == the reference's KTS (loaded as a stand-alone package: `data` itself needs h5py)."""
+    import contextlib, importlib.util, io
+    from oracle import kts_ref
+    d = os.path.join(REFERENCE, "data/preprocess/segmentations/kts")
+    spec = importlib.util.spec_from_file_location("ref_kts_live", os.path.join(d, "__init__.py"), submodule_search_locations=[d])
+    ref = importlib.util.module_from_spec(spec)
+    sys.modules["ref_kts_live"] = ref
+    spec.loader.exec_module(ref)
+    for seed, (n, dim, ncp, kw) in enumerate([(70, 16, 12, {}), (45, 8, 6, dict(lmin=2, lmax=15)), (20, 4, 19, {}), (90, 32, 1, {})]):
+        rng = np.random.default_rng(100 + seed)
+        x = rng.random((n, dim), dtype=np.float32)
+        x[n // 3:] += 0.7
+        K = np.dot(x, x.T)
+        with contextlib.redirect_stdout(io.StringIO()):
+            want = ref.kts_segmentation(K, ncp, 0.8, **kw)
+        got = kts_ref.kts_segmentation(K, ncp, 0.8, **kw)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1].view(np.int64), want[1].view(np.int64))

@@ -27,6 +27,7 @@ EXPORTS = (
     "vsum_debug_gemm_tc05", "vsum_debug_wgrad_tc05", "vsum_debug_attention_tc05",
     "vsum_debug_attention_train_tc05", "vsum_debug_attention_bwd_tc05",
     "vsum_linear_workspace_bytes", "vsum_linear_forward", "vsum_linear_backward",
+    "vsum_kts_workspace_bytes", "vsum_kts_gram", "vsum_kts_dp",
     "vsum_pack_open", "vsum_pack_close", "vsum_pack_num_videos", "vsum_pack_feature_dim", "vsum_pack_video_info",
     "vsum_pack_array", "vsum_pack_collate", "vsum_summary_frames", "vsum_rank_correlation_workspace_bytes", "vsum_rank_correlation",
     "vsum_pretrain_saved_bytes", "vsum_pretrain_losses_forward", "vsum_pretrain_losses_backward",
@@ -128,6 +129,10 @@ def load():
     L.vsum_pretrain_saved_bytes.argtypes = [i64, i32, i32]
     L.vsum_pretrain_losses_forward.argtypes = [vp, vp, vp, i32, i64, i32, i32, C.c_float, vp, i32, vp, vp, C.c_size_t, vp]
     L.vsum_pretrain_losses_backward.argtypes = [vp, vp, i32, i64, i32, i32, C.c_float, i32, vp, vp, vp, vp, vp]
+    L.vsum_kts_workspace_bytes.restype = C.c_size_t
+    L.vsum_kts_workspace_bytes.argtypes = [i32, i32]
+    L.vsum_kts_gram.argtypes = [vp, i32, i32, vp, vp, vp]
+    L.vsum_kts_dp.argtypes = [vp, i32, i32, i32, i32, vp, C.c_size_t, vp, vp, vp]
     L.vsum_pack_open.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.vsum_pack_close.argtypes = [vp]
     L.vsum_pack_close.restype = None
