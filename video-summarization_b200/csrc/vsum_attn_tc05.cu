@@ -226,9 +226,16 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
         for (int ch = 0; ch < 8; ++ch) p_off[ch] = (uint32_t)((ch ^ (r & 7)) << 4);
         const float2 c2 = make_float2(scale_log2e, scale_log2e);
 
+#ifdef VSUM_ATTN_TIMING
+        long long tph[6] = {0, 0, 0, 0, 0, 0}, tmark = clock64();
+#define TMARK(i) do { const long long _n = clock64(); tph[i] += _n - tmark; tmark = _n; } while (0)
+#else
+#define TMARK(i) do { } while (0)
+#endif
         for (int j = 0; j < nkv; ++j) {
             uint32_t s[64];
             tc::mbar_wait(s_full, j & 1);
+            TMARK(0);
             tc::tc_fence_after();
             {
                 uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
@@ -239,6 +246,7 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
             tc::tmem_wait_ld();
             tc::tc_fence_before();
             tc::mbar_arrive(s_empty);
+            TMARK(1);
 
             const int valid = n - j * BKV - hf * 64;      // keys of this half-tile inside the video
             if (valid < 64) {
@@ -269,7 +277,9 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
             if (__any_sync(0xffffffffu, bump)) {
                 if (bump) { alpha = ex2(m_run - mx); m_run = mx; }      // alpha = 0 on the first tile
             }
+            TMARK(2);
             tc::mbar_wait(p_empty + (j & 1), ((j >> 1) & 1) ^ 1);    // PV(j-2) done: this P buffer is free
+            TMARK(3);
             if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {   // rare: rescale my 32 columns of O
                 tc::mbar_wait(p_empty + ((j - 1) & 1), ((j - 1) >> 1) & 1);   // PV(j-1) done: O is stable
                 tc::tc_fence_after();
@@ -311,12 +321,19 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
                              "r"(pack2(pv[1].x, pv[1].y)), "r"(pack2(pv[2].x, pv[2].y)), "r"(pack2(pv[3].x, pv[3].y))
                              : "memory");
             }
+            TMARK(4);
             tc::fence_proxy_async_smem();
             tc::tc_fence_before();
             tc::mbar_arrive(p_full + (j & 1));
+            TMARK(5);
             const float2 pq = fadd2(fadd2(ps[0], ps[1]), fadd2(ps[2], ps[3]));
             l_part = fmaf(l_part, alpha, pq.x + pq.y);
         }
+#ifdef VSUM_ATTN_TIMING
+        if (blockIdx.x == 700 && blockIdx.y == 1 && lane == 0)
+            printf("warp %2d nkv %d | wait S %lld | tmem ld %lld | max+exchange %lld | wait P buf %lld | exps+stores %lld | fence+arrive %lld (clk per tile)\n",
+                   warp, nkv, tph[0] / nkv, tph[1] / nkv, tph[2] / nkv, tph[3] / nkv, tph[4] / nkv, tph[5] / nkv);
+#endif
         // epilogue: O / l for my 32 head-dim columns of this row
         tc::mbar_wait(p_empty + ((nkv - 1) & 1), ((nkv - 1) >> 1) & 1);   // last PV done
         tc::tc_fence_after();
