@@ -191,21 +191,32 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             tc::tc_fence_before();
             tc::mbar_arrive(sdp_empty);
 
-            // Pd -> s[], dS -> g[]  (fp32 in place)
+            // Pd -> s[], dS -> g[]  (fp32 in place); the tail-masked and the dropout variants are separate
+            // warp-uniform paths so the common full, p = 0 tile pays for neither
+            if (valid_k < 64) {
 #pragma unroll
-            for (int c = 0; c < 64; c += 4) {
-                unsigned long long z = ~0ull;
-                if (drop_thresh16 != 0)
-                    z = dropout_bits64(seed, attn_drop_group_index(base + qr, h_idx, NH, (k0 + hf * 64 + c) >> 2));
+                for (int c = 0; c < 64; ++c)
+                    if (c >= valid_k) s[c] = 0xff800000u;         // exp2(-inf) = 0: key past the end of the video
+            }
+            if (drop_thresh16 != 0) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float p = ex2(fmaf(__uint_as_float(s[c + e]), scale_log2e, -lse_r));
-                    if (c + e >= valid_k) p = 0.f;
-                    const bool keep = (uint32_t)((z >> (16 * e)) & 0xffffu) >= drop_thresh16;
-                    const float ks = keep ? keep_scale : 0.f;
-                    const float dpd = __uint_as_float(g[c + e]) * ks;
-                    s[c + e] = __float_as_uint(p * ks);
-                    g[c + e] = __float_as_uint(p * (dpd - dl_r));
+                for (int c = 0; c < 64; c += 4) {
+                    const unsigned long long z = dropout_bits64(seed, attn_drop_group_index(base + qr, h_idx, NH, (k0 + hf * 64 + c) >> 2));
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float p = ex2(fmaf(__uint_as_float(s[c + e]), scale_log2e, -lse_r));
+                        const float ks = (uint32_t)((z >> (16 * e)) & 0xffffu) >= drop_thresh16 ? keep_scale : 0.f;
+                        const float dpd = __uint_as_float(g[c + e]) * ks;
+                        s[c + e] = __float_as_uint(p * ks);
+                        g[c + e] = __float_as_uint(p * (dpd - dl_r));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 64; ++c) {
+                    const float p = ex2(fmaf(__uint_as_float(s[c]), scale_log2e, -lse_r));
+                    s[c] = __float_as_uint(p);
+                    g[c] = __float_as_uint(p * (__uint_as_float(g[c]) - dl_r));
                 }
             }
             if (i > 0) {   // MMAs of block i-1 done: Pd / dS buffers are free and dQ(i-1) is complete
