@@ -102,7 +102,7 @@ VSUM_API int vsum_scorer_forward(vsum_scorer_t h, const float *features, const i
                         size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
- * Training step of the scorer (fp32 kernels): replaces autograd through SimNet.forward as used by
+ * Training step of the scorer: replaces autograd through SimNet.forward as used by
  * src/train.py:111-131 and src/pretrain.py:49-86, including the four dropout sites of
  * simnet.py:107,110,159,181 (counter-based masks recomputed from `seed` in the backward pass).
  *   forward_train keeps every activation the backward needs in `tape` (vsum_scorer_tape_bytes);

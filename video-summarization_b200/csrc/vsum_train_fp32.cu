@@ -1,5 +1,6 @@
-// fp32 training path of the frame scorer (first correct version: plain SIMT kernels, fp32
-// everywhere).  Backward of everything under SimNet.forward (src/model/simnet.py:32-45) plus the
+// fp32 SIMT kernels of the scorer's training path: the exact (2e-4 vs autograd) mode of every op and the
+// element-wise / LayerNorm / loss kernels all modes share (the tensor-core linears and attention live in
+// vsum_gemm_tc05.cu, vsum_wgrad_tc05.cu, vsum_attn_tc05.cu, vsum_attn_bwd_tc05.cu).  Backward of everything under SimNet.forward (src/model/simnet.py:32-45) plus the
 // masked MSE of src/utils/utils.py:45-56, as called by src/train.py:111-131.
 // Dropout (simnet.py:107,110,159,181) is counter-based: masks are recomputed from (seed, index).
 #include "vsum_kernels.cuh"

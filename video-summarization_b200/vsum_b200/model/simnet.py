@@ -93,7 +93,7 @@ def _layer_tensors(blk):
 
 
 class _ScorerTrainFn(torch.autograd.Function):
-    """Autograd bridge to vsum_scorer_forward_train / vsum_scorer_backward (fp32 kernels)."""
+    """Autograd bridge to vsum_scorer_forward_train / vsum_scorer_backward (arithmetic per `train_precision`)."""
 
     @staticmethod
     def forward(ctx, model, features, cu_seqlens, seqlens_host, drop_p, seed, *params):
@@ -307,7 +307,7 @@ class SimNet(nn.Module):
         yield self.final_layer.bias
 
     def forward_packed_train(self, features: Tensor, cu_seqlens: Tensor, seqlens_host: Sequence[int]):
-        """Differentiable packed forward (fp32 kernels + native backward).  Dropout follows
+        """Differentiable packed forward (native forward with tape + native backward).  Dropout follows
         `self.training` / `self.dropout` like nn.Dropout in the reference (simnet.py:107,110,159,181)."""
         if not features.is_cuda:
             raise _cabi.VsumError("vsum_b200 runs on CUDA devices only (no CPU fallback)")
