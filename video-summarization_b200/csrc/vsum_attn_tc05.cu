@@ -9,9 +9,8 @@
 //   S = Q K^T      : A = Q tile (K-major, SW128), B = K tile (K-major, SW128)   -> TMEM [128 x 128] fp32
 //   softmax        : tcgen05.ld S -> registers, online max/sum in the exp2 domain, P -> bf16 ->
 //                    128B-swizzled shared memory (K-major A operand of the second MMA)
-//   O_j = P V_j    : B = V tile as loaded by TMA ([key][head_dim], i.e. MN-major, SW128)
-//                    -> TMEM [128 x 64] fp32, double buffered; accumulated and rescaled in
-//                    registers: O = (O + O_{j-1}) * exp2(m_{j-1} - m_j)
+//   O_h += P_h V_h : B = V tile as loaded by TMA ([key][head_dim], i.e. MN-major, SW128); one fp32
+//                    accumulator [128 x 64] in TMEM per 64-key half h of the tiles, merged in the epilogue
 // Packed layout: a tile may read rows of the next video (or TMA zero fill past T); those key
 // columns are masked to -inf and those query rows are never stored.
 #include "vsum_kernels.cuh"
@@ -28,8 +27,8 @@ constexpr int NH = 4;
 constexpr int BQ = 128, BKV = 128;
 constexpr int TILE_BYTES = 128 * 128;   // 128 rows x 64 bf16 = 16 KB
 constexpr int ATT_THREADS = 384;        // 4 control warps + 8 softmax warps
-constexpr int ATT_TMEM_COLS = 256;      // S: [0,128)  O: [128,192)  row-max / row-sum exchange: [192,198)
-constexpr size_t ATT_SMEM = 7 * (size_t)TILE_BYTES + 128;   // Q, K0, V0, K1, V1, P(2 halves) + barriers: 2 CTAs / SM
+constexpr int ATT_TMEM_COLS = 256;      // S: [0,128)  O of key half 0: [128,192)  O of key half 1: [192,256)
+constexpr size_t ATT_SMEM = 7 * (size_t)TILE_BYTES + 128;   // Q, K, V, P (2 buffers x 2 halves) + barriers: 2 CTAs / SM
 
 __device__ __forceinline__ float ex2(float x) {
     float y;
@@ -98,9 +97,13 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 
 // One CTA = (video, head, 128 queries); 2 CTAs / SM.  Each query row is shared by TWO softmax
 // threads (64 key columns each, warps q+4 and q+8 of the same TMEM lane quarter), which puts four
-// softmax warps on every SM sub-partition -- the MUFU pipe, not issue latency, becomes the limit.
-// O accumulates in TMEM across KV tiles; the exponent reference only moves when the row max grew
-// by more than 2^8 (lazy rescale), so the read-modify-write of O is rare.
+// softmax warps on every SM sub-partition.  The two threads never talk inside the KV loop: each
+// 64-key half of a row has its own exponent reference, row sum and its own O accumulator in TMEM
+// (O0: keys 0..63 of every tile, O1: keys 64..127; the PV MMA of a tile is split accordingly), and the
+// halves are merged once in the epilogue: O = (O0 2^(m0-m) + O1 2^(m1-m)) / (l0 2^(m0-m) + l1 2^(m1-m)).
+// (A per-tile row-max exchange through TMEM + a named barrier cost ~450 of 2800 clk per tile.)
+// The exponent reference only moves when the half-row max grew by more than 2^8 (lazy rescale), so
+// the read-modify-write of O is rare.
 // TRAIN: additionally writes the log-sum-exp of every (row, head) in the exp2 domain for the backward
 // kernel (vsum_attn_bwd_tc05.cu) and applies dropout to P (simnet.py:159); the row sum stays un-dropped.
 template <bool TRAIN>
@@ -145,7 +148,7 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tS = tmem_base, tO = tmem_base + 128, tX = tmem_base + 192;
+    const uint32_t tS = tmem_base, tO = tmem_base + 128;          // tO + 64 * half: one accumulator per 64-key half
 
     if (warp < 4) {
         tc::setmaxnreg_dec<32>();
@@ -203,9 +206,9 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
                 const uint64_t p_desc = p_desc0 + (uint64_t)((j & 1) * (2 * TILE_BYTES >> 4));
                 if (tc::elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BKV / 16; ++k)
-                        tc::mma_f16_ss(tO, p_desc + (uint64_t)((k >> 2) * (TILE_BYTES >> 4) + (k & 3) * 2),
-                                       v_desc + (uint64_t)(k * v_step), IDESC_PV, (j | k) != 0);   // O accumulates over all KV tiles
+                    for (int k = 0; k < BKV / 16; ++k)               // keys 0..63 -> O half 0, keys 64..127 -> O half 1
+                        tc::mma_f16_ss(tO + (uint32_t)((k >> 2) * HD), p_desc + (uint64_t)((k >> 2) * (TILE_BYTES >> 4) + (k & 3) * 2),
+                                       v_desc + (uint64_t)(k * v_step), IDESC_PV, (j | (k & 3)) != 0);   // accumulates over all KV tiles
                     tc::mma_commit(v_empty);
                     tc::mma_commit(p_empty + (j & 1));           // also means "PV(j) done"
                 }
@@ -217,9 +220,9 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
         const int qd = warp & 3, hf = (warp - 4) >> 2;       // TMEM lane quarter, column half
         const int r = qd * 32 + lane;
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        const uint32_t tS_h = tS + lane_off + hf * 64, tO_h = tO + lane_off + hf * 32, tX_q = tX + lane_off;
-        const int pair_bar = 2 + qd;                          // named barrier of the two warps sharing these rows
-        float m_run = -INFINITY, l_part = 0.f;                // m_run: exponent reference (exp2 domain)
+        const uint32_t tS_h = tS + lane_off + hf * 64, tO_mine = tO + lane_off + hf * HD;   // my key half's own accumulator
+        const int pair_bar = 2 + qd;                          // named barrier of the two warps sharing these rows (epilogue only)
+        float m_run = -INFINITY, l_part = 0.f;                // exponent reference (exp2 domain) and row sum of MY key half
         const uint32_t p_row_u32 = tc::smem_u32(sP) + (uint32_t)hf * TILE_BYTES + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
         uint32_t p_off[8];                                    // swizzled 16-byte chunk offsets of this row
 #pragma unroll
@@ -263,35 +266,33 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
                 for (int e = 0; e < 8; ++e) mx8[e] = fmaxf(mx8[e], __uint_as_float(s[c + e]));
             const float mxl = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
                                     fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]))) * scale_log2e;
-            // row max across the two halves: through two spare TMEM columns (parity double-buffered)
-            const uint32_t xcol = tX_q + (uint32_t)((j & 1) * 2);
-            tc::tmem_st1(xcol + hf, __float_as_uint(mxl));
-            tc::tmem_wait_st();
-            tc::tc_fence_before();
-            tc::bar_sync(pair_bar, 64);
-            tc::tc_fence_after();
-            const float mx = fmaxf(mxl, __uint_as_float(tc::tmem_ld1(xcol + (hf ^ 1))));
-            tc::tmem_wait_ld();
+            // No exchange with the partner thread: each 64-key half of a row keeps its own exponent reference, row sum
+            // and O accumulator in TMEM; the two halves are merged once, in the epilogue.
+            const float mx = mxl;
             float alpha = 1.0f;
-            const bool bump = mx > m_run + 8.0f;              // identical decision in both threads of the row
+            const bool bump = mx > m_run + 8.0f;
             if (__any_sync(0xffffffffu, bump)) {
                 if (bump) { alpha = ex2(m_run - mx); m_run = mx; }      // alpha = 0 on the first tile
             }
             TMARK(2);
             tc::mbar_wait(p_empty + (j & 1), ((j >> 1) & 1) ^ 1);    // PV(j-2) done: this P buffer is free
             TMARK(3);
-            if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {   // rare: rescale my 32 columns of O
+            if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {   // rare: rescale my accumulator (64 columns of my row)
                 tc::mbar_wait(p_empty + ((j - 1) & 1), ((j - 1) >> 1) & 1);   // PV(j-1) done: O is stable
                 tc::tc_fence_after();
-                uint32_t t[32];
-                tc::tmem_ld32(tO_h, t);
-                tc::tmem_wait_ld();
+#pragma unroll 1
+                for (int hc = 0; hc < 2; ++hc) {
+                    uint32_t t[32];
+                    tc::tmem_ld32(tO_mine + hc * 32, t);
+                    tc::tmem_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
-                tc::tmem_st32(tO_h, t);
-                tc::tmem_wait_st();
+                    for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+                    tc::tmem_st32(tO_mine + hc * 32, t);
+                    tc::tmem_wait_st();
+                }
             }
-            const float2 nm2 = make_float2(-m_run, -m_run);
+            const float nm = m_run == -INFINITY ? 0.f : -m_run;      // no valid key in my half so far: exp2(-inf) = 0, not NaN
+            const float2 nm2 = make_float2(nm, nm);
             const uint32_t p_buf = p_row_u32 + (uint32_t)(j & 1) * 2 * TILE_BYTES;
             float2 ps[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
@@ -337,17 +338,25 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
         // epilogue: O / l for my 32 head-dim columns of this row
         tc::mbar_wait(p_empty + ((nkv - 1) & 1), ((nkv - 1) >> 1) & 1);   // last PV done
         tc::tc_fence_after();
-        tc::tmem_st1(tX_q + 4 + hf, __float_as_uint(l_part));
-        tc::tmem_wait_st();
-        tc::tc_fence_before();
+        // merge the two key halves of the row: (m, l) through the Q tile's shared memory (dead after the last QK^T)
+        float2 *xch = reinterpret_cast<float2 *>(sQ);
+        xch[hf * 128 + r] = make_float2(m_run, l_part);
         tc::bar_sync(pair_bar, 64);
-        tc::tc_fence_after();
-        const float l_tot = l_part + __uint_as_float(tc::tmem_ld1(tX_q + 4 + (hf ^ 1)));
+        const float2 oth = xch[(hf ^ 1) * 128 + r];
+        const float m_all = fmaxf(m_run, oth.x);
+        const float a_mine = m_run == -INFINITY ? 0.f : ex2(m_run - m_all), a_oth = oth.x == -INFINITY ? 0.f : ex2(oth.x - m_all);
+        const float l_tot = l_part * a_mine + oth.y * a_oth;
         uint32_t t[32];
-        tc::tmem_ld32(tO_h, t);
-        tc::tmem_wait_ld();
+        {
+            uint32_t to[32];
+            tc::tmem_ld32(tO + lane_off + hf * HD + hf * 32, t);             // my 32 output columns of my half's accumulator
+            tc::tmem_ld32(tO + lane_off + (hf ^ 1) * HD + hf * 32, to);      // ... and of the partner's
+            tc::tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * a_mine + __uint_as_float(to[i]) * a_oth);
+        }
         const float inv = (TRAIN ? keep_scale : 1.0f) / l_tot;
-        if (TRAIN && hf == 0 && q0 + r < n) lse2[(int64_t)(base + q0 + r) * NH + h_idx] = m_run + log2f(l_tot);
+        if (TRAIN && hf == 0 && q0 + r < n) lse2[(int64_t)(base + q0 + r) * NH + h_idx] = m_all + log2f(l_tot);
         if (TRAIN) {   // fp32 output: the backward's delta = rowsum(dO o O) must not see a rounded O
             if (q0 + r < n) {
                 float *dst = reinterpret_cast<float *>(out) + (int64_t)(base + q0 + r) * DM + h_idx * HD + hf * 32;
