@@ -130,14 +130,19 @@ def test_wgrad_tc05(M, N, K, bf16):
 
 
 def _drop_keep(seed, q_rows, h, keys, thresh):
-    """numpy restatement of the grouped dropout hash (vsum_kernels.cuh: dropout_bits64 / attn_drop_group_index)."""
+    """numpy restatement of the grouped dropout draw (vsum_kernels.cuh: dropout_bits64 = 4 Philox-2x32 rounds,
+    attn_drop_group_index)."""
+    M32 = np.uint64(0xFFFFFFFF)
     with np.errstate(over="ignore"):
         idx = ((q_rows.astype(np.uint64)[:, None] * np.uint64(4) + np.uint64(h)) << np.uint64(20)) \
             ^ (keys.astype(np.uint64)[None, :] >> np.uint64(2)) ^ np.uint64(0x5A5A000000000000)
-        z = np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * (idx + np.uint64(1))
-        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-        z = z ^ (z >> np.uint64(31))
+        x0, x1 = idx & M32, idx >> np.uint64(32)
+        k = (np.uint64(seed) & M32) ^ (((np.uint64(seed) >> np.uint64(32)) * np.uint64(0x85EBCA6B)) & M32)
+        for _ in range(4):
+            m = x0 * np.uint64(0xD256D193)
+            x0, x1 = ((m >> np.uint64(32)) ^ k ^ x1) & M32, m & M32
+            k = (k + np.uint64(0x9E3779B9)) & M32
+        z = (x0 << np.uint64(32)) | x1
         lane = (keys.astype(np.uint64)[None, :] & np.uint64(3)) * np.uint64(16)
         return ((z >> lane) & np.uint64(0xFFFF)) >= np.uint64(thresh)
 

@@ -13,7 +13,7 @@ cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, dev
 tgt = torch.rand(1, T, device="cuda")
 nopad = torch.zeros(1, T, dtype=torch.bool, device="cuda")
 for prec in ("fp32", "tf32", "bf16"):
-    model = SimNet(num_heads=4, d_model=256, num_layers=4, sparsity=0., dropout=0.3).cuda().train()
+    model = SimNet(num_heads=4, d_model=256, num_layers=4, sparsity=0., dropout=float(__import__("os").environ.get("DROP", "0.3"))).cuda().train()
     model.train_precision = prec
     def step():
         model.zero_grad(set_to_none=True)

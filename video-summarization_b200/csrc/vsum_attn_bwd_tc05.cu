@@ -169,6 +169,12 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             }
         };
 
+#ifdef VSUM_BWD_TIMING
+        long long tph[7] = {0, 0, 0, 0, 0, 0, 0}, tmark = clock64();
+#define TMB(i) do { const long long _n = clock64(); tph[i] += _n - tmark; tmark = _n; } while (0)
+#else
+#define TMB(i) do { } while (0)
+#endif
         for (int i = 0; i < nq; ++i) {
             const int qr = i * BLK + r;
             const bool vq = qr < n;
@@ -176,6 +182,7 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             const float dl_r = vq ? __ldg(delta + (int64_t)(base + qr) * NH + h_idx) : 0.f;
             uint32_t s[64], g[64];
             tc::mbar_wait(sdp_full, i & 1);
+            TMB(0);
             tc::tc_fence_after();
             {
                 uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
@@ -190,6 +197,7 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             tc::tmem_wait_ld();
             tc::tc_fence_before();
             tc::mbar_arrive(sdp_empty);
+            TMB(1);
 
             // Pd -> s[], dS -> g[]  (fp32 in place); the tail-masked and the dropout variants are separate
             // warp-uniform paths so the common full, p = 0 tile pays for neither
@@ -219,8 +227,10 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                     g[c] = __float_as_uint(p * (__uint_as_float(g[c]) - dl_r));
                 }
             }
+            TMB(2);
             if (i > 0) {   // MMAs of block i-1 done: Pd / dS buffers are free and dQ(i-1) is complete
                 tc::mbar_wait(done345, (i - 1) & 1);
+                TMB(3);
                 tc::tc_fence_after();
                 uint32_t(&t)[32] = *reinterpret_cast<uint32_t(*)[32]>(&dq[0]);
                 tc::tmem_ld32(tDQ + lane_off + hf * 32, t);
@@ -241,11 +251,19 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                              "r"(pack2(__uint_as_float(g[c + 4]), __uint_as_float(g[c + 5]))), "r"(pack2(__uint_as_float(g[c + 6]), __uint_as_float(g[c + 7])))
                              : "memory");
             }
+            TMB(4);
             tc::fence_proxy_async_smem();
             tc::tc_fence_before();
             tc::mbar_arrive(pds_full);
+            TMB(5);
             if (i > 0) flush_dq(i - 1);
+            TMB(6);
         }
+#ifdef VSUM_BWD_TIMING
+        if (blockIdx.x == 70 && blockIdx.y == 1 && lane == 0 && (warp == 4 || warp == 9))
+            printf("bwd warp %2d nq %d | wait S,dP %lld | tmem ld %lld | exps, dS %lld | wait MMA345(i-1) %lld | dQ ld + P,dS stores %lld | fence+arrive %lld | dQ atomics %lld (clk per query block)\n",
+                   warp, nq, tph[0] / nq, tph[1] / nq, tph[2] / nq, tph[3] / nq, tph[4] / nq, tph[5] / nq, tph[6] / nq);
+#endif
         // last dQ block, then dK / dV of my key row
         tc::mbar_wait(done345, (nq - 1) & 1);
         tc::tc_fence_after();

@@ -307,19 +307,18 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
                         pv[e] = make_float2(ex2(x.x), ex2(x.y));
                     ps[e] = fadd2(ps[e], pv[e]);
                 }
-                if (TRAIN && drop_thresh16 != 0) {            // two 4-key groups per 8 columns
+                uint32_t w[4] = {pack2(pv[0].x, pv[0].y), pack2(pv[1].x, pv[1].y), pack2(pv[2].x, pv[2].y), pack2(pv[3].x, pv[3].y)};
+                if (TRAIN && drop_thresh16 != 0) {            // two 4-key groups per 8 columns; the row sum above stays un-dropped
+                    const uint32_t th2 = drop_thresh16 * 0x00010001u;
 #pragma unroll
-                    for (int g = 0; g < 2; ++g) {
+                    for (int g = 0; g < 2; ++g) {             // 16-bit lane k of the draw <-> key 4g+k <-> half-word of the packed pair
                         const int key = j * BKV + hf * 64 + c + 4 * g;
                         const unsigned long long z = dropout_bits64(seed, attn_drop_group_index(base + q0 + r, h_idx, NH, key >> 2));
-                        if ((uint32_t)(z & 0xffffu) < drop_thresh16) pv[2 * g].x = 0.f;
-                        if ((uint32_t)((z >> 16) & 0xffffu) < drop_thresh16) pv[2 * g].y = 0.f;
-                        if ((uint32_t)((z >> 32) & 0xffffu) < drop_thresh16) pv[2 * g + 1].x = 0.f;
-                        if ((uint32_t)(z >> 48) < drop_thresh16) pv[2 * g + 1].y = 0.f;
+                        w[2 * g] &= __vcmpgeu2((uint32_t)z, th2);
+                        w[2 * g + 1] &= __vcmpgeu2((uint32_t)(z >> 32), th2);
                     }
                 }
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_buf + p_off[c >> 3]), "r"(pack2(pv[0].x, pv[0].y)),
-                             "r"(pack2(pv[1].x, pv[1].y)), "r"(pack2(pv[2].x, pv[2].y)), "r"(pack2(pv[3].x, pv[3].y))
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_buf + p_off[c >> 3]), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
                              : "memory");
             }
             TMARK(4);

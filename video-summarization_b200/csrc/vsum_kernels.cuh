@@ -38,11 +38,20 @@ __host__ __device__ __forceinline__ unsigned long long attn_drop_index(long long
 }
 // Tensor-core attention (training): one 64-bit draw decides FOUR consecutive keys of a query row, 16 bits
 // each (drop iff bits < thresh16 = round(p * 65536)), so forward and backward hash once per 4 elements.
+// The draw is four Philox-2x32 rounds (mulhi/mullo by 0xD256D193, key schedule += 0x9E3779B9) keyed by the
+// 64-bit seed: one IMAD.WIDE + one LOP3 per round, ~2 instructions per attention element -- the splitmix64
+// used by the other dropout sites costs ~7 on 32-bit ALUs and doubled the forward kernel's time.
 __host__ __device__ __forceinline__ unsigned long long dropout_bits64(unsigned long long seed, unsigned long long idx) {
-    unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (idx + 1);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-    return z ^ (z >> 31);
+    unsigned int x0 = (unsigned int)idx, x1 = (unsigned int)(idx >> 32);
+    unsigned int k = (unsigned int)seed ^ ((unsigned int)(seed >> 32) * 0x85EBCA6Bu);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const unsigned long long m = (unsigned long long)x0 * 0xD256D193ull;
+        x0 = (unsigned int)(m >> 32) ^ k ^ x1;
+        x1 = (unsigned int)m;
+        k += 0x9E3779B9u;
+    }
+    return ((unsigned long long)x0 << 32) | x1;
 }
 __host__ __device__ __forceinline__ unsigned long long attn_drop_group_index(long long q_row, int h, int H, int key_group) {
     return ((unsigned long long)(q_row * H + h) << 20) ^ (unsigned long long)key_group ^ 0x5A5A000000000000ULL;
