@@ -183,6 +183,10 @@ knapsack_kernel(const double *__restrict__ val, const int32_t *__restrict__ wt,
         const int w_min = wi > 1 ? wi : 1;                // K[i][0] stays 0 (line 14)
         const double *rd = row + tid - wi;                // rd[k*THREADS] = K[i-1][w - wt]
         uint32_t *bw = bits + (int64_t)i * WORDS + warp;  // this warp's ballot word of chunk k: bw[k*THREADS/32]
+        // Lane k keeps the ballot word of chunk k (and k + 32) in a register and the warp writes them with two
+        // predicated stores after the loop: a store by lane 0 inside the loop costs a divergent branch per chunk,
+        // which -- not shared memory or FP64 -- dominated the row update (profiles/r01_knapsack_phases.txt).
+        uint32_t my_lo = 0, my_hi = 0;
 #pragma unroll
         for (int k = 0; k < EPT; ++k) {
             const bool can = k * THREADS + tid >= w_min;
@@ -193,8 +197,11 @@ knapsack_kernel(const double *__restrict__ val, const int32_t *__restrict__ wt,
             const bool take = can && !(b >= a);
             cur[k] = take ? a : b;
             const unsigned word = __ballot_sync(0xffffffffu, take);
-            if (lane == 0) bw[k * (THREADS / 32)] = word;
+            if (k < 32) my_lo = lane == k ? word : my_lo;
+            else my_hi = lane == k - 32 ? word : my_hi;
         }
+        if (lane < (EPT < 32 ? EPT : 32)) bw[lane * (THREADS / 32)] = my_lo;
+        if (EPT > 32 && lane < EPT - 32) bw[(32 + lane) * (THREADS / 32)] = my_hi;
         __syncthreads();                                  // everyone has read the old row
 #pragma unroll
         for (int k = 0; k < EPT; ++k) row[k * THREADS + tid] = cur[k];
