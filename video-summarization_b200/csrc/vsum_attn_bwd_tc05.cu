@@ -332,11 +332,7 @@ int launch_attention_bwd_tc05(const __nv_bfloat16 *qkv16, const __nv_bfloat16 *d
     int rc = make_tensor_map_2d(&tmQKV, qkv16, 2, 3 * DM, (uint64_t)T, (uint64_t)3 * DM * 2, 64, 128);
     if (rc) return rc;
     if ((rc = make_tensor_map_2d(&tmDO, dO16, 2, DM, (uint64_t)T, (uint64_t)DM * 2, 64, 128))) return rc;
-    static bool configured = false;
-    if (!configured) {
-        VSUM_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
-        configured = true;
-    }
+    VSUM_ONCE_PER_DEVICE(VSUM_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM)));
     // dQ is accumulated with red.add from every key block; dK / dV rows are each written by one CTA
     VSUM_CUDA_OK(cudaMemsetAsync(dqkv, 0, (size_t)T * 3 * DM * sizeof(float), s));
     const uint32_t thresh = attn_drop_thresh16(drop_p);

@@ -437,12 +437,7 @@ int launch_attention_tc05(const __nv_bfloat16 *qkv, const int32_t *cu_seqlens, c
     CUtensorMap tm;
     int rc = make_tensor_map_2d(&tm, qkv, 2, 3 * DM, (uint64_t)T, (uint64_t)3 * DM * 2, 64, 128);
     if (rc) return rc;
-    static bool configured = false;
-    if (!configured) {
-        VSUM_CUDA_OK(cudaFuncSetAttribute(attn_tc05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
-        VSUM_CUDA_OK(cudaFuncSetAttribute(attn_tc05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
-        configured = true;
-    }
+    VSUM_ONCE_PER_DEVICE(VSUM_CUDA_OK(cudaFuncSetAttribute(attn_tc05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM)); VSUM_CUDA_OK(cudaFuncSetAttribute(attn_tc05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM)));
     // V operand descriptor (MN-major, 128B swizzle): 8-key groups are 1024 bytes apart (SBO); the
     // 64-wide head dim is a single swizzle atom so LBO is unused; one MMA K step = 16 keys = 2048 B.
     uint32_t v_lbo = 16, v_sbo = 1024, v_kstep = 2048;

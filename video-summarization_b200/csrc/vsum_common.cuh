@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <cstdarg>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 
@@ -42,6 +43,20 @@ int scorer_sm_reserve();    // persistent scorer GEMMs leave this many SMs free
             return ::vsum::set_error(VSUM_ECUDA, "launch of %s failed: %s", name,               \
                                      cudaGetErrorString(_e));                                   \
         ::vsum::count_launch();                                                                 \
+    } while (0)
+
+// cudaFuncSetAttribute applies to the CURRENT device only: run `stmt` once per device (a process may drive several
+// GPUs through one copy of the library).  Racing threads at worst set the same attribute twice.
+#define VSUM_ONCE_PER_DEVICE(stmt)                                                               \
+    do {                                                                                        \
+        static std::atomic<unsigned long long> _done{0};                                        \
+        int _dev = 0;                                                                           \
+        VSUM_CUDA_OK(cudaGetDevice(&_dev));                                                     \
+        const unsigned long long _bit = 1ull << (_dev & 63);                                    \
+        if (!(_done.load(std::memory_order_acquire) & _bit)) {                                  \
+            stmt;                                                                               \
+            _done.fetch_or(_bit, std::memory_order_release);                                    \
+        }                                                                                       \
     } while (0)
 
 // Optional per-kernel timing with CUDA events on the launching stream (vsum_profile_begin/end).

@@ -422,11 +422,7 @@ extern "C" int vsum_rank_correlation(const float *scores, const int32_t *cu_step
     int P = 1;
     while (P < max_steps + 1) P <<= 1;
     const size_t smem = (size_t)P * 16;
-    static bool configured = false;
-    if (!configured) {
-        VSUM_CUDA_OK(cudaFuncSetAttribute(corr_classes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXSEG * 16));
-        configured = true;
-    }
+    VSUM_ONCE_PER_DEVICE(VSUM_CUDA_OK(cudaFuncSetAttribute(corr_classes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXSEG * 16)));
     {
         ProfScope prof(PROF_OTHER, s);
         corr_classes_kernel<<<B, CT, smem, s>>>(scores, cu_steps, picks, n_frames, w.seg_class, w.seg_dest, w.class_start, w.class_dx2, w.vstats);

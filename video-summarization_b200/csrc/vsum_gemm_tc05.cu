@@ -417,11 +417,7 @@ template <bool TF32, int EPI, bool WRES>
 int launch_variant(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmOut, const CUtensorMap &tmRes,
                    const GemmParams &p, cudaStream_t s, int cat) {
     auto kern = gemm_tc05_kernel<TF32, EPI, WRES>;
-    static bool configured = false;
-    if (!configured) {
-        VSUM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-        configured = true;
-    }
+    VSUM_ONCE_PER_DEVICE(VSUM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM)));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -131,11 +131,7 @@ static int launch_wgrad(const void *dY, const void *X, float *dW, int64_t M, int
     rc = make_tensor_map_2d(&tmX, X, ELT, (uint64_t)K, (uint64_t)M, (uint64_t)K * ELT, E, R);
     if (rc) return rc;
     auto kern = wgrad_tc05_kernel<BF16>;
-    static bool configured = false;
-    if (!configured) {
-        VSUM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM));
-        configured = true;
-    }
+    VSUM_ONCE_PER_DEVICE(VSUM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM)));
     const int tiles = (N / WG_BM) * (K / WG_BN);
     int splits = (int)max((int64_t)1, min((int64_t)(2 * 148 / tiles), ceil_div(M, 4 * R)));
     const int64_t rows = ceil_div(ceil_div(M, splits), R) * R;
