@@ -60,13 +60,28 @@ constexpr int BN = 256;                 // columns per tile (UMMA N) -- one full
 constexpr int STAGES = 4;
 constexpr int A_STAGE = BM * 128;       // 16 KB: 128 rows x 128 B
 constexpr int B_STAGE = BN * 128;       // 32 KB
-constexpr int RING_BYTES = STAGES * (A_STAGE + B_STAGE);   // 192 KB (WRES: 128 KB of W + 4 x 16 KB of A)
+
 constexpr int STG_BYTES = BM * 128;     // 16 KB: one [128 rows x 64 bf16] SW128 staging tile
-constexpr int GEMM_THREADS = 256;
+
 constexpr int TMEM_COLS = 512;          // 2 accumulator stages x 256 fp32 columns
 constexpr int WRES_MAX_KB = 4;          // weight-stationary variant: K = 256 bf16 -> 4 k-blocks = 128 KB
-constexpr size_t GEMM_SMEM = (size_t)RING_BYTES + 2 * STG_BYTES + 256 /*barriers*/;
-constexpr int EPI_BAR = 1;              // named barrier of the 128 epilogue threads
+constexpr int EPI_BAR = 1;              // named barrier of 128 epilogue threads (EPI_BAR + half with eight epilogue warps)
+
+// The plain bf16 epilogues (bias, bias+ReLU, bias+positions) run on EIGHT epilogue warps: warps 4..7 drain columns
+// [0,128) of the accumulator, warps 8..11 columns [128,256), each half with its own staging tile, named barrier and
+// TMA-store leader (one warp per SM sub-partition cannot hide its own TMEM-load / store latency).  The operand ring
+// keeps its four stages: taking shared memory from it for double-buffered staging per half (3 stages, or 2 A stages in
+// the weight-stationary variant) made the K = 256 GEMMs 20-30 % SLOWER, so each half waits for its previous TMA
+// store to finish reading the tile instead.  Measured on the same box: QKV GEMM 1.38 -> 1.09 ms per step.
+__host__ __device__ constexpr bool epi_uses_8_warps(int epi) { return epi == TC_EPI_BIAS || epi == TC_EPI_BIAS_RELU || epi == TC_EPI_BIAS_POS; }
+__host__ __device__ constexpr int gemm_threads(int epi) { return epi_uses_8_warps(epi) ? 384 : 256; }
+__host__ __device__ constexpr int gemm_ring_stages(int epi, bool wres) { return STAGES; }
+__host__ __device__ constexpr int gemm_stg_tiles(int epi) { return 2; }
+__host__ __device__ constexpr size_t gemm_ring_bytes(int epi, bool wres) {
+    return wres ? (size_t)WRES_MAX_KB * B_STAGE + (size_t)gemm_ring_stages(epi, wres) * A_STAGE
+                : (size_t)gemm_ring_stages(epi, wres) * (A_STAGE + B_STAGE);
+}
+__host__ __device__ constexpr size_t gemm_smem(int epi, bool wres) { return gemm_ring_bytes(epi, wres) + (size_t)gemm_stg_tiles(epi) * STG_BYTES + 256 /*barriers*/; }
 
 struct GemmParams {
     int64_t M;
@@ -100,16 +115,18 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 // instruction): bf16 outputs are written to a 128B-swizzled staging tile and leave through TMA
 // stores, the LayerNorm residual arrives through TMA loads into the same two staging tiles.
 template <bool TF32, int EPI, bool WRES>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                  const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((tc::smem_u32(smem) & 1023u) != 0) __trap();
     // non-WRES: stage s = {A: s*48K, B: s*48K + 16K}.  WRES: W k-blocks at kb*32K, A ring after 128K.
+    constexpr bool EPI8 = epi_uses_8_warps(EPI);
+    constexpr int NST = gemm_ring_stages(EPI, WRES);            // operand ring depth
     uint8_t *ring = smem;
-    uint8_t *stg = smem + RING_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + RING_BYTES + 2 * STG_BYTES);
+    uint8_t *stg = smem + gemm_ring_bytes(EPI, WRES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stg + (size_t)gemm_stg_tiles(EPI) * STG_BYTES);
     uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = tfull + 2;
     uint64_t *wfull = tempty + 2, *rfull = wfull + 1;     // rfull[2]: residual staging tiles
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(rfull + 2);
@@ -133,7 +150,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); }
-        for (int a = 0; a < 2; ++a) { tc::mbar_init(tfull + a, 1); tc::mbar_init(tempty + a, 128); tc::mbar_init(rfull + a, 1); }
+        for (int a = 0; a < 2; ++a) { tc::mbar_init(tfull + a, 1); tc::mbar_init(tempty + a, EPI8 ? 256 : 128); tc::mbar_init(rfull + a, 1); }
         tc::mbar_init(wfull, 1);
         tc::fence_barrier_init();
     }
@@ -162,8 +179,8 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int64_t m_blk = WRES ? t : t / p.n_tiles;
                 const int n_blk = WRES ? (int)blockIdx.y : (int)(t % p.n_tiles);
                 for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
+                    const int s = it % NST;
+                    const uint32_t ph = (it / NST) & 1;
                     tc::mbar_wait(empty + s, ph ^ 1);
                     tc::mbar_arrive_expect_tx(full + s, WRES ? A_STAGE : A_STAGE + B_STAGE);
                     tc::tma_load_2d(a_stage(s), &tmA, full + s, kb * KELTS, (int)(m_blk * BM));
@@ -184,8 +201,8 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc::tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BN;
             for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-                const int s = it % STAGES;
-                tc::mbar_wait(full + s, (it / STAGES) & 1);
+                const int s = it % NST;
+                tc::mbar_wait(full + s, (it / NST) & 1);
                 tc::tc_fence_after();
                 // descriptor start-address field is in 16-byte units
                 const uint32_t a_off = (uint32_t)(a_stage(s) - ring) >> 4;
@@ -205,11 +222,14 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else if (warp >= 4) {  // ===== epilogue: thread <-> one output row =====
-        const int q = warp - 4;
+        const int q = (warp - 4) & 3;                       // TMEM lane quarter
+        const int half = EPI8 ? (warp - 4) >> 2 : 0;        // column half of the accumulator (eight-warp epilogues)
         const int r = q * 32 + lane;                        // row inside the tile
-        const bool leader = r == 0;
-        // this row's eight 16-byte chunks inside a [128 x 64 bf16] SW128 staging tile
-        const uint32_t stg_row = tc::smem_u32(stg) + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+        const bool leader = r == 0;                         // one TMA-store leader per half
+        const int epi_bar = EPI_BAR + half;
+        // this row's eight 16-byte chunks inside a [128 x 64 bf16] SW128 staging tile (each half owns two tiles)
+        const uint32_t stg_row = tc::smem_u32(stg) + (uint32_t)half * STG_BYTES + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+        uint8_t *const stg_half = stg + (size_t)half * STG_BYTES;
         uint32_t sw_off[8];
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) sw_off[ch] = (uint32_t)((ch ^ (r & 7)) << 4);
@@ -272,14 +292,14 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (EPI == TC_EPI_BIAS_POS && valid)
                     pos = p.pos_table + (int64_t)min(__ldg(p.row_pos + row), p.pos_rows - 1) * BN;
 #pragma unroll 1
-                for (int cc = 0; cc < 4; ++cc) {             // 64 output columns per pass
+                for (int cc = EPI8 ? 2 * half : 0; cc < (EPI8 ? 2 * half + 2 : 4); ++cc) {   // 64 output columns per pass
                     tc::tmem_ld32(taddr + cc * 64, ra);
                     tc::tmem_ld32(taddr + cc * 64 + 32, rb);
                     tc::tmem_wait_ld();
-                    if (cc == 3) { tc::tc_fence_before(); tc::mbar_arrive(tempty + acc); }   // accumulator drained
-                    if (leader) tc::bulk_wait_read<1>();      // the store that last used this staging tile is done reading
-                    tc::bar_sync(EPI_BAR, 128);
-                    const uint32_t dst = stg_row + (uint32_t)(cc & 1) * STG_BYTES;
+                    if (cc == (EPI8 ? 2 * half + 1 : 3)) { tc::tc_fence_before(); tc::mbar_arrive(tempty + acc); }   // my part of the accumulator is drained
+                    if (leader) { if (EPI8) tc::bulk_wait_read<0>(); else tc::bulk_wait_read<1>(); }   // the store that last used this staging tile is done reading
+                    tc::bar_sync(epi_bar, 128);
+                    const uint32_t dst = stg_row + (EPI8 ? 0u : (uint32_t)(cc & 1) * STG_BYTES);
 #pragma unroll
                     for (int ch = 0; ch < 8; ++ch) {         // 8 columns -> one 16-byte chunk
                         const uint32_t *src = ch < 4 ? &ra[ch * 8] : &rb[(ch - 4) * 8];
@@ -301,9 +321,9 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         sts128(dst + sw_off[ch], pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
                     }
                     tc::fence_proxy_async_smem();
-                    tc::bar_sync(EPI_BAR, 128);
+                    tc::bar_sync(epi_bar, 128);
                     if (leader) {
-                        tc::tma_store_2d(stg + (cc & 1) * STG_BYTES, &tmOut, n0 + cc * 64, (int)(m_blk * BM));
+                        tc::tma_store_2d(stg_half + (EPI8 ? 0 : (cc & 1)) * STG_BYTES, &tmOut, n0 + cc * 64, (int)(m_blk * BM));
                         tc::bulk_commit();
                     }
                 }
@@ -417,7 +437,8 @@ template <bool TF32, int EPI, bool WRES>
 int launch_variant(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmOut, const CUtensorMap &tmRes,
                    const GemmParams &p, cudaStream_t s, int cat) {
     auto kern = gemm_tc05_kernel<TF32, EPI, WRES>;
-    VSUM_ONCE_PER_DEVICE(VSUM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM)));
+    constexpr size_t SMEM = gemm_smem(EPI, WRES);
+    VSUM_ONCE_PER_DEVICE(VSUM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM)));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -426,7 +447,7 @@ int launch_variant(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtenso
     if (WRES) grid = dim3((unsigned)max((int64_t)1, min(p.m_tiles, (int64_t)(sms / p.n_tiles))), (unsigned)p.n_tiles);
     else grid = dim3((unsigned)min(p.m_tiles * p.n_tiles, (int64_t)sms));
     ProfScope prof(cat, s);
-    kern<<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmOut, tmRes, p);
+    kern<<<grid, gemm_threads(EPI), SMEM, s>>>(tmA, tmB, tmOut, tmRes, p);
     VSUM_LAUNCH_OK("gemm_tc05_kernel");
     return VSUM_OK;
 }
