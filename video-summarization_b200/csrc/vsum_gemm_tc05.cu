@@ -67,13 +67,15 @@ constexpr int TMEM_COLS = 512;          // 2 accumulator stages x 256 fp32 colum
 constexpr int WRES_MAX_KB = 4;          // weight-stationary variant: K = 256 bf16 -> 4 k-blocks = 128 KB
 constexpr int EPI_BAR = 1;              // named barrier of 128 epilogue threads (EPI_BAR + half with eight epilogue warps)
 
-// The plain bf16 epilogues (bias, bias+ReLU, bias+positions) run on EIGHT epilogue warps: warps 4..7 drain columns
+// Every bf16-output epilogue runs on EIGHT epilogue warps: warps 4..7 drain columns
 // [0,128) of the accumulator, warps 8..11 columns [128,256), each half with its own staging tile, named barrier and
 // TMA-store leader (one warp per SM sub-partition cannot hide its own TMEM-load / store latency).  The operand ring
 // keeps its four stages: taking shared memory from it for double-buffered staging per half (3 stages, or 2 A stages in
 // the weight-stationary variant) made the K = 256 GEMMs 20-30 % SLOWER, so each half waits for its previous TMA
-// store to finish reading the tile instead.  Measured on the same box: QKV GEMM 1.38 -> 1.09 ms per step.
-__host__ __device__ constexpr bool epi_uses_8_warps(int epi) { return epi == TC_EPI_BIAS || epi == TC_EPI_BIAS_RELU || epi == TC_EPI_BIAS_POS; }
+// store to finish reading the tile instead.  Measured on the same box: QKV GEMM 1.38 -> 1.09 ms per step; the
+// LayerNorm epilogues (two threads per row, partial sums exchanged through shared memory) gain 4 %.
+__host__ __device__ constexpr bool epi_uses_8_warps(int epi) { return epi < TC_EPI_BIAS_F32; }   // every bf16-output epilogue
+__host__ __device__ constexpr bool epi_is_ln(int epi) { return epi == TC_EPI_BIAS_RES_LN || epi == TC_EPI_BIAS_RES_LN_HEAD; }
 __host__ __device__ constexpr int gemm_threads(int epi) { return epi_uses_8_warps(epi) ? 384 : 256; }
 __host__ __device__ constexpr int gemm_ring_stages(int epi, bool wres) { return STAGES; }
 __host__ __device__ constexpr int gemm_stg_tiles(int epi) { return 2; }
@@ -81,7 +83,9 @@ __host__ __device__ constexpr size_t gemm_ring_bytes(int epi, bool wres) {
     return wres ? (size_t)WRES_MAX_KB * B_STAGE + (size_t)gemm_ring_stages(epi, wres) * A_STAGE
                 : (size_t)gemm_ring_stages(epi, wres) * (A_STAGE + B_STAGE);
 }
-__host__ __device__ constexpr size_t gemm_smem(int epi, bool wres) { return gemm_ring_bytes(epi, wres) + (size_t)gemm_stg_tiles(epi) * STG_BYTES + 256 /*barriers*/; }
+__host__ __device__ constexpr size_t gemm_smem(int epi, bool wres) {   // + 2.5 KB: row-statistics / head-dot exchange of the LayerNorm epilogues
+    return gemm_ring_bytes(epi, wres) + (size_t)gemm_stg_tiles(epi) * STG_BYTES + 256 /*barriers*/ + (epi_is_ln(epi) ? 2560 : 0);
+}
 
 struct GemmParams {
     int64_t M;
@@ -241,12 +245,10 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int64_t row = m_blk * BM + r;
             const bool valid = row < p.M;
             const int n0 = n_blk * BN;
-            if (IS_LN && leader) {   // residual chunks 0,1 on their way while the MMAs still run
-                tc::bulk_wait_read<0>();                     // earlier stores no longer read the staging tiles
-                for (int cc = 0; cc < 2; ++cc) {
-                    tc::mbar_arrive_expect_tx(rfull + cc, STG_BYTES);
-                    tc::tma_load_2d(stg + cc * STG_BYTES, &tmRes, rfull + cc, cc * 64, (int)(m_blk * BM));
-                }
+            if (IS_LN && leader) {   // my half's first residual chunk is on its way while the MMAs still run
+                tc::bulk_wait_read<0>();                     // my earlier stores no longer read the staging tile
+                tc::mbar_arrive_expect_tx(rfull + half, STG_BYTES);
+                tc::tma_load_2d(stg_half, &tmRes, rfull + half, 2 * half * 64, (int)(m_blk * BM));
             }
             tc::mbar_wait(tfull + acc, (tl >> 1) & 1);
             tc::tc_fence_after();
@@ -327,18 +329,20 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         tc::bulk_commit();
                     }
                 }
-            } else {  // bias + residual + LayerNorm (+ head): N == 256, the tile is the whole row
+            } else {  // bias + residual + LayerNorm (+ head): N == 256, the tile is the whole row.  Two threads per row
+                      // (columns [128 half, 128 half + 128) each) exchange their partial sums through shared memory.
+                float *xch = reinterpret_cast<float *>(bars) + 64;          // [2 halves][128 rows][2], after the 256 B of barriers
                 float sum = 0.f, sumsq = 0.f;
 #pragma unroll 1
-                for (int cc = 0; cc < 4; ++cc) {
+                for (int i = 0; i < 2; ++i) {
+                    const int cc = 2 * half + i;
                     tc::tmem_ld32(taddr + cc * 64, ra);
                     tc::tmem_ld32(taddr + cc * 64 + 32, rb);
-                    tc::mbar_wait(rfull + (cc & 1), (res_it >> 1) & 1);
+                    tc::mbar_wait(rfull + half, res_it & 1);
                     ++res_it;
-                    const uint32_t srcrow = stg_row + (uint32_t)(cc & 1) * STG_BYTES;
                     uint4 rs[8];
 #pragma unroll
-                    for (int ch = 0; ch < 8; ++ch) rs[ch] = lds128(srcrow + sw_off[ch]);
+                    for (int ch = 0; ch < 8; ++ch) rs[ch] = lds128(stg_row + sw_off[ch]);
                     tc::tmem_wait_ld();
 #pragma unroll
                     for (int ch = 0; ch < 8; ++ch) {
@@ -360,28 +364,34 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                     tc::tmem_st32(taddr + cc * 64, ra);       // park the pre-norm row in TMEM
                     tc::tmem_st32(taddr + cc * 64 + 32, rb);
-                    tc::bar_sync(EPI_BAR, 128);               // everyone has read this residual tile
-                    if (leader && cc < 2) {
-                        tc::mbar_arrive_expect_tx(rfull + cc, STG_BYTES);
-                        tc::tma_load_2d(stg + cc * STG_BYTES, &tmRes, rfull + cc, (cc + 2) * 64, (int)(m_blk * BM));
+                    tc::bar_sync(epi_bar, 128);               // my half has read this residual chunk
+                    if (leader && i == 0) {
+                        tc::mbar_arrive_expect_tx(rfull + half, STG_BYTES);
+                        tc::tma_load_2d(stg_half, &tmRes, rfull + half, (cc + 1) * 64, (int)(m_blk * BM));
                     }
                 }
                 tc::tmem_wait_st();
+                xch[(half * 128 + r) * 2] = sum;
+                xch[(half * 128 + r) * 2 + 1] = sumsq;
+                tc::bar_sync(EPI_BAR + 2, 256);               // both halves of every row have published their sums
+                sum += xch[((half ^ 1) * 128 + r) * 2];
+                sumsq += xch[((half ^ 1) * 128 + r) * 2 + 1];
+                tc::bar_sync(EPI_BAR + 2, 256);               // ... and everyone has read them (the next tile overwrites the slots)
                 const float mean = sum * (1.0f / BN);
                 const float var = fmaxf(sumsq * (1.0f / BN) - mean * mean, 0.f);
                 const float rstd = rsqrtf(var + 1e-5f);
                 float dot = 0.f;
 #pragma unroll 1
-                for (int cc = 0; cc < 4; ++cc) {
+                for (int i = 0; i < 2; ++i) {
+                    const int cc = 2 * half + i;
                     tc::tmem_ld32(taddr + cc * 64, ra);
                     tc::tmem_ld32(taddr + cc * 64 + 32, rb);
                     tc::tmem_wait_ld();
-                    if (cc == 3) { tc::tc_fence_before(); tc::mbar_arrive(tempty + acc); }
+                    if (i == 1) { tc::tc_fence_before(); tc::mbar_arrive(tempty + acc); }
                     if (p.store_out) {
-                        if (leader) tc::bulk_wait_read<1>();
-                        tc::bar_sync(EPI_BAR, 128);
+                        if (leader) tc::bulk_wait_read<0>();  // my previous store is done reading the staging tile
+                        tc::bar_sync(epi_bar, 128);
                     }
-                    const uint32_t dst = stg_row + (uint32_t)(cc & 1) * STG_BYTES;
 #pragma unroll
                     for (int ch = 0; ch < 8; ++ch) {
                         const uint32_t *a = ch < 4 ? &ra[ch * 8] : &rb[(ch - 4) * 8];
@@ -404,21 +414,25 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             }
                         }
                         if (p.store_out)
-                            sts128(dst + sw_off[ch], pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
+                            sts128(stg_row + sw_off[ch], pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
                     }
                     if (p.store_out) {
                         tc::fence_proxy_async_smem();
-                        tc::bar_sync(EPI_BAR, 128);
+                        tc::bar_sync(epi_bar, 128);
                         if (leader) {
-                            tc::tma_store_2d(stg + (cc & 1) * STG_BYTES, &tmOut, cc * 64, (int)(m_blk * BM));
+                            tc::tma_store_2d(stg_half, &tmOut, cc * 64, (int)(m_blk * BM));
                             tc::bulk_commit();
                         }
                     }
                 }
-                if (EPI == TC_EPI_BIAS_RES_LN_HEAD && valid) {
-                    float sc = dot + __ldg(p.head_b);
-                    if (p.apply_sigmoid) sc = 1.0f / (1.0f + __expf(-sc));
-                    p.scores_out[row] = sc;
+                if (EPI == TC_EPI_BIAS_RES_LN_HEAD) {            // the two half-row dot products meet in half 0
+                    if (half == 1) xch[512 + r] = dot;           // own 512-byte region after the sums
+                    tc::bar_sync(EPI_BAR + 2, 256);
+                    if (half == 0 && valid) {
+                        float sc = dot + xch[512 + r] + __ldg(p.head_b);
+                        if (p.apply_sigmoid) sc = 1.0f / (1.0f + __expf(-sc));
+                        p.scores_out[row] = sc;
+                    }
                 }
             }
         }
