@@ -77,14 +77,18 @@ constexpr int EPI_BAR = 1;              // named barrier of 128 epilogue threads
 __host__ __device__ constexpr bool epi_uses_8_warps(int epi) { return epi < TC_EPI_BIAS_F32; }   // every bf16-output epilogue
 __host__ __device__ constexpr bool epi_is_ln(int epi) { return epi == TC_EPI_BIAS_RES_LN || epi == TC_EPI_BIAS_RES_LN_HEAD; }
 __host__ __device__ constexpr int gemm_threads(int epi) { return epi_uses_8_warps(epi) ? 384 : 256; }
-__host__ __device__ constexpr int gemm_ring_stages(int epi, bool wres) { return STAGES; }
-__host__ __device__ constexpr int gemm_stg_tiles(int epi) { return 2; }
-__host__ __device__ constexpr size_t gemm_ring_bytes(int epi, bool wres) {
-    return wres ? (size_t)WRES_MAX_KB * B_STAGE + (size_t)gemm_ring_stages(epi, wres) * A_STAGE
-                : (size_t)gemm_ring_stages(epi, wres) * (A_STAGE + B_STAGE);
+// DBL variant (out-projection + LayerNorm, K = 256): staging double-buffered per half (4 tiles) on a 3-stage ring that
+// streams W from L2 instead of keeping it resident -- the epilogue chain (residual load -> statistics -> normalise ->
+// store) is what bounds that tiny GEMM, 1.18 -> 0.96 ms per step.  With K = 1024 the 3-stage ring costs more than the
+// staging returns (fc2 + LayerNorm +10 %, embedding +6 %), so those keep 4 stages and one staging tile per half.
+__host__ __device__ constexpr int gemm_ring_stages(bool dbl) { return dbl ? 3 : STAGES; }
+__host__ __device__ constexpr int gemm_stg_tiles(bool dbl) { return dbl ? 4 : 2; }
+__host__ __device__ constexpr size_t gemm_ring_bytes(bool wres, bool dbl) {
+    return wres ? (size_t)WRES_MAX_KB * B_STAGE + (size_t)gemm_ring_stages(dbl) * A_STAGE
+                : (size_t)gemm_ring_stages(dbl) * (A_STAGE + B_STAGE);
 }
-__host__ __device__ constexpr size_t gemm_smem(int epi, bool wres) {   // + 2.5 KB: row-statistics / head-dot exchange of the LayerNorm epilogues
-    return gemm_ring_bytes(epi, wres) + (size_t)gemm_stg_tiles(epi) * STG_BYTES + 256 /*barriers*/ + (epi_is_ln(epi) ? 2560 : 0);
+__host__ __device__ constexpr size_t gemm_smem(int epi, bool wres, bool dbl) {   // + 2.5 KB: row-statistics / head-dot exchange of the LayerNorm epilogues
+    return gemm_ring_bytes(wres, dbl) + (size_t)gemm_stg_tiles(dbl) * STG_BYTES + 256 /*barriers*/ + (epi_is_ln(epi) ? 2560 : 0);
 }
 
 struct GemmParams {
@@ -118,7 +122,7 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 // The epilogue never touches global memory row-by-row (that costs one L1 wavefront per row and
 // instruction): bf16 outputs are written to a 128B-swizzled staging tile and leave through TMA
 // stores, the LayerNorm residual arrives through TMA loads into the same two staging tiles.
-template <bool TF32, int EPI, bool WRES>
+template <bool TF32, int EPI, bool WRES, bool DBL>
 __global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
@@ -127,13 +131,14 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if ((tc::smem_u32(smem) & 1023u) != 0) __trap();
     // non-WRES: stage s = {A: s*48K, B: s*48K + 16K}.  WRES: W k-blocks at kb*32K, A ring after 128K.
     constexpr bool EPI8 = epi_uses_8_warps(EPI);
-    constexpr int NST = gemm_ring_stages(EPI, WRES);            // operand ring depth
+    static_assert(!DBL || (epi_uses_8_warps(EPI) && !WRES), "double-buffered staging: eight-warp, non weight-stationary only");
+    constexpr int NST = gemm_ring_stages(DBL);                  // operand ring depth
     uint8_t *ring = smem;
-    uint8_t *stg = smem + gemm_ring_bytes(EPI, WRES);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(stg + (size_t)gemm_stg_tiles(EPI) * STG_BYTES);
+    uint8_t *stg = smem + gemm_ring_bytes(WRES, DBL);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stg + (size_t)gemm_stg_tiles(DBL) * STG_BYTES);
     uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = tfull + 2;
-    uint64_t *wfull = tempty + 2, *rfull = wfull + 1;     // rfull[2]: residual staging tiles
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(rfull + 2);
+    uint64_t *wfull = tempty + 2, *rfull = wfull + 1;     // rfull[4]: residual staging tiles (half, buffer)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(rfull + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int KELTS = TF32 ? 32 : 64;          // elements per 128-byte k-block
@@ -154,7 +159,8 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); }
-        for (int a = 0; a < 2; ++a) { tc::mbar_init(tfull + a, 1); tc::mbar_init(tempty + a, EPI8 ? 256 : 128); tc::mbar_init(rfull + a, 1); }
+        for (int a = 0; a < 2; ++a) { tc::mbar_init(tfull + a, 1); tc::mbar_init(tempty + a, EPI8 ? 256 : 128); }
+        for (int a = 0; a < 4; ++a) tc::mbar_init(rfull + a, 1);
         tc::mbar_init(wfull, 1);
         tc::fence_barrier_init();
     }
@@ -232,8 +238,9 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool leader = r == 0;                         // one TMA-store leader per half
         const int epi_bar = EPI_BAR + half;
         // this row's eight 16-byte chunks inside a [128 x 64 bf16] SW128 staging tile (each half owns two tiles)
-        const uint32_t stg_row = tc::smem_u32(stg) + (uint32_t)half * STG_BYTES + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
-        uint8_t *const stg_half = stg + (size_t)half * STG_BYTES;
+        constexpr int HALF_TILES = DBL ? 2 : 1;
+        const uint32_t stg_row = tc::smem_u32(stg) + (uint32_t)(half * HALF_TILES) * STG_BYTES + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+        uint8_t *const stg_half = stg + (size_t)(half * HALF_TILES) * STG_BYTES;
         uint32_t sw_off[8];
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) sw_off[ch] = (uint32_t)((ch ^ (r & 7)) << 4);
@@ -245,10 +252,12 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int64_t row = m_blk * BM + r;
             const bool valid = row < p.M;
             const int n0 = n_blk * BN;
-            if (IS_LN && leader) {   // my half's first residual chunk is on its way while the MMAs still run
-                tc::bulk_wait_read<0>();                     // my earlier stores no longer read the staging tile
-                tc::mbar_arrive_expect_tx(rfull + half, STG_BYTES);
-                tc::tma_load_2d(stg_half, &tmRes, rfull + half, 2 * half * 64, (int)(m_blk * BM));
+            if (IS_LN && leader) {   // my half's residual chunk(s) on their way while the MMAs still run
+                tc::bulk_wait_read<0>();                     // my earlier stores no longer read the staging tiles
+                for (int i = 0; i < HALF_TILES; ++i) {
+                    tc::mbar_arrive_expect_tx(rfull + half * 2 + i, STG_BYTES);
+                    tc::tma_load_2d(stg_half + i * STG_BYTES, &tmRes, rfull + half * 2 + i, (2 * half + i) * 64, (int)(m_blk * BM));
+                }
             }
             tc::mbar_wait(tfull + acc, (tl >> 1) & 1);
             tc::tc_fence_after();
@@ -299,9 +308,9 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tc::tmem_ld32(taddr + cc * 64 + 32, rb);
                     tc::tmem_wait_ld();
                     if (cc == (EPI8 ? 2 * half + 1 : 3)) { tc::tc_fence_before(); tc::mbar_arrive(tempty + acc); }   // my part of the accumulator is drained
-                    if (leader) { if (EPI8) tc::bulk_wait_read<0>(); else tc::bulk_wait_read<1>(); }   // the store that last used this staging tile is done reading
+                    if (leader) { if (EPI8 && !DBL) tc::bulk_wait_read<0>(); else tc::bulk_wait_read<1>(); }   // the store that last used this staging tile is done reading
                     tc::bar_sync(epi_bar, 128);
-                    const uint32_t dst = stg_row + (EPI8 ? 0u : (uint32_t)(cc & 1) * STG_BYTES);
+                    const uint32_t dst = stg_row + ((EPI8 && !DBL) ? 0u : (uint32_t)(cc & 1) * STG_BYTES);
 #pragma unroll
                     for (int ch = 0; ch < 8; ++ch) {         // 8 columns -> one 16-byte chunk
                         const uint32_t *src = ch < 4 ? &ra[ch * 8] : &rb[(ch - 4) * 8];
@@ -325,7 +334,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tc::fence_proxy_async_smem();
                     tc::bar_sync(epi_bar, 128);
                     if (leader) {
-                        tc::tma_store_2d(stg_half + (EPI8 ? 0 : (cc & 1)) * STG_BYTES, &tmOut, n0 + cc * 64, (int)(m_blk * BM));
+                        tc::tma_store_2d(stg_half + ((EPI8 && !DBL) ? 0 : (cc & 1)) * STG_BYTES, &tmOut, n0 + cc * 64, (int)(m_blk * BM));
                         tc::bulk_commit();
                     }
                 }
@@ -338,11 +347,12 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const int cc = 2 * half + i;
                     tc::tmem_ld32(taddr + cc * 64, ra);
                     tc::tmem_ld32(taddr + cc * 64 + 32, rb);
-                    tc::mbar_wait(rfull + half, res_it & 1);
+                    const int sb = DBL ? i : 0;               // staging buffer of this chunk
+                    tc::mbar_wait(rfull + half * 2 + sb, DBL ? (tl & 1) : (res_it & 1));
                     ++res_it;
                     uint4 rs[8];
 #pragma unroll
-                    for (int ch = 0; ch < 8; ++ch) rs[ch] = lds128(stg_row + sw_off[ch]);
+                    for (int ch = 0; ch < 8; ++ch) rs[ch] = lds128(stg_row + sb * STG_BYTES + sw_off[ch]);
                     tc::tmem_wait_ld();
 #pragma unroll
                     for (int ch = 0; ch < 8; ++ch) {
@@ -365,9 +375,9 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tc::tmem_st32(taddr + cc * 64, ra);       // park the pre-norm row in TMEM
                     tc::tmem_st32(taddr + cc * 64 + 32, rb);
                     tc::bar_sync(epi_bar, 128);               // my half has read this residual chunk
-                    if (leader && i == 0) {
-                        tc::mbar_arrive_expect_tx(rfull + half, STG_BYTES);
-                        tc::tma_load_2d(stg_half, &tmRes, rfull + half, (cc + 1) * 64, (int)(m_blk * BM));
+                    if (!DBL && leader && i == 0) {           // single staging tile: the second chunk can only be fetched now
+                        tc::mbar_arrive_expect_tx(rfull + half * 2, STG_BYTES);
+                        tc::tma_load_2d(stg_half, &tmRes, rfull + half * 2, (cc + 1) * 64, (int)(m_blk * BM));
                     }
                 }
                 tc::tmem_wait_st();
@@ -388,7 +398,8 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tc::tmem_ld32(taddr + cc * 64 + 32, rb);
                     tc::tmem_wait_ld();
                     if (i == 1) { tc::tc_fence_before(); tc::mbar_arrive(tempty + acc); }
-                    if (p.store_out) {
+                    const int sb = DBL ? i : 0;
+                    if (p.store_out && !DBL) {                // (double-buffered: the tile was last read as residual, before a barrier)
                         if (leader) tc::bulk_wait_read<0>();  // my previous store is done reading the staging tile
                         tc::bar_sync(epi_bar, 128);
                     }
@@ -414,13 +425,13 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             }
                         }
                         if (p.store_out)
-                            sts128(stg_row + sw_off[ch], pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
+                            sts128(stg_row + sb * STG_BYTES + sw_off[ch], pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
                     }
                     if (p.store_out) {
                         tc::fence_proxy_async_smem();
                         tc::bar_sync(epi_bar, 128);
                         if (leader) {
-                            tc::tma_store_2d(stg_half, &tmOut, cc * 64, (int)(m_blk * BM));
+                            tc::tma_store_2d(stg_half + sb * STG_BYTES, &tmOut, cc * 64, (int)(m_blk * BM));
                             tc::bulk_commit();
                         }
                     }
@@ -447,11 +458,11 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
-template <bool TF32, int EPI, bool WRES>
+template <bool TF32, int EPI, bool WRES, bool DBL = false>
 int launch_variant(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmOut, const CUtensorMap &tmRes,
                    const GemmParams &p, cudaStream_t s, int cat) {
-    auto kern = gemm_tc05_kernel<TF32, EPI, WRES>;
-    constexpr size_t SMEM = gemm_smem(EPI, WRES);
+    auto kern = gemm_tc05_kernel<TF32, EPI, WRES, DBL>;
+    constexpr size_t SMEM = gemm_smem(EPI, WRES, DBL);
     VSUM_ONCE_PER_DEVICE(VSUM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM)));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -522,7 +533,9 @@ int launch_gemm_tc05(const Tc05GemmArgs &a, cudaStream_t s) {
         case TC_EPI_BIAS_RELU:
             return wres ? launch_variant<false, TC_EPI_BIAS_RELU, true>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat) : launch_variant<false, TC_EPI_BIAS_RELU, false>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat);
         case TC_EPI_BIAS_RES_LN:
-            return wres ? launch_variant<false, TC_EPI_BIAS_RES_LN, true>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat) : launch_variant<false, TC_EPI_BIAS_RES_LN, false>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat);
+            // K = 256 (out-projection): not weight-stationary -- the 128 KB a resident W block would take double-buffers the staging tiles
+            return p.num_kb <= WRES_MAX_KB ? launch_variant<false, TC_EPI_BIAS_RES_LN, false, true>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat)
+                                           : launch_variant<false, TC_EPI_BIAS_RES_LN, false, false>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat);
         case TC_EPI_BIAS_RES_LN_HEAD:
             return launch_variant<false, TC_EPI_BIAS_RES_LN_HEAD, false>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat);
         default:
