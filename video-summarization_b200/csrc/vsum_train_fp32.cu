@@ -78,48 +78,50 @@ int launch_dropout_inplace_f32(float *x, int64_t n, float drop_p, unsigned long 
 // LayerNorm backward.  y = (s - mean) * rstd * gamma + beta.  Each warp walks rows m, m + W, ...
 // and keeps its share of dgamma / dbeta in registers until the end (one atomic per column and warp).
 // ---------------------------------------------------------------------------------------------
+// PER = d / 32 columns per lane (compile-time for the common widths so the four per-lane arrays live in
+// exactly PER registers each).  dgamma / dbeta: per-warp register accumulation over the warp's rows, then
+// one reduction over the block's warps through shared memory and ONE atomic per column and block -- with
+// one atomic per column and WARP, 4736 warps hammered 512 addresses and the kernel ran at 10 % of HBM speed.
+template <int PER, bool EXACT>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_f32_kernel(const float *__restrict__ dy, const float *__restrict__ s_in,
                          const float *__restrict__ gamma, float *__restrict__ ds, float *__restrict__ d_a,
                          float *__restrict__ dgamma, float *__restrict__ dbeta, int64_t M, int d, float drop_p,
                          unsigned long long seed) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    __shared__ float red[2][8][PER * 32 > 256 ? 1 : PER * 32];      // [gamma|beta][warp][column] (PER <= 8 only)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    const int per = d >> 5;
     const float ks = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
-    float g_acc[32], b_acc[32];
+    const int per = EXACT ? PER : (d >> 5);               // columns per lane actually present
+    float g_acc[PER], b_acc[PER], gam[PER];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) { g_acc[i] = 0.f; b_acc[i] = 0.f; }
+    for (int i = 0; i < PER; ++i) { g_acc[i] = 0.f; b_acc[i] = 0.f; gam[i] = i < per ? __ldg(gamma + i * 32 + lane) : 0.f; }
     for (int64_t m = warp0; m < M; m += nwarps) {
-        float x[32], g[32];
+        float x[PER], g[PER];
         float sum = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-            if (i < per) { x[i] = s_in[m * d + i * 32 + lane]; sum += x[i]; }
+        for (int i = 0; i < PER; ++i) { x[i] = i < per ? s_in[m * d + i * 32 + lane] : 0.f; sum += x[i]; }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         const float mean = sum / (float)d;
         float var = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-            if (i < per) { x[i] -= mean; var = fmaf(x[i], x[i], var); }
+        for (int i = 0; i < PER; ++i) { x[i] = i < per ? x[i] - mean : 0.f; var = fmaf(x[i], x[i], var); }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
         const float rstd = rsqrtf(var / (float)d + 1e-5f);
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-            if (i < per) {
-                const int c = i * 32 + lane;
-                const float dyv = dy[m * d + c];
-                x[i] *= rstd;                                   // xhat
-                g[i] = dyv * __ldg(gamma + c);                  // dxhat
-                g_acc[i] = fmaf(dyv, x[i], g_acc[i]);
-                b_acc[i] += dyv;
-                s1 += g[i];
-                s2 = fmaf(g[i], x[i], s2);
-            }
+        for (int i = 0; i < PER; ++i) {
+            const float dyv = i < per ? dy[m * d + i * 32 + lane] : 0.f;
+            x[i] *= rstd;                                   // xhat
+            g[i] = dyv * gam[i];                            // dxhat
+            g_acc[i] = fmaf(dyv, x[i], g_acc[i]);
+            b_acc[i] += dyv;
+            s1 += g[i];
+            s2 = fmaf(g[i], x[i], s2);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             s1 += __shfl_xor_sync(0xffffffffu, s1, o);
@@ -127,20 +129,33 @@ layernorm_bwd_f32_kernel(const float *__restrict__ dy, const float *__restrict__
         }
         s1 /= (float)d; s2 /= (float)d;
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-            if (i < per) {
-                const int c = i * 32 + lane;
-                const float v = rstd * (g[i] - s1 - x[i] * s2);
-                ds[m * d + c] = v;
-                if (d_a) d_a[m * d + c] = (drop_p > 0.f && !dropout_keep(seed, (unsigned long long)(m * d + c), drop_p)) ? 0.f : v * ks;
-            }
+        for (int i = 0; i < PER; ++i) {
+            if (i >= per) continue;
+            const int c = i * 32 + lane;
+            const float v = rstd * (g[i] - s1 - x[i] * s2);
+            ds[m * d + c] = v;
+            if (d_a) d_a[m * d + c] = (drop_p > 0.f && !dropout_keep(seed, (unsigned long long)(m * d + c), drop_p)) ? 0.f : v * ks;
+        }
     }
+    if (PER <= 8) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-        if (i < per) {
+        for (int i = 0; i < PER; ++i) { red[0][warp][i * 32 + lane] = g_acc[i]; red[1][warp][i * 32 + lane] = b_acc[i]; }
+        __syncthreads();
+        for (int c = threadIdx.x; c < PER * 32; c += blockDim.x) {
+            float gs = 0.f, bs = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { gs += red[0][w][c]; bs += red[1][w][c]; }
+            atomicAdd(dgamma + c, gs);
+            atomicAdd(dbeta + c, bs);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            if (i >= per) continue;
             atomicAdd(dgamma + i * 32 + lane, g_acc[i]);
             atomicAdd(dbeta + i * 32 + lane, b_acc[i]);
         }
+    }
 }
 
 int launch_layernorm_bwd_f32(const float *dy, const float *s_in, const float *gamma, float *ds, float *d_a,
@@ -148,8 +163,15 @@ int launch_layernorm_bwd_f32(const float *dy, const float *s_in, const float *ga
                              unsigned long long seed, cudaStream_t s) {
     VSUM_REQUIRE(d % 32 == 0 && d <= 1024, VSUM_EUNSUPPORTED, "layernorm_bwd_f32: d_model=%d", d);
     if (M == 0) return VSUM_OK;
-    const unsigned blocks = (unsigned)max((int64_t)1, min(ceil_div(M, 8), (int64_t)592));
-    layernorm_bwd_f32_kernel<<<blocks, 256, 0, s>>>(dy, s_in, gamma, ds, d_a, dgamma, dbeta, M, d, drop_p, seed);
+    const unsigned blocks = (unsigned)max((int64_t)1, min(ceil_div(M, 8), (int64_t)(2 * 148)));
+#define VSUM_LNB(P, E) layernorm_bwd_f32_kernel<P, E><<<blocks, 256, 0, s>>>(dy, s_in, gamma, ds, d_a, dgamma, dbeta, M, d, drop_p, seed)
+    switch (d / 32) {
+        case 2: VSUM_LNB(2, true); break;
+        case 4: VSUM_LNB(4, true); break;
+        case 8: VSUM_LNB(8, true); break;
+        default: VSUM_LNB(32, false); break;              // any other width up to 1024: guarded generic instantiation
+    }
+#undef VSUM_LNB
     VSUM_LAUNCH_OK("layernorm_bwd_f32_kernel");
     return VSUM_OK;
 }
