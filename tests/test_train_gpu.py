@@ -115,7 +115,7 @@ def test_dropout_is_active_and_consistent():
     model.zero_grad()
     mse_with_mask_loss(pred, tgt, mask).backward()
     analytic = (p.grad * direction).sum().item()
-    h = 1e-2
+    h = 3e-3                                                # small enough that few ReLU / LayerNorm kinks are crossed
     numeric = (loss_at(h).item() - loss_at(-h).item()) / (2 * h)
     assert abs(analytic - numeric) <= 5e-2 * max(abs(numeric), 1e-3), (analytic, numeric)
 

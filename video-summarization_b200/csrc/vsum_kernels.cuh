@@ -26,13 +26,6 @@ int launch_attention_f32(const float *qkv, const int32_t *cu_seqlens, int B, int
 // ---- fp32 training path (vsum_train_fp32.cu) --------------------------------------------------
 // Counter-based dropout: the keep decision is a pure function of (seed, element index), so the
 // backward pass recomputes the forward's masks instead of storing them.
-__host__ __device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned long long idx, float p) {
-    unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (idx + 1);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-    z ^= z >> 31;
-    return (float)(z >> 40) * (1.0f / 16777216.0f) >= p;      // 24 uniform bits
-}
 __host__ __device__ __forceinline__ unsigned long long attn_drop_index(long long q_row, int h, int H, int key) {
     return ((unsigned long long)(q_row * H + h) << 20) ^ (unsigned long long)key ^ 0xA5A5000000000000ULL;
 }
@@ -52,6 +45,13 @@ __host__ __device__ __forceinline__ unsigned long long dropout_bits64(unsigned l
         k += 0x9E3779B9u;
     }
     return ((unsigned long long)x0 << 32) | x1;
+}
+// Element idx is lane (idx & 3) of draw (idx >> 2): kernels that walk four consecutive elements per thread pay
+// for one draw, and the decision is the same whatever the access pattern (forward and backward agree).
+__host__ __device__ __forceinline__ unsigned int dropout_thresh16(float p) { return p <= 0.f ? 0u : (unsigned int)(p * 65536.0f + 0.5f); }
+__host__ __device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned long long idx, float p) {
+    const unsigned long long z = dropout_bits64(seed, idx >> 2);
+    return (unsigned int)((z >> (16 * (idx & 3))) & 0xffffu) >= dropout_thresh16(p);
 }
 __host__ __device__ __forceinline__ unsigned long long attn_drop_group_index(long long q_row, int h, int H, int key_group) {
     return ((unsigned long long)(q_row * H + h) << 20) ^ (unsigned long long)key_group ^ 0x5A5A000000000000ULL;

@@ -50,26 +50,98 @@ add_dropout_layernorm_f32_kernel(const float *__restrict__ a, const float *__res
         }
 }
 
+// Same op for d = NV * 128: every lane owns NV groups of four consecutive columns -- 16-byte accesses and one
+// dropout draw per group (the generic kernel above pays one draw per element and 4-byte accesses).
+template <int NV>
+__global__ void __launch_bounds__(256)
+add_dropout_layernorm_v4_kernel(const float *__restrict__ a, const float *__restrict__ res,
+                                const float *__restrict__ gamma, const float *__restrict__ beta,
+                                float *__restrict__ s_out, float *__restrict__ out, int64_t M, float drop_p,
+                                unsigned long long seed) {
+    constexpr int d = NV * 128;
+    const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (m >= M) return;
+    const float ks = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+    const unsigned int th = dropout_thresh16(drop_p);
+    float4 x[NV];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int64_t e = m * d + j * 128 + lane * 4;
+        float4 av = *reinterpret_cast<const float4 *>(a + e);
+        if (drop_p > 0.f) {
+            const unsigned long long z = dropout_bits64(seed, (unsigned long long)e >> 2);
+            av.x = (unsigned int)(z & 0xffffu) >= th ? av.x * ks : 0.f;
+            av.y = (unsigned int)((z >> 16) & 0xffffu) >= th ? av.y * ks : 0.f;
+            av.z = (unsigned int)((z >> 32) & 0xffffu) >= th ? av.z * ks : 0.f;
+            av.w = (unsigned int)(z >> 48) >= th ? av.w * ks : 0.f;
+        }
+        const float4 rv = *reinterpret_cast<const float4 *>(res + e);
+        x[j] = make_float4(av.x + rv.x, av.y + rv.y, av.z + rv.z, av.w + rv.w);
+        *reinterpret_cast<float4 *>(s_out + e) = x[j];
+        sum += (x[j].x + x[j].y) + (x[j].z + x[j].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)d;
+    float var = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        x[j].x -= mean; x[j].y -= mean; x[j].z -= mean; x[j].w -= mean;
+        var = fmaf(x[j].x, x[j].x, fmaf(x[j].y, x[j].y, fmaf(x[j].z, x[j].z, fmaf(x[j].w, x[j].w, var))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = rsqrtf(var / (float)d + 1e-5f);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = j * 128 + lane * 4;
+        const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma + c)), bt = __ldg(reinterpret_cast<const float4 *>(beta + c));
+        *reinterpret_cast<float4 *>(out + m * d + c) = make_float4(x[j].x * rstd * g.x + bt.x, x[j].y * rstd * g.y + bt.y,
+                                                                   x[j].z * rstd * g.z + bt.z, x[j].w * rstd * g.w + bt.w);
+    }
+}
+
 int launch_add_dropout_layernorm_f32(const float *a, const float *res, const float *gamma, const float *beta,
                                      float *s_out, float *out, int64_t M, int d, float drop_p,
                                      unsigned long long seed, cudaStream_t s) {
     VSUM_REQUIRE(d % 32 == 0 && d <= 1024, VSUM_EUNSUPPORTED, "add_dropout_layernorm_f32: d_model=%d", d);
     if (M == 0) return VSUM_OK;
-    add_dropout_layernorm_f32_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, s>>>(a, res, gamma, beta, s_out, out, M, d, drop_p, seed);
+    const bool aligned = ((((uintptr_t)a | (uintptr_t)res | (uintptr_t)s_out | (uintptr_t)out | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0);
+    const unsigned blocks = (unsigned)ceil_div(M, 8);
+    if (aligned && d == 256) add_dropout_layernorm_v4_kernel<2><<<blocks, 256, 0, s>>>(a, res, gamma, beta, s_out, out, M, drop_p, seed);
+    else if (aligned && d == 128) add_dropout_layernorm_v4_kernel<1><<<blocks, 256, 0, s>>>(a, res, gamma, beta, s_out, out, M, drop_p, seed);
+    else if (aligned && d == 512) add_dropout_layernorm_v4_kernel<4><<<blocks, 256, 0, s>>>(a, res, gamma, beta, s_out, out, M, drop_p, seed);
+    else add_dropout_layernorm_f32_kernel<<<blocks, 256, 0, s>>>(a, res, gamma, beta, s_out, out, M, d, drop_p, seed);
     VSUM_LAUNCH_OK("add_dropout_layernorm_f32_kernel");
     return VSUM_OK;
 }
 
 __global__ void __launch_bounds__(256)
 dropout_inplace_f32_kernel(float *__restrict__ x, int64_t n, float drop_p, unsigned long long seed) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // one draw = four consecutive elements
+    const int64_t i = i4 * 4;
     if (i >= n) return;
-    x[i] = dropout_keep(seed, (unsigned long long)i, drop_p) ? x[i] * (1.0f / (1.0f - drop_p)) : 0.f;
+    const float ks = 1.0f / (1.0f - drop_p);
+    const unsigned int th = dropout_thresh16(drop_p);
+    const unsigned long long z = dropout_bits64(seed, (unsigned long long)i4);
+    if (i + 3 < n && ((uintptr_t)(x + i) & 15) == 0) {
+        float4 v = *reinterpret_cast<float4 *>(x + i);
+        v.x = (unsigned int)(z & 0xffffu) >= th ? v.x * ks : 0.f;
+        v.y = (unsigned int)((z >> 16) & 0xffffu) >= th ? v.y * ks : 0.f;
+        v.z = (unsigned int)((z >> 32) & 0xffffu) >= th ? v.z * ks : 0.f;
+        v.w = (unsigned int)(z >> 48) >= th ? v.w * ks : 0.f;
+        *reinterpret_cast<float4 *>(x + i) = v;
+    } else {
+        for (int e = 0; e < 4 && i + e < n; ++e)
+            x[i + e] = (unsigned int)((z >> (16 * e)) & 0xffffu) >= th ? x[i + e] * ks : 0.f;
+    }
 }
 
 int launch_dropout_inplace_f32(float *x, int64_t n, float drop_p, unsigned long long seed, cudaStream_t s) {
     if (n == 0 || drop_p <= 0.f) return VSUM_OK;
-    dropout_inplace_f32_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(x, n, drop_p, seed);
+    dropout_inplace_f32_kernel<<<(unsigned)ceil_div(ceil_div(n, 4), 256), 256, 0, s>>>(x, n, drop_p, seed);
     VSUM_LAUNCH_OK("dropout_inplace_f32_kernel");
     return VSUM_OK;
 }
@@ -291,13 +363,22 @@ int launch_linear_dgrad_f32(const float *dY, const float *W, float *dX, int64_t 
 
 __global__ void __launch_bounds__(256)
 relu_dropout_bwd_f32_kernel(const float *__restrict__ hid, float *__restrict__ dhid, int64_t n, float ks) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dhid[i] = hid[i] > 0.f ? dhid[i] * ks : 0.f;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    if (i + 3 < n && (((uintptr_t)(hid + i) | (uintptr_t)(dhid + i)) & 15) == 0) {
+        const float4 h = *reinterpret_cast<const float4 *>(hid + i);
+        float4 g = *reinterpret_cast<float4 *>(dhid + i);
+        g.x = h.x > 0.f ? g.x * ks : 0.f; g.y = h.y > 0.f ? g.y * ks : 0.f;
+        g.z = h.z > 0.f ? g.z * ks : 0.f; g.w = h.w > 0.f ? g.w * ks : 0.f;
+        *reinterpret_cast<float4 *>(dhid + i) = g;
+    } else {
+        for (int e = 0; e < 4 && i + e < n; ++e) dhid[i + e] = hid[i + e] > 0.f ? dhid[i + e] * ks : 0.f;
+    }
 }
 
 int launch_relu_dropout_bwd_f32(const float *hid, float *dhid, int64_t n, float drop_p, cudaStream_t s) {
     if (n == 0) return VSUM_OK;
-    relu_dropout_bwd_f32_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(hid, dhid, n, drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f);
+    relu_dropout_bwd_f32_kernel<<<(unsigned)ceil_div(ceil_div(n, 4), 256), 256, 0, s>>>(hid, dhid, n, drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f);
     VSUM_LAUNCH_OK("relu_dropout_bwd_f32_kernel");
     return VSUM_OK;
 }
