@@ -99,7 +99,10 @@ wgrad_tc05_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
                 tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
                 tc::tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) atomicAdd(dst + c * 32 + j, __uint_as_float(v[j]));
+                for (int j = 0; j < 32; j += 4)   // 16-byte vector reductions: a quarter of the atomic instructions
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c * 32 + j), "f"(__uint_as_float(v[j])),
+                                 "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                                 : "memory");
             }
         }
     }
