@@ -112,15 +112,20 @@ wgrad_tc05_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
     if (warp == 2) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, WG_BN); }
 }
 
-// db[n] += sum_m dY[m, n]
+// One pass over dY: db[n] += sum_m dY[m, n] (when db != NULL) and the bf16 copy the wgrad MMAs consume.
 __global__ void __launch_bounds__(256)
-colsum_f32_kernel(const float *__restrict__ dY, float *__restrict__ db, int64_t M, int N, int64_t rows_per_block) {
+colsum_convert_kernel(const float *__restrict__ dY, __nv_bfloat16 *__restrict__ dY16, float *__restrict__ db, int64_t M, int N,
+                      int64_t rows_per_block) {
     const int n = blockIdx.x * 256 + threadIdx.x;
     if (n >= N) return;
     const int64_t m0 = (int64_t)blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
     float acc = 0.f;
-    for (int64_t m = m0; m < m1; ++m) acc += dY[m * N + n];
-    atomicAdd(db + n, acc);
+    for (int64_t m = m0; m < m1; ++m) {
+        const float v = dY[m * N + n];
+        dY16[m * N + n] = __float2bfloat16_rn(v);
+        acc += v;
+    }
+    if (db) atomicAdd(db + n, acc);
 }
 
 }  // namespace
@@ -154,16 +159,14 @@ int launch_linear_wgrad_tc05(const float *dY, const float *X, float *dW, float *
     if (M == 0) return VSUM_OK;
     int rc;
     VSUM_REQUIRE(dY16 && X16, VSUM_EINVAL, "wgrad_tc05: bf16 scratch buffers are required");
-    if ((rc = launch_f32_to_bf16(dY, dY16, M * N, s))) return rc;
-    if ((rc = launch_f32_to_bf16(X, X16, M * K, s))) return rc;
-    if ((rc = launch_wgrad<true>(dY16, X16, dW, M, N, K, s))) return rc;
-    if (db) {
-        const int64_t rpb = ceil_div(M, 256);
+    {   // dY -> bf16 and its column sums in one pass
+        const int64_t rpb = ceil_div(M, 512);
         dim3 g2((unsigned)ceil_div(N, 256), (unsigned)ceil_div(M, rpb));
-        colsum_f32_kernel<<<g2, 256, 0, s>>>(dY, db, M, N, rpb);
-        VSUM_LAUNCH_OK("colsum_f32_kernel");
+        colsum_convert_kernel<<<g2, 256, 0, s>>>(dY, dY16, db, M, N, rpb);
+        VSUM_LAUNCH_OK("colsum_convert_kernel");
     }
-    return VSUM_OK;
+    if ((rc = launch_f32_to_bf16(X, X16, M * K, s))) return rc;
+    return launch_wgrad<true>(dY16, X16, dW, M, N, K, s);
 }
 
 }  // namespace vsum
