@@ -34,6 +34,19 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&h);
 }
+// packed fp32x2 arithmetic (sm_100): half the FFMA / FMUL issue slots of the dS computation
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(*reinterpret_cast<uint64_t *>(&d))
+        : "l"(*reinterpret_cast<const uint64_t *>(&a)), "l"(*reinterpret_cast<const uint64_t *>(&b)), "l"(*reinterpret_cast<const uint64_t *>(&c)));
+    return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    float2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<uint64_t *>(&d))
+        : "l"(*reinterpret_cast<const uint64_t *>(&a)), "l"(*reinterpret_cast<const uint64_t *>(&b)));
+    return d;
+}
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -206,25 +219,35 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                 for (int c = 0; c < 64; ++c)
                     if (c >= valid_k) s[c] = 0xff800000u;         // exp2(-inf) = 0: key past the end of the video
             }
+            const float2 c2 = make_float2(scale_log2e, scale_log2e), nl2 = make_float2(-lse_r, -lse_r), nd2 = make_float2(-dl_r, -dl_r);
             if (drop_thresh16 != 0) {
 #pragma unroll
                 for (int c = 0; c < 64; c += 4) {
                     const unsigned long long z = dropout_bits64(seed, attn_drop_group_index(base + qr, h_idx, NH, (k0 + hf * 64 + c) >> 2));
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float p = ex2(fmaf(__uint_as_float(s[c + e]), scale_log2e, -lse_r));
-                        const float ks = (uint32_t)((z >> (16 * e)) & 0xffffu) >= drop_thresh16 ? keep_scale : 0.f;
-                        const float dpd = __uint_as_float(g[c + e]) * ks;
-                        s[c + e] = __float_as_uint(p * ks);
-                        g[c + e] = __float_as_uint(p * (dpd - dl_r));
+                    for (int e = 0; e < 4; e += 2) {
+                        const float2 x = ffma2(make_float2(__uint_as_float(s[c + e]), __uint_as_float(s[c + e + 1])), c2, nl2);
+                        const float2 p = make_float2(ex2(x.x), ex2(x.y));
+                        const float2 ks = make_float2((uint32_t)((z >> (16 * e)) & 0xffffu) >= drop_thresh16 ? keep_scale : 0.f,
+                                                      (uint32_t)((z >> (16 * e + 16)) & 0xffffu) >= drop_thresh16 ? keep_scale : 0.f);
+                        const float2 pd = fmul2(p, ks);
+                        // dS = P (dropout(dP) - delta)
+                        const float2 t = ffma2(make_float2(__uint_as_float(g[c + e]), __uint_as_float(g[c + e + 1])), ks, nd2);
+                        const float2 ds = fmul2(p, t);
+                        s[c + e] = __float_as_uint(pd.x); s[c + e + 1] = __float_as_uint(pd.y);
+                        g[c + e] = __float_as_uint(ds.x); g[c + e + 1] = __float_as_uint(ds.y);
                     }
                 }
             } else {
+                const float2 one2 = make_float2(1.f, 1.f);
 #pragma unroll
-                for (int c = 0; c < 64; ++c) {
-                    const float p = ex2(fmaf(__uint_as_float(s[c]), scale_log2e, -lse_r));
-                    s[c] = __float_as_uint(p);
-                    g[c] = __float_as_uint(p * (__uint_as_float(g[c]) - dl_r));
+                for (int c = 0; c < 64; c += 2) {
+                    const float2 x = ffma2(make_float2(__uint_as_float(s[c]), __uint_as_float(s[c + 1])), c2, nl2);
+                    const float2 p = make_float2(ex2(x.x), ex2(x.y));
+                    const float2 t = ffma2(make_float2(__uint_as_float(g[c]), __uint_as_float(g[c + 1])), one2, nd2);
+                    const float2 ds = fmul2(p, t);
+                    s[c] = __float_as_uint(p.x); s[c + 1] = __float_as_uint(p.y);
+                    g[c] = __float_as_uint(ds.x); g[c + 1] = __float_as_uint(ds.y);
                 }
             }
             TMB(2);
