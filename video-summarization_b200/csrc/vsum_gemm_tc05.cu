@@ -74,7 +74,7 @@ constexpr int EPI_BAR = 1;              // named barrier of 128 epilogue threads
 // the weight-stationary variant) made the K = 256 GEMMs 20-30 % SLOWER, so each half waits for its previous TMA
 // store to finish reading the tile instead.  Measured on the same box: QKV GEMM 1.38 -> 1.09 ms per step; the
 // LayerNorm epilogues (two threads per row, partial sums exchanged through shared memory) gain 4 %.
-__host__ __device__ constexpr bool epi_uses_8_warps(int epi) { return epi < TC_EPI_BIAS_F32; }   // every bf16-output epilogue
+__host__ __device__ constexpr bool epi_uses_8_warps(int epi) { return true; }   // every epilogue (kept as a switch for experiments)
 __host__ __device__ constexpr bool epi_is_ln(int epi) { return epi == TC_EPI_BIAS_RES_LN || epi == TC_EPI_BIAS_RES_LN_HEAD; }
 __host__ __device__ constexpr int gemm_threads(int epi) { return epi_uses_8_warps(epi) ? 384 : 256; }
 // DBL variant (out-projection + LayerNorm, K = 256): staging double-buffered per half (4 tiles) on a 3-stage ring that
@@ -269,13 +269,13 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (EPI == TC_EPI_BIAS_POS_F32 && valid)
                     pos = p.pos_table + (int64_t)min(__ldg(p.row_pos + row), p.pos_rows - 1) * BN;
 #pragma unroll 1
-                for (int cc = 0; cc < 8; ++cc) {
+                for (int cc = EPI8 ? 4 * half : 0; cc < (EPI8 ? 4 * half + 4 : 8); ++cc) {
                     tc::tmem_ld32(taddr + cc * 32, ra);
                     tc::tmem_wait_ld();
-                    if (cc == 7) { tc::tc_fence_before(); tc::mbar_arrive(tempty + acc); }
-                    if (leader) tc::bulk_wait_read<1>();
-                    tc::bar_sync(EPI_BAR, 128);
-                    const uint32_t dst = stg_row + (uint32_t)(cc & 1) * STG_BYTES;
+                    if (cc == (EPI8 ? 4 * half + 3 : 7)) { tc::tc_fence_before(); tc::mbar_arrive(tempty + acc); }
+                    if (leader) { if (EPI8 && !DBL) tc::bulk_wait_read<0>(); else tc::bulk_wait_read<1>(); }
+                    tc::bar_sync(epi_bar, 128);
+                    const uint32_t dst = stg_row + ((EPI8 && !DBL) ? 0u : (uint32_t)(cc & 1) * STG_BYTES);
 #pragma unroll
                     for (int ch = 0; ch < 8; ++ch) {         // 4 columns -> one 16-byte chunk
                         const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + cc * 32 + ch * 4));
@@ -292,9 +292,9 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         sts128(dst + sw_off[ch], __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
                     }
                     tc::fence_proxy_async_smem();
-                    tc::bar_sync(EPI_BAR, 128);
+                    tc::bar_sync(epi_bar, 128);
                     if (leader) {
-                        tc::tma_store_2d(stg + (cc & 1) * STG_BYTES, &tmOut, n0 + cc * 32, (int)(m_blk * BM));
+                        tc::tma_store_2d(stg_half + ((EPI8 && !DBL) ? 0 : (cc & 1)) * STG_BYTES, &tmOut, n0 + cc * 32, (int)(m_blk * BM));
                         tc::bulk_commit();
                     }
                 }
