@@ -557,6 +557,8 @@ __global__ void __launch_bounds__(256)
 head_bwd_f32_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ d_scores,
                     const float *__restrict__ d_feats, float *__restrict__ dx, float *__restrict__ dw,
                     float *__restrict__ db, int64_t M, int d, int C) {
+    __shared__ float red[8][1024];
+    __shared__ float red_b[8];
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -579,12 +581,26 @@ head_bwd_f32_kernel(const float *__restrict__ x, const float *__restrict__ w, co
                 }
             }
         }
+        // one atomic per column and BLOCK: the eight warps meet in shared memory first
+        __syncthreads();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
             const int k = i * 32 + lane;
-            if (k < d) atomicAdd(dw + (int64_t)c * d + k, w_acc[i]);
+            if (k < d) red[threadIdx.x >> 5][k] = w_acc[i];
         }
-        if (lane == 0) atomicAdd(db + c, b_acc);
+        if (lane == 0) red_b[threadIdx.x >> 5] = b_acc;
+        __syncthreads();
+        for (int k = threadIdx.x; k < d; k += blockDim.x) {
+            float t = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) t += red[w8][k];
+            atomicAdd(dw + (int64_t)c * d + k, t);
+        }
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int w8 = 0; w8 < 8; ++w8) t += red_b[w8];
+            atomicAdd(db + c, t);
+        }
     }
 }
 
@@ -592,7 +608,7 @@ int launch_head_bwd_f32(const float *x, const float *w, const float *d_scores, c
                         float *dw, float *db, int64_t M, int d, int C, cudaStream_t s) {
     VSUM_REQUIRE(d <= 1024, VSUM_EUNSUPPORTED, "head_bwd_f32: d_model=%d", d);
     if (M == 0) return VSUM_OK;
-    const unsigned blocks = (unsigned)max((int64_t)1, min(ceil_div(M, 8), (int64_t)592));
+    const unsigned blocks = (unsigned)max((int64_t)1, min(ceil_div(M, 8), (int64_t)(2 * 148)));
     head_bwd_f32_kernel<<<blocks, 256, 0, s>>>(x, w, d_scores, d_feats, dx, dw, db, M, d, C);
     VSUM_LAUNCH_OK("head_bwd_f32_kernel");
     return VSUM_OK;
