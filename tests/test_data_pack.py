@@ -77,3 +77,24 @@ def test_open_errors(tmp_path):
     (tmp_path / "trunc.vspack").write_bytes(data[: len(data) // 2])
     with pytest.raises(_cabi.VsumError):
         PackedDataset(str(tmp_path / "trunc.vspack"))
+
+
+def test_optional_arrays_and_pretrain_collate(tmp_path):
+    """Videos without annotations (pretraining data, dataset.py:14-37): only features + video_rep; arrays that were not
+    written come back as None and the pretrain collate stacks the video representations."""
+    rng = np.random.default_rng(5)
+    vids = [dict(name=f"p{i}", features=rng.random((n, 1024), dtype=np.float32), video_rep=rng.random(512, dtype=np.float32))
+            for i, n in enumerate((40, 3, 77))]
+    path = str(tmp_path / "p.vspack")
+    write_pack(path, vids)
+    ds = PackedDataset(path, split="pretrain")
+    assert ds.array(0, _cabi.PACK_GTSCORE) is None and ds.array(1, _cabi.PACK_USER_SUMMARY) is None
+    assert ds.array(2, _cabi.PACK_CHANGE_POINTS) is None and ds.array(0, _cabi.PACK_PICKS) is None
+    (b,) = list(PackedLoader(ds, batch_size=8, device="cpu"))
+    assert b.targets is None and b.video_rep.shape == (3, 512)
+    assert np.array_equal(b.video_rep.numpy(), np.stack([v["video_rep"] for v in vids]))
+    assert np.array_equal(b.features.numpy(), np.concatenate([v["features"] for v in vids])) and b.cu_seqlens.tolist() == [0, 40, 43, 120]
+    with pytest.raises(_cabi.VsumError):                      # the train split needs gtscore, which this file does not have
+        list(PackedLoader(PackedDataset(path, split="train"), batch_size=2, device="cpu"))
+    with pytest.raises(ValueError):
+        write_pack(str(tmp_path / "bad.vspack"), [dict(name="x", features=np.zeros((4, 8), np.float32))])
