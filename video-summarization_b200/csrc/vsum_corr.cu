@@ -64,6 +64,33 @@ struct OpSeg {
     }
 };
 
+// Exclusive block scan of segmented-sum items (0 is the identity of OpSeg); `total` = combination of all items.
+__device__ __forceinline__ unsigned long long block_scan_seg_excl(unsigned long long v, unsigned long long *wbuf, unsigned long long &total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    OpSeg op;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long y = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc = op(y, inc);
+    }
+    unsigned long long exc = __shfl_up_sync(FULL, inc, 1);
+    if (lane == 0) exc = 0;
+    __syncthreads();
+    if (lane == 31) wbuf[w] = inc;
+    __syncthreads();
+    const unsigned long long wt = wbuf[lane];
+    unsigned long long winc = wt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long y = __shfl_up_sync(FULL, winc, o);
+        if (lane >= o) winc = op(y, winc);
+    }
+    total = __shfl_sync(FULL, winc, 31);
+    const unsigned long long prev = __shfl_sync(FULL, winc, (w + 31) & 31);      // inclusive value of warp w-1
+    return w == 0 ? exc : op(prev, exc);
+}
+
 __device__ __forceinline__ long long block_sum_ll(long long v, long long *wbuf) {
     long long t;
     block_scan_incl(v, OpAdd(), wbuf, t);
@@ -305,40 +332,52 @@ corr_pair_kernel(PairArgs a) {
         __syncthreads();
     }
 
-    // 4. inversions of the class sequence: MSD one-bit stable partitions
+    // 4. inversions of the class sequence: MSD one-bit stable partitions, four consecutive elements per thread
+    //    (tiles of 4096) and the class histogram in shared memory -- the group boundaries of every pass come from it
     long long dis = 0;
     const int A = st.A;
-    auto cstart = [&](int c) -> int { return c >= A ? n : cs[c]; };
+    extern __shared__ int s_cs[];                                  // class_start[0..A]
+    for (int i = tid; i <= A; i += CT) s_cs[i] = cs[i];
+    __syncthreads();
+    auto cstart = [&](int c) -> int { return c >= A ? n : s_cs[c]; };
     for (int bit = st.nb - 1, it = 0; bit >= 0; --bit, ++it) {
         const uint16_t *src = (it & 1) ? cB : cA; uint16_t *dst = (it & 1) ? cA : cB;
         if (tid == 0) s_carry_seg = 0;
         __syncthreads();
-        for (int t0 = 0; t0 < n; t0 += CT) {
-            const int j = t0 + tid;
-            int c = 0, gs = 0, one = 0; bool act = j < n;
-            unsigned long long item = 0;
-            if (act) {
-                c = src[j];
-                const int g0 = (c >> (bit + 1)) << (bit + 1);
-                gs = cstart(g0);
-                one = (c >> bit) & 1;
-                item = ((unsigned long long)(j == gs ? 1 : 0) << 32) | (unsigned)one;
+        for (int t0 = 0; t0 < n; t0 += 4 * CT) {
+            const int jb = t0 + tid * 4;
+            int c[4], gs[4];
+            unsigned long long pre[4], agg = 0;
+            OpSeg op;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                unsigned long long item = 0;
+                c[e] = 0; gs[e] = 0;
+                if (jb + e < n) {
+                    c[e] = src[jb + e];
+                    gs[e] = cstart((c[e] >> (bit + 1)) << (bit + 1));
+                    item = ((unsigned long long)(jb + e == gs[e] ? 1 : 0) << 32) | (unsigned)((c[e] >> bit) & 1);
+                }
+                pre[e] = agg;                                      // my items before e
+                agg = op(agg, item);
             }
             unsigned long long tot;
             const unsigned long long carry = s_carry_seg;
-            unsigned long long inc = block_scan_incl(item, OpSeg(), wbufu, tot);
-            inc = OpSeg()(carry, inc);
-            if (act) {
-                const int ones_before = (int)(uint32_t)inc - one;            // within the group
-                const int g0 = (c >> (bit + 1)) << (bit + 1);
-                const int zeros_total = cstart(g0 + (1 << bit)) - gs;
+            const unsigned long long before = op(carry, block_scan_seg_excl(agg, wbufu, tot));   // everything before my first item
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (jb + e >= n) continue;
+                const int j = jb + e, one = (c[e] >> bit) & 1;
+                const int ones_before = (j == gs[e]) ? 0 : (int)(uint32_t)op(before, pre[e]);   // within the group
+                const int g0 = (c[e] >> (bit + 1)) << (bit + 1);
+                const int zeros_total = cstart(g0 + (1 << bit)) - gs[e];
                 int pos;
-                if (one) pos = gs + zeros_total + ones_before;
-                else { pos = gs + (j - gs - ones_before); dis += ones_before; }
-                dst[pos] = (uint16_t)c;
+                if (one) pos = gs[e] + zeros_total + ones_before;
+                else { pos = gs[e] + (j - gs[e] - ones_before); dis += ones_before; }
+                dst[pos] = (uint16_t)c[e];
             }
             __syncthreads();
-            if (tid == 0) s_carry_seg = OpSeg()(carry, tot) & 0x00000000ffffffffull;   // flag consumed, keep the count
+            if (tid == 0) s_carry_seg = op(carry, tot) & 0x00000000ffffffffull;   // flag consumed, keep the count
             __syncthreads();
         }
     }
@@ -422,7 +461,8 @@ extern "C" int vsum_rank_correlation(const float *scores, const int32_t *cu_step
     int P = 1;
     while (P < max_steps + 1) P <<= 1;
     const size_t smem = (size_t)P * 16;
-    VSUM_ONCE_PER_DEVICE(VSUM_CUDA_OK(cudaFuncSetAttribute(corr_classes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXSEG * 16)));
+    VSUM_ONCE_PER_DEVICE(VSUM_CUDA_OK(cudaFuncSetAttribute(corr_classes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXSEG * 16));
+                         VSUM_CUDA_OK(cudaFuncSetAttribute(corr_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (MAXSEG + 2) * (int)sizeof(int))));
     {
         ProfScope prof(PROF_OTHER, s);
         corr_classes_kernel<<<B, CT, smem, s>>>(scores, cu_steps, picks, n_frames, w.seg_class, w.seg_dest, w.class_start, w.class_dx2, w.vstats);
@@ -433,7 +473,7 @@ extern "C" int vsum_rank_correlation(const float *scores, const int32_t *cu_step
         PairArgs a{user_scores, us_offsets, cu_users, us_cols, cu_steps, picks, w.seg_class, w.seg_dest, w.class_start, w.class_dx2,
                    w.vstats, w.keyA, w.keyB, w.clsA, w.clsB, w.sbuf, tau, rho, B};
         ProfScope prof(PROF_OTHER, s);
-        corr_pair_kernel<<<total_users, CT, 0, s>>>(a);
+        corr_pair_kernel<<<total_users, CT, (size_t)(max_steps + 2) * sizeof(int), s>>>(a);
         VSUM_LAUNCH_OK("corr_pair_kernel");
     }
     corr_finalize_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, s>>>(tau, rho, cu_users, B, kendall_out, spearman_out);
