@@ -92,7 +92,7 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320, tDQ = tmem_base + 384;
 
     if (warp < 4) {
-        tc::setmaxnreg_dec<40>();
+        tc::setmaxnreg_dec<104>();
         if (warp == 0 && lane == 0) {   // ===== TMA producer =====
             tc::mbar_arrive_expect_tx(kv_full, 2 * TILE_BYTES);
             tc::tma_load_2d(sK, &tmQKV, kv_full, DM + h_idx * HD, base + k0);
