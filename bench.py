@@ -273,6 +273,24 @@ def main_b200(args):
     ms_e2e = timed(step_e2e, e2e_steps) / e2e_steps
     e2e_value = world * V / (ms_e2e * 1e-3)
 
+    # ---- the same end-to-end pass with the user summaries as the packed dataset stores them (uint8, lossless for
+    # the 0/1 rows): a secondary figure -- `e2e` above keeps the h5 files' float32 rows the reference hands over
+    from vsum_b200.evaluation import _engine
+    from vsum_b200.pipeline import HostBatch
+    vs = [videos[i] for i in hb.order]
+    meta8 = _engine.HostEvalBatch.build([v.change_points for v in vs], [v.n_frames for v in vs], [v.picks for v in vs],
+                                        [v.user_summary.astype(np.uint8) for v in vs])
+    hb8 = HostBatch(hb.features, hb.seqlens, hb.cu_steps, meta8, hb.order, hb.names)
+    dbe8 = [DeviceBatch(hb8, dev, pin_meta=True) for _ in range(2)]
+
+    def step_e2e_u8(i):
+        return summ.submit_host(dbe8[i & 1], 2 + (i & 1))
+    for i in range(2):
+        step_e2e_u8(i)
+    summ.drain(dev)
+    ms_e2e_u8 = timed(step_e2e_u8, e2e_steps) / e2e_steps
+    h2d_u8 = int(dbe8[0].h2d_bytes)
+
     if world > 1:
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
         dist.all_reduce(lt)
@@ -309,6 +327,9 @@ def main_b200(args):
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(db.h2d_bytes) * world,
                     "d2h_bytes_per_step": 8 * V * world, "ms_per_step": ms_e2e},
+            "e2e_u8_user_summaries": {"value": world * V / (ms_e2e_u8 * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_u8,
+                                      "h2d_bytes_per_step": h2d_u8 * world,
+                                      "note": "same pass, user summaries as uint8 (PackedDataset user_summary_u8); e2e keeps float32"},
             "gpu_launches": launches,
             "roofline": {"kernel": "attn_tc05_kernel (varlen QK^T/softmax/PV, tcgen05)", "bound": "tensor",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",

@@ -175,14 +175,16 @@ VSUM_API int vsum_knapsack(const double *val, const int32_t *wt, const int32_t *
 /* ------------------------------------------------------------------------------------------
  * Summary mask + keyshot F-score: replaces generate_summary.py:51-53 and evaluate_summary
  * (src/evaluation/evaluation_metrics.py:4-33).
- *   user_summary: float32, video v holds n_users[v] rows of us_cols[v] columns starting at
+ *   user_summary: float32 (as the h5 files hold it) or uint8 (the packed dataset's lossless form of 0/1 rows),
+ *   per user_summary_dtype; video v holds n_users[v] rows of us_cols[v] columns starting at
  *   element us_offsets[v] (int64[B+1]).  summary_out int8: video v occupies exactly
  *   [sum_offsets[v], sum_offsets[v+1]) (int64[B+1]), i.e. last_shot_end+1 entries.  With
  *   selected == NULL, summary_out is an INPUT holding the masks (evaluate_summary on its own).  counts_ws: scratch of 3*sum(n_users) int64.
  *   f_out fp64[B]; per_user_out fp64[sum(n_users)] or NULL.  cu_users int32[B+1].
  * ------------------------------------------------------------------------------------------ */
+enum { VSUM_USER_SUMMARY_F32 = 0, VSUM_USER_SUMMARY_U8 = 1 };   /* the values vsum_pack_info.user_summary_dtype takes */
 VSUM_API int vsum_summary_fscore(const uint8_t *selected, const int32_t *cps, const int32_t *cu_shots,
-                        const float *user_summary, const int64_t *us_offsets,
+                        const void *user_summary, int32_t user_summary_dtype, const int64_t *us_offsets,
                         const int32_t *cu_users, const int32_t *us_cols, int32_t B,
                         int32_t total_users, int32_t method, int8_t *summary_out,
                         const int64_t *sum_offsets, int64_t summary_total, int64_t *counts_ws,

@@ -107,6 +107,43 @@ def test_reference_call_surface(eval_golden):
     assert bits_equal(np.float64(evaluate_summary(long_, us, "max")), np.float64(c_oracle.fscore(long_, us, "max")[0]))
 
 
+def test_fscore_uint8_user_summaries_match_float32():
+    """The packed dataset's uint8 user summaries go through their own overlap kernel: same counts, same fp64 F as the
+    float32 rows, for every alignment of the rows and of the mask, ragged lengths and values other than 0 / 1."""
+    rng = np.random.default_rng(77)
+    masks, users_f32 = [], []
+    for k in range(40):
+        cols = int(rng.integers(1, 700)) if k % 4 else int(rng.integers(3000, 9000))
+        slen = max(1, cols + int(rng.integers(-40, 40))) if k % 3 else cols
+        U = int(rng.integers(1, 6))
+        us = (rng.random((U, cols)) < 0.3).astype(np.float32)
+        if k % 5 == 0:
+            us[rng.integers(0, U), rng.integers(0, cols)] = float(rng.integers(2, 256))     # general (non 0/1) path
+        us[:, 0] = 1.0                                     # no 0/0: NaN payloads are not part of the contract
+        m = (rng.random(slen) < 0.2).astype(np.int8)
+        m[0] = 1
+        masks.append(m)
+        users_f32.append(us)
+    for method in ("avg", "max"):
+        f32 = _engine.fscore_of_masks(masks, users_f32, method)
+        u8 = _engine.fscore_of_masks(masks, [u.astype(np.uint8) for u in users_f32], method)
+        assert bits_equal(f32, u8)
+        for m, us, f in zip(masks[:12], users_f32[:12], u8[:12]):
+            assert bits_equal(np.float64(f), np.float64(c_oracle.fscore(m, us, method)[0]))
+    # whole batched path: uint8 rows in the evaluation batch
+    videos = [make_video(v, n, n_users=7, with_features=False) for v, n in ((3, 150), (4, 333), (5, 64), (9, 901))]
+    scores = [make_scores(v, n) for v, n in ((3, 150), (4, 333), (5, 64), (9, 901))]
+    dev_scores = torch.from_numpy(np.concatenate(scores)).cuda()
+    cu = torch.from_numpy(_engine._cu([len(s) for s in scores]).astype(np.int32)).cuda()
+    out = []
+    for cast in (np.float32, np.uint8):
+        hb = _engine.HostEvalBatch.build([v.change_points for v in videos], [v.n_frames for v in videos],
+                                         [v.picks for v in videos], [v.user_summary.astype(cast) for v in videos])
+        assert hb.user_summary.dtype == cast
+        out.append(_engine.summarize(_engine.DeviceEvalBatch(hb), dev_scores, cu, "avg")["f"].cpu().numpy())
+    assert bits_equal(out[0], out[1])
+
+
 def test_eval_metrics_golden():
     import os
     from conftest import GOLDEN

@@ -307,6 +307,21 @@ __device__ __forceinline__ long long block_sum_i64(long long x, long long *smem)
     return x;
 }
 
+// This thread's share of sum(S) over one video's int8 mask: bytes up to the first aligned word, then four
+// frames per 32-bit load (signed byte sum = dp4a with 0x01010101), then the tail.
+__device__ __forceinline__ long long mask_sum_partial(const int8_t *__restrict__ sm, int slen) {
+    int head = (int)((4 - ((uintptr_t)sm & 3)) & 3);
+    if (head > slen) head = slen;
+    const int nw = (slen - head) >> 2;
+    int acc = 0;                                                     // |sum| <= 128 * slen / blockDim: fits
+    if ((int)threadIdx.x < head) acc += sm[threadIdx.x];
+    const int *w = reinterpret_cast<const int *>(sm + head);
+    for (int q = threadIdx.x; q < nw; q += blockDim.x) acc = __dp4a(__ldg(w + q), 0x01010101, acc);
+    const int c = head + 4 * nw + threadIdx.x;
+    if (c < slen) acc += sm[c];
+    return (long long)acc;
+}
+
 // One CTA per (video, user) row: o = sum(S & G), g = sum(G), s = sum(S) as int64
 // (evaluation_metrics.py:20-25).  The user row is streamed with 16-byte loads.
 __global__ void __launch_bounds__(256)
@@ -378,11 +393,85 @@ overlap_kernel(const int8_t *__restrict__ summary, const int64_t *__restrict__ s
         const long long si = c < slen ? (long long)sm[c] : 0;
         o_cnt += si & gi; g_cnt += gi;
     }
-    for (int c = threadIdx.x; c < slen; c += blockDim.x) s_cnt += (long long)sm[c];
+    s_cnt = mask_sum_partial(sm, slen);
 
     o_cnt = block_sum_i64(o_cnt, red);
     g_cnt = block_sum_i64(g_cnt, red);
     s_cnt = block_sum_i64(s_cnt, red);
+    if (threadIdx.x == 0) {
+        counts[3 * (int64_t)rowid + 0] = o_cnt;
+        counts[3 * (int64_t)rowid + 1] = g_cnt;
+        counts[3 * (int64_t)rowid + 2] = s_cnt;
+    }
+  }
+}
+
+// The same counts for user summaries stored as uint8 (the packed dataset's lossless form of the 0/1 float32 rows:
+// a quarter of the bytes over PCIe and out of HBM).  Sixteen frames per 16-byte load; the mask bytes of each
+// four-frame word come from one or two aligned words of the int8 summary.
+__global__ void __launch_bounds__(256)
+overlap_u8_kernel(const int8_t *__restrict__ summary, const int64_t *__restrict__ sum_offsets,
+                  const uint8_t *__restrict__ user_summary, const int64_t *__restrict__ us_offsets,
+                  const int32_t *__restrict__ cu_users, const int32_t *__restrict__ us_cols, int B,
+                  long long *__restrict__ counts, int total_rows) {
+    __shared__ long long red[32];
+  for (int rowid = blockIdx.x; rowid < total_rows; rowid += gridDim.x) {
+    const int v = find_segment(cu_users, B, rowid);
+    const int u = rowid - __ldg(cu_users + v);
+    const int cols = __ldg(us_cols + v);
+    const int slen = (int)(__ldg(sum_offsets + v + 1) - __ldg(sum_offsets + v));
+    const int8_t *sm = summary + __ldg(sum_offsets + v);
+    const uint8_t *g = user_summary + __ldg(us_offsets + v) + (int64_t)u * cols;
+    unsigned o_acc = 0, g_acc = 0;                                   // per thread <= 255 * cols / 256 + slack
+
+    int head = (int)((16 - ((uintptr_t)g & 15)) & 15);
+    if (head > cols) head = cols;
+    const int nvec = (cols - head) >> 4;
+    auto scalar = [&](int c) {                                        // S & G on the integer values
+        const int gi = (int)__ldg(g + c);
+        g_acc += gi;
+        if (c < slen) o_acc += (unsigned)((int)sm[c] & gi);
+    };
+    if ((int)threadIdx.x < head) scalar(threadIdx.x);
+    const uintptr_t sm_addr = (uintptr_t)(sm + head);
+    const uint32_t *smw = reinterpret_cast<const uint32_t *>(sm_addr & ~(uintptr_t)3);
+    const int sm_shift = (int)(sm_addr & 3) * 8;
+    // four-frame words that lie wholly inside the summary (minus one when unaligned: the funnel shift reads on)
+    const int full_words = max(0, min(4 * nvec, (slen - head) >> 2) - (sm_shift != 0 ? 1 : 0));
+    auto add_word = [&](uint32_t gw, int w) {
+        if (w < full_words) {
+            const uint32_t w0 = __ldg(smw + w);
+            const uint32_t m = sm_shift == 0 ? w0 : __funnelshift_r(w0, __ldg(smw + w + 1), sm_shift);
+            if (((gw | m) & 0xfefefefeu) == 0u) {                    // all eight bytes are 0 / 1
+                g_acc += __popc(gw);
+                o_acc += __popc(gw & m);
+                return;
+            }
+        }
+        const int c = head + 4 * w;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gi = (int)((gw >> (8 * j)) & 0xffu);
+            g_acc += gi;
+            if (c + j < slen) o_acc += (unsigned)((int)sm[c + j] & gi);
+        }
+    };
+    const uint4 *g16 = reinterpret_cast<const uint4 *>(g + head);
+    auto add_group = [&](const uint4 &x, int q) {
+        add_word(x.x, 4 * q); add_word(x.y, 4 * q + 1); add_word(x.z, 4 * q + 2); add_word(x.w, 4 * q + 3);
+    };
+    int q = threadIdx.x;
+    for (; q + (int)blockDim.x < nvec; q += 2 * blockDim.x) {
+        const uint4 x0 = __ldcs(g16 + q), x1 = __ldcs(g16 + q + blockDim.x);          // streamed once
+        add_group(x0, q);
+        add_group(x1, q + blockDim.x);
+    }
+    if (q < nvec) add_group(__ldcs(g16 + q), q);
+    { const int c = head + 16 * nvec + threadIdx.x; if (c < cols) scalar(c); }       // < 16 tail frames
+
+    const long long o_cnt = block_sum_i64((long long)o_acc, red);
+    const long long g_cnt = block_sum_i64((long long)g_acc, red);
+    const long long s_cnt = block_sum_i64(mask_sum_partial(sm, slen), red);
     if (threadIdx.x == 0) {
         counts[3 * (int64_t)rowid + 0] = o_cnt;
         counts[3 * (int64_t)rowid + 1] = g_cnt;
@@ -500,7 +589,7 @@ extern "C" int vsum_knapsack(const double *val, const int32_t *wt, const int32_t
 }
 
 extern "C" int vsum_summary_fscore(const uint8_t *selected, const int32_t *cps,
-                                   const int32_t *cu_shots, const float *user_summary,
+                                   const int32_t *cu_shots, const void *user_summary, int32_t user_summary_dtype,
                                    const int64_t *us_offsets, const int32_t *cu_users,
                                    const int32_t *us_cols, int32_t B, int32_t total_users,
                                    int32_t method, int8_t *summary_out, const int64_t *sum_offsets,
@@ -523,13 +612,20 @@ extern "C" int vsum_summary_fscore(const uint8_t *selected, const int32_t *cps,
     if (!f_out) return VSUM_OK;                                          // generate_summary only
     VSUM_REQUIRE(user_summary && us_offsets && cu_users && us_cols && counts_ws, VSUM_EINVAL,
                  "vsum_summary_fscore: null pointer");
+    VSUM_REQUIRE(user_summary_dtype == VSUM_USER_SUMMARY_F32 || user_summary_dtype == VSUM_USER_SUMMARY_U8, VSUM_EINVAL,
+                 "vsum_summary_fscore: user_summary_dtype must be VSUM_USER_SUMMARY_F32 or VSUM_USER_SUMMARY_U8");
     if (total_users > 0) {
         ProfScope prof(PROF_OVERLAP, s);
         int grid = total_users;
         if (const int budget = eval_sm_budget()) grid = min(total_users, budget * 8);
-        overlap_kernel<<<grid, 256, 0, s>>>(summary_out, sum_offsets, user_summary,
-                                            us_offsets, cu_users, us_cols, B,
-                                            reinterpret_cast<long long *>(counts_ws), total_users);
+        if (user_summary_dtype == VSUM_USER_SUMMARY_U8)
+            overlap_u8_kernel<<<grid, 256, 0, s>>>(summary_out, sum_offsets, static_cast<const uint8_t *>(user_summary),
+                                                   us_offsets, cu_users, us_cols, B,
+                                                   reinterpret_cast<long long *>(counts_ws), total_users);
+        else
+            overlap_kernel<<<grid, 256, 0, s>>>(summary_out, sum_offsets, static_cast<const float *>(user_summary),
+                                                us_offsets, cu_users, us_cols, B,
+                                                reinterpret_cast<long long *>(counts_ws), total_users);
         VSUM_LAUNCH_OK("overlap_kernel");
     }
     ProfScope prof(PROF_FSCORE, s);

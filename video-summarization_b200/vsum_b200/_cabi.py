@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("VSUM_LIB", os.path.join(_HERE, "libvsum_b200.so"))   
 VSUM_MAX_LAYERS = 16
 MODE_FP32, MODE_BF16 = 0, 1
 FSCORE_AVG, FSCORE_MAX = 0, 1
+USER_SUMMARY_F32, USER_SUMMARY_U8 = 0, 1
 
 # every symbol include/vsum_b200.h declares (checked by tests/test_cabi_symbols.py)
 EXPORTS = (
@@ -116,7 +117,7 @@ def load():
     L.vsum_knapsack_scratch_words.restype = i64
     L.vsum_knapsack_scratch_words.argtypes = [i32, i32]
     L.vsum_knapsack.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp]
-    L.vsum_summary_fscore.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, i64, vp, vp, vp, vp]
+    L.vsum_summary_fscore.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, vp, vp, i64, vp, vp, vp, vp]
     L.vsum_debug_gemm_tc05.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]
     L.vsum_debug_attention_tc05.argtypes = [vp, vp, i32, i64, vp, vp, vp]
     L.vsum_debug_attention_train_tc05.argtypes = [vp, vp, i32, i64, vp, vp, C.c_float, C.c_uint64, vp, vp]

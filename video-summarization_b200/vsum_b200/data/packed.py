@@ -91,6 +91,8 @@ def write_pack(path: str, videos: Iterable[dict], feature_dim: int = 1024, user_
                 n_users, n_frames = us.shape[0], n_frames or us.shape[1]
                 if us.shape[1] != n_frames:
                     raise ValueError("user_summary rows must have n_frames columns")
+                if user_summary_u8 and not np.array_equal(us, us.astype(np.uint8)):
+                    raise ValueError("user_summary_u8 needs integer values in [0, 255] (the byte form must be lossless)")
                 put(_cabi.PACK_USER_SUMMARY, us.astype(np.uint8 if user_summary_u8 else np.float32), _ALIGN)
             if v.get("user_scores") is not None:
                 sc = np.asarray(v["user_scores"], dtype=np.float32)

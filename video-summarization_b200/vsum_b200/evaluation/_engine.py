@@ -66,7 +66,7 @@ class HostEvalBatch:
     max_cap: int
     launches: list               # [(first index into order, count, max capacity)] one per kernel class
     sum_offsets: np.ndarray      # int64[B+1]  summary v occupies [sum_offsets[v], sum_offsets[v+1])
-    user_summary: Optional[np.ndarray]   # float32 flat
+    user_summary: Optional[np.ndarray]   # flat; float32, or uint8 when every video's rows came as uint8 / bool
     us_offsets: Optional[np.ndarray]     # int64[B+1]
     cu_users: Optional[np.ndarray]       # int32[B+1]
     us_cols: Optional[np.ndarray]        # int32[B]
@@ -97,8 +97,8 @@ class HostEvalBatch:
             pos = end
         us = us_off = cu_users = us_cols = None
         if user_summaries is not None:
-            mats = [np.ascontiguousarray(np.asarray(u), dtype=np.float32).reshape(len(u), -1) for u in user_summaries]
-            us = np.concatenate([m.reshape(-1) for m in mats]) if B else np.zeros(0, np.float32)
+            mats, us_dt = _user_matrices(user_summaries)
+            us = np.concatenate([m.reshape(-1) for m in mats]) if B else np.zeros(0, us_dt)
             us_off = _cu([m.size for m in mats])
             cu_users = _cu([m.shape[0] for m in mats]).astype(np.int32)
             us_cols = np.asarray([m.shape[1] for m in mats], dtype=np.int32)
@@ -115,6 +115,18 @@ class HostEvalBatch:
             launches=launches,
             sum_offsets=_cu([e + 1 for e in last_end]),
             user_summary=us, us_offsets=us_off, cu_users=cu_users, us_cols=us_cols)
+
+
+def _user_matrices(user_summaries):
+    """[U, n_frames] matrices of one dtype for the overlap kernel: uint8 when every video's user summary is stored as
+    uint8 / bool (the packed dataset's lossless form of the 0/1 rows), else float32 as the h5 files hold them."""
+    arrs = [np.asarray(u) for u in user_summaries]
+    dt = np.uint8 if arrs and all(a.dtype in (np.uint8, np.bool_) for a in arrs) else np.float32
+    return [np.ascontiguousarray(a, dtype=dt).reshape(len(a), -1) for a in arrs], dt
+
+
+def _us_dtype_code(a) -> int:
+    return _cabi.USER_SUMMARY_U8 if a is not None and a.dtype == np.uint8 else _cabi.USER_SUMMARY_F32
 
 
 _FIELDS = ("picks", "cu_picks", "n_frames", "cps", "cu_shots", "bit_offsets", "order", "sum_offsets")
@@ -206,7 +218,8 @@ def summarize(db: DeviceEvalBatch, scores: torch.Tensor, cu_steps: torch.Tensor,
                 per_user = torch.empty(total_users, dtype=torch.float64, device=dev)
         _cabi.check(L.vsum_summary_fscore(
             selected.data_ptr(), db.cps.data_ptr(), db.cu_shots.data_ptr(),
-            _ptr(db.user_summary) if want_f else None, _ptr(db.us_offsets) if want_f else None,
+            _ptr(db.user_summary) if want_f else None, _us_dtype_code(hb.user_summary),
+            _ptr(db.us_offsets) if want_f else None,
             _ptr(db.cu_users) if want_f else None, _ptr(db.us_cols) if want_f else None,
             B, total_users, _cabi.FSCORE_MAX if method == "max" else _cabi.FSCORE_AVG,
             summary.data_ptr(), db.sum_offsets.data_ptr(), int(hb.sum_offsets[-1]), _ptr(counts),
@@ -222,7 +235,7 @@ def fscore_of_masks(summaries: Sequence[np.ndarray], user_summaries: Sequence[np
     L = _cabi.load()
     B = len(summaries)
     masks = [np.ascontiguousarray(np.asarray(s), dtype=np.int8) for s in summaries]
-    mats = [np.ascontiguousarray(np.asarray(u), dtype=np.float32).reshape(len(u), -1) for u in user_summaries]
+    mats, us_dt = _user_matrices(user_summaries)
     sum_off = _cu([len(m) for m in masks])
     us_off = _cu([m.size for m in mats])
     cu_users = _cu([m.shape[0] for m in mats]).astype(np.int32)
@@ -232,12 +245,13 @@ def fscore_of_masks(summaries: Sequence[np.ndarray], user_summaries: Sequence[np
         stream = torch.cuda.current_stream(dev).cuda_stream
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
         d_mask = t(np.concatenate(masks) if B else np.zeros(0, np.int8))
-        d_us = t(np.concatenate([m.reshape(-1) for m in mats]) if B else np.zeros(0, np.float32))
+        d_us = t(np.concatenate([m.reshape(-1) for m in mats]) if B else np.zeros(0, us_dt))
         d_sum_off, d_us_off, d_cu_users, d_cols = t(sum_off), t(us_off), t(cu_users), t(us_cols)
         f = torch.empty(B, dtype=torch.float64, device=dev)
         counts = _scratch_buf("counts", max(total_users, 1) * 24, dev)
         _cabi.check(L.vsum_summary_fscore(
-            None, None, None, d_us.data_ptr(), d_us_off.data_ptr(), d_cu_users.data_ptr(), d_cols.data_ptr(),
+            None, None, None, d_us.data_ptr(), _cabi.USER_SUMMARY_U8 if us_dt is np.uint8 else _cabi.USER_SUMMARY_F32,
+            d_us_off.data_ptr(), d_cu_users.data_ptr(), d_cols.data_ptr(),
             B, total_users, _cabi.FSCORE_MAX if method == "max" else _cabi.FSCORE_AVG,
             d_mask.data_ptr(), d_sum_off.data_ptr(), int(sum_off[-1]), counts.data_ptr(), f.data_ptr(), None,
             stream), "vsum_summary_fscore")
