@@ -44,6 +44,13 @@ def test_roundtrip_and_records(tmp_path, u8):
     assert rep.shape == (512,) and np.array_equal(rep.numpy(), vids[2]["video_rep"])
 
 
+def test_byte_user_summaries_must_be_lossless(tmp_path):
+    vids = _videos((40,))
+    vids[0]["user_summary"] = vids[0]["user_summary"] * 0.5          # not representable as bytes
+    with pytest.raises(ValueError, match="lossless"):
+        write_pack(str(tmp_path / "d.vspack"), vids, user_summary_u8=True)
+
+
 @pytest.mark.parametrize("threads", [1, 5])
 def test_collate_is_packed_and_ordered(tmp_path, threads):
     vids = _videos((60, 7, 131, 300, 1, 2000), first=720)

@@ -90,3 +90,28 @@ def test_packed_loader_feeds_the_scorer(tmp_path):
         assert np.array_equal(b.targets.cpu().numpy(), tgt)
         seen += len(b.ids)
     assert seen == 5
+
+
+def test_val_split_of_a_byte_pack_scores_like_the_float32_one(tmp_path):
+    """`val` records of a pack written with user_summary_u8 keep the byte rows all the way into the overlap kernel;
+    the F-scores are the float32 pack's, bit for bit (src/train.py:134-152 on either file)."""
+    import numpy as np
+    from conftest import bits_equal
+    from vsum_b200.data import PackedDataset, write_pack
+    from vsum_b200.evaluation import eval_fscores
+    from vsum_b200.synthetic import make_scores, make_video
+    vids = [make_video(2600 + i, n, n_users=5) for i, n in enumerate((150, 61, 333, 412))]
+    recs = [dict(name=v.name, features=v.features, gtscore=v.gtscore, picks=v.picks, change_points=v.change_points,
+                 n_frames=v.n_frames, user_summary=v.user_summary) for v in vids]
+    got = []
+    for u8 in (False, True):
+        path = str(tmp_path / ("u8.vspack" if u8 else "f32.vspack"))
+        write_pack(path, recs, user_summary_u8=u8)
+        ds = PackedDataset(path, split="val")
+        data, users = {}, {}
+        for i, v in enumerate(vids):
+            _, _, user = ds[i]
+            assert user.user_summary.dtype == (np.uint8 if u8 else np.float32)
+            data[user.name], users[user.name] = make_scores(2600 + i, v.n_steps), user
+        got.append(np.asarray(eval_fscores(data, users)))
+    assert len(got[0]) == 4 and bits_equal(got[0], got[1])
