@@ -178,11 +178,21 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
             const uint64_t v_desc = tc::make_smem_desc_sw128(tc::smem_u32(sV), v_lbo, v_sbo);   // + v_kstep/16 per 16 keys
             const uint64_t p_desc0 = tc::make_smem_desc_sw128(tc::smem_u32(sP), 16, 1024);
             const uint32_t v_step = v_kstep >> 4;
+            // Per-MMA descriptors are re-derived at the point of use (one 32-bit add on the address field; the add is
+            // opaque to the compiler).  Hoisted out of the KV loop, the 24 descriptors of a tile do not fit the
+            // 32 registers this warp keeps after setmaxnreg.dec and came back from local memory before every MMA group.
+            const uint32_t q_lo = (uint32_t)q_desc, k_lo = (uint32_t)k_desc, v_lo = (uint32_t)v_desc, p_lo0 = (uint32_t)p_desc0;
+            const uint32_t hi_qkp = (uint32_t)(q_desc >> 32), hi_v = (uint32_t)(v_desc >> 32);
+            auto desc_at = [](uint32_t lo, uint32_t off, uint32_t hi) -> uint64_t {
+                uint32_t l;
+                asm volatile("add.u32 %0, %1, %2;" : "=r"(l) : "r"(lo), "r"(off));
+                return ((uint64_t)hi << 32) | l;
+            };
             auto issue_qk = [&]() {
                 if (tc::elect_one()) {
 #pragma unroll
                     for (int k = 0; k < HD / 16; ++k)
-                        tc::mma_f16_ss(tS, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), IDESC_QK, k != 0);
+                        tc::mma_f16_ss(tS, desc_at(q_lo, k * 2, hi_qkp), desc_at(k_lo, k * 2, hi_qkp), IDESC_QK, k != 0);
                     tc::mma_commit(s_full);
                     tc::mma_commit(k_empty);
                 }
@@ -203,12 +213,12 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
                 tc::mbar_wait(v_full, j & 1);
                 tc::tc_fence_after();
                 // A: P buffer (j&1): half k/4 (16 KB apart), 32-byte step inside the 128-byte swizzled row
-                const uint64_t p_desc = p_desc0 + (uint64_t)((j & 1) * (2 * TILE_BYTES >> 4));
+                const uint32_t p_lo = p_lo0 + (uint32_t)((j & 1) * (2 * TILE_BYTES >> 4));
                 if (tc::elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BKV / 16; ++k)               // keys 0..63 -> O half 0, keys 64..127 -> O half 1
-                        tc::mma_f16_ss(tO + (uint32_t)((k >> 2) * HD), p_desc + (uint64_t)((k >> 2) * (TILE_BYTES >> 4) + (k & 3) * 2),
-                                       v_desc + (uint64_t)(k * v_step), IDESC_PV, (j | (k & 3)) != 0);   // accumulates over all KV tiles
+                        tc::mma_f16_ss(tO + (uint32_t)((k >> 2) * HD), desc_at(p_lo, (k >> 2) * (TILE_BYTES >> 4) + (k & 3) * 2, hi_qkp),
+                                       desc_at(v_lo, k * v_step, hi_v), IDESC_PV, (j | (k & 3)) != 0);   // accumulates over all KV tiles
                     tc::mma_commit(v_empty);
                     tc::mma_commit(p_empty + (j & 1));           // also means "PV(j) done"
                 }
