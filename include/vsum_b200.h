@@ -40,6 +40,8 @@ extern "C" {
 
 #define VSUM_MODE_FP32 0       /* fp32 SIMT kernels: <=1e-5 vs the reference's fp32 path */
 #define VSUM_MODE_BF16 1       /* bf16 tcgen05/TMEM/TMA kernels (tf32 for the fp32 feature GEMM) */
+#define VSUM_MODE_BF16_FEATURES 2   /* the same kernels fed with bf16 FEATURES (a pack written with features_bf16: half the
+                                       bytes over PCIe and out of HBM); the feature GEMM then runs in bf16 as well */
 
 #define VSUM_FSCORE_AVG 0      /* evaluation_metrics.py:32-33 ('avg', TVSum) */
 #define VSUM_FSCORE_MAX 1      /* evaluation_metrics.py:30-31 ('max', SumMe) */
@@ -92,11 +94,11 @@ VSUM_API int vsum_scorer_destroy(vsum_scorer_t h);
 VSUM_API int vsum_scorer_load_weights(vsum_scorer_t h, const vsum_scorer_weights *w_host, void *stream);
 /* Bytes of scratch vsum_scorer_forward needs for T packed frames in B videos. */
 VSUM_API size_t vsum_scorer_workspace_bytes(vsum_scorer_t h, int64_t T, int32_t B, int32_t mode);
-/* features [T,in_features] fp32, cu_seqlens int32[B+1].  Key masking follows simnet.py:156-157:
+/* features [T,in_features] fp32 (bf16 with VSUM_MODE_BF16_FEATURES), cu_seqlens int32[B+1].  Key masking follows simnet.py:156-157:
  * with packed videos no key is ever padded.  scores_out [T,num_classes] fp32 logits (or their
  * sigmoid when apply_sigmoid != 0, src/train.py:144); feats_out [T,d_model] fp32 or NULL
  * (the second element of SimNet.forward's tuple).  max_len = longest video in the batch. */
-VSUM_API int vsum_scorer_forward(vsum_scorer_t h, const float *features, const int32_t *cu_seqlens,
+VSUM_API int vsum_scorer_forward(vsum_scorer_t h, const void *features, const int32_t *cu_seqlens,
                         int32_t B, int64_t T, int32_t max_len, int32_t mode, int32_t apply_sigmoid,
                         float *scores_out, float *feats_out, void *workspace,
                         size_t workspace_bytes, void *stream);
@@ -293,11 +295,13 @@ VSUM_API int vsum_kts_dp(const float *K, int32_t n, int32_t m, int32_t lmin, int
  * multi-threaded padding-free collate that gathers a batch straight into one caller buffer (pinned
  * host memory) as packed rows + cu_seqlens -- the layout vsum_scorer_forward consumes.
  *   vsum_pack_array returns a zero-copy view into the mapping (NULL / 0 bytes when the array is absent).
- *   vsum_pack_collate: features_out [sum N, feature_dim] fp32, gtscore_out [sum N] or NULL,
+ *   vsum_pack_collate: features_out [sum N, feature_dim] in the pack's feature dtype (vsum_pack_feature_dtype:
+ *   float32 as in the h5 files, or bfloat16 for VSUM_MODE_BF16_FEATURES), gtscore_out [sum N] or NULL,
  *   cu_seqlens_out int32[n+1]; `threads` host threads split the bytes evenly.
  * ------------------------------------------------------------------------------------------ */
 enum { VSUM_PACK_FEATURES = 0, VSUM_PACK_GTSCORE, VSUM_PACK_PICKS, VSUM_PACK_CHANGE_POINTS, VSUM_PACK_USER_SUMMARY,
        VSUM_PACK_USER_SCORES, VSUM_PACK_VIDEO_REP, VSUM_PACK_NUM_ARRAYS };
+enum { VSUM_FEATURES_F32 = 0, VSUM_FEATURES_BF16 = 1 };
 typedef struct vsum_pack *vsum_pack_t;
 typedef struct {
     char name[96];
@@ -308,10 +312,11 @@ VSUM_API int vsum_pack_open(const char *path, vsum_pack_t *out);
 VSUM_API void vsum_pack_close(vsum_pack_t pack);
 VSUM_API int32_t vsum_pack_num_videos(vsum_pack_t pack);
 VSUM_API int32_t vsum_pack_feature_dim(vsum_pack_t pack);
+VSUM_API int32_t vsum_pack_feature_dtype(vsum_pack_t pack);
 VSUM_API int vsum_pack_video_info(vsum_pack_t pack, int32_t video, vsum_pack_info *out);
 VSUM_API int vsum_pack_array(vsum_pack_t pack, int32_t video, int32_t kind, const void **ptr, uint64_t *bytes);
 VSUM_API int vsum_pack_collate(vsum_pack_t pack, const int32_t *videos, int32_t n, int32_t threads,
-                               float *features_out, float *gtscore_out, int32_t *cu_seqlens_out);
+                               void *features_out, float *gtscore_out, int32_t *cu_seqlens_out);
 
 /* ------------------------------------------------------------------------------------------
  * Diagnostics: the two tcgen05 kernels on their own, so tests can pin them individually.

@@ -44,6 +44,27 @@ def test_roundtrip_and_records(tmp_path, u8):
     assert rep.shape == (512,) and np.array_equal(rep.numpy(), vids[2]["video_rep"])
 
 
+def test_bf16_feature_pack(tmp_path):
+    """features_bf16: rows are the round-to-nearest-even bfloat16 of the float32 features (what torch's .bfloat16() gives),
+    served to the val split only, and the collate gathers them as bf16 rows."""
+    vids = _videos((60, 7, 131), first=810)
+    vids[0]["features"] = vids[0]["features"].copy()
+    vids[0]["features"][0, :4] = np.array([1.00390625, 1.01171875, -3.0e-39, 65504.0], np.float32)   # ties, a denormal, a large value
+    path = str(tmp_path / "d.vspack")
+    write_pack(path, vids, features_bf16=True, user_summary_u8=True)
+    ds = PackedDataset(path, split="val")
+    assert ds.features_bf16
+    for i, v in enumerate(vids):
+        feats, tgt, user = ds[i]
+        assert feats.dtype == torch.bfloat16 and torch.equal(feats, torch.from_numpy(v["features"]).bfloat16())
+        assert torch.equal(tgt, torch.from_numpy(v["gtscore"])) and user.user_summary.dtype == np.uint8
+    b = next(iter(PackedLoader(ds, batch_size=3, device="cpu", collate_threads=3)))
+    assert b.features.dtype == torch.bfloat16 and b.cu_seqlens.tolist() == [0, 60, 67, 198]
+    assert torch.equal(b.features, torch.cat([torch.from_numpy(v["features"]).bfloat16() for v in vids]))
+    with pytest.raises(ValueError, match="inference"):
+        PackedDataset(path, split="train")
+
+
 def test_byte_user_summaries_must_be_lossless(tmp_path):
     vids = _videos((40,))
     vids[0]["user_summary"] = vids[0]["user_summary"] * 0.5          # not representable as bytes

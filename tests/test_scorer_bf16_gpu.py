@@ -55,6 +55,25 @@ def test_bf16_tracks_fp32_on_packed_varlen(models):
     assert none is None and torch.equal(a, c)
 
 
+def test_bf16_features_track_fp32(models):
+    """VSUM_MODE_BF16_FEATURES: features rounded to bf16 once (a `features_bf16` pack), feature GEMM in bf16.  Scores stay
+    within the 1e-2 tolerance of the fp32 path run on the ORIGINAL float32 features."""
+    bf, fp = models
+    lens = [700, 128, 1, 129, 2500, 64]
+    vids = [make_video(640 + i, n) for i, n in enumerate(lens)]
+    feats = torch.from_numpy(np.concatenate([v.features for v in vids])).cuda()
+    cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32).cuda()
+    a, fa = bf.forward_packed(feats.bfloat16(), cu, lens, apply_sigmoid=True)
+    b, fb = fp.forward_packed(feats, cu, lens, apply_sigmoid=True)
+    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=TOL, atol=0)
+    assert (fa - fb).abs().max().item() < 0.15
+    # the tf32 feature GEMM on the same (already rounded) values gives nearly the same scores: only the weight rounding differs
+    c, _ = bf.forward_packed(feats.bfloat16().float(), cu, lens, apply_sigmoid=True)
+    np.testing.assert_allclose(a.cpu().numpy(), c.cpu().numpy(), rtol=TOL / 2, atol=0)
+    with pytest.raises(ValueError, match="bf16 scorer"):
+        fp.forward_packed(feats.bfloat16(), cu, lens)
+
+
 def test_deterministic(models):
     bf, _ = models
     x = torch.from_numpy(make_video(700, 900).features).unsqueeze(0).cuda()

@@ -530,6 +530,8 @@ int launch_gemm_tc05(const Tc05GemmArgs &a, cudaStream_t s) {
     switch (a.epi) {
         case TC_EPI_BIAS:
             return wres ? launch_variant<false, TC_EPI_BIAS, true>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat) : launch_variant<false, TC_EPI_BIAS, false>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat);
+        case TC_EPI_BIAS_POS:     // feature GEMM from bf16 features (VSUM_MODE_BF16_FEATURES): K = 1024, W streamed
+            return launch_variant<false, TC_EPI_BIAS_POS, false>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat);
         case TC_EPI_BIAS_RELU:
             return wres ? launch_variant<false, TC_EPI_BIAS_RELU, true>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat) : launch_variant<false, TC_EPI_BIAS_RELU, false>(tmA, tmB, tmOut, tmRes, p, s, a.prof_cat);
         case TC_EPI_BIAS_RES_LN:

@@ -5,8 +5,9 @@
 // with the 1000 sentinel, no mask round trip (src/train.py:115-118).
 //
 // File layout (little endian), written by vsum_b200/data/packed.py:
-//   header  64 B : magic "VSPACK01", u32 version, u32 n_videos, u64 index_offset, u64 file_bytes, u32 feature_dim
-//   arrays       : per video features f32[N,dim] (4096-aligned), gtscore f32[N], picks i32[N], change_points
+//   header  64 B : magic "VSPACK01", u32 version, u32 n_videos, u64 index_offset, u64 file_bytes, u32 feature_dim,
+//                  u32 feature_dtype (0 = float32 as in the h5 files, 1 = bfloat16)
+//   arrays       : per video features f32|bf16 [N,dim] (4096-aligned), gtscore f32[N], picks i32[N], change_points
 //                  i32[S,2], user_summary f32|u8 [U,n_frames], user_scores f32[U,n_frames], video_rep f32[rep_dim]
 //   index        : n_videos entries of 256 B (name, sizes, byte offsets; offset 0 = array absent)
 #include "vsum_common.cuh"
@@ -26,7 +27,7 @@
 namespace {
 
 struct FileHeader {
-    char magic[8]; uint32_t version, n_videos; uint64_t index_offset, file_bytes; uint32_t feature_dim, pad[7];
+    char magic[8]; uint32_t version, n_videos; uint64_t index_offset, file_bytes; uint32_t feature_dim, feature_dtype, pad[6];
 };
 static_assert(sizeof(FileHeader) == 64, "header is 64 bytes");
 
@@ -50,7 +51,7 @@ struct vsum_pack {
 
 static uint64_t array_bytes(const FileHeader *h, const IndexEntry &e, int kind) {
     switch (kind) {
-        case VSUM_PACK_FEATURES: return (uint64_t)e.n_steps * h->feature_dim * 4;
+        case VSUM_PACK_FEATURES: return (uint64_t)e.n_steps * h->feature_dim * (h->feature_dtype == VSUM_FEATURES_BF16 ? 2 : 4);
         case VSUM_PACK_GTSCORE: return (uint64_t)e.n_steps * 4;
         case VSUM_PACK_PICKS: return (uint64_t)e.n_steps * 4;
         case VSUM_PACK_CHANGE_POINTS: return (uint64_t)e.n_shots * 8;
@@ -85,6 +86,7 @@ extern "C" int vsum_pack_open(const char *path, vsum_pack_t *out) {
     };
     if (memcmp(p->hdr->magic, "VSPACK01", 8) != 0 || p->hdr->version != 1) return fail("bad magic or version");
     if (p->hdr->file_bytes != p->bytes) return fail("truncated file (size differs from the header)");
+    if (p->hdr->feature_dtype != VSUM_FEATURES_F32 && p->hdr->feature_dtype != VSUM_FEATURES_BF16) return fail("unknown feature dtype");
     if (p->hdr->index_offset + (uint64_t)p->hdr->n_videos * sizeof(IndexEntry) > p->bytes) return fail("index outside the file");
     p->index = (const IndexEntry *)(p->base + p->hdr->index_offset);
     for (uint32_t i = 0; i < p->hdr->n_videos; ++i) {
@@ -107,6 +109,7 @@ extern "C" void vsum_pack_close(vsum_pack_t p) {
 
 extern "C" int32_t vsum_pack_num_videos(vsum_pack_t p) { return p ? (int32_t)p->hdr->n_videos : 0; }
 extern "C" int32_t vsum_pack_feature_dim(vsum_pack_t p) { return p ? (int32_t)p->hdr->feature_dim : 0; }
+extern "C" int32_t vsum_pack_feature_dtype(vsum_pack_t p) { return p ? (int32_t)p->hdr->feature_dtype : 0; }
 
 extern "C" int vsum_pack_video_info(vsum_pack_t p, int32_t i, vsum_pack_info *out) {
     VSUM_REQUIRE(p && out && i >= 0 && (uint32_t)i < p->hdr->n_videos, VSUM_EINVAL, "vsum_pack_video_info: bad video index %d", i);
@@ -130,10 +133,10 @@ extern "C" int vsum_pack_array(vsum_pack_t p, int32_t i, int32_t kind, const voi
 // Padding-free collate: features of the listed videos back to back into features_out [sum N, dim] (and their
 // gtscore into gtscore_out [sum N] when non-NULL), cu_seqlens_out[k] = first row of the k-th listed video.
 // The byte range is split evenly over `threads` workers (each memcpy also faults the mapped pages in).
-extern "C" int vsum_pack_collate(vsum_pack_t p, const int32_t *ids, int32_t n, int32_t threads, float *features_out,
+extern "C" int vsum_pack_collate(vsum_pack_t p, const int32_t *ids, int32_t n, int32_t threads, void *features_out,
                                  float *gtscore_out, int32_t *cu_seqlens_out) {
     VSUM_REQUIRE(p && ids && n >= 0 && features_out && cu_seqlens_out, VSUM_EINVAL, "vsum_pack_collate: null argument");
-    const uint64_t row = (uint64_t)p->hdr->feature_dim * 4;
+    const uint64_t row = (uint64_t)p->hdr->feature_dim * (p->hdr->feature_dtype == VSUM_FEATURES_BF16 ? 2 : 4);
     std::vector<uint64_t> dst(n + 1, 0);
     cu_seqlens_out[0] = 0;
     for (int k = 0; k < n; ++k) {

@@ -24,6 +24,7 @@ struct vsum_scorer {
     float *pos_table = nullptr;
     int pos_rows = 0;
     size_t embed_w, embed_b, final_w, final_b, n32 = 0, n16 = 0;
+    size_t h_embed = 0;            // bf16 copy of embed_w in the bf16 blob (VSUM_MODE_BF16_FEATURES)
     LayerOffsets L[VSUM_MAX_LAYERS];
     bool loaded = false;
     bool tc05_shape = false;
@@ -69,6 +70,7 @@ extern "C" int vsum_scorer_create(vsum_scorer_t *out, const vsum_scorer_config *
         o.t_wqkv = take(c32, 3 * d * d); o.t_wo = take(c32, d * d);
         o.t_fc1 = take(c32, ff * d); o.t_fc2 = take(c32, d * ff);
     }
+    h->h_embed = take(c16, d * in);
     h->n32 = c32; h->n16 = c16;
     h->tc05_shape = cfg->d_model == 256 && cfg->num_heads == 4 && cfg->d_ff == 1024 && cfg->num_classes == 1 &&
                     cfg->in_features % 32 == 0;
@@ -113,6 +115,7 @@ extern "C" int vsum_scorer_load_weights(vsum_scorer_t h, const vsum_scorer_weigh
         VSUM_CUDA_OK(cudaMemcpyAsync(h->pos_table, w->pos_table, (size_t)w->pos_rows * d * sizeof(float),
                                      cudaMemcpyDeviceToDevice, s));
     }
+    if (int rc = launch_f32_to_bf16(h->w32 + h->embed_w, h->w16 + h->h_embed, d * in, s)) return rc;
     for (int l = 0; l < h->cfg.num_layers; ++l) {
         const vsum_layer_weights &lw = w->layers[l];
         const LayerOffsets &o = h->L[l];
@@ -199,7 +202,8 @@ static int forward_fp32(vsum_scorer_t h, const float *x, const int32_t *cu, int 
     return VSUM_OK;
 }
 
-static int forward_bf16(vsum_scorer_t h, const float *x, const int32_t *cu, int B, int64_t T, int sigm,
+// x: fp32 features (tf32 feature GEMM) or, with x_is_bf16, bf16 features (bf16 feature GEMM on the bf16 copy of the weight)
+static int forward_bf16(vsum_scorer_t h, const void *x, bool x_is_bf16, const int32_t *cu, int B, int64_t T, int sigm,
                         float *scores, float *feats, void *ws, cudaStream_t s) {
     const vsum_scorer_config &c = h->cfg;
     VSUM_REQUIRE(h->tc05_shape, VSUM_EUNSUPPORTED,
@@ -213,7 +217,8 @@ static int forward_bf16(vsum_scorer_t h, const float *x, const int32_t *cu, int 
     RUN(launch_row_positions(cu, B, T, w.row_pos, nullptr, s));
     RUN(launch_attn_schedule(cu, B, w.tile_video, w.tile_q0, w.n_tiles, max_tiles, s));
     Tc05GemmArgs g{};
-    g.A = x; g.W = h->w32 + h->embed_w; g.M = T; g.N = 256; g.K = c.in_features; g.a_is_f32 = 1;
+    g.A = x; g.M = T; g.N = 256; g.K = c.in_features; g.a_is_f32 = x_is_bf16 ? 0 : 1;
+    g.W = x_is_bf16 ? (const void *)(h->w16 + h->h_embed) : (const void *)(h->w32 + h->embed_w);
     g.epi = c.use_pos ? TC_EPI_BIAS_POS : TC_EPI_BIAS; g.bias = h->w32 + h->embed_b; g.out = w.xa;
     g.pos_table = h->pos_table; g.row_pos = w.row_pos; g.pos_rows = h->pos_rows; g.prof_cat = PROF_EMBED;
     RUN(launch_gemm_tc05(g, s));
@@ -248,7 +253,7 @@ static int forward_bf16(vsum_scorer_t h, const float *x, const int32_t *cu, int 
     return VSUM_OK;
 }
 
-extern "C" int vsum_scorer_forward(vsum_scorer_t h, const float *features, const int32_t *cu_seqlens,
+extern "C" int vsum_scorer_forward(vsum_scorer_t h, const void *features, const int32_t *cu_seqlens,
                                    int32_t B, int64_t T, int32_t max_len, int32_t mode, int32_t apply_sigmoid,
                                    float *scores_out, float *feats_out, void *workspace, size_t workspace_bytes,
                                    void *stream) {
@@ -257,7 +262,10 @@ extern "C" int vsum_scorer_forward(vsum_scorer_t h, const float *features, const
     VSUM_REQUIRE(B >= 0 && T >= 0 && max_len >= 0, VSUM_EINVAL, "vsum_scorer_forward: negative sizes");
     if (B == 0 || T == 0) return VSUM_OK;
     VSUM_REQUIRE(features && cu_seqlens && scores_out && workspace, VSUM_EINVAL, "vsum_scorer_forward: null pointer");
-    VSUM_REQUIRE(mode == VSUM_MODE_FP32 || mode == VSUM_MODE_BF16, VSUM_EINVAL, "vsum_scorer_forward: unknown mode %d", mode);
+    VSUM_REQUIRE(mode == VSUM_MODE_FP32 || mode == VSUM_MODE_BF16 || mode == VSUM_MODE_BF16_FEATURES, VSUM_EINVAL,
+                 "vsum_scorer_forward: unknown mode %d", mode);
+    VSUM_REQUIRE(mode != VSUM_MODE_BF16_FEATURES || h->cfg.in_features % 64 == 0, VSUM_EUNSUPPORTED,
+                 "vsum_scorer_forward: bf16 features need in_features to be a multiple of 64 (got %d)", h->cfg.in_features);
     VSUM_REQUIRE(T < ((int64_t)1 << 31), VSUM_EUNSUPPORTED, "vsum_scorer_forward: T=%lld frames exceed one call", (long long)T);
     VSUM_REQUIRE(!h->cfg.use_pos || max_len <= h->pos_rows, VSUM_EINVAL,
                  "vsum_scorer_forward: video of %d frames exceeds the positional table (%d rows); the reference "
@@ -268,8 +276,9 @@ extern "C" int vsum_scorer_forward(vsum_scorer_t h, const float *features, const
                  "vsum_scorer_forward: workspace must be 1024-byte and features 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     if (mode == VSUM_MODE_FP32)
-        return forward_fp32(h, features, cu_seqlens, B, T, max_len, apply_sigmoid, scores_out, feats_out, workspace, s);
-    return forward_bf16(h, features, cu_seqlens, B, T, apply_sigmoid, scores_out, feats_out, workspace, s);
+        return forward_fp32(h, static_cast<const float *>(features), cu_seqlens, B, T, max_len, apply_sigmoid, scores_out, feats_out,
+                            workspace, s);
+    return forward_bf16(h, features, mode == VSUM_MODE_BF16_FEATURES, cu_seqlens, B, T, apply_sigmoid, scores_out, feats_out, workspace, s);
 }
 
 // ---- training (fp32) ---------------------------------------------------------------------------

@@ -13,9 +13,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VSUM_LIB", os.path.join(_HERE, "libvsum_b200.so"))   # VSUM_LIB: debug builds only
 
 VSUM_MAX_LAYERS = 16
-MODE_FP32, MODE_BF16 = 0, 1
+MODE_FP32, MODE_BF16, MODE_BF16_FEATURES = 0, 1, 2
 FSCORE_AVG, FSCORE_MAX = 0, 1
 USER_SUMMARY_F32, USER_SUMMARY_U8 = 0, 1
+FEATURES_F32, FEATURES_BF16 = 0, 1
 
 # every symbol include/vsum_b200.h declares (checked by tests/test_cabi_symbols.py)
 EXPORTS = (
@@ -29,7 +30,7 @@ EXPORTS = (
     "vsum_debug_attention_train_tc05", "vsum_debug_attention_bwd_tc05",
     "vsum_linear_workspace_bytes", "vsum_linear_forward", "vsum_linear_backward",
     "vsum_kts_workspace_bytes", "vsum_kts_gram", "vsum_kts_dp",
-    "vsum_pack_open", "vsum_pack_close", "vsum_pack_num_videos", "vsum_pack_feature_dim", "vsum_pack_video_info",
+    "vsum_pack_open", "vsum_pack_close", "vsum_pack_num_videos", "vsum_pack_feature_dim", "vsum_pack_feature_dtype", "vsum_pack_video_info",
     "vsum_pack_array", "vsum_pack_collate", "vsum_summary_frames", "vsum_rank_correlation_workspace_bytes", "vsum_rank_correlation",
     "vsum_pretrain_saved_bytes", "vsum_pretrain_losses_forward", "vsum_pretrain_losses_backward",
     "vsum_profile_begin", "vsum_profile_end", "vsum_profile_num_categories", "vsum_profile_category_name",
@@ -141,6 +142,8 @@ def load():
     L.vsum_pack_num_videos.restype = i32
     L.vsum_pack_feature_dim.argtypes = [vp]
     L.vsum_pack_feature_dim.restype = i32
+    L.vsum_pack_feature_dtype.argtypes = [vp]
+    L.vsum_pack_feature_dtype.restype = i32
     L.vsum_pack_video_info.argtypes = [vp, i32, C.POINTER(PackInfo)]
     L.vsum_pack_array.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.vsum_pack_collate.argtypes = [vp, vp, i32, i32, vp, vp, vp]

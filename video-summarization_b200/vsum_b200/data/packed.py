@@ -50,11 +50,21 @@ def _pad_to(f, align):
     return pos + pad
 
 
-def write_pack(path: str, videos: Iterable[dict], feature_dim: int = 1024, user_summary_u8: bool = False) -> None:
+def to_bf16_bits(a: np.ndarray) -> np.ndarray:
+    """float32 -> bfloat16 bit patterns (uint16), round to nearest even -- the rounding `__float2bfloat16_rn` and
+    torch's `.bfloat16()` apply (NaN payloads aside; features are finite)."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    return ((u + (np.uint32(0x7fff) + ((u >> np.uint32(16)) & np.uint32(1)))) >> np.uint32(16)).astype(np.uint16)
+
+
+def write_pack(path: str, videos: Iterable[dict], feature_dim: int = 1024, user_summary_u8: bool = False,
+               features_bf16: bool = False) -> None:
     """`videos`: dicts with `name`, `features` f32[N,dim], and optionally `gtscore` f32[N], `picks` int[N],
     `change_points` int[S,2], `n_frames`, `user_summary` [U,n_frames], `user_scores` [U,n_frames],
     `video_rep` f32[rep_dim] (the pretraining target, dataset.py:26).  `user_summary_u8` stores the 0/1
-    user summaries as bytes (4x smaller than the h5 files' float32)."""
+    user summaries as bytes (4x smaller than the h5 files' float32).  `features_bf16` stores the features rounded to
+    bfloat16 (half the bytes on disk, over PCIe and out of HBM): an inference-side option -- the bf16 scorer then runs
+    its feature GEMM in bf16 (`VSUM_MODE_BF16_FEATURES`); training packs keep float32."""
     entries = []
     with open(path, "wb") as f:
         f.write(b"\0" * 64)
@@ -67,7 +77,7 @@ def write_pack(path: str, videos: Iterable[dict], feature_dim: int = 1024, user_
             def put(kind, arr, align=64):
                 off[kind] = _pad_to(f, align)
                 f.write(np.ascontiguousarray(arr).tobytes())
-            put(_cabi.PACK_FEATURES, feats, _ALIGN)
+            put(_cabi.PACK_FEATURES, to_bf16_bits(feats) if features_bf16 else feats, _ALIGN)
             n_frames = n_shots = n_users = rep_dim = has_scores = 0
             if v.get("gtscore") is not None:
                 g = np.ascontiguousarray(v["gtscore"], dtype=np.float32).reshape(-1)
@@ -113,7 +123,8 @@ def write_pack(path: str, videos: Iterable[dict], feature_dim: int = 1024, user_
             f.write(e)
         total = f.tell()
         f.seek(0)
-        f.write(struct.pack("<8sIIQQI", MAGIC, 1, len(entries), index_offset, total, feature_dim).ljust(64, b"\0"))
+        f.write(struct.pack("<8sIIQQII", MAGIC, 1, len(entries), index_offset, total, feature_dim,
+                            _cabi.FEATURES_BF16 if features_bf16 else _cabi.FEATURES_F32).ljust(64, b"\0"))
 
 
 def convert_h5(h5_path: str, out_path: str, video_rep_dir: Optional[str] = None, **kw) -> None:
@@ -154,6 +165,9 @@ class PackedDataset(torch.utils.data.Dataset):
         _cabi.check(L.vsum_pack_open(os.fsencode(path), C.byref(h)), "vsum_pack_open")
         self._h, self._L = h, L
         self.feature_dim = int(L.vsum_pack_feature_dim(h))
+        self.features_bf16 = int(L.vsum_pack_feature_dtype(h)) == _cabi.FEATURES_BF16
+        if self.features_bf16 and split != "val":
+            raise ValueError("a pack written with features_bf16 serves inference (split='val'); training reads float32 features")
         self.info: List[_cabi.PackInfo] = []
         for i in range(int(L.vsum_pack_num_videos(h))):
             inf = _cabi.PackInfo()
@@ -188,6 +202,8 @@ class PackedDataset(torch.utils.data.Dataset):
             return None
         inf = self.info[i]
         dt = _NP.get(kind) or (np.uint8 if inf.user_summary_dtype == 1 else np.float32)
+        if kind == _cabi.PACK_FEATURES and self.features_bf16:
+            dt = np.uint16                                      # bfloat16 bit patterns (numpy has no bf16)
         buf = (C.c_uint8 * nbytes.value).from_address(ptr.value)
         a = np.frombuffer(buf, dtype=dt)
         a.flags.writeable = False
@@ -205,6 +221,8 @@ class PackedDataset(torch.utils.data.Dataset):
 
     def __getitem__(self, idx):
         feats = torch.from_numpy(np.array(self.array(idx, _cabi.PACK_FEATURES)))          # owned copy, like dataset.py:131-134
+        if self.features_bf16:
+            feats = feats.view(torch.bfloat16)
         if self.split == "pretrain":
             return feats, torch.from_numpy(np.array(self.array(idx, _cabi.PACK_VIDEO_REP)))
         targets = torch.from_numpy(np.array(self.array(idx, _cabi.PACK_GTSCORE)))
@@ -218,7 +236,7 @@ class PackedBatch:
     """One collated batch: packed rows on `device` plus the host-side lengths."""
     ids: List[int]                     # dataset indices, batch order
     seqlens: List[int]
-    features: torch.Tensor             # [sum N, dim] fp32 on the device
+    features: torch.Tensor             # [sum N, dim] on the device: fp32, or bf16 from a features_bf16 pack
     targets: Optional[torch.Tensor]    # [sum N] fp32 on the device (train / val)
     cu_seqlens: torch.Tensor           # int32[B+1] on the device
     video_rep: Optional[torch.Tensor]  # [B, rep_dim] (pretrain)
@@ -259,7 +277,7 @@ class PackedLoader:
         ds, L = self.ds, self.ds._L
         lens = [ds.n_steps(i) for i in ids]
         T, pin = sum(lens), self.device.type == "cuda"
-        feats = torch.empty((T, ds.feature_dim), dtype=torch.float32, pin_memory=pin)
+        feats = torch.empty((T, ds.feature_dim), dtype=torch.bfloat16 if ds.features_bf16 else torch.float32, pin_memory=pin)
         with_t = ds.split != "pretrain"
         tgt = torch.empty(T, dtype=torch.float32, pin_memory=pin) if with_t else None
         cu = torch.empty(len(ids) + 1, dtype=torch.int32, pin_memory=pin)

@@ -323,11 +323,16 @@ class SimNet(nn.Module):
                        scores_out: Optional[Tensor] = None):
         """features [T,1024] fp32 on a CUDA device, rows of video v = [cu[v], cu[v+1]).
         Returns (scores [T,num_classes] fp32, feats [T,d_model] fp32 | None).  `scores_out` lets a
-        pipelined caller supply the (contiguous fp32 [T,num_classes]) output buffer."""
+        pipelined caller supply the (contiguous fp32 [T,num_classes]) output buffer.
+        bf16 features (a pack written with `features_bf16`) are accepted by the bf16 scorer: the feature GEMM
+        then runs in bf16 like the rest of the network instead of tf32."""
         if not features.is_cuda:
             raise _cabi.VsumError("vsum_b200 runs on CUDA devices only (no CPU fallback); move the input with .cuda()")
-        if features.dtype != torch.float32 or features.dim() != 2 or features.shape[1] != self.in_features:
-            raise ValueError(f"features must be float32 [T,{self.in_features}], got {tuple(features.shape)} {features.dtype}")
+        bf16_in = features.dtype == torch.bfloat16
+        if bf16_in and self.precision != "bf16":
+            raise ValueError("bf16 features need the bf16 scorer (precision='bf16'); the fp32 mode reads float32 features")
+        if features.dtype not in (torch.float32, torch.bfloat16) or features.dim() != 2 or features.shape[1] != self.in_features:
+            raise ValueError(f"features must be float32 (or bfloat16) [T,{self.in_features}], got {tuple(features.shape)} {features.dtype}")
         features = features.contiguous()
         dev = features.device
         T, B = features.shape[0], len(seqlens_host)
@@ -344,7 +349,7 @@ class SimNet(nn.Module):
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             self._sync_weights(max_len, dev, stream)
-            L, mode = _cabi.load(), self._mode()
+            L, mode = _cabi.load(), (_cabi.MODE_BF16_FEATURES if bf16_in else self._mode())
             need = L.vsum_scorer_workspace_bytes(self._handle, T, B, mode)
             ws = self._workspace_for(need, dev)
             ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024

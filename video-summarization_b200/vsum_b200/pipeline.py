@@ -24,7 +24,7 @@ from .synthetic import SyntheticVideo
 
 @dataclass
 class HostBatch:
-    features: torch.Tensor            # float32 [T,1024] (pinned when pin=True)
+    features: torch.Tensor            # float32 (or bfloat16, see data.write_pack) [T,1024] (pinned when pin=True)
     seqlens: List[int]                # per packed video
     cu_steps: np.ndarray              # int32[B+1]
     meta: _engine.HostEvalBatch
@@ -67,7 +67,7 @@ class DeviceBatch:
         if pin_meta:
             self._cu_host = self._cu_host.pin_memory()
         self.cu_steps = self._cu_host.to(dev, non_blocking=True)
-        self.h2d_bytes = self.meta.h2d_bytes + hb.features.numel() * 4 + hb.cu_steps.nbytes
+        self.h2d_bytes = self.meta.h2d_bytes + hb.features.numel() * hb.features.element_size() + hb.cu_steps.nbytes
 
     def refill(self) -> None:
         """Copy features + metadata of the host batch into the existing device buffers again."""
