@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__restrict__ cu,
                  const int32_t *__restrict__ tile_video, const int32_t *__restrict__ tile_q0,
                  const int32_t *__restrict__ n_tiles_ptr, __nv_bfloat16 *__restrict__ out,
-                 float scale_log2e, uint32_t v_lbo, uint32_t v_sbo, uint32_t v_kstep,
+                 float scale_log2e,
                  float *__restrict__ lse2, float keep_scale, uint32_t drop_thresh16, unsigned long long seed) {
     if ((int)blockIdx.x >= __ldg(n_tiles_ptr)) return;
     extern __shared__ __align__(1024) uint8_t smem[];    // no alignment slack: it would cost the 2nd CTA / SM
@@ -175,9 +175,11 @@ attn_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__res
             constexpr uint32_t IDESC_PV = tc::make_idesc(1, BQ, HD, 0, 1);    // O[128x64], B (=V) MN-major
             const uint64_t q_desc = tc::make_smem_desc_sw128(tc::smem_u32(sQ), 16, 1024);   // + 2 per 32-byte K step
             const uint64_t k_desc = tc::make_smem_desc_sw128(tc::smem_u32(sK), 16, 1024);
-            const uint64_t v_desc = tc::make_smem_desc_sw128(tc::smem_u32(sV), v_lbo, v_sbo);   // + v_kstep/16 per 16 keys
+            // V operand (MN-major, 128B swizzle): 8-key groups are 1024 bytes apart (SBO); the 64-wide head dim is a single
+            // swizzle atom so LBO is unused; one MMA K step = 16 keys = 2048 bytes
+            const uint64_t v_desc = tc::make_smem_desc_sw128(tc::smem_u32(sV), 16, 1024);
             const uint64_t p_desc0 = tc::make_smem_desc_sw128(tc::smem_u32(sP), 16, 1024);
-            const uint32_t v_step = v_kstep >> 4;
+            constexpr uint32_t v_step = 2048 >> 4;
             // Per-MMA descriptors are re-derived at the point of use (one 32-bit add on the address field; the add is
             // opaque to the compiler).  Hoisted out of the KV loop, the 24 descriptors of a tile do not fit the
             // 32 registers this warp keeps after setmaxnreg.dec and came back from local memory before every MMA group.
@@ -448,23 +450,16 @@ int launch_attention_tc05(const __nv_bfloat16 *qkv, const int32_t *cu_seqlens, c
     int rc = make_tensor_map_2d(&tm, qkv, 2, 3 * DM, (uint64_t)T, (uint64_t)3 * DM * 2, 64, 128);
     if (rc) return rc;
     VSUM_ONCE_PER_DEVICE(VSUM_CUDA_OK(cudaFuncSetAttribute(attn_tc05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM)); VSUM_CUDA_OK(cudaFuncSetAttribute(attn_tc05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM)));
-    // V operand descriptor (MN-major, 128B swizzle): 8-key groups are 1024 bytes apart (SBO); the
-    // 64-wide head dim is a single swizzle atom so LBO is unused; one MMA K step = 16 keys = 2048 B.
-    uint32_t v_lbo = 16, v_sbo = 1024, v_kstep = 2048;
-    if (const char *e = getenv("VSUM_ATTN_V_DESC")) {   // debugging aid: "lbo,sbo,kstep"
-        unsigned a, b, c;
-        if (sscanf(e, "%u,%u,%u", &a, &b, &c) == 3) { v_lbo = a; v_sbo = b; v_kstep = c; }
-    }
     dim3 grid((unsigned)max_tiles, NH);
     ProfScope prof(PROF_ATTN, s);
     const float sl2 = scale * 1.4426950408889634f;
     if (lse2) {
         const uint32_t thresh = attn_drop_thresh16(drop_p);
-        attn_tc05_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, s>>>(tm, cu_seqlens, tile_video, tile_q0, n_tiles_ptr, (__nv_bfloat16 *)out, sl2, v_lbo,
-                                                                   v_sbo, v_kstep, lse2, 65536.0f / (float)(65536u - thresh), thresh, seed);
+        attn_tc05_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, s>>>(tm, cu_seqlens, tile_video, tile_q0, n_tiles_ptr, (__nv_bfloat16 *)out, sl2,
+                                                                   lse2, 65536.0f / (float)(65536u - thresh), thresh, seed);
     } else {
-        attn_tc05_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, s>>>(tm, cu_seqlens, tile_video, tile_q0, n_tiles_ptr, (__nv_bfloat16 *)out, sl2, v_lbo,
-                                                                    v_sbo, v_kstep, nullptr, 1.0f, 0u, 0ull);
+        attn_tc05_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, s>>>(tm, cu_seqlens, tile_video, tile_q0, n_tiles_ptr, (__nv_bfloat16 *)out, sl2,
+                                                                    nullptr, 1.0f, 0u, 0ull);
     }
     VSUM_LAUNCH_OK("attn_tc05_kernel");
     return VSUM_OK;
