@@ -195,6 +195,11 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tc::mbar_arrive_expect_tx(full + s, WRES ? A_STAGE : A_STAGE + B_STAGE);
                     tc::tma_load_2d(a_stage(s), &tmA, full + s, kb * KELTS, (int)(m_blk * BM));
                     if (!WRES) tc::tma_load_2d(b_stage(s), &tmB, full + s, kb * KELTS, n_blk * BN);
+                    // Weight-stationary variant (K = 256): the activation ring holds exactly one tile, so a tile's loads are
+                    // issued one tile period ahead at best.  Pull the rows of this CTA's NEXT tile into L2 now (one of the
+                    // column-block CTAs walking the same rows does it): QKV GEMM -4 %, fc1 -2.5 % on the same box.  Not for
+                    // K = 1024: there the ring already streams 16 k-blocks per tile and the extra requests cost 15-30 %.
+                    if (WRES && blockIdx.y == 0 && t + step < total) tc::tma_prefetch_l2_2d(&tmA, kb * KELTS, (int)((t + step) * BM));
                 }
             }
         }

@@ -84,6 +84,12 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
+// Same box pulled into L2 only (no shared-memory destination, no completion to wait for).
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap *m, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1) : "memory");
+}
+
 // 2-D tiled store smem -> global (bulk async-group completion); rows past the tensor bound are clipped.
 __device__ __forceinline__ void tma_store_2d(const void *smem_src, const CUtensorMap *m, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
