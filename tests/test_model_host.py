@@ -100,6 +100,28 @@ def test_host_eval_batch_packing():
     assert sum(c for _, c, _ in hb.launches) == 3 and hb.launches[0] == (0, 1, caps[1])
 
 
+def test_user_summary_dtype_selection_and_bf16_rounding():
+    """Byte user summaries stay bytes only when EVERY video brings them as uint8 / bool (one dtype per batch); the pack
+    writer's float32 -> bfloat16 rounding is round-to-nearest-even, i.e. torch's."""
+    import torch
+    from vsum_b200.data.packed import to_bf16_bits
+    vids = [make_video(900 + i, n, n_users=3, with_features=False) for i, n in enumerate((20, 64))]
+    build = lambda us: _engine.HostEvalBatch.build([v.change_points for v in vids], [np.array(v.n_frames) for v in vids],
+                                                   [v.picks for v in vids], us)
+    all_u8 = build([v.user_summary.astype(np.uint8) for v in vids])
+    assert all_u8.user_summary.dtype == np.uint8 and _engine._us_dtype_code(all_u8.user_summary) == 1
+    assert build([v.user_summary.astype(bool) for v in vids]).user_summary.dtype == np.uint8
+    mixed = build([vids[0].user_summary.astype(np.uint8), vids[1].user_summary])
+    assert mixed.user_summary.dtype == np.float32 and _engine._us_dtype_code(mixed.user_summary) == 0
+    assert np.array_equal(mixed.user_summary, all_u8.user_summary.astype(np.float32))
+    assert all_u8.us_offsets.tolist() == mixed.us_offsets.tolist()
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.standard_normal(4096).astype(np.float32) * 10.0 ** rng.integers(-20, 20, 4096).astype(np.float32),
+                        np.array([0.0, -0.0, 1.00390625, 1.01171875, 3.3895314e38, -1e-40, np.inf], np.float32)])
+    want = torch.from_numpy(x).bfloat16().view(torch.int16).numpy().view(np.uint16)
+    assert np.array_equal(to_bf16_bits(x), want)
+
+
 def test_partition_is_balanced_and_complete():
     rng = np.random.default_rng(3)
     ns = [int(x) for x in np.exp(rng.uniform(np.log(128), np.log(8192), 500))]
