@@ -55,6 +55,19 @@ def test_videos_against_live_reference(ref_eval):
                 assert bits_equal(want, np.float64(ref_port.fscore_video(ref_summary, v.user_summary, method)))
 
 
+def test_compact_input_forms_are_lossless_for_the_reference(ref_eval):
+    """The packed dataset may hold the 0/1 user summaries as uint8: the reference's own evaluate_summary returns the same
+    bits for either dtype (it copies the row into an int array, evaluation_metrics.py:13-19), which is what makes
+    `write_pack(user_summary_u8=True)` a lossless storage choice rather than a change of inputs."""
+    for v_id, n, users in ((350, 90, 3), (351, 400, 20), (352, 7, 1)):
+        v = make_video(v_id, n, n_users=users, with_features=False)
+        summary = ref_eval["gs"].generate_summary([v.change_points], [make_scores(v_id, n)], [np.array(v.n_frames)], [v.picks])[0]
+        for method in ("avg", "max"):
+            f32 = np.float64(ref_eval["em"].evaluate_summary(summary, v.user_summary, method))
+            u8 = np.float64(ref_eval["em"].evaluate_summary(summary, v.user_summary.astype(np.uint8), method))
+            assert bits_equal(f32, u8)
+
+
 def test_random_knapsacks_against_live_reference(ref_eval):
     rng = np.random.default_rng(12)
     for _ in range(200):
