@@ -78,6 +78,22 @@ def test_scorer_restatement_matches_reference(scorer_golden, seeded_model_kwargs
     np.testing.assert_allclose(feats[0, :4].numpy(), scorer_golden[f"feats_head_{vid}"], rtol=1e-5, atol=1e-5)
 
 
+def test_bf16_feature_rounding_stays_far_inside_the_score_tolerance(seeded_model_kwargs):
+    """What `write_pack(features_bf16=True)` does to the inputs, seen through the fp32 restatement of the reference
+    scorer: rounding the features to bfloat16 once moves the importance scores by a few 1e-4 relative, against the 1e-2
+    the bf16 path is allowed (BASELINE.json) -- the input rounding is a small part of that budget."""
+    from vsum_b200.model import SimNet
+    torch.manual_seed(1234)
+    sd = SimNet(**seeded_model_kwargs).state_dict()
+    worst = 0.0
+    for vid, n in ((120, 64), (121, 300), (122, 700)):
+        x = torch.from_numpy(make_video(vid, n).features).unsqueeze(0)
+        a = torch.sigmoid(scorer_ref.scorer_forward(sd, x, num_heads=4)[0]).view(-1)
+        b = torch.sigmoid(scorer_ref.scorer_forward(sd, x.bfloat16().float(), num_heads=4)[0]).view(-1)
+        worst = max(worst, float(((a - b).abs() / a).max()))
+    assert worst < 2e-3, worst
+
+
 def test_kts_restatement_matches_reference_golden():
     """oracle/kts_ref.py against the reference's own kts_segmentation / cpd_nonlin outputs (tests/golden/kts_golden.npz,
     written by make_golden.py from src/data/preprocess/segmentations/kts): bit-exact costs, same change points."""
