@@ -36,7 +36,8 @@ MODEL_KW = dict(num_heads=4, d_model=256, num_layers=4, sparsity=0., use_cls=Fal
                 num_classes=1, use_pos=True)                 # run_finetune.sh:1 / train.py:29-34
 N_LO, N_HI, N_USERS = 128, 8192, 20
 METRIC, UNIT = "summarized_videos_per_sec", "videos/s"
-REF_SAMPLE_N = (256, 1024, 4096)        # one video per third of the log-uniform length range
+# CPU sample: one video per twelfth of the log-uniform length range (geometric midpoints of [128, 8192])
+REF_SAMPLE_N = tuple(int(round(128 * 64 ** ((i + 0.5) / 12))) for i in range(12))
 
 
 def workload_name(videos, lo=None, hi=None):
@@ -162,7 +163,7 @@ def run_cpu_baseline(steps=1, warmup=0):
         cpu_reference_step(sd, sample)
     dt = (time.perf_counter() - t0) / steps
     return {"value": len(sample) / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{len(sample)} videos, N={list(REF_SAMPLE_N)} (one per third of the log-uniform length range), "
+            "sample": f"{len(sample)} videos, N={list(REF_SAMPLE_N)} (one per twelfth of the log-uniform length range), "
                       f"{dt:.2f} s/step; torch fp32 CPU scorer ({cores} threads) + pure-Python pooling/knapsack/F-score "
                       "as the reference runs them"}, dt
 
