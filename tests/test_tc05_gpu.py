@@ -76,19 +76,61 @@ def attention_ref(qkv, lens):
     return out
 
 
-@pytest.mark.parametrize("lens", [[128], [1], [37], [129], [256, 64], [300, 1, 127, 128, 513], [2048], [1000, 3000],
+@pytest.fixture(params=[2, 1], ids=["two_tile_persistent", "one_tile_per_cta"])
+def attn_kernel(request):
+    """Both forward kernels behind vsum_set_attention_kernel (2 is the default the scorer runs)."""
+    L = _cabi.load()
+    _cabi.check(L.vsum_set_attention_kernel(request.param), "vsum_set_attention_kernel")
+    yield request.param
+    _cabi.check(L.vsum_set_attention_kernel(2), "vsum_set_attention_kernel")
+
+
+@pytest.mark.parametrize("lens", [[128], [1], [37], [129], [256], [257], [256, 64], [300, 1, 127, 128, 513], [2048], [1000, 3000],
                                   [300] * 150, [8192, 4000, 77], [1] * 700, [129, 128, 127] * 60])
-def test_attention(lens):   # the last four have more work items than resident CTAs (persistent loop)
+def test_attention(lens, attn_kernel):   # the last four have more work items than resident CTAs (persistent loop)
     T = sum(lens)
     g = torch.Generator(device="cuda").manual_seed(T)
     qkv = torch.randn((T, 768), device="cuda", generator=g).bfloat16()
     cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device="cuda")
     out = torch.zeros((T, 256), dtype=torch.bfloat16, device="cuda")
-    scratch = torch.zeros(2 * (T // 128 + len(lens)) + 1, dtype=torch.int32, device="cuda")
+    scratch = torch.zeros(2 * (T // 128 + len(lens)) + 8, dtype=torch.int32, device="cuda")
     _cabi.check(_cabi.load().vsum_debug_attention_tc05(qkv.data_ptr(), cu.data_ptr(), len(lens), T, out.data_ptr(),
                                                        scratch.data_ptr(), _stream()), "vsum_debug_attention_tc05")
     torch.cuda.synchronize()
     torch.testing.assert_close(out.float(), attention_ref(qkv, lens), rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("case", ["rising", "falling", "far_below_zero", "far_above_zero", "one_hot"])
+def test_attention_exponent_reference_moves(case, attn_kernel):
+    """Score distributions that push the running exponent reference of the softmax around: the two-tile kernel
+    exponentiates against a reference that only moves when a tile maximum leaves a +-24 (log2) window and then
+    recomputes the tile; the result must not depend on any of that."""
+    lens = [640, 300, 129]
+    T = sum(lens)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    qkv = torch.randn((T, 768), device="cuda", generator=g)
+    if case == "rising":          # later keys score much higher: the reference climbs tile after tile
+        qkv[:, 256:512] *= torch.linspace(0.2, 14.0, T, device="cuda")[:, None]
+    elif case == "falling":       # the first tile holds the maximum
+        qkv[:, 256:512] *= torch.linspace(14.0, 0.2, T, device="cuda")[:, None]
+    elif case == "far_below_zero":   # every logit around -60 log2 units: exp2(s) alone would underflow to nothing useful
+        qkv[:, 0:256] = 0.3 * qkv[:, 0:256] + 4.0
+        qkv[:, 256:512] = 0.3 * qkv[:, 256:512] - 4.0
+    elif case == "far_above_zero":   # every logit around +90 log2 units
+        qkv[:, 0:256] = 0.3 * qkv[:, 0:256] + 5.0
+        qkv[:, 256:512] = 0.3 * qkv[:, 256:512] + 5.0
+    else:                         # one key per row dominates by a huge margin
+        qkv[:, 0:512] *= 6.0
+    qkv = qkv.bfloat16()
+    cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device="cuda")
+    out = torch.zeros((T, 256), dtype=torch.bfloat16, device="cuda")
+    scratch = torch.zeros(2 * (T // 128 + len(lens)) + 8, dtype=torch.int32, device="cuda")
+    _cabi.check(_cabi.load().vsum_debug_attention_tc05(qkv.data_ptr(), cu.data_ptr(), len(lens), T, out.data_ptr(),
+                                                       scratch.data_ptr(), _stream()), "vsum_debug_attention_tc05")
+    torch.cuda.synchronize()
+    want = attention_ref(qkv, lens)
+    assert torch.isfinite(out.float()).all()
+    torch.testing.assert_close(out.float(), want, rtol=3e-2, atol=3e-2)
 
 
 @pytest.mark.parametrize("M,N,K,epi", [(300, 256, 1024, 5), (5000, 768, 256, 5), (777, 1024, 256, 6), (40000, 256, 256, 5)])
@@ -149,7 +191,7 @@ def _drop_keep(seed, q_rows, h, keys, thresh):
 
 @pytest.mark.parametrize("lens,p", [([128], 0.0), ([37], 0.0), ([129, 300], 0.0), ([300, 1, 127, 513], 0.3), ([1000, 2100], 0.0),
                                     ([700, 260], 0.1)])
-def test_attention_train_and_backward(lens, p):
+def test_attention_train_and_backward(lens, p, attn_kernel):
     """tcgen05 attention with log-sum-exp + dropout, and its tcgen05 backward, against torch autograd (fp32
     math on the same bf16-rounded operands, the same dropout mask)."""
     T, B, seed = sum(lens), len(lens), 0x1234567 + sum(lens)
@@ -159,7 +201,7 @@ def test_attention_train_and_backward(lens, p):
     cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device="cuda")
     out = torch.zeros((T, 256), device="cuda")                      # the training variant writes fp32
     lse2 = torch.zeros((T, 4), device="cuda")
-    scratch = torch.zeros(2 * (T // 128 + B) + 1, dtype=torch.int32, device="cuda")
+    scratch = torch.zeros(2 * (T // 128 + B) + 8, dtype=torch.int32, device="cuda")
     L = _cabi.load()
     _cabi.check(L.vsum_debug_attention_train_tc05(qkv.data_ptr(), cu.data_ptr(), B, T, out.data_ptr(), lse2.data_ptr(), p, seed,
                                                   scratch.data_ptr(), _stream()), "vsum_debug_attention_train_tc05")

@@ -21,6 +21,7 @@ int set_error(int code, const char *fmt, ...);
 void count_launch(int n = 1);
 int eval_sm_budget();       // 0 = unlimited; else the evaluation kernels keep at most this many SMs busy
 int scorer_sm_reserve();    // persistent scorer GEMMs leave this many SMs free
+int attention_kernel_version();   // 2 = persistent two-query-tile forward kernel (default), 1 = one 128-query tile per CTA
 
 #define VSUM_CUDA_OK(expr)                                                                      \
     do {                                                                                        \

@@ -2,6 +2,7 @@
 #include "vsum_common.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -27,6 +28,19 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 static std::atomic<int> g_eval_sm_budget{0}, g_scorer_sm_reserve{0};
 int eval_sm_budget() { return g_eval_sm_budget.load(std::memory_order_relaxed); }
 int scorer_sm_reserve() { return g_scorer_sm_reserve.load(std::memory_order_relaxed); }
+
+// Attention forward kernel: 2 = persistent two-query-tile kernel (vsum_attn2_tc05.cu, default), 1 = one 128-query tile
+// per CTA (vsum_attn_tc05.cu).  VSUM_ATTN_KERNEL in the environment overrides the default at first use.
+static std::atomic<int> g_attn_kernel{0};
+int attention_kernel_version() {
+    int v = g_attn_kernel.load(std::memory_order_relaxed);
+    if (v == 0) {
+        const char *e = getenv("VSUM_ATTN_KERNEL");
+        v = (e && e[0] == '1') ? 1 : 2;
+        g_attn_kernel.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
 
 // ---- profiling -------------------------------------------------------------------------------
 struct ProfRecord { int cat; cudaEvent_t a, b; };
@@ -87,6 +101,12 @@ extern "C" int vsum_set_sm_partition(int32_t eval_sms, int32_t scorer_reserved_s
                  "vsum_set_sm_partition: eval_sms=%d scorer_reserved_sms=%d", eval_sms, scorer_reserved_sms);
     vsum::g_eval_sm_budget.store(eval_sms);
     vsum::g_scorer_sm_reserve.store(scorer_reserved_sms);
+    return VSUM_OK;
+}
+
+extern "C" int vsum_set_attention_kernel(int32_t version) {
+    VSUM_REQUIRE(version == 1 || version == 2, VSUM_EINVAL, "vsum_set_attention_kernel: version %d (1 or 2)", version);
+    vsum::g_attn_kernel.store(version);
     return VSUM_OK;
 }
 

@@ -145,6 +145,13 @@ int launch_attention_tc05(const __nv_bfloat16 *qkv, const int32_t *cu_seqlens, c
                           const int32_t *tile_q0, const int32_t *n_tiles_ptr, int max_tiles, int64_t T,
                           float scale, void *out, cudaStream_t s, float *lse2 = nullptr, float drop_p = 0.f,
                           unsigned long long seed = 0);
+// Second-generation forward (vsum_attn2_tc05.cu): persistent, two 128-query tiles per CTA, P in tensor memory.  Same
+// arguments; `scratch` holds attention2_scratch_ints(T, B) int32 and is filled once per batch by launch_attn2_schedule.
+size_t attention2_scratch_ints(int64_t T, int B);
+int launch_attn2_schedule(const int32_t *cu_seqlens, int B, int64_t T, int32_t *scratch, cudaStream_t s);
+int launch_attention2_tc05(const __nv_bfloat16 *qkv, const int32_t *cu_seqlens, int B, int64_t T, float scale, void *out,
+                           int32_t *scratch, cudaStream_t s, float *lse2 = nullptr, float drop_p = 0.f,
+                           unsigned long long seed = 0);
 inline uint32_t attn_drop_thresh16(float p) { return p <= 0.f ? 0u : (uint32_t)(p * 65536.0f + 0.5f); }
 // Backward of the above on tcgen05 (vsum_attn_bwd_tc05.cu): qkv16 [T,768], dO16 [T,256] bf16, lse2 / delta [T,4]
 // fp32 -> dqkv [T,768] fp32 (overwritten).  Tiles = the forward's schedule (video, first key row).

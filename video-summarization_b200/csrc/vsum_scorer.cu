@@ -145,7 +145,7 @@ extern "C" int vsum_scorer_load_weights(vsum_scorer_t h, const vsum_scorer_weigh
 namespace {
 
 struct Ws32 { int32_t *row_pos; float *xa, *xb, *qkv, *att, *tmp, *hid; };
-struct Ws16 { int32_t *row_pos, *tile_video, *tile_q0, *n_tiles; __nv_bfloat16 *xa, *xb, *qkv, *att, *hid; };
+struct Ws16 { int32_t *row_pos, *tile_video, *tile_q0, *n_tiles, *a2; __nv_bfloat16 *xa, *xb, *qkv, *att, *hid; };
 
 size_t carve32(const vsum_scorer_config &c, int64_t T, void *base, Ws32 &w) {
     Carver k{(uint8_t *)base};
@@ -160,6 +160,7 @@ size_t carve16(const vsum_scorer_config &c, int64_t T, int max_tiles, void *base
     const size_t t = (size_t)T, d = c.d_model;
     w.row_pos = k.get<int32_t>(t);
     w.tile_video = k.get<int32_t>(max_tiles); w.tile_q0 = k.get<int32_t>(max_tiles); w.n_tiles = k.get<int32_t>(1);
+    w.a2 = k.get<int32_t>(2 * (size_t)max_tiles + 8);      // >= attention2_scratch_ints(T, B): work list of the two-tile attention kernel
     w.xa = k.get<__nv_bfloat16>(t * d); w.xb = k.get<__nv_bfloat16>(t * d);
     w.qkv = k.get<__nv_bfloat16>(t * 3 * d); w.att = k.get<__nv_bfloat16>(t * d);
     w.hid = k.get<__nv_bfloat16>(t * c.d_ff);
@@ -215,7 +216,9 @@ static int forward_bf16(vsum_scorer_t h, const void *x, bool x_is_bf16, const in
     carve16(c, T, max_tiles, ws, w);
     int rc;
     RUN(launch_row_positions(cu, B, T, w.row_pos, nullptr, s));
-    RUN(launch_attn_schedule(cu, B, w.tile_video, w.tile_q0, w.n_tiles, max_tiles, s));
+    const bool attn2 = attention_kernel_version() == 2;
+    if (attn2) RUN(launch_attn2_schedule(cu, B, T, w.a2, s));
+    else RUN(launch_attn_schedule(cu, B, w.tile_video, w.tile_q0, w.n_tiles, max_tiles, s));
     Tc05GemmArgs g{};
     g.A = x; g.M = T; g.N = 256; g.K = c.in_features; g.a_is_f32 = x_is_bf16 ? 0 : 1;
     g.W = x_is_bf16 ? (const void *)(h->w16 + h->h_embed) : (const void *)(h->w32 + h->embed_w);
@@ -230,7 +233,8 @@ static int forward_bf16(vsum_scorer_t h, const void *x, bool x_is_bf16, const in
         q.A = w.xa; q.W = h->w16 + o.h_wqkv; q.M = T; q.N = 768; q.K = 256; q.epi = TC_EPI_BIAS;
         q.bias = h->w32 + o.bqkv; q.out = w.qkv; q.prof_cat = PROF_QKV;
         RUN(launch_gemm_tc05(q, s));
-        RUN(launch_attention_tc05(w.qkv, cu, w.tile_video, w.tile_q0, w.n_tiles, max_tiles, T, scale, w.att, s));
+        if (attn2) RUN(launch_attention2_tc05(w.qkv, cu, B, T, scale, w.att, w.a2, s));
+        else RUN(launch_attention_tc05(w.qkv, cu, w.tile_video, w.tile_q0, w.n_tiles, max_tiles, T, scale, w.att, s));
         Tc05GemmArgs p{};
         p.A = w.att; p.W = h->w16 + o.h_wo; p.M = T; p.N = 256; p.K = 256; p.epi = TC_EPI_BIAS_RES_LN;
         p.bias = h->w32 + o.bo; p.residual = w.xa; p.gamma = h->w32 + o.ln1g; p.beta = h->w32 + o.ln1b; p.out = w.xb;
@@ -300,6 +304,7 @@ size_t carve_tape(const vsum_scorer_config &c, int64_t T, void *base, Tape &t) {
 struct TrainWs {
     int32_t *row_pos; float *a, *b, *c, *dd, *dhid, *dqkv, *delta, *dwqkv, *dbqkv; __nv_bfloat16 *y16, *x16;
     int32_t *tile_video, *tile_q0, *n_tiles; int max_tiles;       // tile list of the tcgen05 attention kernels
+    int32_t *a2;                                                  // work list of the two-tile forward kernel
 };
 size_t carve_train_ws(const vsum_scorer_config &c, int64_t T, int32_t B, void *base, TrainWs &w) {
     Carver k{(uint8_t *)base};
@@ -312,6 +317,7 @@ size_t carve_train_ws(const vsum_scorer_config &c, int64_t T, int32_t B, void *b
     w.y16 = k.get<__nv_bfloat16>(n * widest); w.x16 = k.get<__nv_bfloat16>(n * widest);   // bf16 operands of the tcgen05 wgrad / attention
     w.max_tiles = (int)(T / 128 + B);
     w.tile_video = k.get<int32_t>(w.max_tiles); w.tile_q0 = k.get<int32_t>(w.max_tiles); w.n_tiles = k.get<int32_t>(1);
+    w.a2 = k.get<int32_t>(2 * (size_t)w.max_tiles + 8);
     return align_up(k.off, 1024);
 }
 }  // namespace
@@ -387,14 +393,17 @@ extern "C" int vsum_scorer_forward_train(vsum_scorer_t h, const float *x, const 
     const float scale = 1.0f / sqrtf((float)d);
     const float *xin = t.x0;
     const bool tc_attn = h->train_mode == 2;
-    if (tc_attn) RUN(launch_attn_schedule(cu, B, w.tile_video, w.tile_q0, w.n_tiles, w.max_tiles, s));
+    const bool attn2 = tc_attn && attention_kernel_version() == 2;
+    if (attn2) RUN(launch_attn2_schedule(cu, B, T, w.a2, s));
+    else if (tc_attn) RUN(launch_attn_schedule(cu, B, w.tile_video, w.tile_q0, w.n_tiles, w.max_tiles, s));
     for (int l = 0; l < c.num_layers; ++l) {
         const LayerOffsets &o = h->L[l];
         TapeLayer &L = t.L[l];
         RUN(lin_fwd(h, xin, h->w32 + o.wqkv, h->w32 + o.bqkv, L.qkv, T, 3 * d, d, EPI_BIAS, nullptr, s));
         if (tc_attn) {   // bf16 operands on tcgen05; L.lse holds log2-domain values in this mode
             RUN(launch_f32_to_bf16(L.qkv, w.x16, (int64_t)T * 3 * d, s));
-            RUN(launch_attention_tc05(w.x16, cu, w.tile_video, w.tile_q0, w.n_tiles, w.max_tiles, T, scale, L.att, s, L.lse, p,
+            if (attn2) RUN(launch_attention2_tc05(w.x16, cu, B, T, scale, L.att, w.a2, s, L.lse, p, site_seed(seed, SITE_ATTN, l)));
+            else RUN(launch_attention_tc05(w.x16, cu, w.tile_video, w.tile_q0, w.n_tiles, w.max_tiles, T, scale, L.att, s, L.lse, p,
                                       site_seed(seed, SITE_ATTN, l)));
         } else
         RUN(launch_attention_f32(L.qkv, cu, B, max_len, d, c.num_heads, scale, L.att, s, L.lse, p, site_seed(seed, SITE_ATTN, l)));
@@ -576,6 +585,11 @@ extern "C" int vsum_debug_attention_train_tc05(const void *qkv, const int32_t *c
     VSUM_REQUIRE(qkv && cu_seqlens && out && lse2 && scratch, VSUM_EINVAL, "vsum_debug_attention_train_tc05: null pointer");
     const int max_tiles = (int)(T / 128 + B);
     cudaStream_t s = (cudaStream_t)stream;
+    if (attention_kernel_version() == 2) {
+        int rc2 = launch_attn2_schedule(cu_seqlens, B, T, scratch, s);
+        if (rc2) return rc2;
+        return launch_attention2_tc05((const __nv_bfloat16 *)qkv, cu_seqlens, B, T, 1.0f / 16.0f, out, scratch, s, lse2, drop_p, seed);
+    }
     int rc = launch_attn_schedule(cu_seqlens, B, scratch, scratch + max_tiles, scratch + 2 * max_tiles, max_tiles, s);
     if (rc) return rc;
     return launch_attention_tc05((const __nv_bfloat16 *)qkv, cu_seqlens, scratch, scratch + max_tiles, scratch + 2 * max_tiles,
@@ -600,6 +614,11 @@ extern "C" int vsum_debug_attention_tc05(const void *qkv, const int32_t *cu_seql
     VSUM_REQUIRE(qkv && cu_seqlens && out && scratch, VSUM_EINVAL, "vsum_debug_attention_tc05: null pointer");
     const int max_tiles = (int)(T / 128 + B);
     cudaStream_t s = (cudaStream_t)stream;
+    if (attention_kernel_version() == 2) {
+        int rc2 = launch_attn2_schedule(cu_seqlens, B, T, scratch, s);
+        if (rc2) return rc2;
+        return launch_attention2_tc05((const __nv_bfloat16 *)qkv, cu_seqlens, B, T, 1.0f / 16.0f, out, scratch, s);
+    }
     int rc = launch_attn_schedule(cu_seqlens, B, scratch, scratch + max_tiles, scratch + 2 * max_tiles, max_tiles, s);
     if (rc) return rc;
     return launch_attention_tc05((const __nv_bfloat16 *)qkv, cu_seqlens, scratch, scratch + max_tiles,
