@@ -39,6 +39,12 @@ def scorer_golden():
 
 
 @pytest.fixture(scope="session")
+def scorer_long_golden():
+    """Reference logits at N = 4096 and 8192 (tests/golden/make_golden.py::scorer_long_goldens)."""
+    return np.load(os.path.join(GOLDEN, "scorer_long_golden.npz"))
+
+
+@pytest.fixture(scope="session")
 def seeded_model_kwargs():
     return dict(num_heads=4, d_model=256, num_layers=4, sparsity=0., use_cls=False, dropout=0.3,
                 num_classes=1, use_pos=True)

@@ -137,6 +137,27 @@ def scorer_goldens(mods):
     np.savez_compressed(os.path.join(HERE, "scorer_golden.npz"), **out)
 
 
+SCORER_XLONG = [(107, 4096), (108, 8192)]   # BASELINE config 5 goes to N = 8192
+
+
+@torch.no_grad()
+def scorer_long_goldens(mods):
+    """Reference logits at N = 4096 and 8192: the reference's own SimNet with its own PositionalEncoding class built with
+    maxlen=8192 (simnet.py:220-238; the shipped table stops at 2000 rows, simnet.py:188).  ~10 s of CPU each."""
+    torch.set_num_threads(8)
+    mods["utils"].set_seed(1234)
+    net = mods["model"].SimNet(**MODEL_KW).eval()
+    simnet_mod = importlib.import_module("model.simnet")
+    net.embedding_layer.positional_encoding = simnet_mod.PositionalEncoding(emb_size=256, dropout=0., maxlen=8192).eval()
+    out = {"versions": versions(), "cases": np.array(SCORER_XLONG, dtype=np.int64)}
+    for vid, n in SCORER_XLONG:
+        logits, feats = net(torch.from_numpy(make_video(vid, n).features).unsqueeze(0))
+        out[f"logits_{vid}"] = logits.view(-1).numpy()
+        out[f"feats_rowsum_{vid}"] = feats[0].double().sum(dim=1).numpy()
+    np.savez_compressed(os.path.join(HERE, "scorer_long_golden.npz"), **out)
+    print("scorer_long_golden.npz written")
+
+
 KTS_CASES = [(0, 80, 32, 10, 1, 100000), (1, 150, 64, 20, 1, 100000), (2, 60, 16, 5, 3, 20), (3, 40, 8, 39, 1, 100000),
              (4, 33, 4, 0, 1, 100000), (5, 300, 128, 40, 2, 100000)]       # (seed, n, dim, ncp, lmin, lmax)
 
@@ -192,6 +213,10 @@ def pretrain_golden(mods):
 
 if __name__ == "__main__":
     mods = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "scorer_long":      # only the N = 4096 / 8192 scorer fixture
+        scorer_long_goldens(mods)
+        sys.exit(0)
+    scorer_long_goldens(mods)
     eval_goldens(mods["evaluation"])
     eval_metrics_golden(mods["evaluation"])
     scorer_goldens(mods)

@@ -132,9 +132,13 @@ def test_partition_is_balanced_and_complete():
         assert max(loads) / (sum(loads) / world) < 1.05
 
 
-def test_masked_mse_matches_reference_semantics():
+def test_masked_mse_has_no_cpu_path_and_oracle_keeps_reference_semantics():
+    from oracle import scorer_ref
+    from vsum_b200._cabi import VsumError
     from vsum_b200.utils import mse_with_mask_loss
     out = torch.tensor([[[1.0], [2.0], [9.0]]])
     tgt = torch.tensor([[0.0, 0.0, 1000.0]])
     mask = torch.tensor([[False, False, True]])
-    assert mse_with_mask_loss(out, tgt, mask).item() == pytest.approx((1 + 4 + 0) / 3)   # divides by bs*Nmax
+    assert scorer_ref.masked_mse(out, tgt, mask).item() == pytest.approx((1 + 4 + 0) / 3)   # divides by bs*Nmax (utils.py:55)
+    with pytest.raises(VsumError):
+        mse_with_mask_loss(out, tgt, mask)

@@ -78,6 +78,31 @@ def test_scorer_restatement_matches_reference(scorer_golden, seeded_model_kwargs
     np.testing.assert_allclose(feats[0, :4].numpy(), scorer_golden[f"feats_head_{vid}"], rtol=1e-5, atol=1e-5)
 
 
+def test_masked_mse_restatement_matches_reference_loss(scorer_golden):
+    """oracle/scorer_ref.masked_mse against the loss the reference's `mse_with_mask_loss` (utils.py:45-56) returned on its own
+    padded-batch logits (tests/golden/make_golden.py: padded_loss)."""
+    lens = (300, 180, 77)
+    logits = torch.full((3, 300, 1), -3.0)
+    tgt = torch.full((3, 300), 1000.0)
+    mask = torch.ones((3, 300), dtype=torch.bool)
+    for b, n in enumerate(lens):
+        logits[b, :n, 0] = torch.from_numpy(scorer_golden[f"padded_logits_{b}"])
+        tgt[b, :n] = torch.from_numpy(make_video(110 + b, n).gtscore)
+        mask[b, :n] = False
+    np.testing.assert_allclose(scorer_ref.masked_mse(logits, tgt, mask).item(), float(scorer_golden["padded_loss"]), rtol=1e-6)
+
+
+@pytest.mark.parametrize("vid,n", [(107, 4096)])
+def test_scorer_restatement_matches_reference_at_full_length(scorer_long_golden, seeded_model_kwargs, vid, n):
+    """The torch restatement (with the extended sinusoid table) against the reference at N = 4096."""
+    from vsum_b200.model import SimNet
+    torch.manual_seed(1234)
+    sd = SimNet(**seeded_model_kwargs).state_dict()
+    x = torch.from_numpy(make_video(vid, n).features).unsqueeze(0)
+    logits, _ = scorer_ref.scorer_forward(sd, x, num_heads=4)
+    np.testing.assert_allclose(logits.view(-1).numpy(), scorer_long_golden[f"logits_{vid}"], rtol=1e-5, atol=1e-5)
+
+
 def test_bf16_feature_rounding_stays_far_inside_the_score_tolerance(seeded_model_kwargs):
     """What `write_pack(features_bf16=True)` does to the inputs, seen through the fp32 restatement of the reference
     scorer: rounding the features to bfloat16 once moves the importance scores by a few 1e-4 relative, against the 1e-2

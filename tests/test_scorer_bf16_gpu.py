@@ -40,6 +40,18 @@ def test_golden_scores(models, scorer_golden):
         assert feats.shape == (1, n, 256) and torch.isfinite(feats).all()
 
 
+def test_full_length_videos_against_reference(models, scorer_long_golden):
+    """N = 4096 and 8192 against the REFERENCE's outputs (not against this repo's fp32 kernels): 1e-2 on the scores."""
+    bf, _ = models
+    for vid, n in [tuple(int(x) for x in r) for r in scorer_long_golden["cases"]]:
+        x = torch.from_numpy(make_video(vid, n).features).unsqueeze(0).cuda()
+        with torch.no_grad():
+            logits, _ = bf(x)
+        got, want = logits.view(-1).cpu().numpy(), scorer_long_golden[f"logits_{vid}"]
+        np.testing.assert_allclose(sigmoid(got), sigmoid(want), rtol=TOL, atol=0)
+        np.testing.assert_allclose(got, want, rtol=0, atol=4 * TOL)
+
+
 def test_bf16_tracks_fp32_on_packed_varlen(models):
     bf, fp = models
     lens = [700, 128, 1, 129, 2500, 64]

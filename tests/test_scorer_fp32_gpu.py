@@ -43,6 +43,40 @@ def test_longer_than_reference_table(model, scorer_golden):
     np.testing.assert_allclose(logits.view(-1).cpu().numpy(), scorer_golden["logits_106"], rtol=RTOL, atol=ATOL)
 
 
+def test_full_length_videos_against_reference(model, scorer_long_golden):
+    """N = 4096 and 8192 (BASELINE config 5's upper end) against the reference's own outputs (its PositionalEncoding class
+    with maxlen=8192, simnet.py:220-238)."""
+    for vid, n in [tuple(int(x) for x in r) for r in scorer_long_golden["cases"]]:
+        x = torch.from_numpy(make_video(vid, n).features).unsqueeze(0).cuda()
+        with torch.no_grad():
+            logits, feats = model(x)
+        np.testing.assert_allclose(logits.view(-1).cpu().numpy(), scorer_long_golden[f"logits_{vid}"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(feats[0].double().sum(1).cpu().numpy(), scorer_long_golden[f"feats_rowsum_{vid}"], rtol=1e-4, atol=3e-4)
+
+
+def test_masked_mse_against_reference_loss(scorer_golden):
+    """`mse_with_mask_loss` (utils.py:45-56) through vsum_masked_mse on the reference's own padded-batch logits: the
+    reference's loss value (tests/golden/make_golden.py: padded_loss) must come back, and the gradient must be the
+    analytic one with the reference's bs * Nmax normalisation."""
+    from vsum_b200.utils import mse_with_mask_loss
+    lens = (300, 180, 77)
+    logits = torch.full((3, 300, 1), 7.0)                                 # padded rows: arbitrary finite values, masked out
+    tgt = torch.full((3, 300), 1000.0)
+    mask = torch.ones((3, 300), dtype=torch.bool)
+    for b, n in enumerate(lens):
+        logits[b, :n, 0] = torch.from_numpy(scorer_golden[f"padded_logits_{b}"])
+        tgt[b, :n] = torch.from_numpy(make_video(110 + b, n).gtscore)
+        mask[b, :n] = False
+    out = logits.cuda().requires_grad_(True)
+    loss = mse_with_mask_loss(out, tgt.cuda(), mask.cuda())
+    np.testing.assert_allclose(loss.item(), float(scorer_golden["padded_loss"]), rtol=2e-6, atol=0)
+    loss.backward()
+    want_grad = 2.0 * (logits[:, :, 0] - tgt) * (~mask) / (3 * 300)
+    np.testing.assert_allclose(out.grad[:, :, 0].cpu().numpy(), want_grad.numpy(), rtol=1e-6, atol=1e-9)
+    with pytest.raises(Exception):                                        # no CPU fallback
+        mse_with_mask_loss(logits, tgt, mask)
+
+
 def test_padded_batch_with_key_mask(model, scorer_golden):
     lens = (300, 180, 77)
     x = torch.full((3, 300, 1024), 1000.0)

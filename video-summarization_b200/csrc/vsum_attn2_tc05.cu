@@ -111,6 +111,14 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
         : "memory");
 }
 
+#ifdef VSUM_A2_TIMING      // clock64 phase stamps (timing experiments only): per-tile averages printed by CTA 0 after its first long item
+#define A2_TDECL(n) long long tph[n] = {}, tmark = clock64(); int tcount = 0
+#define A2_TMARK(i) do { const long long _n = clock64(); tph[i] += _n - tmark; tmark = _n; } while (0)
+#else
+#define A2_TDECL(n) do { } while (0)
+#define A2_TMARK(i) do { } while (0)
+#endif
+
 struct ItemInfo {
     int base, n, q0, head, nkv;
     bool has_b;
@@ -239,6 +247,7 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
             uint32_t g0 = 0;             // ring position of the item's first K/V tile
             uint32_t cs = 0;             // S tiles issued so far for this tile slot
             uint32_t cp = 0;             // PV products issued so far
+            A2_TDECL(8);
             for (int it = 0;; ++it) {
                 const int idx = next_item(it);
                 __syncwarp();
@@ -262,8 +271,11 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
                 auto issue_qk = [&](int j) {     // S_t = Q_t K(j)^T once the rows hold the previous S_t in registers
                     const uint32_t g = g0 + j;
                     const int s = g % KV_STAGES;
+                    A2_TMARK(0);
                     tc::mbar_wait(k_full + s, (g / KV_STAGES) & 1);
+                    A2_TMARK(1);
                     tc::mbar_wait(s_empty + t, (cs & 1) ^ 1);
+                    A2_TMARK(2);
                     tc::tc_fence_after();
                     if (tc::elect_one()) {
 #pragma unroll
@@ -275,6 +287,7 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
                         if (j == w.nkv - 1) tc::mma_commit(q_empty + qb);
                     }
                     __syncwarp();
+                    A2_TMARK(3);
                     ++cs;
                 };
                 tc::mbar_wait(q_full + qb, (it >> 1) & 1);
@@ -283,8 +296,11 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
                     if (j + 1 < w.nkv) issue_qk(j + 1);
                     const uint32_t g = g0 + j;
                     const int s = g % KV_STAGES;
+                    A2_TMARK(0);
                     tc::mbar_wait(p_full + t, cp & 1);                    // P_t(j) stored (and O_t rescaled where needed)
+                    A2_TMARK(4);
                     tc::mbar_wait(v_full + s, (g / KV_STAGES) & 1);
+                    A2_TMARK(5);
                     tc::tc_fence_after();
                     if (tc::elect_one()) {
 #pragma unroll
@@ -295,8 +311,16 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
                         tc::mma_commit(v_empty + s);
                     }
                     __syncwarp();
+                    A2_TMARK(6);
                     ++cp;
                 }
+#ifdef VSUM_A2_TIMING
+                if (blockIdx.x == 0 && lane == 0 && w.nkv >= 16 && tcount++ == 1)
+                    printf("issuer %d nkv %d | other %lld | wait K %lld | wait S-empty %lld | issue QK %lld | wait P-full %lld | wait V %lld | issue PV %lld (clk per tile)\n",
+                           t, w.nkv, tph[0] / w.nkv, tph[1] / w.nkv, tph[2] / w.nkv, tph[3] / w.nkv, tph[4] / w.nkv, tph[5] / w.nkv, tph[6] / w.nkv);
+                for (int i = 0; i < 8; ++i) tph[i] = 0;
+                tmark = clock64();
+#endif
                 g0 += w.nkv;
             }
         }
@@ -309,6 +333,7 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
                        tP_r = tP + lane_off + (uint32_t)(t * 64);
         const float2 c2 = make_float2(scale_log2e, scale_log2e);
         uint32_t c = 0;                                        // tiles processed so far by this tile slot (barrier phases)
+        A2_TDECL(10);
         for (int it = 0;; ++it) {
             const int idx = next_item(it);
             __syncwarp();
@@ -319,7 +344,9 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
             const int row = w.q0 + t * 128 + r;                // query row inside the video
             float m_ref = 0.f, l_run = 0.f;
             for (int j = 0; j < w.nkv; ++j, ++c) {
+                A2_TMARK(0);
                 tc::mbar_wait(s_full + t, c & 1);
+                A2_TMARK(1);
                 tc::tc_fence_after();
                 const int valid = w.n - j * BKV;               // keys of this tile inside the video (>= 1)
                 bool p_free = false;                           // the previous P of this tile slot has been consumed by its PV product
@@ -366,17 +393,21 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
                     };
                     tc::tmem_ld32(tS_r, sa);
                     tmem_wait_ld_on(sa);
+                    A2_TMARK(2);
                     tc::tmem_ld32(tS_r + 32, sb);
                     premax(sa, 0);
                     chunk(sa, 0);
+                    A2_TMARK(3);
                     tmem_wait_ld_on(sb);
                     tc::tmem_ld32(tS_r + 64, sa);
                     premax(sb, 1);
                     chunk(sb, 1);
+                    A2_TMARK(4);
                     tmem_wait_ld_on(sa);
                     tc::tmem_ld32(tS_r + 96, sb);
                     premax(sa, 2);
                     chunk(sa, 2);
+                    A2_TMARK(5);
                     tmem_wait_ld_on(sb);
                     premax(sb, 3);                             // the tile maximum is known before the last chunk is exponentiated
                     const float m_tile = mx * scale_log2e;
@@ -406,7 +437,9 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
                     }
                     tc::tc_fence_before();
                     tc::mbar_arrive(s_empty + t);              // S_t is in registers: QK(j+1) may overwrite it while the last chunk runs
+                    A2_TMARK(6);
                     chunk(sb, 3);
+                    A2_TMARK(7);
                     const float2 pq = fadd2(fadd2(ps[0], ps[1]), fadd2(ps[2], ps[3]));
                     psum = pq.x + pq.y;
                     break;
@@ -414,8 +447,16 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
                 tc::tmem_wait_st();
                 tc::tc_fence_before();
                 tc::mbar_arrive(p_full + t);
+                A2_TMARK(8);
                 l_run += psum;
             }
+#ifdef VSUM_A2_TIMING
+            if (blockIdx.x == 0 && lane == 0 && w.nkv >= 16 && tcount++ == 1)
+                printf("softmax warp %2d nkv %d | other %lld | wait S %lld | first ld %lld | chunk0 %lld | chunk1 %lld | chunk2 %lld | max+decide+arrive %lld | chunk3 %lld | wait st + arrive %lld (clk per tile)\n",
+                       warp, w.nkv, tph[0] / w.nkv, tph[1] / w.nkv, tph[2] / w.nkv, tph[3] / w.nkv, tph[4] / w.nkv, tph[5] / w.nkv, tph[6] / w.nkv, tph[7] / w.nkv, tph[8] / w.nkv);
+            for (int i = 0; i < 10; ++i) tph[i] = 0;
+            tmark = clock64();
+#endif
             // ---- epilogue: O_t / l -> global
             tc::mbar_wait(p_empty + t, (c & 1) ^ 1);           // the last PV product of the item has completed
             tc::tc_fence_after();

@@ -1,7 +1,6 @@
 """Host helpers with the reference's names (`src/utils/utils.py`).  Only `mse_with_mask_loss`
-(lines 45-56) touches the hot path: on CUDA tensors it runs the native fwd+bwd kernel behind
-`vsum_masked_mse`; the CPU expression below exists for host-side
-unit tests of the normalisation only."""
+(lines 45-56) touches the hot path: it runs the native fwd+bwd kernel behind `vsum_masked_mse`
+(SURVEY.md section 8 row a9).  There is no CPU fallback: host tensors raise."""
 from __future__ import annotations
 
 import json
@@ -66,13 +65,12 @@ class _MaskedMSE(torch.autograd.Function):
 
 
 def mse_with_mask_loss(output, targets, mask, reduction="avg", denom=None):
-    """Masked MSE normalised by the PADDED size bs*Nmax, not by the valid frames (utils.py:55).
-    On CUDA tensors this is the native kernel behind `vsum_masked_mse` (forward and backward)."""
-    if output.is_cuda:
-        squeezed = output.squeeze(2)
-        if denom is None:       # data-parallel callers pass sharding.global_loss_denominator(...)
-            denom = float(squeezed.numel()) if reduction == "avg" else 1.0
-        return _MaskedMSE.apply(squeezed, targets, mask, float(denom))
-    keep = (~mask).to(output.dtype)
-    err = ((output.squeeze(2) - targets) * keep) ** 2
-    return err.mean() if reduction == "avg" else err.sum()
+    """Masked MSE normalised by the PADDED size bs*Nmax, not by the valid frames (utils.py:55): the native kernel behind
+    `vsum_masked_mse` (forward and backward).  CUDA tensors only -- this package has no CPU path."""
+    if not output.is_cuda:
+        from .._cabi import VsumError
+        raise VsumError("mse_with_mask_loss: vsum_b200 runs on CUDA tensors only (no CPU fallback)")
+    squeezed = output.squeeze(2)
+    if denom is None:       # data-parallel callers pass sharding.global_loss_denominator(...)
+        denom = float(squeezed.numel()) if reduction == "avg" else 1.0
+    return _MaskedMSE.apply(squeezed, targets, mask, float(denom))
