@@ -324,13 +324,14 @@ VSUM_API int vsum_pack_collate(vsum_pack_t pack, const int32_t *videos, int32_t 
  *     a_is_f32 (tf32 MMA).  epi: 0 bias, 1 bias+ReLU, 3 bias+residual+LayerNorm (N == 256),
  *     5 / 6: bias (+ReLU) with an fp32 output (tf32 operands only).
  *   vsum_debug_attention_tc05: qkv [T,768] bf16 -> out [T,256] bf16 (4 heads of 64, scale 1/16);
- *     scratch_i32 holds 2*(T/128+B)+8 int32 (all three attention entry points).
+ *     scratch_i32 holds vsum_attention_scratch_ints(T, B) int32 (all three attention entry points).
  *   vsum_set_attention_kernel: which forward kernel the scorer and these entry points run --
  *     2 (default): persistent kernel, two 128-query tiles per CTA, probabilities in tensor memory
  *     (csrc/vsum_attn2_tc05.cu); 1: one 128-query tile per CTA (csrc/vsum_attn_tc05.cu).  Both replace
  *     src/model/simnet.py:155-161.  The environment variable VSUM_ATTN_KERNEL sets the initial value.
  * ------------------------------------------------------------------------------------------ */
 VSUM_API int vsum_set_attention_kernel(int32_t version);
+VSUM_API size_t vsum_attention_scratch_ints(int64_t T, int32_t B);
 VSUM_API int vsum_debug_gemm_tc05(const void *A, const void *W, const float *bias, const void *residual_bf16,
                          const float *gamma, const float *beta, void *out_bf16, int64_t M, int32_t N,
                          int32_t K, int32_t a_is_f32, int32_t epi, void *stream);

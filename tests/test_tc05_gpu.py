@@ -93,14 +93,14 @@ def test_attention(lens, attn_kernel):   # the last four have more work items th
     qkv = torch.randn((T, 768), device="cuda", generator=g).bfloat16()
     cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device="cuda")
     out = torch.zeros((T, 256), dtype=torch.bfloat16, device="cuda")
-    scratch = torch.zeros(2 * (T // 128 + len(lens)) + 8, dtype=torch.int32, device="cuda")
+    scratch = torch.zeros(_cabi.load().vsum_attention_scratch_ints(T, len(lens)), dtype=torch.int32, device="cuda")
     _cabi.check(_cabi.load().vsum_debug_attention_tc05(qkv.data_ptr(), cu.data_ptr(), len(lens), T, out.data_ptr(),
                                                        scratch.data_ptr(), _stream()), "vsum_debug_attention_tc05")
     torch.cuda.synchronize()
     torch.testing.assert_close(out.float(), attention_ref(qkv, lens), rtol=2e-2, atol=2e-2)
 
 
-@pytest.mark.parametrize("case", ["rising", "falling", "far_below_zero", "far_above_zero", "one_hot"])
+@pytest.mark.parametrize("case", ["rising", "falling", "below_zero", "far_below_zero", "far_above_zero", "one_hot"])
 def test_attention_exponent_reference_moves(case, attn_kernel):
     """Score distributions that push the running exponent reference of the softmax around: the two-tile kernel
     exponentiates against a reference that only moves when a tile maximum leaves a +-24 (log2) window and then
@@ -113,9 +113,12 @@ def test_attention_exponent_reference_moves(case, attn_kernel):
         qkv[:, 256:512] *= torch.linspace(0.2, 14.0, T, device="cuda")[:, None]
     elif case == "falling":       # the first tile holds the maximum
         qkv[:, 256:512] *= torch.linspace(14.0, 0.2, T, device="cuda")[:, None]
-    elif case == "far_below_zero":   # every logit around -60 log2 units: exp2(s) alone would underflow to nothing useful
-        qkv[:, 0:256] = 0.3 * qkv[:, 0:256] + 4.0
-        qkv[:, 256:512] = 0.3 * qkv[:, 256:512] - 4.0
+    elif case == "below_zero":       # every logit around -60 log2 units: the reference moves down after the first tile
+        qkv[:, 0:256] = 0.3 * qkv[:, 0:256] + 3.3
+        qkv[:, 256:512] = 0.3 * qkv[:, 256:512] - 3.3
+    elif case == "far_below_zero":   # every logit around -140 log2 units: exp2(s) alone underflows (exact pass)
+        qkv[:, 0:256] = 0.3 * qkv[:, 0:256] + 5.0
+        qkv[:, 256:512] = 0.3 * qkv[:, 256:512] - 5.0
     elif case == "far_above_zero":   # every logit around +90 log2 units
         qkv[:, 0:256] = 0.3 * qkv[:, 0:256] + 5.0
         qkv[:, 256:512] = 0.3 * qkv[:, 256:512] + 5.0
@@ -124,7 +127,7 @@ def test_attention_exponent_reference_moves(case, attn_kernel):
     qkv = qkv.bfloat16()
     cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device="cuda")
     out = torch.zeros((T, 256), dtype=torch.bfloat16, device="cuda")
-    scratch = torch.zeros(2 * (T // 128 + len(lens)) + 8, dtype=torch.int32, device="cuda")
+    scratch = torch.zeros(_cabi.load().vsum_attention_scratch_ints(T, len(lens)), dtype=torch.int32, device="cuda")
     _cabi.check(_cabi.load().vsum_debug_attention_tc05(qkv.data_ptr(), cu.data_ptr(), len(lens), T, out.data_ptr(),
                                                        scratch.data_ptr(), _stream()), "vsum_debug_attention_tc05")
     torch.cuda.synchronize()
@@ -201,7 +204,7 @@ def test_attention_train_and_backward(lens, p, attn_kernel):
     cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device="cuda")
     out = torch.zeros((T, 256), device="cuda")                      # the training variant writes fp32
     lse2 = torch.zeros((T, 4), device="cuda")
-    scratch = torch.zeros(2 * (T // 128 + B) + 8, dtype=torch.int32, device="cuda")
+    scratch = torch.zeros(_cabi.load().vsum_attention_scratch_ints(T, B), dtype=torch.int32, device="cuda")
     L = _cabi.load()
     _cabi.check(L.vsum_debug_attention_train_tc05(qkv.data_ptr(), cu.data_ptr(), B, T, out.data_ptr(), lse2.data_ptr(), p, seed,
                                                   scratch.data_ptr(), _stream()), "vsum_debug_attention_train_tc05")

@@ -24,7 +24,7 @@ g = torch.Generator(device="cuda").manual_seed(T)
 qkv = torch.randn((T, 768), device="cuda", generator=g).bfloat16()
 cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device="cuda")
 out = torch.zeros((T, 256), dtype=torch.bfloat16, device="cuda")
-scratch = torch.zeros(2 * (T // 128 + len(lens)) + 8, dtype=torch.int32, device="cuda")
+scratch = torch.zeros(8 * (T // 128 + len(lens)) + 16, dtype=torch.int32, device="cuda")
 def call():
     rc = entry(qkv.data_ptr(), cu.data_ptr(), len(lens), T, out.data_ptr(), scratch.data_ptr(), torch.cuda.current_stream().cuda_stream)
     assert rc == 0, rc

@@ -160,7 +160,7 @@ size_t carve16(const vsum_scorer_config &c, int64_t T, int max_tiles, void *base
     const size_t t = (size_t)T, d = c.d_model;
     w.row_pos = k.get<int32_t>(t);
     w.tile_video = k.get<int32_t>(max_tiles); w.tile_q0 = k.get<int32_t>(max_tiles); w.n_tiles = k.get<int32_t>(1);
-    w.a2 = k.get<int32_t>(2 * (size_t)max_tiles + 8);      // >= attention2_scratch_ints(T, B): work list of the two-tile attention kernel
+    w.a2 = k.get<int32_t>(6 * (size_t)max_tiles + 8);      // >= attention2_scratch_ints(T, B): work list + exact-pass flags of the two-tile attention kernel
     w.xa = k.get<__nv_bfloat16>(t * d); w.xb = k.get<__nv_bfloat16>(t * d);
     w.qkv = k.get<__nv_bfloat16>(t * 3 * d); w.att = k.get<__nv_bfloat16>(t * d);
     w.hid = k.get<__nv_bfloat16>(t * c.d_ff);
@@ -317,7 +317,7 @@ size_t carve_train_ws(const vsum_scorer_config &c, int64_t T, int32_t B, void *b
     w.y16 = k.get<__nv_bfloat16>(n * widest); w.x16 = k.get<__nv_bfloat16>(n * widest);   // bf16 operands of the tcgen05 wgrad / attention
     w.max_tiles = (int)(T / 128 + B);
     w.tile_video = k.get<int32_t>(w.max_tiles); w.tile_q0 = k.get<int32_t>(w.max_tiles); w.n_tiles = k.get<int32_t>(1);
-    w.a2 = k.get<int32_t>(2 * (size_t)w.max_tiles + 8);
+    w.a2 = k.get<int32_t>(6 * (size_t)w.max_tiles + 8);
     return align_up(k.off, 1024);
 }
 }  // namespace

@@ -49,8 +49,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > VSUM_MBAR_TIMEOUT_CYCLES) {
+#ifdef VSUM_MBAR_VERBOSE     // debugging builds name the barrier; the printf costs every caller registers and a stack frame
             printf("vsum: mbarrier timeout (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x,
                    blockIdx.y, threadIdx.x, smem_u32(bar), parity);
+#endif
             __trap();
         }
     }
