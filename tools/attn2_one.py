@@ -11,6 +11,8 @@ ap.add_argument("--lib", default=os.path.join(os.path.dirname(os.path.abspath(__
 ap.add_argument("--version", type=int, default=2)
 ap.add_argument("--workload", action="store_true")
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--lens", default=None, help="python expression for the list of video lengths, e.g. \"[300]*150\"")
+ap.add_argument("--check", action="store_true", help="compare with fp32 softmax attention")
 a = ap.parse_args()
 vp = C.c_void_p
 L = C.CDLL(a.lib)
@@ -18,7 +20,7 @@ entry = L.vsum_debug_attention_tc05
 entry.argtypes = [vp, vp, C.c_int32, C.c_int64, vp, vp, vp]; entry.restype = C.c_int
 L.vsum_set_attention_kernel.argtypes = [C.c_int32]
 assert L.vsum_set_attention_kernel(a.version) == 0
-lens = sorted((video_length(v, 128, 8192) for v in range(256)), reverse=True) if a.workload else [2048] * 148
+lens = eval(a.lens) if a.lens else (sorted((video_length(v, 128, 8192) for v in range(256)), reverse=True) if a.workload else [2048] * 148)
 T = sum(lens)
 g = torch.Generator(device="cuda").manual_seed(T)
 qkv = torch.randn((T, 768), device="cuda", generator=g).bfloat16()
@@ -29,6 +31,14 @@ def call():
     rc = entry(qkv.data_ptr(), cu.data_ptr(), len(lens), T, out.data_ptr(), scratch.data_ptr(), torch.cuda.current_stream().cuda_stream)
     assert rc == 0, rc
 call(); torch.cuda.synchronize()
+if a.check:
+    ref = torch.empty((T, 256), device="cuda"); off = 0
+    for n in lens:
+        x = qkv[off:off + n].float()
+        q, k, v = (x[:, i * 256:(i + 1) * 256].view(n, 4, 64).permute(1, 0, 2) for i in range(3))
+        ref[off:off + n] = (torch.softmax(q @ k.transpose(1, 2) / 16.0, dim=-1) @ v).permute(1, 0, 2).reshape(n, 256)
+        off += n
+    print("max err", (out.float() - ref).abs().max().item())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(a.reps): call()

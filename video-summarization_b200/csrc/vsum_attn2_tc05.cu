@@ -3,32 +3,34 @@
 // simnet.py:159 in the TRAIN variant) for d_model 256, 4 heads of 64.
 //
 // PERSISTENT kernel, one CTA per SM, work items = (video, head, 256 queries) handed out longest-video-first by an
-// atomic counter.  A CTA works on TWO 128-query tiles (A, B) of its item at once, each tile an independent pipeline:
-//   warp 0      work scheduler (atomicAdd -> shared-memory ring) and TMA producer: Q tiles of the item (double-buffered
+// atomic counter.  A CTA works on TWO 128-query tiles (A, B) of its item; a "unit" is one (tile, 128-key block) pair and
+// the units of all items form one sequence A0 B0 A1 B1 ... that every role walks in the same order.
+//   warps 0-3   softmax of tile A, warps 4-7 softmax of tile B: one thread per query row
+//   warp 8      work scheduler (atomicAdd -> shared-memory ring) and TMA producer: Q tiles of the item (double-buffered
 //               across items), K / V tiles through a shared ring
-//   warp 1 / 2  tcgen05.mma issuer of tile A / tile B (warp 2 also owns the TMEM allocation)
-//   warp 3      idle: it only hands its registers to the softmax warps (setmaxnreg moves registers inside the CTA's own
-//               allocation, 640 threads x 96 at launch)
-//   warps 4-19  softmax: TWO threads per query row (64 key columns each), i.e. four warps on every SM sub-partition --
-//               with one thread per row (two warps per sub-partition) the warps ran at one instruction per 4 clocks and
-//               nothing hid their tensor-memory loads and barrier waits (profiles/r02_attn2_one_thread_per_row.txt)
-// Tensor memory (512 columns): S_A, S_B fp32 [128 x 128] (0..255), O_A, O_B fp32 [128 x 64] (256..383),
-// P_A, P_B bf16 [128 x 128] as packed pairs (384..511).  P is written with tcgen05.st and consumed as the TMEM A operand
-// of the PV MMA, so the probabilities never touch shared memory, every K / V tile is fetched once per 256 queries, and
-// the shared-memory port carries 64 KB per 128 x 128 tile instead of 144 KB (profiles/r01_microbench_mma_rate.txt).
+//   warp 9      tcgen05.mma issuer of all QK^T products
+//   warp 10/11  tcgen05.mma issuer of the PV products of tile A / tile B (warp 10 also owns the TMEM allocation)
+// (the control warps carry the HIGH warp ids: the sub-partition schedulers favour them, and an issuer that has to wait
+// for the softmax warps' idle slots delays every tile)
+// Tensor memory (512 columns): THREE S buffers fp32 [128 x 128] (0..383) used round-robin by the unit sequence, O_A,
+// O_B fp32 [128 x 64] (384..511).  The probabilities of a unit are written IN PLACE over the first 64 columns of its S
+// buffer (bf16 pairs, tcgen05.st) and consumed from there as the TMEM A operand of the PV MMA, so P never touches shared
+// memory and every K / V tile is fetched once per 256 queries (profiles/r01_microbench_mma_rate.txt: the one-tile kernel
+// ran at 82 % of its shared-memory bandwidth).  With three buffers for two tiles the issuer runs QK^T three units ahead
+// of PV: S of unit u+3 goes into the buffer PV(u) has just read (the tensor pipe executes in order), i.e. it depends on
+// the OTHER tile's previous step, not on the softmax that will consume it -- a row finds its next S ready when it has
+// stored its P, where the two-buffer version of this kernel waited ~20 % of the time (profiles/r02_attn2_*.txt).
 //
-// Exponent reference without a per-tile exchange.  The two threads of a row share ONE accumulator O and must therefore
-// exponentiate against the same reference m_ref, but they never wait for each other inside a tile: every thread
-// publishes the maximum of its 64 columns of tile j to shared memory BEFORE it releases S (s_empty), so when either of
-// them gets the next S (s_full of tile j+1, which the MMA warp only issues after BOTH released tile j) both maxima of
-// tile j are visible, and both derive the same decision from the same two numbers: m_ref (0 at the start of an item)
-// moves to the row maximum when that maximum has left the window [m_ref - 24, m_ref + 24] (log2 units), O and the row
-// sums being rescaled by the owner of each half.  Softmax is shift-invariant and fp32 / bf16 keep their relative
-// precision, so a reference that lags one tile behind gives the same result as the exact running maximum -- as long as
-// no exponential overflows or the whole first tile underflows, i.e. while a tile's scores stay within +-96 log2 units
-// (+-66 nats) of the reference.  A row that sees more than that raises its item's flag, and a second launch of the same
-// kernel (SAFE = true: exact maximum per tile, the two threads of a row exchange through a named barrier) recomputes
-// the flagged items; with no flag raised that launch ends after reading one flag per item.
+// One-pass streaming softmax against a LAGGING reference.  A row exponentiates tile j against m_ref, which was fixed
+// before the tile started from the maxima of the tiles before it (0 at the start of an item; it moves to the running
+// maximum when that has left the window [m_ref - 24, m_ref + 24], log2 units, with O and the row sum rescaled).  The
+// tile's own maximum is only tracked on the side (FMNMX3) for the next decision.  Softmax is shift-invariant and fp32 /
+// bf16 keep their relative precision, so this equals the exact running maximum as long as no exponential overflows and
+// the first tile does not underflow as a whole, i.e. while a tile's scores stay within +-96 log2 units (+-66 nats) of
+// the reference.  A row that sees more raises its item's flag, and a second launch of the same kernel (SAFE = true: one
+// extra sweep over S for the exact tile maximum before exponentiating) recomputes the flagged items; with no flag
+// raised that launch ends after reading one flag per item.
+// The row streams S in four 32-column chunks whose tensor-memory loads overlap the exponentials of the previous chunk.
 // A share of the exponentials runs as a degree-3 polynomial on the FMA pipe (the MUFU pipe, 16 ex2 / clk / SM, is the
 // limiter at head_dim 64: profiles/r01_microbench_mufu_ex2.txt).
 #include "vsum_kernels.cuh"
@@ -40,15 +42,15 @@ namespace {
 constexpr int HD = 64, DM = 256, NH = 4;
 constexpr int BQ2 = 256, BKV = 128;
 constexpr int TILE_BYTES = 128 * 128;            // 128 rows x 64 bf16
-constexpr int A2_THREADS = 640;                  // 3 control warps + 1 register donor + 16 softmax warps; 640 x 96 registers at launch
-constexpr int A2_REGS_CONTROL = 64, A2_REGS_DONOR = 24, A2_REGS_SOFTMAX = 104;   // setmaxnreg: 96 x (96 - 64) + 32 x (96 - 24) released >= 512 x (104 - 96) acquired
+constexpr int A2_THREADS = 384;                  // 4 control warps + 8 softmax warps; 384 x 168 registers at launch
+constexpr int A2_REGS_CONTROL = 80, A2_REGS_SOFTMAX = 208;   // setmaxnreg: 128 x (168 - 80) released >= 256 x (208 - 168) acquired
 constexpr int A2_TMEM_COLS = 512;
 #ifndef VSUM_A2_STAGES
 #define VSUM_A2_STAGES 4
 #endif
 constexpr int KV_STAGES = VSUM_A2_STAGES;
 constexpr int SCHED_RING = 4;
-constexpr size_t A2_SMEM = (4 + 2 * (size_t)KV_STAGES) * TILE_BYTES + 512 + 6 * 1024;   // Q (2 items x 2 tiles), K ring, V ring, barriers, row exchange
+constexpr size_t A2_SMEM = (4 + 2 * (size_t)KV_STAGES) * TILE_BYTES + 512;   // Q (2 items x 2 tiles), K ring, V ring, barriers
 #ifndef VSUM_A2_POLY_PERIOD
 #define VSUM_A2_POLY_PERIOD 4        // every k-th pair of exponentials is a polynomial on the FMA pipe (0 = none)
 #endif
@@ -162,38 +164,39 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
     uint8_t *sK = smem + 4 * (size_t)TILE_BYTES;                 // ring
     uint8_t *sV = sK + (size_t)KV_STAGES * TILE_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sV + (size_t)KV_STAGES * TILE_BYTES);
-    uint64_t *q_full = bars, *q_empty = bars + 2;                // [2]
+    uint64_t *q_full = bars, *q_empty = bars + 2;                // [item parity]
     uint64_t *k_full = bars + 4, *k_empty = k_full + KV_STAGES, *v_full = k_empty + KV_STAGES, *v_empty = v_full + KV_STAGES;
-    uint64_t *s_full = v_empty + KV_STAGES, *s_empty = s_full + 2, *p_full = s_full + 4, *p_empty = s_full + 6;   // [tile]
-    uint64_t *sched_full = s_full + 8, *sched_empty = sched_full + SCHED_RING;
+    uint64_t *s_full = v_empty + KV_STAGES;                      // [tile][the tile's unit count % 3]: S of that unit is complete (a tile's rows
+                                                                 // must see every phase of the barriers they wait on, so these are per tile)
+    uint64_t *p_full = s_full + 6;                               // [tile][count % 3]: the P of that unit is stored (128 arrivals)
+    uint64_t *pv_done = p_full + 6;                              // [tile]: a PV product of the tile has completed
+    uint64_t *buf_free = pv_done + 2;                            // [S buffer]: the PV product that read P from the buffer has completed
+    uint64_t *sched_full = buf_free + 3, *sched_empty = sched_full + SCHED_RING;
     int32_t *sched_idx = reinterpret_cast<int32_t *>(sched_empty + SCHED_RING);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sched_idx + SCHED_RING);
-    float *hm = reinterpret_cast<float *>(smem + (4 + 2 * (size_t)KV_STAGES) * TILE_BYTES + 512);   // [tile][parity][half][128] half-row maxima
-    float *lx = hm + 2 * 2 * 2 * 128;                                                               // [tile][half][128] half-row sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = __ldg(counters) * NH;
 
-    if (warp == 0 && lane == 0) tc::tma_prefetch_desc(&tmQKV);
-    if (warp == 1 && lane == 0) {
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(q_full + i, 1); tc::mbar_init(q_empty + i, 2); }
+    if (warp == 8 && lane == 0) tc::tma_prefetch_desc(&tmQKV);
+    if (warp == 9 && lane == 0) {
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(q_full + i, 1); tc::mbar_init(q_empty + i, 1); }
         for (int s = 0; s < KV_STAGES; ++s) {
-            tc::mbar_init(k_full + s, 1); tc::mbar_init(k_empty + s, 2);
+            tc::mbar_init(k_full + s, 1); tc::mbar_init(k_empty + s, 1);
             tc::mbar_init(v_full + s, 1); tc::mbar_init(v_empty + s, 2);
         }
-        for (int t = 0; t < 2; ++t) {
-            tc::mbar_init(s_full + t, 1); tc::mbar_init(s_empty + t, 256);
-            tc::mbar_init(p_full + t, 256); tc::mbar_init(p_empty + t, 1);
-        }
-        for (int i = 0; i < SCHED_RING; ++i) { tc::mbar_init(sched_full + i, 1); tc::mbar_init(sched_empty + i, 18); }
+        for (int i = 0; i < 6; ++i) { tc::mbar_init(s_full + i, 1); tc::mbar_init(p_full + i, 128); }
+        for (int i = 0; i < 3; ++i) tc::mbar_init(buf_free + i, 1);
+        for (int t = 0; t < 2; ++t) tc::mbar_init(pv_done + t, 1);
+        for (int i = 0; i < SCHED_RING; ++i) { tc::mbar_init(sched_full + i, 1); tc::mbar_init(sched_empty + i, 11); }
         tc::fence_barrier_init();
     }
-    if (warp == 2) { tc::tmem_alloc(tmem_slot, A2_TMEM_COLS); tc::tmem_relinquish(); }
+    if (warp == 10) { tc::tmem_alloc(tmem_slot, A2_TMEM_COLS); tc::tmem_relinquish(); }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tS = tmem_base, tO = tmem_base + 256, tP = tmem_base + 384;
+    const uint32_t tO = tmem_base + 384;                         // S buffer b at tmem_base + 128 b
 
     // Every role walks the same item sequence through the scheduler ring.
     auto next_item = [&](int it) -> int {
@@ -203,11 +206,9 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
     };
     auto release_item = [&](int it) { tc::mbar_arrive(sched_empty + (it % SCHED_RING)); };
 
-    if (warp == 3) {
-        tc::setmaxnreg_dec<A2_REGS_DONOR>();
-    } else if (warp < 3) {
+    if (warp >= 8) {
         tc::setmaxnreg_dec<A2_REGS_CONTROL>();
-        if (warp == 0) {                 // ===== work scheduler + TMA producer =====
+        if (warp == 8) {                 // ===== work scheduler + TMA producer =====
             if (lane == 0) {
                 uint32_t g = 0;                                           // running K/V tile counter (ring position)
                 for (int it = 0;; ++it) {
@@ -237,13 +238,12 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
                     }
                 }
             }
-        } else {                         // ===== MMA issuer of tile t (whole warp, warp-uniform control flow, one elected lane) =====
-            const int t = warp - 1;
+        } else if (warp == 9) {          // ===== QK^T issuer (whole warp, warp-uniform control flow, one elected lane) =====
+            // One thread cannot issue both products of both tiles fast enough (12 MMAs + commits + three waits cost it
+            // ~1000 clk per unit, tools/microbench/mma_hazard.cu), so QK^T and the two tiles' PV have a warp each.
             constexpr uint32_t IDESC_QK = tc::make_idesc(1, 128, BKV, 0, 0);   // S[128 x 128], A and B K-major
-            constexpr uint32_t IDESC_PV = tc::make_idesc(1, 128, HD, 0, 1);    // O[128 x 64], A = P in TMEM, B = V MN-major
             const uint32_t q_lo = (uint32_t)tc::make_smem_desc_sw128(tc::smem_u32(sQ), 16, 1024);
             const uint32_t k_lo = (uint32_t)tc::make_smem_desc_sw128(tc::smem_u32(sK), 16, 1024);
-            const uint32_t v_lo = (uint32_t)tc::make_smem_desc_sw128(tc::smem_u32(sV), 16, 1024);
             const uint32_t hi = (uint32_t)(tc::make_smem_desc_sw128(tc::smem_u32(sQ), 16, 1024) >> 32);
             auto desc_at = [hi](uint32_t lo, uint32_t off) -> uint64_t {       // derived at the point of use (see vsum_attn_tc05.cu)
                 uint32_t l;
@@ -251,83 +251,101 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
                 return ((uint64_t)hi << 32) | l;
             };
             constexpr uint32_t TILE16 = TILE_BYTES >> 4;
-            const uint32_t tS_t = tS + (uint32_t)(t * 128), tO_t = tO + (uint32_t)(t * HD), tP_t = tP + (uint32_t)(t * 64);
-            uint32_t g0 = 0;             // ring position of the item's first K/V tile
-            uint32_t cs = 0;             // S tiles issued so far for this tile slot
-            uint32_t cp = 0;             // PV products issued so far
+            uint32_t n_qk = 0, cs0 = 0, cs1 = 0, g0 = 0;   // units issued (S buffer = unit % 3), S tiles issued per tile, K/V ring position
             for (int it = 0;; ++it) {
                 const int idx = next_item(it);
                 __syncwarp();
                 if (lane == 0) release_item(it);
                 if (idx >= n_items) break;
                 const ItemInfo w = decode_item(idx, cu, item_video, item_q0);
-                const int qb = it & 1;
-                if (t == 1 && !w.has_b) {        // no second tile: keep the shared barriers' arrival counts whole
-                    for (int j = 0; j < w.nkv; ++j) {
-                        const uint32_t g = g0 + j;
-                        const int s = g % KV_STAGES;
-                        const uint32_t ph = (g / KV_STAGES) & 1;
-                        tc::mbar_wait(k_full + s, ph);
-                        tc::mbar_wait(v_full + s, ph);
-                        if (lane == 0) { tc::mbar_arrive(k_empty + s); tc::mbar_arrive(v_empty + s); }
-                    }
-                    if (lane == 0) tc::mbar_arrive(q_empty + qb);
-                    g0 += w.nkv;
-                    continue;
-                }
-                auto issue_qk = [&](int j) {     // S_t = Q_t K(j)^T once the rows hold the previous S_t in registers
-                    const uint32_t g = g0 + j;
+                const int qb = it & 1, n_q = w.has_b ? 2 : 1;
+                tc::mbar_wait(q_full + qb, (it >> 1) & 1);
+                for (int j = 0; j < w.nkv; ++j) {
+                    const uint32_t g = g0 + (uint32_t)j;
                     const int s = g % KV_STAGES;
                     tc::mbar_wait(k_full + s, (g / KV_STAGES) & 1);
-                    tc::mbar_wait(s_empty + t, (cs & 1) ^ 1);
-                    tc::tc_fence_after();
-                    if (tc::elect_one()) {
+                    for (int t = 0; t < n_q; ++t, ++n_qk) {
+                        const uint32_t buf = n_qk % 3;
+                        if (n_qk >= 3) tc::mbar_wait(buf_free + buf, (n_qk / 3 - 1) & 1);   // the PV product of unit n_qk - 3 has read its P
+                        tc::tc_fence_after();
+                        if (tc::elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < HD / 16; ++k)
-                            tc::mma_f16_ss(tS_t, desc_at(q_lo, (uint32_t)(qb * 2 + t) * TILE16 + k * 2),
-                                           desc_at(k_lo, (uint32_t)s * TILE16 + k * 2), IDESC_QK, k != 0);
-                        tc::mma_commit(s_full + t);
-                        tc::mma_commit(k_empty + s);
-                        if (j == w.nkv - 1) tc::mma_commit(q_empty + qb);
+                            for (int k = 0; k < HD / 16; ++k)
+                                tc::mma_f16_ss(tmem_base + buf * 128, desc_at(q_lo, (uint32_t)(qb * 2 + t) * TILE16 + k * 2),
+                                               desc_at(k_lo, (uint32_t)s * TILE16 + k * 2), IDESC_QK, k != 0);
+                            tc::mma_commit(s_full + t * 3 + (t ? cs1 : cs0) % 3);
+                            if (t == n_q - 1) tc::mma_commit(k_empty + s);
+                            if (j == w.nkv - 1 && t == n_q - 1) tc::mma_commit(q_empty + qb);
+                        }
+                        __syncwarp();
+                        if (t) ++cs1; else ++cs0;
                     }
-                    __syncwarp();
-                    ++cs;
-                };
-                tc::mbar_wait(q_full + qb, (it >> 1) & 1);
-                issue_qk(0);
+                }
+                g0 += (uint32_t)w.nkv;
+            }
+        } else {                         // ===== PV issuer of tile t (warp 10: A, warp 11: B) =====
+            const int t = warp - 10;
+            constexpr uint32_t IDESC_PV = tc::make_idesc(1, 128, HD, 0, 1);    // O[128 x 64], A = P in TMEM, B = V MN-major
+            const uint32_t v_lo = (uint32_t)tc::make_smem_desc_sw128(tc::smem_u32(sV), 16, 1024);
+            const uint32_t hi = (uint32_t)(tc::make_smem_desc_sw128(tc::smem_u32(sV), 16, 1024) >> 32);
+            auto desc_at = [hi](uint32_t lo, uint32_t off) -> uint64_t {
+                uint32_t l;
+                asm volatile("add.u32 %0, %1, %2;" : "=r"(l) : "r"(lo), "r"(off));
+                return ((uint64_t)hi << 32) | l;
+            };
+            constexpr uint32_t TILE16 = TILE_BYTES >> 4;
+            const uint32_t tO_t = tO + (uint32_t)(t * HD);
+            uint32_t n_unit0 = 0, cpt = 0, g0 = 0;         // first unit of the item, P tiles of this tile consumed, K/V ring position
+            for (int it = 0;; ++it) {
+                const int idx = next_item(it);
+                __syncwarp();
+                if (lane == 0) release_item(it);
+                if (idx >= n_items) break;
+                const ItemInfo w = decode_item(idx, cu, item_video, item_q0);
+                const int n_q = w.has_b ? 2 : 1;
+                const uint32_t unit0 = n_unit0;
+                n_unit0 += (uint32_t)(w.nkv * n_q);
                 for (int j = 0; j < w.nkv; ++j) {
-                    if (j + 1 < w.nkv) issue_qk(j + 1);
-                    const uint32_t g = g0 + j;
+                    const uint32_t g = g0 + (uint32_t)j;
                     const int s = g % KV_STAGES;
-                    tc::mbar_wait(p_full + t, cp & 1);                    // P_t(j) stored (and O_t rescaled where needed)
+                    if (t == 1 && !w.has_b) {       // no second tile: keep the V ring's arrival count whole
+                        tc::mbar_wait(v_full + s, (g / KV_STAGES) & 1);
+                        if (lane == 0) tc::mbar_arrive(v_empty + s);
+                        continue;
+                    }
+                    const uint32_t buf = (unit0 + (uint32_t)(j * n_q + t)) % 3;
+                    tc::mbar_wait(p_full + t * 3 + cpt % 3, (cpt / 3) & 1);        // P_t(j) stored (and O_t rescaled where needed)
                     tc::mbar_wait(v_full + s, (g / KV_STAGES) & 1);
                     tc::tc_fence_after();
                     if (tc::elect_one()) {
 #pragma unroll
                         for (int k = 0; k < BKV / 16; ++k)
-                            tc::mma_f16_ts(tO_t, tP_t + (uint32_t)(k * 8), desc_at(v_lo, (uint32_t)s * TILE16 + k * 128), IDESC_PV,
+                            tc::mma_f16_ts(tO_t, tmem_base + buf * 128 + (uint32_t)(k * 8), desc_at(v_lo, (uint32_t)s * TILE16 + k * 128), IDESC_PV,
                                            (j | k) != 0);
-                        tc::mma_commit(p_empty + t);
+                        tc::mma_commit(pv_done + t);
+                        tc::mma_commit(buf_free + buf);
                         tc::mma_commit(v_empty + s);
                     }
                     __syncwarp();
-                    ++cp;
+                    ++cpt;
                 }
-                g0 += w.nkv;
+                g0 += (uint32_t)w.nkv;
             }
         }
-    } else {   // ===== softmax: two threads per query row, 64 key columns each =====
+    } else {   // ===== softmax: one thread per query row =====
         tc::setmaxnreg_inc<A2_REGS_SOFTMAX>();
-        const int grp = (warp - 4) >> 2;                          // warps 4..7, 8..11, 12..15, 16..19: each group covers the four lane quarters
-        const int t = grp >> 1, hf = grp & 1, qd = warp & 3;      // tile, column half, TMEM lane quarter (= warp % 4 = SM sub-partition)
+        const int t = warp >> 2, qd = warp & 3;                   // tile, TMEM lane quarter (= SM sub-partition)
         const int r = qd * 32 + lane;
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        const uint32_t tS_r = tS + lane_off + (uint32_t)(t * 128 + hf * 64), tO_r = tO + lane_off + (uint32_t)(t * HD + hf * 32),
-                       tP_r = tP + lane_off + (uint32_t)(t * 64 + hf * 32);
-        const int pair_bar = 1 + t * 4 + qd;                      // named barrier of the two warps that share these rows
-        float *hm_mine = hm + (t * 4 + hf) * 128 + r, *hm_other = hm + (t * 4 + (hf ^ 1)) * 128 + r;   // + parity * 256
+        const uint32_t tO_r = tO + lane_off + (uint32_t)(t * HD);
         const float2 c2 = make_float2(scale_log2e, scale_log2e);
-        uint32_t c = 0;                                           // tiles processed so far by this tile slot (barrier phases)
+        uint32_t c = 0;                                           // units of this tile processed so far (barrier phases)
+        uint32_t n_unit0 = 0;                                     // position of the item's first unit in the CTA's unit sequence
+        uint32_t pv_seen = 0;                                     // PV completions of this tile consumed so far
+        auto pv_wait_upto = [&](uint32_t upto) {                  // all PV products of this tile's units < upto have completed
+            while (pv_seen < upto) { tc::mbar_wait(pv_done + t, pv_seen & 1); ++pv_seen; }
+            tc::tc_fence_after();
+        };
         A2_TDECL(10);
         for (int it = 0;; ++it) {
             const int idx = next_item(it);
@@ -335,70 +353,70 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
             if (lane == 0) release_item(it);
             if (idx >= n_items) break;
             const ItemInfo w = decode_item(idx, cu, item_video, item_q0);
+            const int n_q = w.has_b ? 2 : 1;
+            const uint32_t unit0 = n_unit0;
+            n_unit0 += (uint32_t)(w.nkv * n_q);
             if (t == 1 && !w.has_b) continue;
             const int row = w.q0 + t * 128 + r;                   // query row inside the video
-            float m_ref = 0.f, l_part = 0.f, m_prev = 0.f;        // exponent reference, row sum of MY columns, my maximum of the previous tile
+            float m_ref = 0.f, l_run = 0.f, m_prev = 0.f;         // exponent reference, row sum, maximum of the previous tile
             for (int j = 0; j < w.nkv; ++j, ++c) {
+                const uint32_t unit = unit0 + (uint32_t)(j * n_q + t), buf = unit % 3;
+                const uint32_t tS_r = tmem_base + lane_off + buf * 128;   // my row of the unit's S / P buffer
                 A2_TMARK(0);
-                tc::mbar_wait(s_full + t, c & 1);
+                tc::mbar_wait(s_full + t * 3 + c % 3, (c / 3) & 1);
                 A2_TMARK(1);
                 tc::tc_fence_after();
+                const int valid = w.n - j * BKV;                  // keys of this tile inside the video (>= 1)
                 uint32_t sa[32], sb[32];
-                tc::tmem_ld32(tS_r, sa);
-                tc::tmem_ld32(tS_r + 32, sb);
-                bool p_free = false;                              // PV(j-1) has completed: P_t may be overwritten, O_t is stable
-                auto move_reference = [&](float m_row, bool low_side_too) {   // same decision in both threads of the row
+                auto move_reference = [&](float m_row, bool low_side_too) {
                     const bool move = (m_row - m_ref > VSUM_A2_WINDOW) || (low_side_too && m_row - m_ref < -VSUM_A2_WINDOW);
                     if (__any_sync(0xffffffffu, move)) {           // rare
-                        if (!p_free) { tc::mbar_wait(p_empty + t, (c & 1) ^ 1); tc::tc_fence_after(); p_free = true; }
                         float alpha = 1.0f;
                         if (move) { alpha = ex2f(m_ref - m_row); m_ref = m_row; }
-                        if (j > 0) {                              // my 32 columns of O_t and my half of the row sum
-                            l_part *= alpha;
-                            uint32_t o[32];
-                            tc::tmem_ld32(tO_r, o);
-                            tmem_wait_ld_on(o);
+                        if (j > 0) {                              // rescale what has been accumulated: PV(j-1) must have completed
+                            pv_wait_upto(c);
+                            l_run *= alpha;
+#pragma unroll 1
+                            for (int hc = 0; hc < 2; ++hc) {
+                                uint32_t o[32];
+                                tc::tmem_ld32(tO_r + hc * 32, o);
+                                tmem_wait_ld_on(o);
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                            tc::tmem_st32(tO_r, o);
+                                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                                tc::tmem_st32(tO_r + hc * 32, o);
+                            }
                             tc::tmem_wait_st();
                         }
                     }
                 };
-                if (!SAFE && j > 0)      // reference for this tile from BOTH halves' maxima of the previous tile (visible: see the header)
-                    move_reference(fmaxf(m_prev, hm_other[((c - 1) & 1) * 256]), j == 1);
-                tmem_wait_ld_on(sa);
-                tmem_wait_ld_on(sb);
-                A2_TMARK(2);
-                const int valid = w.n - j * BKV - hf * 64;        // keys of my half-tile inside the video (may be <= 0)
-                if (valid < 64) {                                 // last tile of the video: next video's rows / TMA zero fill
+                auto mask_tail = [&](uint32_t (&s)[32], int ch) {  // last tile of the video: keys past its end (next video's rows / TMA zero fill)
+                    if (valid < BKV) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        if (i >= valid) sa[i] = 0xff800000u;
-                        if (32 + i >= valid) sb[i] = 0xff800000u;
+                        for (int i = 0; i < 32; ++i)
+                            if (ch * 32 + i >= valid) s[i] = 0xff800000u;
                     }
+                };
+                if (SAFE) {              // exact pass: one extra sweep over S for this tile's own maximum
+                    float mx0 = -INFINITY;
+#pragma unroll 1
+                    for (int ch = 0; ch < 4; ++ch) {
+                        tc::tmem_ld32(tS_r + ch * 32, sa);
+                        tmem_wait_ld_on(sa);
+                        mask_tail(sa, ch);
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) mx0 = fmax3(mx0, __uint_as_float(sa[i]), __uint_as_float(sa[i + 1]));
+                    }
+                    move_reference(mx0 * scale_log2e, j == 0);
+                } else if (j > 0) {
+                    move_reference(m_prev, j == 1);                // lagging reference: the maxima of the tiles before this one
                 }
                 float mx = -INFINITY;
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(sa[i]), __uint_as_float(sa[i + 1]));
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(sb[i]), __uint_as_float(sb[i + 1]));
-                const float m_half = mx * scale_log2e;
-                hm_mine[(c & 1) * 256] = m_half;
-                if (SAFE) {              // exact: this tile's own row maximum, exchanged now
-                    tc::bar_sync(pair_bar, 64);
-                    move_reference(fmaxf(m_half, hm_other[(c & 1) * 256]), j == 0);
-                } else if (row < w.n && (m_half - m_ref > VSUM_A2_DANGER || (j == 0 && m_half < -VSUM_A2_DANGER && valid > 0))) {
-                    *reinterpret_cast<volatile int32_t *>(flags + idx) = 1;   // the exact pass redoes this item
-                }
-                m_prev = m_half;
-                tc::tc_fence_before();
-                tc::mbar_arrive(s_empty + t);                     // S_t is in registers (and my maximum published): QK(j+1) may overwrite it
-                A2_TMARK(3);
-
-                const float2 nm2 = make_float2(-m_ref, -m_ref);
                 float2 ps[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-                auto chunk = [&](const uint32_t (&s)[32], int ch) {
+                const float2 nm2 = make_float2(-m_ref, -m_ref);
+                auto chunk = [&](uint32_t (&s)[32], int ch) {
+                    mask_tail(s, ch);
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
                     uint32_t wv[16];
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
@@ -412,71 +430,87 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
                         const uint32_t th2 = drop_thresh16 * 0x00010001u;
 #pragma unroll
                         for (int gq = 0; gq < 8; ++gq) {
-                            const int key = j * BKV + hf * 64 + ch * 32 + 4 * gq;
+                            const int key = j * BKV + ch * 32 + 4 * gq;
                             const unsigned long long z = dropout_bits64(seed, attn_drop_group_index(w.base + row, w.head, NH, key >> 2));
                             wv[2 * gq] &= __vcmpgeu2((uint32_t)z, th2);
                             wv[2 * gq + 1] &= __vcmpgeu2((uint32_t)(z >> 32), th2);
                         }
                     }
-                    if (!p_free) { tc::mbar_wait(p_empty + t, (c & 1) ^ 1); tc::tc_fence_after(); p_free = true; }
-                    tmem_st16(tP_r + (uint32_t)(ch * 16), wv);
+                    tmem_st16(tS_r + (uint32_t)(ch * 16), wv);    // in place: columns [16 ch, 16 ch + 16) belong to chunks already in registers
                 };
+                tc::tmem_ld32(tS_r, sa);
+                tmem_wait_ld_on(sa);
+                A2_TMARK(2);
+                tc::tmem_ld32(tS_r + 32, sb);
                 chunk(sa, 0);
-                A2_TMARK(4);
+                A2_TMARK(3);
+                tmem_wait_ld_on(sb);
+                tc::tmem_ld32(tS_r + 64, sa);
                 chunk(sb, 1);
+                A2_TMARK(4);
+                tmem_wait_ld_on(sa);
+                tc::tmem_ld32(tS_r + 96, sb);
+                chunk(sa, 2);
                 A2_TMARK(5);
+                tmem_wait_ld_on(sb);
+                chunk(sb, 3);
+                A2_TMARK(6);
+                m_prev = fmaxf(mx * scale_log2e, j == 0 ? -INFINITY : m_prev);      // running maximum of the item so far
+                if (!SAFE && row < w.n && (mx * scale_log2e - m_ref > VSUM_A2_DANGER || (j == 0 && mx * scale_log2e < -VSUM_A2_DANGER)))
+                    *reinterpret_cast<volatile int32_t *>(flags + idx) = 1;           // the exact pass redoes this item
+                pv_wait_upto(c);                                  // keeps the phase bookkeeping in step (PV(j-1) completed long ago)
                 tc::tmem_wait_st();
                 tc::tc_fence_before();
-                tc::mbar_arrive(p_full + t);
+                tc::mbar_arrive(p_full + t * 3 + c % 3);
                 const float2 pq = fadd2(fadd2(ps[0], ps[1]), fadd2(ps[2], ps[3]));
-                l_part += pq.x + pq.y;
-                A2_TMARK(6);
+                l_run += pq.x + pq.y;
+                A2_TMARK(7);
             }
 #ifdef VSUM_A2_TIMING
             if (blockIdx.x == 0 && lane == 0 && w.nkv >= 16 && tcount++ == 1)
-                printf("softmax warp %2d nkv %d | other %lld | wait S %lld | agree + ld %lld | mask + max + publish + arrive %lld | chunk0 %lld | chunk1 %lld | "
-                       "wait st + arrive %lld (clk per tile)\n", warp, w.nkv, tph[0] / w.nkv, tph[1] / w.nkv, tph[2] / w.nkv, tph[3] / w.nkv,
-                       tph[4] / w.nkv, tph[5] / w.nkv, tph[6] / w.nkv);
+                printf("softmax warp %2d nkv %d | other %lld | wait S %lld | first ld %lld | chunk0 %lld | chunk1 %lld | chunk2 %lld | chunk3 %lld | "
+                       "pv wait + wait st + arrive %lld (clk per tile)\n", warp, w.nkv, tph[0] / w.nkv, tph[1] / w.nkv, tph[2] / w.nkv, tph[3] / w.nkv,
+                       tph[4] / w.nkv, tph[5] / w.nkv, tph[6] / w.nkv, tph[7] / w.nkv);
             for (int i = 0; i < 10; ++i) tph[i] = 0;
             tmark = clock64();
 #endif
-            // ---- epilogue: O_t / l -> global, my 32 of the head's 64 columns
-            tc::mbar_wait(p_empty + t, (c & 1) ^ 1);              // the last PV product of the item has completed
-            tc::tc_fence_after();
-            lx[(t * 2 + hf) * 128 + r] = l_part;
-            tc::bar_sync(pair_bar, 64);
-            const float l_tot = l_part + lx[(t * 2 + (hf ^ 1)) * 128 + r];
-            const float inv = (TRAIN ? keep_scale : 1.0f) / l_tot;
-            if (TRAIN && hf == 0 && row < w.n) lse2[(int64_t)(w.base + row) * NH + w.head] = m_ref + log2f(l_tot);
-            uint32_t o[32];
-            tc::tmem_ld32(tO_r, o);
-            tmem_wait_ld_on(o);
-            if (row < w.n) {
-                if (TRAIN) {   // fp32 output: the backward's delta = rowsum(dO o O) must not see a rounded O
-                    float *dst = reinterpret_cast<float *>(out_v) + (int64_t)(w.base + row) * DM + w.head * HD + hf * 32;
+            // ---- epilogue: O_t / l -> global
+            pv_wait_upto(c);                                      // the last PV product of the item has completed
+            const float inv = (TRAIN ? keep_scale : 1.0f) / l_run;
+            if (TRAIN && row < w.n) lse2[(int64_t)(w.base + row) * NH + w.head] = m_ref + log2f(l_run);
+#pragma unroll 1
+            for (int hc = 0; hc < 2; ++hc) {
+                uint32_t o[32];
+                tc::tmem_ld32(tO_r + hc * 32, o);
+                tmem_wait_ld_on(o);
+                if (row < w.n) {
+                    if (TRAIN) {   // fp32 output: the backward's delta = rowsum(dO o O) must not see a rounded O
+                        float *dst = reinterpret_cast<float *>(out_v) + (int64_t)(w.base + row) * DM + w.head * HD + hc * 32;
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4)
-                        *reinterpret_cast<float4 *>(dst + i) = make_float4(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv,
-                                                                           __uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
-                } else {
-                    __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(out_v) + (int64_t)(w.base + row) * DM + w.head * HD + hf * 32;
+                        for (int i = 0; i < 32; i += 4)
+                            *reinterpret_cast<float4 *>(dst + i) = make_float4(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv,
+                                                                               __uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+                    } else {
+                        __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(out_v) + (int64_t)(w.base + row) * DM + w.head * HD + hc * 32;
 #pragma unroll
-                    for (int i = 0; i < 32; i += 8) {
-                        uint4 pk;
-                        pk.x = pack_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
-                        pk.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
-                        pk.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
-                        pk.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
-                        *reinterpret_cast<uint4 *>(dst + i) = pk;
+                        for (int i = 0; i < 32; i += 8) {
+                            uint4 pk;
+                            pk.x = pack_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
+                            pk.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+                            pk.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+                            pk.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+                            *reinterpret_cast<uint4 *>(dst + i) = pk;
+                        }
                     }
                 }
             }
+            tc::tc_fence_before();        // the O loads above are ordered before the first P of the next item, whose PV overwrites O_t
         }
     }
     __syncwarp();
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 2) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, A2_TMEM_COLS); }
+    if (warp == 10) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, A2_TMEM_COLS); }
     // The last CTA to leave rewinds the work counter, so one schedule serves every launch over the same batch.
     if (threadIdx.x == 0 && atomicAdd(counters + 2, 1) == (int)gridDim.x - 1) {
         counters[1] = 0;
@@ -560,7 +594,7 @@ int launch_attention2_tc05(const __nv_bfloat16 *qkv, const int32_t *cu_seqlens, 
             cudaFuncAttributes fb;
             VSUM_CUDA_OK(cudaFuncGetAttributes(&fb, attn2_tc05_kernel<true, false>));
             const int e = fa.numRegs < fb.numRegs ? fa.numRegs : fb.numRegs;
-            VSUM_REQUIRE(96 * (e - A2_REGS_CONTROL) + 32 * (e - A2_REGS_DONOR) >= 512 * (A2_REGS_SOFTMAX - e), VSUM_EUNSUPPORTED,
+            VSUM_REQUIRE(128 * (e - A2_REGS_CONTROL) >= 256 * (A2_REGS_SOFTMAX - e), VSUM_EUNSUPPORTED,
                          "attn2_tc05_kernel was compiled with %d registers per thread: the softmax warps could not grow to %d", e, A2_REGS_SOFTMAX);
             checked.store(1, std::memory_order_relaxed);
         }
