@@ -350,6 +350,11 @@ VSUM_API int vsum_debug_attention_bwd_tc05(const void *qkv_bf16, const void *d_o
                                            float drop_p, uint64_t seed, float *dqkv, int32_t *scratch, void *stream);
 VSUM_API int vsum_debug_attention_tc05(const void *qkv_bf16, const int32_t *cu_seqlens, int32_t B, int64_t T,
                               void *out_bf16, int32_t *scratch_i32, void *stream);
+/* Same with an explicit softmax scale: P = softmax(scale * Q K^T).  scale = 1 / log2(e) is the form the scorer runs
+ * (it folds d_model^-0.5 * log2(e) into its bf16 copy of W_q, so Q K^T already is the base-2 exponent): the two-tile
+ * kernel then exponentiates the scores as they come out of tensor memory. */
+VSUM_API int vsum_debug_attention_scaled_tc05(const void *qkv_bf16, const int32_t *cu_seqlens, int32_t B, int64_t T, float scale,
+                                              void *out_bf16, int32_t *scratch_i32, void *stream);
 
 #ifdef __cplusplus
 }

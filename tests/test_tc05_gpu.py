@@ -100,6 +100,30 @@ def test_attention(lens, attn_kernel):   # the last four have more work items th
     torch.testing.assert_close(out.float(), attention_ref(qkv, lens), rtol=2e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("lens", [[37], [300, 1, 127, 128, 513], [2048], [129, 128, 127] * 20])
+def test_attention_prescaled_q(lens, attn_kernel):
+    """The form the scorer runs: d_model^-0.5 * log2(e) folded into Q (vsum_scorer_load_weights), scale = 1 / log2(e), so that
+    the scores are base-2 exponents and the two-tile kernel exponentiates them as they are."""
+    T = sum(lens)
+    g = torch.Generator(device="cuda").manual_seed(T + 3)
+    qkv = torch.randn((T, 768), device="cuda", generator=g)
+    qkv[:, :256] *= 1.4426950408889634 / 16.0
+    qkv = qkv.bfloat16()
+    cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device="cuda")
+    out = torch.zeros((T, 256), dtype=torch.bfloat16, device="cuda")
+    scratch = torch.zeros(_cabi.load().vsum_attention_scratch_ints(T, len(lens)), dtype=torch.int32, device="cuda")
+    _cabi.check(_cabi.load().vsum_debug_attention_scaled_tc05(qkv.data_ptr(), cu.data_ptr(), len(lens), T, 1.0 / 1.4426950408889634,
+                                                              out.data_ptr(), scratch.data_ptr(), _stream()), "vsum_debug_attention_scaled_tc05")
+    torch.cuda.synchronize()
+    want, off = torch.empty((T, 256), device="cuda"), 0
+    for n in lens:
+        x = qkv[off:off + n].float()
+        q, k, v = (x[:, i * 256:(i + 1) * 256].view(n, 4, 64).permute(1, 0, 2) for i in range(3))
+        want[off:off + n] = (torch.softmax(q @ k.transpose(1, 2) * 0.6931471805599453, dim=-1) @ v).permute(1, 0, 2).reshape(n, 256)
+        off += n
+    torch.testing.assert_close(out.float(), want, rtol=2e-2, atol=2e-2)
+
+
 @pytest.mark.parametrize("case", ["rising", "falling", "below_zero", "far_below_zero", "far_above_zero", "one_hot"])
 def test_attention_exponent_reference_moves(case, attn_kernel):
     """Score distributions that push the running exponent reference of the softmax around: the two-tile kernel

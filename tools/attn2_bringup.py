@@ -13,6 +13,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "video-summariz
 from vsum_b200.synthetic import video_length
 
 vp = C.c_void_p
+PRESCALED, PRE_SCALE = True, 1.0 / 1.4426950408889634     # the form the scorer runs: log2(e) / 16 folded into Q
 
 
 def ref(qkv, lens):
@@ -20,7 +21,7 @@ def ref(qkv, lens):
     for n in lens:
         x = qkv[off:off + n].float()
         q, k, v = (x[:, i * 256:(i + 1) * 256].view(n, 4, 64).permute(1, 0, 2) for i in range(3))
-        out[off:off + n] = (torch.softmax(q @ k.transpose(1, 2) / 16.0, dim=-1) @ v).permute(1, 0, 2).reshape(n, 256)
+        out[off:off + n] = (torch.softmax(q @ k.transpose(1, 2) * (0.6931471805599453 if PRESCALED else 1.0 / 16.0), dim=-1) @ v).permute(1, 0, 2).reshape(n, 256)
         off += n
     return out
 
@@ -29,6 +30,8 @@ def setup(lens, entry, scale_k=None):
     T = sum(lens)
     g = torch.Generator(device="cuda").manual_seed(T)
     qkv = torch.randn((T, 768), device="cuda", generator=g)
+    if PRESCALED:
+        qkv[:, :256] *= 1.4426950408889634 / 16.0
     if scale_k is not None:
         qkv[:, 256:512] *= scale_k(T)
     qkv = qkv.bfloat16()
@@ -59,8 +62,9 @@ QUICK = [[128], [37], [129], [257], [300, 1, 127, 128, 513], [1000, 3000]]
 
 def run_lib(path, version, quick, label=None):
     L = C.CDLL(path)
-    entry = L.vsum_debug_attention_tc05
-    entry.argtypes = [vp, vp, C.c_int32, C.c_int64, vp, vp, vp]; entry.restype = C.c_int
+    entry0 = L.vsum_debug_attention_scaled_tc05
+    entry0.argtypes = [vp, vp, C.c_int32, C.c_int64, C.c_float, vp, vp, vp]; entry0.restype = C.c_int
+    entry = lambda a, b, c, d, *r: entry0(a, b, c, d, PRE_SCALE if PRESCALED else 1.0 / 16.0, *r)
     L.vsum_set_attention_kernel.argtypes = [C.c_int32]
     assert L.vsum_set_attention_kernel(version) == 0
     name = label or f"{os.path.basename(path)} v{version}"

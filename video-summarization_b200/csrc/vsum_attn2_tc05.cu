@@ -21,15 +21,16 @@
 // the OTHER tile's previous step, not on the softmax that will consume it -- a row finds its next S ready when it has
 // stored its P, where the two-buffer version of this kernel waited ~20 % of the time (profiles/r02_attn2_*.txt).
 //
-// One-pass streaming softmax against a LAGGING reference.  A row exponentiates tile j against m_ref, which was fixed
-// before the tile started from the maxima of the tiles before it (0 at the start of an item; it moves to the running
-// maximum when that has left the window [m_ref - 24, m_ref + 24], log2 units, with O and the row sum rescaled).  The
-// tile's own maximum is only tracked on the side (FMNMX3) for the next decision.  Softmax is shift-invariant and fp32 /
-// bf16 keep their relative precision, so this equals the exact running maximum as long as no exponential overflows and
-// the first tile does not underflow as a whole, i.e. while a tile's scores stay within +-96 log2 units (+-66 nats) of
-// the reference.  A row that sees more raises its item's flag, and a second launch of the same kernel (SAFE = true: one
-// extra sweep over S for the exact tile maximum before exponentiating) recomputes the flagged items; with no flag
-// raised that launch ends after reading one flag per item.
+// One-pass streaming softmax against the FIXED reference 0.  With the softmax scale and log2(e) folded into W_q
+// (PRESCALED: the scorer's bf16 copy of the weights, vsum_scorer.cu) a score IS the exponent: the fast pass computes
+// P = 2^S straight from the registers tcgen05.ld filled -- no row maximum, no scale, no subtraction, no rescaling of
+// O -- and the row sum.  Softmax is shift-invariant and fp32 / bf16 keep their relative precision, so this equals the
+// usual running-maximum form as long as no exponential overflows and the row does not underflow as a whole, i.e. while
+// the row's largest score stays within about +-90 log2 units (+-62 nats) of zero; attention logits of this model are
+// O(1).  A row checks exactly that on its sums (a tile sum >= 2^90 or not finite, a row sum < 2^-80) and raises its
+// item's flag, and a second launch of the same kernel (SAFE = true: one extra sweep over S for the tile maximum, classic
+// online softmax with a lazily rescaled O) recomputes the flagged items; with no flag raised that launch ends after
+// reading one flag per item.
 // The row streams S in four 32-column chunks whose tensor-memory loads overlap the exponentials of the previous chunk.
 // A share of the exponentials runs as a degree-3 polynomial on the FMA pipe (the MUFU pipe, 16 ex2 / clk / SM, is the
 // limiter at head_dim 64: profiles/r01_microbench_mufu_ex2.txt).
@@ -52,12 +53,8 @@ constexpr int KV_STAGES = VSUM_A2_STAGES;
 constexpr int SCHED_RING = 4;
 constexpr size_t A2_SMEM = (4 + 2 * (size_t)KV_STAGES) * TILE_BYTES + 512;   // Q (2 items x 2 tiles), K ring, V ring, barriers
 #ifndef VSUM_A2_POLY_PERIOD
-#define VSUM_A2_POLY_PERIOD 4        // every k-th pair of exponentials is a polynomial on the FMA pipe (0 = none)
+#define VSUM_A2_POLY_PERIOD 3        // every k-th pair of exponentials is a polynomial on the FMA pipe (0 = none); swept 0 / 2..5 on B200
 #endif
-#ifndef VSUM_A2_WINDOW
-#define VSUM_A2_WINDOW 24.0f         // the exponent reference moves when a tile maximum leaves [m_ref - W, m_ref + W]
-#endif
-#define VSUM_A2_DANGER 96.0f         // scores this far from the reference could overflow / underflow: exact pass for the item
 
 __device__ __forceinline__ float ex2f(float x) {
     float y;
@@ -152,7 +149,7 @@ __device__ __forceinline__ ItemInfo decode_item(int idx, const int32_t *__restri
 // counters[0] = number of 256-query blocks, counters[1] = work counter, counters[2] = CTAs that have finished (both zero
 // between launches: the schedule kernel zeroes them, the last CTA of every launch rewinds them); flags[item] != 0: the
 // item needs the exact pass (raised by the SAFE = false launch, consumed by the SAFE = true launch).
-template <bool TRAIN, bool SAFE>
+template <bool TRAIN, bool SAFE, bool PRESCALED>
 __global__ void __launch_bounds__(A2_THREADS, 1)
 attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__restrict__ cu,
                   const int32_t *__restrict__ item_video, const int32_t *__restrict__ item_q0,
@@ -171,7 +168,8 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
     uint64_t *p_full = s_full + 6;                               // [tile][count % 3]: the P of that unit is stored (128 arrivals)
     uint64_t *pv_done = p_full + 6;                              // [tile]: a PV product of the tile has completed
     uint64_t *buf_free = pv_done + 2;                            // [S buffer]: the PV product that read P from the buffer has completed
-    uint64_t *sched_full = buf_free + 3, *sched_empty = sched_full + SCHED_RING;
+    uint64_t *o_full = buf_free + 3;                             // [tile]: the last PV product of an item has completed (O_t is final)
+    uint64_t *sched_full = o_full + 2, *sched_empty = sched_full + SCHED_RING;
     int32_t *sched_idx = reinterpret_cast<int32_t *>(sched_empty + SCHED_RING);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sched_idx + SCHED_RING);
 
@@ -187,6 +185,7 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
         }
         for (int i = 0; i < 6; ++i) { tc::mbar_init(s_full + i, 1); tc::mbar_init(p_full + i, 128); }
         for (int i = 0; i < 3; ++i) tc::mbar_init(buf_free + i, 1);
+        for (int t = 0; t < 2; ++t) tc::mbar_init(o_full + t, 1);
         for (int t = 0; t < 2; ++t) tc::mbar_init(pv_done + t, 1);
         for (int i = 0; i < SCHED_RING; ++i) { tc::mbar_init(sched_full + i, 1); tc::mbar_init(sched_empty + i, 11); }
         tc::fence_barrier_init();
@@ -323,6 +322,7 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
                             tc::mma_f16_ts(tO_t, tmem_base + buf * 128 + (uint32_t)(k * 8), desc_at(v_lo, (uint32_t)s * TILE16 + k * 128), IDESC_PV,
                                            (j | k) != 0);
                         tc::mma_commit(pv_done + t);
+                        if (j == w.nkv - 1) tc::mma_commit(o_full + t);
                         tc::mma_commit(buf_free + buf);
                         tc::mma_commit(v_empty + s);
                     }
@@ -341,11 +341,8 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
         const float2 c2 = make_float2(scale_log2e, scale_log2e);
         uint32_t c = 0;                                           // units of this tile processed so far (barrier phases)
         uint32_t n_unit0 = 0;                                     // position of the item's first unit in the CTA's unit sequence
-        uint32_t pv_seen = 0;                                     // PV completions of this tile consumed so far
-        auto pv_wait_upto = [&](uint32_t upto) {                  // all PV products of this tile's units < upto have completed
-            while (pv_seen < upto) { tc::mbar_wait(pv_done + t, pv_seen & 1); ++pv_seen; }
-            tc::tc_fence_after();
-        };
+        uint32_t n_done = 0;                                      // items of this tile finished (o_full phases)
+        uint32_t pv_seen = 0;                                     // SAFE: PV completions of this tile consumed so far
         A2_TDECL(10);
         for (int it = 0;; ++it) {
             const int idx = next_item(it);
@@ -358,23 +355,44 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
             n_unit0 += (uint32_t)(w.nkv * n_q);
             if (t == 1 && !w.has_b) continue;
             const int row = w.q0 + t * 128 + r;                   // query row inside the video
-            float m_ref = 0.f, l_run = 0.f, m_prev = 0.f;         // exponent reference, row sum, maximum of the previous tile
+            float m_ref = 0.f, l_run = 0.f;                       // exponent reference (moves in the exact pass only), row sum
+            bool danger = false;
             for (int j = 0; j < w.nkv; ++j, ++c) {
-                const uint32_t unit = unit0 + (uint32_t)(j * n_q + t), buf = unit % 3;
-                const uint32_t tS_r = tmem_base + lane_off + buf * 128;   // my row of the unit's S / P buffer
+                const uint32_t tS_r = tmem_base + lane_off + ((unit0 + (uint32_t)(j * n_q + t)) % 3) * 128;   // my row of the unit's S / P buffer
                 A2_TMARK(0);
                 tc::mbar_wait(s_full + t * 3 + c % 3, (c / 3) & 1);
                 A2_TMARK(1);
                 tc::tc_fence_after();
                 const int valid = w.n - j * BKV;                  // keys of this tile inside the video (>= 1)
                 uint32_t sa[32], sb[32];
-                auto move_reference = [&](float m_row, bool low_side_too) {
-                    const bool move = (m_row - m_ref > VSUM_A2_WINDOW) || (low_side_too && m_row - m_ref < -VSUM_A2_WINDOW);
-                    if (__any_sync(0xffffffffu, move)) {           // rare
+                auto mask_tail = [&](uint32_t (&s)[32], int ch) {  // last tile of the video: keys past its end (next video's rows / TMA zero fill)
+                    if (valid < BKV) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (ch * 32 + i >= valid) s[i] = 0xff800000u;
+                    }
+                };
+                if (SAFE) {              // exact pass: one extra sweep over S for this tile's maximum, classic online softmax
+                    float mx0 = -INFINITY;
+#pragma unroll 1
+                    for (int ch = 0; ch < 4; ++ch) {
+                        tc::tmem_ld32(tS_r + ch * 32, sa);
+                        tmem_wait_ld_on(sa);
+                        mask_tail(sa, ch);
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) mx0 = fmax3(mx0, __uint_as_float(sa[i]), __uint_as_float(sa[i + 1]));
+                    }
+                    const float m_row = mx0 * scale_log2e;
+                    const bool move = j == 0 || m_row - m_ref > 8.0f;
+                    if (j > 0) {         // every PV completion is consumed in order: PV(j-1) has completed, O_t is stable
+                        tc::mbar_wait(pv_done + t, pv_seen & 1);
+                        ++pv_seen;
+                        tc::tc_fence_after();
+                    }
+                    if (__any_sync(0xffffffffu, move)) {
                         float alpha = 1.0f;
-                        if (move) { alpha = ex2f(m_ref - m_row); m_ref = m_row; }
-                        if (j > 0) {                              // rescale what has been accumulated: PV(j-1) must have completed
-                            pv_wait_upto(c);
+                        if (move) { alpha = j == 0 ? 0.f : ex2f(m_ref - m_row); m_ref = m_row; }
+                        if (j > 0) {
                             l_run *= alpha;
 #pragma unroll 1
                             for (int hc = 0; hc < 2; ++hc) {
@@ -388,39 +406,16 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
                             tc::tmem_wait_st();
                         }
                     }
-                };
-                auto mask_tail = [&](uint32_t (&s)[32], int ch) {  // last tile of the video: keys past its end (next video's rows / TMA zero fill)
-                    if (valid < BKV) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (ch * 32 + i >= valid) s[i] = 0xff800000u;
-                    }
-                };
-                if (SAFE) {              // exact pass: one extra sweep over S for this tile's own maximum
-                    float mx0 = -INFINITY;
-#pragma unroll 1
-                    for (int ch = 0; ch < 4; ++ch) {
-                        tc::tmem_ld32(tS_r + ch * 32, sa);
-                        tmem_wait_ld_on(sa);
-                        mask_tail(sa, ch);
-#pragma unroll
-                        for (int i = 0; i < 32; i += 2) mx0 = fmax3(mx0, __uint_as_float(sa[i]), __uint_as_float(sa[i + 1]));
-                    }
-                    move_reference(mx0 * scale_log2e, j == 0);
-                } else if (j > 0) {
-                    move_reference(m_prev, j == 1);                // lagging reference: the maxima of the tiles before this one
                 }
-                float mx = -INFINITY;
                 float2 ps[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
                 const float2 nm2 = make_float2(-m_ref, -m_ref);
                 auto chunk = [&](uint32_t (&s)[32], int ch) {
                     mask_tail(s, ch);
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
                     uint32_t wv[16];
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
-                        const float2 x = ffma2(make_float2(__uint_as_float(s[2 * e]), __uint_as_float(s[2 * e + 1])), c2, nm2);
+                        float2 x = make_float2(__uint_as_float(s[2 * e]), __uint_as_float(s[2 * e + 1]));
+                        if (SAFE || !PRESCALED) x = ffma2(x, c2, nm2);   // fast pass with pre-scaled Q: S already is the exponent, reference 0
                         const bool poly = VSUM_A2_POLY_PERIOD > 0 && (e % (VSUM_A2_POLY_PERIOD > 0 ? VSUM_A2_POLY_PERIOD : 1)) == VSUM_A2_POLY_PERIOD - 1;
                         const float2 p = poly ? exp2_poly2(x) : make_float2(ex2f(x.x), ex2f(x.y));
                         ps[e & 3] = fadd2(ps[e & 3], p);
@@ -455,27 +450,32 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
                 tmem_wait_ld_on(sb);
                 chunk(sb, 3);
                 A2_TMARK(6);
-                m_prev = fmaxf(mx * scale_log2e, j == 0 ? -INFINITY : m_prev);      // running maximum of the item so far
-                if (!SAFE && row < w.n && (mx * scale_log2e - m_ref > VSUM_A2_DANGER || (j == 0 && mx * scale_log2e < -VSUM_A2_DANGER)))
-                    *reinterpret_cast<volatile int32_t *>(flags + idx) = 1;           // the exact pass redoes this item
-                pv_wait_upto(c);                                  // keeps the phase bookkeeping in step (PV(j-1) completed long ago)
                 tc::tmem_wait_st();
                 tc::tc_fence_before();
                 tc::mbar_arrive(p_full + t * 3 + c % 3);
                 const float2 pq = fadd2(fadd2(ps[0], ps[1]), fadd2(ps[2], ps[3]));
-                l_run += pq.x + pq.y;
+                const float psum = pq.x + pq.y;
+                if (!SAFE) danger |= !(psum < 1.2e27f);           // 2^90: an exponential near overflow (or a NaN): the exact pass redoes the item
+                l_run += psum;
                 A2_TMARK(7);
             }
 #ifdef VSUM_A2_TIMING
             if (blockIdx.x == 0 && lane == 0 && w.nkv >= 16 && tcount++ == 1)
                 printf("softmax warp %2d nkv %d | other %lld | wait S %lld | first ld %lld | chunk0 %lld | chunk1 %lld | chunk2 %lld | chunk3 %lld | "
-                       "pv wait + wait st + arrive %lld (clk per tile)\n", warp, w.nkv, tph[0] / w.nkv, tph[1] / w.nkv, tph[2] / w.nkv, tph[3] / w.nkv,
+                       "wait st + arrive %lld (clk per tile)\n", warp, w.nkv, tph[0] / w.nkv, tph[1] / w.nkv, tph[2] / w.nkv, tph[3] / w.nkv,
                        tph[4] / w.nkv, tph[5] / w.nkv, tph[6] / w.nkv, tph[7] / w.nkv);
             for (int i = 0; i < 10; ++i) tph[i] = 0;
             tmark = clock64();
 #endif
+            // The fast pass exponentiates against the fixed reference 0: valid while no exponential overflows (checked per tile
+            // above) and the row as a whole does not underflow (l >= 2^-80, so its largest term is >= 2^-93).
+            if (!SAFE && row < w.n && (danger || !(l_run >= 8.3e-25f)))
+                *reinterpret_cast<volatile int32_t *>(flags + idx) = 1;
             // ---- epilogue: O_t / l -> global
-            pv_wait_upto(c);                                      // the last PV product of the item has completed
+            tc::mbar_wait(o_full + t, n_done & 1);                // the last PV product of the item has completed
+            ++n_done;
+            if (SAFE) ++pv_seen;                                  // ... which is also one more completion of pv_done
+            tc::tc_fence_after();
             const float inv = (TRAIN ? keep_scale : 1.0f) / l_run;
             if (TRAIN && row < w.n) lse2[(int64_t)(w.base + row) * NH + w.head] = m_ref + log2f(l_run);
 #pragma unroll 1
@@ -581,18 +581,20 @@ int launch_attention2_tc05(const __nv_bfloat16 *qkv, const int32_t *cu_seqlens, 
     int dev = 0;
     VSUM_CUDA_OK(cudaGetDevice(&dev));
     VSUM_ONCE_PER_DEVICE(
-        VSUM_CUDA_OK(cudaFuncSetAttribute(attn2_tc05_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A2_SMEM));
-        VSUM_CUDA_OK(cudaFuncSetAttribute(attn2_tc05_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A2_SMEM));
-        VSUM_CUDA_OK(cudaFuncSetAttribute(attn2_tc05_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A2_SMEM));
-        VSUM_CUDA_OK(cudaFuncSetAttribute(attn2_tc05_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A2_SMEM));
+        VSUM_CUDA_OK(cudaFuncSetAttribute(attn2_tc05_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A2_SMEM));
+        VSUM_CUDA_OK(cudaFuncSetAttribute(attn2_tc05_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A2_SMEM));
+        VSUM_CUDA_OK(cudaFuncSetAttribute(attn2_tc05_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A2_SMEM));
+        VSUM_CUDA_OK(cudaFuncSetAttribute(attn2_tc05_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A2_SMEM));
+        VSUM_CUDA_OK(cudaFuncSetAttribute(attn2_tc05_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A2_SMEM));
+        VSUM_CUDA_OK(cudaFuncSetAttribute(attn2_tc05_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A2_SMEM));
         VSUM_CUDA_OK(cudaDeviceGetAttribute(&n_sm[dev & 63], cudaDevAttrMultiProcessorCount, dev)));
     {   // setmaxnreg moves registers inside the CTA's own allocation: what the control warps release must cover what the softmax warps acquire
         static std::atomic<int> checked{0};
         if (!checked.load(std::memory_order_relaxed)) {
             cudaFuncAttributes fa;
-            VSUM_CUDA_OK(cudaFuncGetAttributes(&fa, attn2_tc05_kernel<false, false>));
+            VSUM_CUDA_OK(cudaFuncGetAttributes(&fa, attn2_tc05_kernel<false, false, true>));
             cudaFuncAttributes fb;
-            VSUM_CUDA_OK(cudaFuncGetAttributes(&fb, attn2_tc05_kernel<true, false>));
+            VSUM_CUDA_OK(cudaFuncGetAttributes(&fb, attn2_tc05_kernel<true, false, false>));
             const int e = fa.numRegs < fb.numRegs ? fa.numRegs : fb.numRegs;
             VSUM_REQUIRE(128 * (e - A2_REGS_CONTROL) >= 256 * (A2_REGS_SOFTMAX - e), VSUM_EUNSUPPORTED,
                          "attn2_tc05_kernel was compiled with %d registers per thread: the softmax warps could not grow to %d", e, A2_REGS_SOFTMAX);
@@ -604,18 +606,26 @@ int launch_attention2_tc05(const __nv_bfloat16 *qkv, const int32_t *cu_seqlens, 
     const int max_items = max_blocks * NH;
     if (grid > max_items) grid = max_items;
     ProfScope prof(PROF_ATTN, s);
-    const float sl2 = scale * 1.4426950408889634f;
+    float sl2 = scale * 1.4426950408889634f;
+    const bool prescaled = fabsf(sl2 - 1.0f) < 1e-6f;     // the caller folded scale * log2(e) into Q (vsum_scorer.cu: bf16 weight copy)
+    if (prescaled) sl2 = 1.0f;
+#define A2_LAUNCH(TR, SF, PS, ...) attn2_tc05_kernel<TR, SF, PS><<<grid, A2_THREADS, A2_SMEM, s>>>(tm, cu_seqlens, item_video, item_q0, counters, flags, out, sl2, __VA_ARGS__)
     if (lse2) {
         const uint32_t thresh = attn_drop_thresh16(drop_p);
         const float ks = 65536.0f / (float)(65536u - thresh);
-        attn2_tc05_kernel<true, false><<<grid, A2_THREADS, A2_SMEM, s>>>(tm, cu_seqlens, item_video, item_q0, counters, flags, out, sl2, lse2, ks, thresh, seed);
+        A2_LAUNCH(true, false, false, lse2, ks, thresh, seed);
         VSUM_LAUNCH_OK("attn2_tc05_kernel");
-        attn2_tc05_kernel<true, true><<<grid, A2_THREADS, A2_SMEM, s>>>(tm, cu_seqlens, item_video, item_q0, counters, flags, out, sl2, lse2, ks, thresh, seed);
+        A2_LAUNCH(true, true, false, lse2, ks, thresh, seed);
+    } else if (prescaled) {
+        A2_LAUNCH(false, false, true, nullptr, 1.0f, 0u, 0ull);
+        VSUM_LAUNCH_OK("attn2_tc05_kernel");
+        A2_LAUNCH(false, true, true, nullptr, 1.0f, 0u, 0ull);
     } else {
-        attn2_tc05_kernel<false, false><<<grid, A2_THREADS, A2_SMEM, s>>>(tm, cu_seqlens, item_video, item_q0, counters, flags, out, sl2, nullptr, 1.0f, 0u, 0ull);
+        A2_LAUNCH(false, false, false, nullptr, 1.0f, 0u, 0ull);
         VSUM_LAUNCH_OK("attn2_tc05_kernel");
-        attn2_tc05_kernel<false, true><<<grid, A2_THREADS, A2_SMEM, s>>>(tm, cu_seqlens, item_video, item_q0, counters, flags, out, sl2, nullptr, 1.0f, 0u, 0ull);
+        A2_LAUNCH(false, true, false, nullptr, 1.0f, 0u, 0ull);
     }
+#undef A2_LAUNCH
     VSUM_LAUNCH_OK("attn2_tc05_kernel (exact pass)");
     return VSUM_OK;
 }

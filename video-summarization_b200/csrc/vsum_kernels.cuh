@@ -172,5 +172,7 @@ int launch_transpose_f32(const float *in, float *out, int rows, int cols, cudaSt
 int launch_add_inplace_f32(float *dst, const float *src, int64_t n, cudaStream_t s);         // dst += src
 
 int launch_f32_to_bf16(const float *in, __nv_bfloat16 *out, int64_t n, cudaStream_t s);
+// out16 / out32 (either may be NULL) = scale * in
+int launch_scale_convert(const float *in, __nv_bfloat16 *out16, float *out32, int64_t n, float scale, cudaStream_t s);
 
 }  // namespace vsum

@@ -13,6 +13,7 @@ using namespace vsum;
 
 struct LayerOffsets {
     size_t wqkv, bqkv, wo, bo, ln1g, ln1b, fc1w, fc1b, fc2w, fc2b, ln2g, ln2b;   // fp32 blob (floats)
+    size_t bqkv_s;                                                                  // fp32: bqkv with the q third pre-scaled (bf16 path)
     size_t h_wqkv, h_wo, h_fc1, h_fc2;                                              // bf16 blob (elements)
     size_t t_wqkv, t_wo, t_fc1, t_fc2;                                              // fp32 transposes [in,out] (floats)
 };
@@ -38,6 +39,8 @@ static size_t take(size_t &cursor, size_t n) {
     return at;
 }
 
+static constexpr float kQPrescale = 1.4426950408889634f;      // log2(e): folded, with d_model^-0.5, into the bf16 copy of W_q / b_q
+
 extern "C" int vsum_scorer_create(vsum_scorer_t *out, const vsum_scorer_config *cfg) {
     VSUM_REQUIRE(out && cfg, VSUM_EINVAL, "vsum_scorer_create: null argument");
     VSUM_REQUIRE(cfg->d_model > 0 && cfg->num_heads > 0 && cfg->d_model % cfg->num_heads == 0, VSUM_EINVAL,
@@ -59,7 +62,7 @@ extern "C" int vsum_scorer_create(vsum_scorer_t *out, const vsum_scorer_config *
     h->final_w = take(c32, C * d); h->final_b = take(c32, C);
     for (int l = 0; l < cfg->num_layers; ++l) {
         LayerOffsets &o = h->L[l];
-        o.wqkv = take(c32, 3 * d * d); o.bqkv = take(c32, 3 * d);
+        o.wqkv = take(c32, 3 * d * d); o.bqkv = take(c32, 3 * d); o.bqkv_s = take(c32, 3 * d);
         o.wo = take(c32, d * d); o.bo = take(c32, d);
         o.ln1g = take(c32, d); o.ln1b = take(c32, d);
         o.fc1w = take(c32, ff * d); o.fc1b = take(c32, ff);
@@ -127,7 +130,13 @@ extern "C" int vsum_scorer_load_weights(vsum_scorer_t h, const vsum_scorer_weigh
         CP(o.fc2w, lw.fc2_w, d * ff); CP(o.fc2b, lw.fc2_b, d);
         CP(o.ln2g, lw.ln2_g, d); CP(o.ln2b, lw.ln2_b, d);
         int rc;
-        if ((rc = launch_f32_to_bf16(h->w32 + o.wqkv, h->w16 + o.h_wqkv, 3 * d * d, s))) return rc;
+        // bf16 inference copy of [Wq; Wk; Wv]: the softmax scale d_model^-0.5 (simnet.py:126) and log2(e) are folded into the q
+        // rows and the q bias, so that a score Q K^T already is the base-2 exponent the attention kernel needs
+        const float qs = kQPrescale / sqrtf((float)d);
+        if ((rc = launch_scale_convert(h->w32 + o.wqkv, h->w16 + o.h_wqkv, nullptr, d * d, qs, s))) return rc;
+        if ((rc = launch_f32_to_bf16(h->w32 + o.wqkv + d * d, h->w16 + o.h_wqkv + d * d, 2 * d * d, s))) return rc;
+        if ((rc = launch_scale_convert(h->w32 + o.bqkv, nullptr, h->w32 + o.bqkv_s, d, qs, s))) return rc;
+        if ((rc = launch_scale_convert(h->w32 + o.bqkv + d, nullptr, h->w32 + o.bqkv_s + d, 2 * d, 1.0f, s))) return rc;
         if ((rc = launch_f32_to_bf16(h->w32 + o.wo, h->w16 + o.h_wo, d * d, s))) return rc;
         if ((rc = launch_f32_to_bf16(h->w32 + o.fc1w, h->w16 + o.h_fc1, ff * d, s))) return rc;
         if ((rc = launch_f32_to_bf16(h->w32 + o.fc2w, h->w16 + o.h_fc2, d * ff, s))) return rc;
@@ -225,13 +234,13 @@ static int forward_bf16(vsum_scorer_t h, const void *x, bool x_is_bf16, const in
     g.epi = c.use_pos ? TC_EPI_BIAS_POS : TC_EPI_BIAS; g.bias = h->w32 + h->embed_b; g.out = w.xa;
     g.pos_table = h->pos_table; g.row_pos = w.row_pos; g.pos_rows = h->pos_rows; g.prof_cat = PROF_EMBED;
     RUN(launch_gemm_tc05(g, s));
-    const float scale = 1.0f / 16.0f;                                   // 256 ** -0.5
+    const float scale = 1.0f / kQPrescale;                              // 256 ** -0.5 and log2(e) already sit in q: the kernels see scale * log2(e) = 1
     for (int l = 0; l < c.num_layers; ++l) {
         const LayerOffsets &o = h->L[l];
         const bool last = l == c.num_layers - 1;
         Tc05GemmArgs q{};
         q.A = w.xa; q.W = h->w16 + o.h_wqkv; q.M = T; q.N = 768; q.K = 256; q.epi = TC_EPI_BIAS;
-        q.bias = h->w32 + o.bqkv; q.out = w.qkv; q.prof_cat = PROF_QKV;
+        q.bias = h->w32 + o.bqkv_s; q.out = w.qkv; q.prof_cat = PROF_QKV;      // q arrives pre-scaled (vsum_scorer_load_weights)
         RUN(launch_gemm_tc05(q, s));
         if (attn2) RUN(launch_attention2_tc05(w.qkv, cu, B, T, scale, w.att, w.a2, s));
         else RUN(launch_attention_tc05(w.qkv, cu, w.tile_video, w.tile_q0, w.n_tiles, max_tiles, T, scale, w.att, s));
@@ -609,18 +618,23 @@ extern "C" int vsum_debug_attention_bwd_tc05(const void *qkv, const void *d_out,
                                      scratch + max_tiles, scratch + 2 * max_tiles, max_tiles, T, 1.0f / 16.0f, drop_p, seed, dqkv, s);
 }
 
-extern "C" int vsum_debug_attention_tc05(const void *qkv, const int32_t *cu_seqlens, int32_t B, int64_t T,
-                                         void *out, int32_t *scratch, void *stream) {
-    VSUM_REQUIRE(qkv && cu_seqlens && out && scratch, VSUM_EINVAL, "vsum_debug_attention_tc05: null pointer");
+extern "C" int vsum_debug_attention_scaled_tc05(const void *qkv, const int32_t *cu_seqlens, int32_t B, int64_t T, float scale,
+                                                void *out, int32_t *scratch, void *stream) {
+    VSUM_REQUIRE(qkv && cu_seqlens && out && scratch, VSUM_EINVAL, "vsum_debug_attention_scaled_tc05: null pointer");
     const int max_tiles = (int)(T / 128 + B);
     cudaStream_t s = (cudaStream_t)stream;
     if (attention_kernel_version() == 2) {
         int rc2 = launch_attn2_schedule(cu_seqlens, B, T, scratch, s);
         if (rc2) return rc2;
-        return launch_attention2_tc05((const __nv_bfloat16 *)qkv, cu_seqlens, B, T, 1.0f / 16.0f, out, scratch, s);
+        return launch_attention2_tc05((const __nv_bfloat16 *)qkv, cu_seqlens, B, T, scale, out, scratch, s);
     }
     int rc = launch_attn_schedule(cu_seqlens, B, scratch, scratch + max_tiles, scratch + 2 * max_tiles, max_tiles, s);
     if (rc) return rc;
     return launch_attention_tc05((const __nv_bfloat16 *)qkv, cu_seqlens, scratch, scratch + max_tiles,
-                                 scratch + 2 * max_tiles, max_tiles, T, 1.0f / 16.0f, (__nv_bfloat16 *)out, s);
+                                 scratch + 2 * max_tiles, max_tiles, T, scale, (__nv_bfloat16 *)out, s);
+}
+
+extern "C" int vsum_debug_attention_tc05(const void *qkv, const int32_t *cu_seqlens, int32_t B, int64_t T,
+                                         void *out, int32_t *scratch, void *stream) {
+    return vsum_debug_attention_scaled_tc05(qkv, cu_seqlens, B, T, 1.0f / 16.0f, out, scratch, stream);
 }

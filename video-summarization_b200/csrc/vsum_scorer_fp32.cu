@@ -328,6 +328,23 @@ f32_to_bf16_kernel(const float *__restrict__ in, __nv_bfloat16 *__restrict__ out
     }
 }
 
+// out = scale * in, as bf16 (out16) and / or as fp32 (out32); used once per weight load
+__global__ void __launch_bounds__(256)
+scale_convert_kernel(const float *__restrict__ in, __nv_bfloat16 *__restrict__ out16, float *__restrict__ out32, int64_t n, float scale) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = in[i] * scale;
+    if (out16) out16[i] = __float2bfloat16_rn(v);
+    if (out32) out32[i] = v;
+}
+
+int launch_scale_convert(const float *in, __nv_bfloat16 *out16, float *out32, int64_t n, float scale, cudaStream_t s) {
+    if (n == 0) return VSUM_OK;
+    scale_convert_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(in, out16, out32, n, scale);
+    VSUM_LAUNCH_OK("scale_convert_kernel");
+    return VSUM_OK;
+}
+
 int launch_f32_to_bf16(const float *in, __nv_bfloat16 *out, int64_t n, cudaStream_t s) {
     if (n == 0) return VSUM_OK;
     f32_to_bf16_kernel<<<(unsigned)ceil_div(ceil_div(n, 4), 256), 256, 0, s>>>(in, out, n);
