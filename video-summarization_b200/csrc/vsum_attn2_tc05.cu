@@ -339,7 +339,7 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
         const uint32_t tO_r = tO + lane_off + (uint32_t)(t * HD);
         const float2 c2 = make_float2(scale_log2e, scale_log2e);
-        uint32_t c = 0;                                           // units of this tile processed so far (barrier phases)
+        uint32_t c = 0, c3 = 0, cpar = 0;                         // units of this tile processed so far; c % 3 and (c / 3) & 1 (barrier phases)
         uint32_t n_unit0 = 0;                                     // position of the item's first unit in the CTA's unit sequence
         uint32_t n_done = 0;                                      // items of this tile finished (o_full phases)
         uint32_t pv_seen = 0;                                     // SAFE: PV completions of this tile consumed so far
@@ -357,14 +357,15 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
             const int row = w.q0 + t * 128 + r;                   // query row inside the video
             float m_ref = 0.f, l_run = 0.f;                       // exponent reference (moves in the exact pass only), row sum
             bool danger = false;
+            uint32_t ub = (unit0 + (uint32_t)t) % 3;              // S / P buffer of my current unit: (unit0 + j n_q + t) % 3
+            uint32_t sa[32], sb[32];
             for (int j = 0; j < w.nkv; ++j, ++c) {
-                const uint32_t tS_r = tmem_base + lane_off + ((unit0 + (uint32_t)(j * n_q + t)) % 3) * 128;   // my row of the unit's S / P buffer
+                const uint32_t tS_r = tmem_base + lane_off + ub * 128;   // my row of the unit's S / P buffer
                 A2_TMARK(0);
-                tc::mbar_wait(s_full + t * 3 + c % 3, (c / 3) & 1);
-                A2_TMARK(1);
+                tc::mbar_wait(s_full + t * 3 + c3, cpar);
                 tc::tc_fence_after();
+                A2_TMARK(1);
                 const int valid = w.n - j * BKV;                  // keys of this tile inside the video (>= 1)
-                uint32_t sa[32], sb[32];
                 auto mask_tail = [&](uint32_t (&s)[32], int ch) {  // last tile of the video: keys past its end (next video's rows / TMA zero fill)
                     if (valid < BKV) {
 #pragma unroll
@@ -448,11 +449,14 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
                 chunk(sa, 2);
                 A2_TMARK(5);
                 tmem_wait_ld_on(sb);
+                const uint32_t p_slot = t * 3 + c3;
+                ub += (uint32_t)n_q; if (ub >= 3) ub -= 3;       // next unit of this tile
+                if (++c3 == 3) { c3 = 0; cpar ^= 1; }
                 chunk(sb, 3);
                 A2_TMARK(6);
                 tc::tmem_wait_st();
                 tc::tc_fence_before();
-                tc::mbar_arrive(p_full + t * 3 + c % 3);
+                tc::mbar_arrive(p_full + p_slot);
                 const float2 pq = fadd2(fadd2(ps[0], ps[1]), fadd2(ps[2], ps[3]));
                 const float psum = pq.x + pq.y;
                 if (!SAFE) danger |= !(psum < 1.2e27f);           // 2^90: an exponential near overflow (or a NaN): the exact pass redoes the item

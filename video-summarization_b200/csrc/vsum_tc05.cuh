@@ -40,6 +40,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking probe (try_wait may suspend the warp for a while before it answers "not yet").
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol bug must trap (the launch then fails loudly) instead of hanging the GPU.
 #ifndef VSUM_MBAR_TIMEOUT_CYCLES
 #define VSUM_MBAR_TIMEOUT_CYCLES 4000000000LL   // ~2 s at 1.9 GHz
