@@ -38,6 +38,40 @@ def test_end_to_end_against_oracle(seeded_model_kwargs, precision):
     assert bits_equal(np.float64(np.mean(f_host)), np.float64(np.mean(f[np.argsort(hb.order)])))
 
 
+@pytest.mark.parametrize("dataset,n_videos,n_users,method,lo,hi,test_size", [("summe", 25, 15, "max", 60, 650, 5),
+                                                                              ("tvsum", 50, 20, "avg", 170, 1300, 10)])
+def test_dsnet_split_shapes_against_oracle(seeded_model_kwargs, dataset, n_videos, n_users, method, lo, hi, test_size):
+    """BASELINE config 2: SumMe-like (25 videos, 15 users, 'max') and TVSum-like (50 videos, 20 users, 'avg') sets, 5-fold
+    test splits of the canonical / augmented sizes (src/splits_dsnet/*.yaml: 5 and 10 test keys), each split through
+    `Summarizer.run_host`: given the scores the GPU produced, shot selections, keyshot masks and per-video F are the
+    oracle's bit for bit, and so is the split mean (compute_metrics.py:92)."""
+    torch.manual_seed(1234)
+    model = SimNet(**seeded_model_kwargs).cuda().eval()
+    base = 3000 if dataset == "summe" else 3100
+    vids = [make_video(base + i, video_length(base + i, lo, hi), n_users=n_users) for i in range(n_videos)]
+    summ = Summarizer(model, method)
+    rng = np.random.default_rng(7)
+    for fold in range(5):
+        test = [vids[i] for i in rng.permutation(n_videos)[:test_size]]
+        hb = pack_videos(test)
+        out = summ.run_device(DeviceBatch(hb), want_intermediates=True)
+        torch.cuda.synchronize()
+        scores, f = out["scores"].cpu().numpy(), out["f"].cpu().numpy()
+        masks, cu_frames = out["summary"].cpu().numpy(), hb.meta.sum_offsets
+        want_f = np.empty(len(test))
+        for pos, idx in enumerate(hb.order):
+            v = test[idx]
+            ref = c_oracle.video(scores[hb.cu_steps[pos]:hb.cu_steps[pos + 1]], v.picks, v.n_frames, v.change_points, v.user_summary, method)
+            s0, s1 = hb.meta.cu_shots[pos], hb.meta.cu_shots[pos + 1]
+            assert bits_equal(out["selected"][s0:s1].cpu().numpy(), ref["selected"]), (dataset, fold, pos)
+            assert bits_equal(masks[cu_frames[pos]:cu_frames[pos + 1]].astype(np.int8), ref["summary"].astype(np.int8)), (dataset, fold, pos)
+            assert bits_equal(np.float64(f[pos]), np.float64(ref["f"])), (dataset, fold, pos)
+            want_f[idx] = ref["f"]
+        f_host = summ.run_host(hb)                            # end-to-end call, caller's video order
+        assert bits_equal(f_host, want_f)
+        assert bits_equal(np.float64(np.mean(f_host)), np.float64(np.mean(want_f)))
+
+
 def test_pipelined_submission_matches_single_stream(seeded_model_kwargs):
     torch.manual_seed(1234)
     model = SimNet(**seeded_model_kwargs).cuda().eval()

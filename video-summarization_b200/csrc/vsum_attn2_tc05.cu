@@ -148,13 +148,16 @@ __device__ __forceinline__ ItemInfo decode_item(int idx, const int32_t *__restri
 
 // counters[0] = number of 256-query blocks, counters[1] = work counter, counters[2] = CTAs that have finished (both zero
 // between launches: the schedule kernel zeroes them, the last CTA of every launch rewinds them); flags[item] != 0: the
-// item needs the exact pass (raised by the SAFE = false launch, consumed by the SAFE = true launch).
+// item needs the exact pass (raised by the SAFE = false launch, consumed by the SAFE = true launch), counters[3] = how
+// many items are flagged.  Flags stay up until the next schedule: a later launch over the same batch (the next layer)
+// redoes those items in its exact pass too, which costs time, not correctness.
 template <bool TRAIN, bool SAFE, bool PRESCALED>
 __global__ void __launch_bounds__(A2_THREADS, 1)
 attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__restrict__ cu,
                   const int32_t *__restrict__ item_video, const int32_t *__restrict__ item_q0,
                   int32_t *__restrict__ counters, int32_t *__restrict__ flags, void *__restrict__ out_v, float scale_log2e,
                   float *__restrict__ lse2, float keep_scale, uint32_t drop_thresh16, unsigned long long seed) {
+    if (SAFE && *reinterpret_cast<volatile int32_t *>(counters + 3) == 0) return;   // no item was flagged (every CTA sees the same count)
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((tc::smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t *sQ = smem;                                          // [item parity][tile] x 16 KB
@@ -473,8 +476,8 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
 #endif
             // The fast pass exponentiates against the fixed reference 0: valid while no exponential overflows (checked per tile
             // above) and the row as a whole does not underflow (l >= 2^-80, so its largest term is >= 2^-93).
-            if (!SAFE && row < w.n && (danger || !(l_run >= 8.3e-25f)))
-                *reinterpret_cast<volatile int32_t *>(flags + idx) = 1;
+            if (!SAFE && row < w.n && (danger || !(l_run >= 8.3e-25f)) && atomicExch(flags + idx, 1) == 0)
+                atomicAdd(counters + 3, 1);                       // number of flagged items: the exact pass returns at once when it is 0
             // ---- epilogue: O_t / l -> global
             tc::mbar_wait(o_full + t, n_done & 1);                // the last PV product of the item has completed
             ++n_done;
@@ -543,6 +546,7 @@ attn2_schedule_kernel(const int32_t *__restrict__ cu, int B, int32_t *__restrict
         counters[0] = min(run, max_blocks);
         counters[1] = 0;
         counters[2] = 0;
+        counters[3] = 0;
     }
     __syncthreads();
     for (int v = threadIdx.x; v < B; v += blockDim.x) {

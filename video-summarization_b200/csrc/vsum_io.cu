@@ -87,13 +87,20 @@ extern "C" int vsum_pack_open(const char *path, vsum_pack_t *out) {
     if (memcmp(p->hdr->magic, "VSPACK01", 8) != 0 || p->hdr->version != 1) return fail("bad magic or version");
     if (p->hdr->file_bytes != p->bytes) return fail("truncated file (size differs from the header)");
     if (p->hdr->feature_dtype != VSUM_FEATURES_F32 && p->hdr->feature_dtype != VSUM_FEATURES_BF16) return fail("unknown feature dtype");
-    if (p->hdr->index_offset + (uint64_t)p->hdr->n_videos * sizeof(IndexEntry) > p->bytes) return fail("index outside the file");
+    if (p->hdr->feature_dim == 0 || p->hdr->feature_dim > (1u << 20)) return fail("feature_dim out of range");
+    // subtraction form: none of these can wrap for a crafted header
+    if (p->hdr->index_offset > p->bytes || (uint64_t)p->hdr->n_videos > (p->bytes - p->hdr->index_offset) / sizeof(IndexEntry))
+        return fail("index outside the file");
     p->index = (const IndexEntry *)(p->base + p->hdr->index_offset);
     for (uint32_t i = 0; i < p->hdr->n_videos; ++i) {
         const IndexEntry &e = p->index[i];
         if (e.n_steps < 0 || e.n_frames < 0 || e.n_shots < 0 || e.n_users < 0 || e.rep_dim < 0) return fail("negative size in the index");
-        for (int k = 0; k < VSUM_PACK_NUM_ARRAYS; ++k)
-            if (e.off[k] && e.off[k] + array_bytes(p->hdr, e, k) > p->hdr->index_offset) return fail("array outside the data region");
+        // n_users * n_frames * 4 and n_steps * feature_dim * 4 stay below 2^63 with these bounds (feature_dim <= 2^20)
+        if ((uint64_t)e.n_users * (uint64_t)e.n_frames > (1ull << 40) || (uint64_t)e.n_steps > (1ull << 31)) return fail("array size out of range");
+        for (int k = 0; k < VSUM_PACK_NUM_ARRAYS; ++k) {
+            const uint64_t nb = array_bytes(p->hdr, e, k);
+            if (e.off[k] && (e.off[k] > p->hdr->index_offset || nb > p->hdr->index_offset - e.off[k])) return fail("array outside the data region");
+        }
     }
     madvise(m, p->bytes, MADV_WILLNEED);
     *out = p;

@@ -243,9 +243,15 @@ class PackedBatch:
     ready: Optional[torch.cuda.Event] = None
 
     def wait(self):
-        """Make the current stream wait for the batch's host-to-device copies."""
+        """Make the current stream wait for the batch's host-to-device copies.  The device tensors were allocated on the
+        loader's copy stream: they are recorded on the consumer's stream, so the caching allocator cannot hand their blocks
+        to the next copy while kernels queued by the consumer still read them."""
         if self.ready is not None:
-            torch.cuda.current_stream(self.features.device).wait_event(self.ready)
+            cur = torch.cuda.current_stream(self.features.device)
+            cur.wait_event(self.ready)
+            for t in (self.features, self.targets, self.cu_seqlens, self.video_rep):
+                if t is not None and t.is_cuda:
+                    t.record_stream(cur)
         return self
 
 

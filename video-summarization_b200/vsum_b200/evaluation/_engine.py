@@ -163,9 +163,15 @@ _scratch: dict = {}
 
 
 def _scratch_buf(key: str, nbytes: int, dev: torch.device) -> torch.Tensor:
-    k = (key, dev.index)
+    """Per (purpose, device, STREAM) scratch: two streams (the pipelined side stream and a caller's main stream, or two
+    Summarizers) never share knapsack decision bits / overlap counts, and a buffer that is outgrown is recorded on its
+    stream before it is dropped."""
+    stream = torch.cuda.current_stream(dev)
+    k = (key, dev.index, stream.cuda_stream)
     t = _scratch.get(k)
     if t is None or t.numel() < nbytes:
+        if t is not None:
+            t.record_stream(stream)
         t = torch.empty(max(int(nbytes * 1.25), 1024), dtype=torch.uint8, device=dev)
         _scratch[k] = t
     return t

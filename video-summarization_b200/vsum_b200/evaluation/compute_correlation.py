@@ -8,7 +8,10 @@ from . import _engine
 
 def evaluate_scores(predicted_summary, user_scores):
     """predicted_summary: float32[n_frames] (upsampled frame scores); user_scores [U, n_frames].
-    Returns (mean Kendall tau-b, mean Spearman rho) over the users."""
+    Returns (mean Kendall tau-b, mean Spearman rho) over the users.
+    Limit: the prediction is handed to the kernels as runs of equal values (what `upsample` produces from per-pick scores,
+    compute_metrics.py:19-39); a prediction with more than 8191 distinct runs (e.g. a dense per-frame score vector on a
+    video longer than ~8k frames) raises VSUM_EUNSUPPORTED where the reference (scipy) would accept it."""
     pred = np.ascontiguousarray(np.asarray(predicted_summary), dtype=np.float32).reshape(-1)
     n = len(pred)
     # the kernels take the piecewise-constant form: run starts are the picks, run values the scores

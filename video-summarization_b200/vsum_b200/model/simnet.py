@@ -311,6 +311,11 @@ class SimNet(nn.Module):
         `self.training` / `self.dropout` like nn.Dropout in the reference (simnet.py:107,110,159,181)."""
         if not features.is_cuda:
             raise _cabi.VsumError("vsum_b200 runs on CUDA devices only (no CPU fallback)")
+        if self.training and float(getattr(self, "sparsity", 0.0) or 0.0) > 0.0:
+            # the reference drops (embedding + positional encoding) with p = sparsity (simnet.py:204-206, 235-237); every caller
+            # of the reference passes 0 (train.py:32, simnet_pretrain.py:30) and this path has no dropout site there
+            raise _cabi.VsumError("SimNet(sparsity > 0) in training mode is not built (the reference's callers use sparsity=0); "
+                                  "construct the model with sparsity=0. or call .eval()")
         drop_p = float(self.dropout) if self.training else 0.0
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if drop_p > 0 else 0
         return _ScorerTrainFn.apply(self, features.contiguous().float(), cu_seqlens, list(seqlens_host), drop_p, seed,
