@@ -127,18 +127,28 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the reference's CPU algorithm (oracle port) on host cores
 # --------------------------------------------------------------------------------------------
-def cpu_reference_step(sd, sample_videos):
-    """One pass of the reference's val_step + eval_metrics body (minus scipy correlations) over
-    the sample, in the reference's own execution model: torch fp32 on CPU for the scorer, pure
-    Python loops for pooling / knapsack / F-score (oracle/ref_port.py)."""
+def _scores_of(sd, sample_videos, device="cpu"):
+    """Scorer of the oracle port (torch fp32 eager, the reference's own module restated) + the caller's sigmoid."""
     import torch
-    from oracle import ref_port, scorer_ref
-    fs = []
+    from oracle import scorer_ref
+    out = []
     for v in sample_videos:
-        logits, _ = scorer_ref.scorer_forward(sd, torch.from_numpy(v.features).unsqueeze(0), num_heads=4)
-        scores = torch.sigmoid(logits.view(1, -1)).squeeze(0).numpy()                  # train.py:144,148
-        summary, *_ = ref_port.summarize_video(v.change_points, scores, v.n_frames, v.picks)
-        fs.append(ref_port.fscore_video(summary, v.user_summary, "avg"))
+        x = torch.from_numpy(v.features).unsqueeze(0).to(device)
+        logits, _ = scorer_ref.scorer_forward(sd, x, num_heads=4)
+        out.append(torch.sigmoid(logits.view(1, -1)).squeeze(0).cpu().numpy())         # train.py:144,148
+    return out
+
+
+def cpu_reference_step(sd, sample_videos, pool=None):
+    """One pass of the reference's val_step + eval_metrics body (minus scipy correlations) over the sample, in the
+    reference's own execution model: torch fp32 on CPU (all host threads) for the scorer, pure Python loops for
+    pooling / knapsack / F-score, builtin `sum()` counts included (oracle/ref_port.py).
+    pool=None: single process, as the reference ships.  pool=multiprocessing pool: the pure-Python stages of the
+    videos run in parallel worker processes (BASELINE.md 4.3 'fair')."""
+    from oracle import ref_port
+    scores = _scores_of(sd, sample_videos)
+    jobs = [(v.change_points, sc, v.n_frames, v.picks, v.user_summary, "avg") for v, sc in zip(sample_videos, scores)]
+    fs = pool.map(ref_port.pool_eval_video, jobs, chunksize=1) if pool is not None else [ref_port.pool_eval_video(j) for j in jobs]
     return float(np.mean(fs))
 
 
@@ -146,7 +156,7 @@ def reference_setup():
     import torch
     from vsum_b200.model import SimNet
     from vsum_b200.synthetic import make_video
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     torch.set_num_threads(cores)
     torch.manual_seed(1234)
     sd = SimNet(**MODEL_KW).state_dict()
@@ -157,13 +167,13 @@ def reference_setup():
 REF_BUDGET_S = 180.0      # the whole reference-arm run (warm-up + timed steps) should end within a few minutes
 
 
-def pick_sample(sd, full, steps, warmup):
+def pick_sample(sd, full, steps, warmup, pool=None):
     """Largest of the 12- / 6- / 3-video samples (every 1st / 2nd / 4th length class) whose estimated run time
     fits REF_BUDGET_S; the estimate comes from one untimed pass over the smallest sample (measured cost ratios
     of the three samples: about 9 : 4 : 1; rounded up)."""
     small = full[1::4]
     t0 = time.perf_counter()
-    cpu_reference_step(sd, small)
+    cpu_reference_step(sd, small, pool)
     dt = time.perf_counter() - t0
     n_steps = max(1, steps + warmup)
     if 10.0 * dt * n_steps <= REF_BUDGET_S:
@@ -173,30 +183,88 @@ def pick_sample(sd, full, steps, warmup):
     return small
 
 
-def run_cpu_baseline(steps=1, warmup=0):
+def _make_pool(cores, n_jobs):
+    import multiprocessing as mp
+    pool = mp.get_context("spawn").Pool(max(1, min(cores, n_jobs)))      # spawn: no fork of a process that owns torch / CUDA threads
+    pool.map(abs, range(pool._processes))                                # workers up and imported before anything is timed
+    return pool
+
+
+def run_cpu_baseline(steps=1, warmup=0, fair_value=False, gpu_eager=False):
+    """`value`: the sample's videos/s.  Two arrangements: 'as shipped' -- one process, torch on all
+    host threads, the pure-Python stages one video after the other -- and 'fair' -- the same with the pure-Python
+    stages of the videos spread over a process pool.  The reference arm (`fair_value`) reports the faster, fair one."""
     sd, sample, cores = reference_setup()
-    sample = pick_sample(sd, sample, steps, warmup)
-    for _ in range(warmup):
-        cpu_reference_step(sd, sample)
+    pool = _make_pool(cores, len(sample))
+    try:
+        sample = pick_sample(sd, sample, 2 * steps, 2 * warmup, pool)
+        for _ in range(warmup):
+            cpu_reference_step(sd, sample, pool)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cpu_reference_step(sd, sample, pool)
+        dt_fair = (time.perf_counter() - t0) / steps
+        n_ship = 1 if fair_value else steps
+        t0 = time.perf_counter()
+        for _ in range(n_ship):
+            cpu_reference_step(sd, sample, None)
+        dt_ship = (time.perf_counter() - t0) / n_ship
+    finally:
+        pool.terminate()
+    desc = (f"{len(sample)} videos, N={[v.n_steps for v in sample]} (evenly spaced classes of the log-uniform length range; "
+            f"mean N^2 {np.mean([v.n_steps ** 2 for v in sample]) / 1e6:.1f} M); oracle port of the reference (kind 'port': "
+            "/root/reference is not on the GPU box): torch fp32 CPU scorer on all host threads + pure-Python pooling / knapsack / "
+            "F-score with the reference's builtin sum() counts")
+    dt = dt_fair if fair_value else dt_ship
+    base = {"value": len(sample) / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+            "arrangement": "fair" if fair_value else "as_shipped",
+            "as_shipped": {"value": len(sample) / dt_ship, "s_per_step": dt_ship,
+                           "what": "single process, torch intra-op threads = all cores, pure-Python stages sequential"},
+            "fair": {"value": len(sample) / dt_fair, "s_per_step": dt_fair, "processes": min(cores, len(sample)),
+                     "what": "scorer as above, pure-Python stages of the videos in a multiprocessing pool"}}
+    if gpu_eager:
+        base["reference_gpu_eager"] = run_gpu_eager(sd, sample)
+    return base, dt
+
+
+def run_gpu_eager(sd, sample):
+    """BASELINE.md 4.7 (secondary): the reference's PyTorch module (oracle restatement, fp32 eager ops, one video per
+    forward as train.py:139-143) with weights and features on the B200; scorer only, and with the pure-Python
+    evaluation stages behind it (as shipped: sequential on the host)."""
+    import torch
+    from oracle import ref_port
+    dev = torch.device("cuda", torch.cuda.current_device())
+    sdg = {k: v.to(dev) for k, v in sd.items()}
+    import oracle.scorer_ref as sr
+    tab = sr.positional_table
+    sr.positional_table = lambda n, d: tab(n, d).to(dev)        # the reference registers the table as a module buffer on the device
+    try:
+        _scores_of(sdg, sample[:2], dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        scores = _scores_of(sdg, sample, dev)                   # .cpu() per video = the reference's own per-video sync
+        dt_sc = time.perf_counter() - t0
+    finally:
+        sr.positional_table = tab
     t0 = time.perf_counter()
-    for _ in range(steps):
-        cpu_reference_step(sd, sample)
-    dt = (time.perf_counter() - t0) / steps
-    return {"value": len(sample) / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{len(sample)} videos, N={[v.n_steps for v in sample]} (evenly spaced classes of the log-uniform length range), "
-                      f"{dt:.2f} s/step; torch fp32 CPU scorer ({cores} threads) + pure-Python pooling/knapsack/F-score "
-                      "as the reference runs them"}, dt
+    for v, sc in zip(sample, scores):
+        ref_port.pool_eval_video((v.change_points, sc, v.n_frames, v.picks, v.user_summary, "avg"))
+    dt_ev = time.perf_counter() - t0
+    return {"scorer_only_videos_per_s": len(sample) / dt_sc, "with_python_eval_videos_per_s": len(sample) / (dt_sc + dt_ev),
+            "what": "torch fp32 eager scorer on cuda:0 (oracle restatement of simnet.py), one video per forward; evaluation stages pure Python on the host"}
 
 
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, dt = run_cpu_baseline(args.steps, args.warmup)
+    base, dt = run_cpu_baseline(args.steps, args.warmup, fair_value=True)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.videos), "l2": "n/a (CPU)"},
+            "config": {"workload": workload_name(args.videos), "l2": "n/a (CPU)",
+                       "sample": "each step is a bounded, length-stratified sample of the workload (see cpu_baseline.sample), "
+                                 "not the 256-video batch"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -206,10 +274,53 @@ def main_reference(args):
 # --------------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------------
+def pin_rank_to_cores(local, world):
+    """Ranks of one node share its host cores evenly (loader thread, pinned allocations and torch's own threads of a rank stay
+    on its slice) instead of every rank spawning threads over all of them."""
+    if world <= 1 or not hasattr(os, "sched_getaffinity"):
+        return None
+    cores = sorted(os.sched_getaffinity(0))
+    per = max(1, len(cores) // world)
+    mine = cores[local * per:(local + 1) * per] or cores
+    try:
+        os.sched_setaffinity(0, mine)
+    except OSError:
+        return None
+    return len(mine)
+
+
+def scratch_dir(need_bytes):
+    """Where the synthetic pack files go: VSUM_BENCH_DIR, else /dev/shm when it has room, else the temp directory."""
+    import shutil
+    import tempfile
+    cands = [os.environ.get("VSUM_BENCH_DIR"), "/dev/shm", tempfile.gettempdir()]
+    for d in cands:
+        if d and os.path.isdir(d) and os.access(d, os.W_OK):
+            try:
+                if shutil.disk_usage(d).free > need_bytes * 1.1:
+                    return d
+            except OSError:
+                pass
+    return tempfile.gettempdir()
+
+
+def write_bench_pack(path, videos, feats_of, compact):
+    """One `.vspack` of the synthetic val videos (fp32 features + fp32 user summaries as the h5 files hold them, or the
+    compact form: bf16 features + uint8 user summaries)."""
+    from vsum_b200.data import write_pack
+
+    def gen():
+        for v in videos:
+            yield dict(name=v.name, features=feats_of(v), picks=v.picks, change_points=v.change_points, n_frames=v.n_frames,
+                       user_summary=v.user_summary)
+    write_pack(path, gen(), user_summary_u8=compact, features_bf16=compact)
+
+
 def main_b200(args):
     import torch
     import torch.distributed as dist
     from vsum_b200 import _cabi
+    from vsum_b200.data import PackedDataset, PackedEvalLoader
     from vsum_b200.model import SimNet
     from vsum_b200.pipeline import DeviceBatch, Summarizer, pack_videos
     from vsum_b200.synthetic import make_video, video_length
@@ -219,6 +330,9 @@ def main_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device; the B200 path has no CPU fallback (use --impl reference)")
+    rank_cores = pin_rank_to_cores(local, world)
+    if rank_cores:
+        torch.set_num_threads(rank_cores)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -227,14 +341,22 @@ def main_b200(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
-    # ---- workload: weak scaling, rank r owns videos [r*V, (r+1)*V) of the global id space
-    V = args.videos
-    ids = [rank * V + i for i in range(V)]
+    # ---- workload: weak scaling, rank r owns videos [r*V*NB, (r+1)*V*NB) of the global id space: NB distinct batches of V
+    # videos; the resident leg (`value`) runs on the first of them
+    V, NB = args.videos, max(1, args.e2e_batches)
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available / max(world, 1)
+        per_batch = V * 2108 * 4096 * 1.3 * 2.2          # pack file (tmpfs) + its page-locked copy, mean 2108 frames / video
+        while NB > 2 and NB * per_batch > 0.6 * avail:
+            NB -= 1
+    except Exception:
+        pass
+    ids = [rank * V * NB + i for i in range(V * NB)]
     videos = [make_video(v, video_length(v, args.len_lo, args.len_hi), n_users=N_USERS, with_features=False) for v in ids]
-    hb = pack_videos(videos, pin=True, with_features=False)
+    hb = pack_videos(videos[:V], pin=True, with_features=False)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     feats_dev = torch.rand((hb.n_steps, 1024), device=dev, generator=g)        # rng.random-like features in [0,1)
-    hb.features.copy_(feats_dev)                                                # pinned host copy for the e2e leg
     torch.manual_seed(1234)
     model = SimNet(**MODEL_KW).to(dev).eval()
     summ = Summarizer(model, "avg", eval_sms=args.eval_sms)
@@ -282,50 +404,92 @@ def main_b200(args):
     ms_step = ms_total / args.steps
     value = world * V / (ms_step * 1e-3)
 
-    # ---- e2e: host (pinned) buffers in, F-scores out, copies inside the timed region
-    dbe = [DeviceBatch(hb, dev, pin_meta=True) for _ in range(2)]     # double-buffered device landing zones
+    # ---- per-kernel times from ONE non-pipelined pass (single stream: side-stream kernels are not timed under the next
+    # batch's scorer)
+    torch.cuda.synchronize()
+    _cabi.profile_begin()
+    summ.run_device(db)
+    torch.cuda.synchronize()
+    prof_alone = _cabi.profile_end()
+    del db, feats_dev
 
-    def step_e2e(i):
-        return summ.submit_host(dbe[i & 1], 2 + (i & 1))
-    for i in range(2):
-        step_e2e(i)
-    summ.drain(dev)
-    e2e_steps = max(2, min(args.steps, 6))
-    ms_e2e = timed(step_e2e, e2e_steps) / e2e_steps
-    e2e_value = world * V / (ms_e2e * 1e-3)
+    # ---- e2e: starts where the reference starts -- a dataset file.  NB distinct batches of V videos in a `.vspack`,
+    # read into page-locked memory once (dataset load, not timed), then per step, INSIDE the timed region: batch building
+    # on the loader's background thread (native metadata gather), one H2D per video out of the dataset on the loader's copy
+    # stream, the whole path, D2H of the F-scores.  Steady state: the loader runs up to `slots - 1` batches ahead both when
+    # the timed region starts and when it ends, so K steps contain the copies of exactly K batches.
+    def e2e_leg(compact):
+        gg = torch.Generator(device=dev).manual_seed(4321 + rank)
 
-    # ---- the same end-to-end pass with the user summaries as the packed dataset stores them (uint8, lossless for
-    # the 0/1 rows): a secondary figure -- `e2e` above keeps the h5 files' float32 rows the reference hands over
-    from vsum_b200.evaluation import _engine
-    from vsum_b200.pipeline import HostBatch
-    vs = [videos[i] for i in hb.order]
-    meta8 = _engine.HostEvalBatch.build([v.change_points for v in vs], [v.n_frames for v in vs], [v.picks for v in vs],
-                                        [v.user_summary.astype(np.uint8) for v in vs])
-    hb8 = HostBatch(hb.features, hb.seqlens, hb.cu_steps, meta8, hb.order, hb.names)
-    dbe8 = [DeviceBatch(hb8, dev, pin_meta=True) for _ in range(2)]
+        def feats_of(v):
+            x = torch.rand((v.n_steps, 1024), device=dev, generator=gg)
+            return (x.bfloat16().view(torch.int16).cpu().numpy().view(np.uint16) if compact else x.cpu().numpy())
+        frames = sum(v.n_steps for v in videos)
+        need = frames * (2048 if compact else 4096) + sum(v.user_summary.size for v in videos) * (1 if compact else 4)
+        path = os.path.join(scratch_dir(need), f"vsum_bench_r{rank}_{os.getpid()}_{'compact' if compact else 'f32'}.vspack")
+        t0 = time.perf_counter()
+        write_bench_pack(path, videos, feats_of, compact)
+        t_write = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        try:
+            ds = PackedDataset(path, split="val", resident="pinned")
+        finally:
+            os.unlink(path)                                 # the page-locked copy is the dataset from here on
+        t_open = time.perf_counter() - t0
+        loader = PackedEvalLoader(ds, batch_size=V, device=dev, slots=3, cycle=True)
+        it = iter(loader)
+        h2d = []
 
-    def step_e2e_u8(i):
-        return summ.submit_host(dbe8[i & 1], 2 + (i & 1))
-    for i in range(2):
-        step_e2e_u8(i)
-    summ.drain(dev)
-    ms_e2e_u8 = timed(step_e2e_u8, e2e_steps) / e2e_steps
-    h2d_u8 = int(dbe8[0].h2d_bytes)
+        def step(i):
+            b = next(it)
+            h2d.append(b.h2d_bytes)
+            return summ.submit_device(b, 2 + (i & 1), to_host=True)
+        for i in range(max(2, NB)):
+            step(i)
+        summ.drain(dev)
+        torch.cuda.synchronize()
+        h2d.clear()
+        n_col = len(loader.collate_ms)
+        steps = max(NB, min(args.steps, 2 * NB))
+        ms = timed(step, steps) / steps
+        col = loader.collate_ms[n_col:]
+        it.close()
+        out = {"value": world * V / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+               "h2d_bytes_per_step": int(np.mean(h2d)) * world, "d2h_bytes_per_step": 8 * V * world,
+               "h2d_gb_per_s_per_gpu": float(np.mean(h2d)) / (ms * 1e-3) / 1e9,
+               "distinct_batches": NB, "frames_per_gpu_per_step": frames / NB,
+               "batch_build_ms": float(np.mean(col)) if col else None,
+               "batch_build": "1 background thread per rank: native metadata gather (vsum_pack_eval_collate) + issuing one "
+                              "cudaMemcpyAsync per video and array out of the page-locked dataset (vsum_pack_h2d); no host-side "
+                              "copy of features / user summaries",
+               "dataset_load_s": {"write_pack": round(t_write, 2), "open_pinned": round(t_open, 2), "bytes": int(need)}}
+        del loader, it
+        ds.close()
+        return out
 
-    # ---- ... and with the features as a `features_bf16` pack stores them (rounded once, offline): half the feature bytes
-    feats16 = torch.empty(hb.features.shape, dtype=torch.bfloat16, pin_memory=True)
-    feats16.copy_(hb.features)
-    hb16 = HostBatch(feats16, hb.seqlens, hb.cu_steps, meta8, hb.order, hb.names)
-    del dbe8
-    dbe16 = [DeviceBatch(hb16, dev, pin_meta=True) for _ in range(2)]
+    e2e = e2e_leg(compact=False)
+    e2e_compact = e2e_leg(compact=True)
+    e2e_compact["note"] = ("same pass from a pack with bf16 features + uint8 user summaries (write_pack features_bf16, user_summary_u8); "
+                           "inputs are rounded once offline, scores stay within the 1e-2 bf16 tolerance")
 
-    def step_e2e_bf16(i):
-        return summ.submit_host(dbe16[i & 1], 2 + (i & 1))
-    for i in range(2):
-        step_e2e_bf16(i)
-    summ.drain(dev)
-    ms_e2e_bf16 = timed(step_e2e_bf16, e2e_steps) / e2e_steps
-    h2d_bf16 = int(dbe16[0].h2d_bytes)
+    # ---- plain pinned host-to-device copy rate with every rank copying at once: the bound the fp32 e2e leg sits on
+    probe_n = 1 << 30
+    src = torch.empty(probe_n, dtype=torch.uint8, pin_memory=True)
+    dst = torch.empty(probe_n, dtype=torch.uint8, device=dev)
+    dst.copy_(src, non_blocking=True)
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(4):
+        dst.copy_(src, non_blocking=True)
+    p1.record()
+    torch.cuda.synchronize()
+    probe = torch.tensor([4 * probe_n / (p0.elapsed_time(p1) * 1e-3) / 1e9], dtype=torch.float64, device=dev)
+    probe_all = [probe.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(probe_all, probe)
+    probe_all = [float(x.item()) for x in probe_all]
+    del src, dst
 
     if world > 1:
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
@@ -339,19 +503,40 @@ def main_b200(args):
         except Exception:
             pass
         peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))       # kernel timed inside a long step
+        peak_hbm = float(peaks.get("hbm_gbs", 6500.0))
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
         traffic, traffic_src = None, None
         try:   # dram bytes per launch from the committed ncu --set full capture of this same workload
-            rec = json.load(open(os.path.join(ROOT, "profiles", "r01_attn_ncu_full_default_workload.json")))
+            tsrc = "profiles/r02_attn2_ncu_full_default_workload.json"
+            rec = json.load(open(os.path.join(ROOT, tsrc)))
             if rec["frames_per_gpu_per_step"] == hb.n_steps:
-                traffic, traffic_src = rec["dram_bytes_total"] / 1e9, "profiles/r01_attn_ncu_full_default_workload.json"
+                traffic, traffic_src = rec["dram_bytes_total"] / 1e9, tsrc
         except Exception:
             pass
         att_ms, att_n = prof.get("attention", (0.0, 0))
         att_flops = attention_flops(hb.seqlens)                            # per launch (one layer, whole batch)
-        achieved = att_flops / (att_ms / max(att_n, 1) * 1e-3) / 1e12 if att_ms > 0 else None
-        kernel_ms = {k: round(v[0] / args.steps, 4) for k, v in prof.items() if v[1]}
+        n_att = 4 * args.steps                                             # fast-pass launches (the exact pass returns at once)
+        achieved = att_flops / (att_ms / n_att * 1e-3) / 1e12 if att_ms > 0 else None
+        kernel_ms = {k: round(v[0], 4) for k, v in prof_alone.items() if v[1]}
+        kernel_ms_pipelined = {k: round(v[0] / args.steps, 4) for k, v in prof.items() if v[1]}
         gpu_ms = sum(kernel_ms.values())
+        scorer_ms = sum(v for k, v in kernel_ms.items() if k in ("embed_gemm", "qkv_gemm", "attention", "oproj_ln_gemm", "fc1_gemm", "fc2_ln_gemm", "ffn_gemm"))
+        m = hb.meta
+        cells = float(sum((int(m.cu_shots[i + 1]) - int(m.cu_shots[i])) * (int((int(m.sum_offsets[i + 1]) - int(m.sum_offsets[i])) * 0.15) + 1)
+                          for i in range(m.B)))
+        us_bytes = float(m.user_summary.nbytes + m.sum_offsets[-1])
+        ev = {}
+        if kernel_ms.get("knapsack"):
+            ev["knapsack"] = {"ms": kernel_ms["knapsack"], "dp_cells": cells, "gcells_per_s": cells / kernel_ms["knapsack"] / 1e6,
+                              "bound": "shared-memory bandwidth + 2 barriers per shot (latency)"}
+        if kernel_ms.get("overlap"):
+            gbs = us_bytes / kernel_ms["overlap"] / 1e6
+            ev["overlap"] = {"ms": kernel_ms["overlap"], "algorithmic_bytes": us_bytes, "gb_per_s": gbs, "hbm_peak_gb_per_s": peak_hbm,
+                             "frac": gbs / peak_hbm, "bound": "hbm"}
+        if kernel_ms.get("shot_mean"):
+            sm_bytes = float(hb.n_steps * 8 + int(m.cu_shots[-1]) * 20)
+            ev["shot_mean"] = {"ms": kernel_ms["shot_mean"], "algorithmic_bytes": sm_bytes, "gb_per_s": sm_bytes / kernel_ms["shot_mean"] / 1e6,
+                               "bound": "latency (one thread per shot walks ~150 frames)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -359,34 +544,33 @@ def main_b200(args):
             "config": {"workload": workload_name(V, args.len_lo, args.len_hi), "videos_per_gpu_per_step": V, "frames_per_gpu_per_step": hb.n_steps,
                        "l2": "inputs (fp32 features, %.2f GB/GPU) are larger than L2; no flush needed" % (hb.n_steps * 4096 / 1e9),
                        "parallelism": f"videos sharded over {world} GPU(s), F-score all-gather",
-                       "pipelining": "scorer(batch i+1) overlaps pooling/knapsack/F-score(batch i) on a side stream; e2e adds a copy stream"},
+                       "pipelining": "scorer(batch i+1) overlaps pooling/knapsack/F-score(batch i) on a side stream; e2e adds the loader's copy stream",
+                       "host_cores_per_rank": rank_cores or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()),
+                       "reference_arm": "bench.py --impl reference times a 12-video length-stratified sample per step (cpu_baseline.sample), not this batch"},
             "clocks": clocks.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(db.h2d_bytes) * world,
-                    "d2h_bytes_per_step": 8 * V * world, "ms_per_step": ms_e2e},
-            "e2e_u8_user_summaries": {"value": world * V / (ms_e2e_u8 * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_u8,
-                                      "h2d_bytes_per_step": h2d_u8 * world,
-                                      "note": "same pass, user summaries as uint8 (PackedDataset user_summary_u8); e2e keeps float32"},
-            "e2e_bf16_features": {"value": world * V / (ms_e2e_bf16 * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_bf16,
-                                  "h2d_bytes_per_step": h2d_bf16 * world,
-                                  "note": "same pass from a pack with bf16 features + uint8 user summaries (write_pack features_bf16, "
-                                          "user_summary_u8); inputs are rounded once offline, scores stay within the 1e-2 bf16 tolerance"},
+            "e2e": e2e,
+            "e2e_compact_pack": e2e_compact,
+            "h2d_probe": {"gb_per_s_per_gpu": probe_all, "aggregate_gb_per_s": sum(probe_all),
+                          "what": "plain cudaMemcpyAsync of one 1 GiB page-locked buffer per rank, all ranks at once, 4 copies"},
             "gpu_launches": launches,
-            "roofline": {"kernel": "attn_tc05_kernel (varlen QK^T/softmax/PV, tcgen05)", "bound": "tensor",
+            "roofline": {"kernel": "attn2_tc05_kernel (varlen QK^T/softmax/PV, tcgen05, two query tiles per CTA, P in tensor memory)", "bound": "tensor",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
                          "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
                          "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch_gb": hb.n_steps * (768 + 256) * 2 / 1e9,
                          "peak_source": peak_src,
-                         "flops_per_launch": att_flops, "launch_ms": att_ms / max(att_n, 1),
-                         "share_of_step": (att_ms / args.steps) / gpu_ms if gpu_ms else None},
-            "scorer_tflops": scorer_flops(hb.seqlens) / (sum(v for k, v in kernel_ms.items() if k in (
-                "embed_gemm", "qkv_gemm", "attention", "oproj_ln_gemm", "fc1_gemm", "fc2_ln_gemm")) * 1e-3) / 1e12
-            if gpu_ms else None,
+                         "flops_per_launch": att_flops, "launch_ms": att_ms / n_att,
+                         "launch_ms_source": "CUDA events around the fast-pass + exact-pass launch pair on the main stream, inside the timed (pipelined) region",
+                         "share_of_step": (kernel_ms.get("attention", 0.0)) / gpu_ms if gpu_ms else None},
+            "scorer_tflops": scorer_flops(hb.seqlens) / (scorer_ms * 1e-3) / 1e12 if scorer_ms else None,
             "kernel_ms_per_step": kernel_ms,
+            "kernel_ms_per_step_source": "one non-pipelined pass on a single stream (no contention between the scorer and the evaluation stream)",
+            "kernel_ms_per_step_pipelined": kernel_ms_pipelined,
+            "eval_kernels": ev,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"], _ = run_cpu_baseline(1, 0)
+            line["cpu_baseline"], _ = run_cpu_baseline(1, 0, gpu_eager=True)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -401,6 +585,7 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--videos", type=int, default=256, help="videos per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-batches", type=int, default=4, help="distinct batches in the end-to-end legs' pack file (reduced when host memory is short)")
     ap.add_argument("--eval-sms", type=int, default=0, help="SMs left to the evaluation stream in pipelined mode (0 = no partition)")
     ap.add_argument("--len-lo", type=int, default=N_LO, help="shortest video (frames); default = BASELINE config 5")
     ap.add_argument("--len-hi", type=int, default=N_HI, help="longest video (frames)")

@@ -318,6 +318,34 @@ VSUM_API int vsum_pack_array(vsum_pack_t pack, int32_t video, int32_t kind, cons
 VSUM_API int vsum_pack_collate(vsum_pack_t pack, const int32_t *videos, int32_t n, int32_t threads,
                                void *features_out, float *gtscore_out, int32_t *cu_seqlens_out);
 
+/* Evaluation-side loader (replaces the val DataLoader + the per-video loop of src/train.py:139-148 and the h5 reads of
+ * src/data/dataset.py:89-103,127-135 for MANY videos per step).
+ *   vsum_pack_open_ex(..., VSUM_PACK_PINNED): the file is read ONCE into page-locked host memory instead of being
+ *     mapped, so every later batch is DMA'd straight out of the dataset -- no host-side collate copy of the big arrays.
+ *   vsum_pack_eval_collate: everything the evaluation kernels need for a batch EXCEPT the two big arrays, written into
+ *     one caller blob (pinned host memory; one H2D copy moves it): the videos are ordered longest first (stable), then
+ *     cu_steps, picks, cu_picks, n_frames, change points, cu_shots, knapsack decision-bit offsets, the knapsack order
+ *     (largest capacity first) and its per-class launches, summary offsets, user-summary offsets / rows / columns.
+ *     `blob_host` == NULL: only the layout (sizes, offsets) is computed.  Offsets are bytes from the blob's start,
+ *     every array 256-byte aligned.  Capacity = (int)((last_end + 1) * 0.15) as generate_summary.py:45-46.
+ *   vsum_pack_h2d: one cudaMemcpyAsync per video and array: features to features_dev + cu_steps[k] rows, user
+ *     summaries to user_summary_dev + us_offsets[k] elements (either may be NULL), in the blob's video order.
+ *     Needs a pack opened with VSUM_PACK_PINNED (fails otherwise: a pageable source would serialise the stream). */
+enum { VSUM_PACK_MMAP = 0, VSUM_PACK_PINNED = 1 };
+typedef struct {
+    int32_t B, total_users, total_shots, max_steps, max_cap, n_launches, user_summary_dtype, reserved;
+    int64_t T, total_picks, summary_frames, bit_words, us_elems, blob_bytes;
+    int64_t off_video_ids, off_cu_steps, off_picks, off_cu_picks, off_n_frames, off_cps, off_cu_shots, off_bit_offsets,
+            off_order, off_sum_offsets, off_us_offsets, off_cu_users, off_us_cols;
+    int32_t launch_first[8], launch_count[8], launch_max_cap[8];
+} vsum_eval_batch_layout;
+VSUM_API int vsum_pack_open_ex(const char *path, int32_t residency, vsum_pack_t *out);
+VSUM_API int32_t vsum_pack_residency(vsum_pack_t pack);
+VSUM_API int vsum_pack_eval_collate(vsum_pack_t pack, const int32_t *videos, int32_t n, void *blob_host, size_t blob_bytes,
+                                    vsum_eval_batch_layout *layout_out);
+VSUM_API int vsum_pack_h2d(vsum_pack_t pack, const void *blob_host, const vsum_eval_batch_layout *layout,
+                           void *features_dev, void *user_summary_dev, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Diagnostics: the two tcgen05 kernels on their own, so tests can pin them individually.
  *   vsum_debug_gemm_tc05: out[M,N] bf16 = epi(A[M,K] W[N,K]^T + bias); A/W bf16, or fp32 when

@@ -131,18 +131,22 @@ def summarize_video(change_points, scores, n_frames, picks):
 # --------------------------------------------------------------------------------------
 # keyshot F-score  (src/evaluation/evaluation_metrics.py:12-33)
 # --------------------------------------------------------------------------------------
-def fscore_users(summary: np.ndarray, user_summary: np.ndarray) -> list:
-    """Per-user F (x100).  Counts are integers; ratios are IEEE fp64 with 0/0 -> NaN."""
+def fscore_users(summary: np.ndarray, user_summary: np.ndarray, builtin_sums: bool = False) -> list:
+    """Per-user F (x100).  Counts are integers; ratios are IEEE fp64 with 0/0 -> NaN.
+    `builtin_sums`: count with Python's builtin `sum()` over the numpy arrays, element by element, exactly as
+    evaluation_metrics.py:23-24 does (same integers, ~100x the time: the reference's slowest F-score loop) -- the
+    timing arm of bench.py uses it; the default `ndarray.sum()` keeps the test suite fast."""
     width = max(len(summary), user_summary.shape[1])
     S = np.zeros(width, dtype=np.int64)
     S[:len(summary)] = summary
-    s_cnt = int(S.sum())
+    count = (lambda a: int(sum(a))) if builtin_sums else (lambda a: int(a.sum()))
     out = []
     with np.errstate(divide="ignore", invalid="ignore"):
         for u in range(user_summary.shape[0]):
             G = np.zeros(width, dtype=np.int64)
             G[:user_summary.shape[1]] = user_summary[u]          # float -> int truncation
-            o_cnt, g_cnt = int((S & G).sum()), int(G.sum())
+            s_cnt = count(S)                                      # the reference re-counts S for every user (line 23)
+            o_cnt, g_cnt = count(S & G), count(G)
             p = np.float64(o_cnt) / np.float64(s_cnt)
             r = np.float64(o_cnt) / np.float64(g_cnt)
             out.append(0 if p + r == 0 else 2 * p * r * 100 / (p + r))
@@ -155,8 +159,16 @@ def fscore_reduce(per_user: list, method: str):
     return sum(per_user) / len(per_user)
 
 
-def fscore_video(summary, user_summary, method: str = "avg"):
-    return fscore_reduce(fscore_users(summary, user_summary), method)
+def fscore_video(summary, user_summary, method: str = "avg", builtin_sums: bool = False):
+    return fscore_reduce(fscore_users(summary, user_summary, builtin_sums), method)
+
+
+def pool_eval_video(args):
+    """multiprocessing worker of bench.py's `fair` CPU figure: the pure-Python stages of one video
+    (generate_summary + evaluate_summary as shipped, builtin sums included) given its scores."""
+    change_points, scores, n_frames, picks, user_summary, method = args
+    summary, *_ = summarize_video(change_points, scores, n_frames, picks)
+    return fscore_video(summary, user_summary, method, builtin_sums=True)
 
 
 # --------------------------------------------------------------------------------------

@@ -126,3 +126,49 @@ def test_optional_arrays_and_pretrain_collate(tmp_path):
         list(PackedLoader(PackedDataset(path, split="train"), batch_size=2, device="cpu"))
     with pytest.raises(ValueError):
         write_pack(str(tmp_path / "bad.vspack"), [dict(name="x", features=np.zeros((4, 8), np.float32))])
+
+
+@pytest.mark.parametrize("u8", [False, True])
+def test_eval_collate_matches_the_host_batch_builder(tmp_path, u8):
+    """vsum_pack_eval_collate (native metadata gather of an evaluation batch) against HostEvalBatch.build over the same
+    videos in pack_videos' longest-first order: every array, the knapsack order and the per-class launches."""
+    import ctypes as C
+    from vsum_b200.evaluation import _engine
+    ns = (60, 7, 131, 300, 1, 2000, 131, 900)
+    vids = _videos(ns, first=900)
+    path = str(tmp_path / "d.vspack")
+    write_pack(path, vids, user_summary_u8=u8)
+    ds = PackedDataset(path, split="val")
+    L = _cabi.load()
+    sel = [5, 0, 2, 6, 7, 4, 1]                                             # a batch in arbitrary dataset order
+    raw = np.asarray([ds.ids[i] for i in sel], dtype=np.int32)
+    lay = _cabi.EvalBatchLayout()
+    _cabi.check(L.vsum_pack_eval_collate(ds._h, raw.ctypes.data, len(sel), None, 0, C.byref(lay)), "layout")
+    blob = np.zeros(int(lay.blob_bytes), np.uint8)
+    lay2 = _cabi.EvalBatchLayout()
+    _cabi.check(L.vsum_pack_eval_collate(ds._h, raw.ctypes.data, len(sel), blob.ctypes.data, blob.nbytes, C.byref(lay2)), "collate")
+    assert bytes(lay) == bytes(lay2)
+    order = sorted(range(len(sel)), key=lambda k: -ns[sel[k]])               # stable, longest first
+    vs = [vids[sel[k]] for k in order]
+    ref = _engine.HostEvalBatch.build([v["change_points"] for v in vs], [v["n_frames"] for v in vs], [v["picks"] for v in vs],
+                                      [v["user_summary"].astype(np.uint8 if u8 else np.float32) for v in vs])
+    B = len(sel)
+    view = lambda off, n, dt: np.frombuffer(blob, dtype=dt, count=n, offset=int(off))
+    assert view(lay.off_video_ids, B, np.int32).tolist() == [sel[k] for k in order]
+    assert view(lay.off_cu_steps, B + 1, np.int32).tolist() == _engine._cu([len(v["picks"]) for v in vs]).tolist()
+    assert np.array_equal(view(lay.off_picks, int(lay.T), np.int32), ref.picks)
+    for name, dt, n in (("cu_picks", np.int32, B + 1), ("n_frames", np.int32, B), ("cu_shots", np.int32, B + 1),
+                        ("bit_offsets", np.int64, B + 1), ("order", np.int32, B), ("sum_offsets", np.int64, B + 1),
+                        ("us_offsets", np.int64, B + 1), ("cu_users", np.int32, B + 1), ("us_cols", np.int32, B)):
+        assert np.array_equal(view(getattr(lay, "off_" + name), n, dt), getattr(ref, name)), name
+    assert np.array_equal(view(lay.off_cps, 2 * lay.total_shots, np.int32).reshape(-1, 2), ref.cps)
+    assert [(lay.launch_first[i], lay.launch_count[i], lay.launch_max_cap[i]) for i in range(lay.n_launches)] == ref.launches
+    assert (lay.max_cap, lay.total_users, lay.us_elems, lay.summary_frames, lay.bit_words) == \
+        (ref.max_cap, int(ref.cu_users[-1]), int(ref.us_offsets[-1]), int(ref.sum_offsets[-1]), int(ref.bit_offsets[-1]))
+    assert lay.user_summary_dtype == (_cabi.USER_SUMMARY_U8 if u8 else _cabi.USER_SUMMARY_F32)
+    # DMA out of the dataset needs page-locked residency: a mapped pack is refused, loudly
+    assert L.vsum_pack_residency(ds._h) == _cabi.PACK_MMAP
+    assert L.vsum_pack_h2d(ds._h, blob.ctypes.data, C.byref(lay), None, None, None) != 0
+    assert b"VSUM_PACK_PINNED" in L.vsum_last_error()
+    bad = np.asarray([99], np.int32)
+    assert L.vsum_pack_eval_collate(ds._h, bad.ctypes.data, 1, None, 0, C.byref(lay)) != 0

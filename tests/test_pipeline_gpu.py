@@ -149,3 +149,53 @@ def test_val_split_of_a_byte_pack_scores_like_the_float32_one(tmp_path):
             data[user.name], users[user.name] = make_scores(2600 + i, v.n_steps), user
         got.append(np.asarray(eval_fscores(data, users)))
     assert len(got[0]) == 4 and bits_equal(got[0], got[1])
+
+
+@pytest.mark.parametrize("u8,bf16", [(False, False), (True, True)])
+def test_eval_loader_batches_match_host_packed_batches(tmp_path, seeded_model_kwargs, u8, bf16):
+    """src/train.py:139-148 for many videos per step, fed from a page-locked pack: every `EvalBatch` of
+    `PackedEvalLoader` (native metadata gather + one DMA per video out of the dataset) gives, bit for bit, the scores and
+    F-scores of the same videos packed on the host (`pack_videos` + `DeviceBatch`), through the pipelined Summarizer and
+    across the loader's slot ring (more batches than slots, two passes)."""
+    from vsum_b200.data import PackedDataset, PackedEvalLoader, write_pack
+    torch.manual_seed(1234)
+    model = SimNet(**seeded_model_kwargs).cuda().eval()
+    vids = [make_video(3100 + i, video_length(3100 + i, 40, 900), n_users=6) for i in range(22)]
+    if bf16:                                                    # what a features_bf16 pack holds: the rounded rows
+        for v in vids:
+            v.features = torch.from_numpy(v.features).bfloat16().float().numpy()
+    path = str(tmp_path / "val.vspack")
+    write_pack(path, [dict(name=v.name, features=v.features, gtscore=v.gtscore, picks=v.picks, change_points=v.change_points,
+                           n_frames=v.n_frames, user_summary=v.user_summary) for v in vids], user_summary_u8=u8, features_bf16=bf16)
+    ds = PackedDataset(path, split="val", resident="pinned")
+    loader = PackedEvalLoader(ds, batch_size=5, slots=2, cycle=True)
+    assert len(loader) == 5
+    summ = Summarizer(model, "avg")
+    want = []
+    for s in range(0, 22, 5):
+        chunk = vids[s:s + 5]
+        hb = pack_videos(chunk)
+        if bf16:
+            hb.features = hb.features.bfloat16()
+        if u8:
+            hb.meta.user_summary = hb.meta.user_summary.astype(np.uint8)
+        out = summ.run_device(DeviceBatch(hb), want_intermediates=True)
+        want.append((out["scores"].cpu().numpy(), out["f"].cpu().numpy(), [v.name for v in (chunk[i] for i in hb.order)]))
+    torch.cuda.synchronize()
+    got_f, names = [], []
+    it = iter(loader)
+    for k in range(10):                                         # two passes over the five batches
+        b = next(it)
+        names.append(b.names)
+        assert b.features.dtype == (torch.bfloat16 if bf16 else torch.float32)
+        got_f.append(summ.submit_device(b, k & 1, to_host=True))
+        if k % 2 == 1:                                          # pinned landing buffers are per slot: read them before reuse
+            summ.drain()
+            torch.cuda.synchronize()
+            got_f[-2], got_f[-1] = got_f[-2].numpy().copy(), got_f[-1].numpy().copy()
+    it.close()
+    for k in range(10):
+        sc, f, nm = want[k % 5]
+        assert names[k] == nm
+        assert bits_equal(got_f[k], f), k
+    assert len(loader.collate_ms) == 10 and ds.resident == "pinned"

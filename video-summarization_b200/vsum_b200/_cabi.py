@@ -31,7 +31,8 @@ EXPORTS = (
     "vsum_linear_workspace_bytes", "vsum_linear_forward", "vsum_linear_backward",
     "vsum_kts_workspace_bytes", "vsum_kts_gram", "vsum_kts_dp",
     "vsum_pack_open", "vsum_pack_close", "vsum_pack_num_videos", "vsum_pack_feature_dim", "vsum_pack_feature_dtype", "vsum_pack_video_info",
-    "vsum_pack_array", "vsum_pack_collate", "vsum_summary_frames", "vsum_rank_correlation_workspace_bytes", "vsum_rank_correlation",
+    "vsum_pack_array", "vsum_pack_collate", "vsum_pack_open_ex", "vsum_pack_residency", "vsum_pack_eval_collate", "vsum_pack_h2d",
+    "vsum_summary_frames", "vsum_rank_correlation_workspace_bytes", "vsum_rank_correlation",
     "vsum_pretrain_saved_bytes", "vsum_pretrain_losses_forward", "vsum_pretrain_losses_backward",
     "vsum_profile_begin", "vsum_profile_end", "vsum_profile_num_categories", "vsum_profile_category_name",
 )
@@ -75,6 +76,18 @@ class PackInfo(C.Structure):
                 ("n_users", C.c_int32), ("rep_dim", C.c_int32), ("has_user_scores", C.c_int32), ("user_summary_dtype", C.c_int32)]
 
 
+class EvalBatchLayout(C.Structure):
+    """vsum_eval_batch_layout (include/vsum_b200.h)."""
+    _fields_ = ([(n, C.c_int32) for n in ("B", "total_users", "total_shots", "max_steps", "max_cap", "n_launches",
+                                           "user_summary_dtype", "reserved")] +
+                [(n, C.c_int64) for n in ("T", "total_picks", "summary_frames", "bit_words", "us_elems", "blob_bytes",
+                                           "off_video_ids", "off_cu_steps", "off_picks", "off_cu_picks", "off_n_frames", "off_cps",
+                                           "off_cu_shots", "off_bit_offsets", "off_order", "off_sum_offsets", "off_us_offsets",
+                                           "off_cu_users", "off_us_cols")] +
+                [("launch_first", C.c_int32 * 8), ("launch_count", C.c_int32 * 8), ("launch_max_cap", C.c_int32 * 8)])
+
+
+PACK_MMAP, PACK_PINNED = 0, 1
 PACK_FEATURES, PACK_GTSCORE, PACK_PICKS, PACK_CHANGE_POINTS, PACK_USER_SUMMARY, PACK_USER_SCORES, PACK_VIDEO_REP = range(7)
 
 _lib = None
@@ -140,6 +153,11 @@ def load():
     L.vsum_kts_gram.argtypes = [vp, i32, i32, vp, vp, vp]
     L.vsum_kts_dp.argtypes = [vp, i32, i32, i32, i32, vp, C.c_size_t, vp, vp, vp]
     L.vsum_pack_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.vsum_pack_open_ex.argtypes = [C.c_char_p, i32, C.POINTER(vp)]
+    L.vsum_pack_residency.argtypes = [vp]
+    L.vsum_pack_residency.restype = i32
+    L.vsum_pack_eval_collate.argtypes = [vp, vp, i32, vp, C.c_size_t, C.POINTER(EvalBatchLayout)]
+    L.vsum_pack_h2d.argtypes = [vp, vp, C.POINTER(EvalBatchLayout), vp, vp, vp]
     L.vsum_pack_close.argtypes = [vp]
     L.vsum_pack_close.restype = None
     L.vsum_pack_num_videos.argtypes = [vp]

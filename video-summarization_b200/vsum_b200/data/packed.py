@@ -63,21 +63,23 @@ def write_pack(path: str, videos: Iterable[dict], feature_dim: int = 1024, user_
     `change_points` int[S,2], `n_frames`, `user_summary` [U,n_frames], `user_scores` [U,n_frames],
     `video_rep` f32[rep_dim] (the pretraining target, dataset.py:26).  `user_summary_u8` stores the 0/1
     user summaries as bytes (4x smaller than the h5 files' float32).  `features_bf16` stores the features rounded to
-    bfloat16 (half the bytes on disk, over PCIe and out of HBM): an inference-side option -- the bf16 scorer then runs
+    bfloat16 (half the bytes on disk, over PCIe and out of HBM; `features` may also arrive already rounded, as uint16
+    bfloat16 bit patterns): an inference-side option -- the bf16 scorer then runs
     its feature GEMM in bf16 (`VSUM_MODE_BF16_FEATURES`); training packs keep float32."""
     entries = []
     with open(path, "wb") as f:
         f.write(b"\0" * 64)
         for v in videos:
-            feats = np.ascontiguousarray(v["features"], dtype=np.float32)
+            pre_rounded = features_bf16 and getattr(v["features"], "dtype", None) == np.uint16     # bfloat16 bit patterns as given
+            feats = np.ascontiguousarray(v["features"]) if pre_rounded else np.ascontiguousarray(v["features"], dtype=np.float32)
             if feats.ndim != 2 or feats.shape[1] != feature_dim:
                 raise ValueError(f"{v.get('name')}: features must be [N,{feature_dim}]")
             n = feats.shape[0]
             off = [0] * 7
             def put(kind, arr, align=64):
                 off[kind] = _pad_to(f, align)
-                f.write(np.ascontiguousarray(arr).tobytes())
-            put(_cabi.PACK_FEATURES, to_bf16_bits(feats) if features_bf16 else feats, _ALIGN)
+                f.write(memoryview(np.ascontiguousarray(arr)).cast("B"))
+            put(_cabi.PACK_FEATURES, feats if (pre_rounded or not features_bf16) else to_bf16_bits(feats), _ALIGN)
             n_frames = n_shots = n_users = rep_dim = has_scores = 0
             if v.get("gtscore") is not None:
                 g = np.ascontiguousarray(v["gtscore"], dtype=np.float32).reshape(-1)
@@ -158,11 +160,18 @@ class PackedDataset(torch.utils.data.Dataset):
     """`split="train"` -> `(features, targets)`; `split="val"` -> `(features, targets, UserSummaries)`;
     `split="pretrain"` -> `(features, video_rep)`  (dataset.py:33-37, 127-135)."""
 
-    def __init__(self, path: str, split: str = "train", keys: Optional[Sequence[str]] = None, min_steps: int = 0):
+    def __init__(self, path: str, split: str = "train", keys: Optional[Sequence[str]] = None, min_steps: int = 0,
+                 resident: str = "mmap"):
+        """`resident="pinned"`: the file is read once into page-locked host memory, so that `PackedEvalLoader` can DMA
+        every batch straight out of the dataset (no host-side gather of the features / user summaries)."""
         self.path, self.split = path, split
+        if resident not in ("mmap", "pinned"):
+            raise ValueError("resident must be 'mmap' or 'pinned'")
         L = _cabi.load()
         h = C.c_void_p()
-        _cabi.check(L.vsum_pack_open(os.fsencode(path), C.byref(h)), "vsum_pack_open")
+        _cabi.check(L.vsum_pack_open_ex(os.fsencode(path), _cabi.PACK_PINNED if resident == "pinned" else _cabi.PACK_MMAP,
+                                        C.byref(h)), "vsum_pack_open_ex")
+        self.resident = resident
         self._h, self._L = h, L
         self.feature_dim = int(L.vsum_pack_feature_dim(h))
         self.features_bf16 = int(L.vsum_pack_feature_dtype(h)) == _cabi.FEATURES_BF16

@@ -78,7 +78,8 @@ class DeviceBatch:
 
 class _Slot:
     def __init__(self):
-        self.scores = None      # fp32 [T,1] score buffer owned by the slot
+        self.buf = None         # fp32 [>=T,1] score buffer owned by the slot
+        self.scores = None      # its [:T] view for the current batch
         self.done = None        # event: evaluation of the batch that last used this slot finished
         self.f_host = None      # pinned fp64 [B] landing buffer (end-to-end path)
         self.copied = None      # event: H2D of this slot finished
@@ -136,16 +137,22 @@ class Summarizer:
         return torch.cuda.current_stream(dev), self._side, self._copy
 
     def _slot(self, slot: int, db: DeviceBatch) -> _Slot:
+        """Per-slot score buffer, grow-only (batches of different sizes share it through a [:T] view)."""
         st = self._slots.setdefault(slot, _Slot())
         T = db.features.shape[0]
-        if st.scores is None or st.scores.shape[0] != T or st.scores.device != db.features.device:
-            st.scores = torch.empty((T, 1), dtype=torch.float32, device=db.features.device)
+        if st.buf is None or st.buf.shape[0] < T or st.buf.device != db.features.device:
+            if st.buf is not None and self._side is not None:
+                st.buf.record_stream(self._side)              # the evaluation stream may still read the outgrown buffer
+            st.buf = torch.empty((int(T * 1.25) + 1, 1), dtype=torch.float32, device=db.features.device)
+        st.scores = st.buf[:T]
         return st
 
     @torch.no_grad()
-    def submit_device(self, db: DeviceBatch, slot: int) -> torch.Tensor:
-        """Queue one resident batch.  Returns the per-video F tensor, valid after `drain()` (or
-        after waiting on the slot).  Use two slots alternately."""
+    def submit_device(self, db: DeviceBatch, slot: int, to_host: bool = False) -> torch.Tensor:
+        """Queue one resident batch (a `DeviceBatch`, or an `EvalBatch` from `data.PackedEvalLoader`, whose device slot
+        is handed back to the loader when the evaluation has consumed it).  Returns the per-video F tensor, valid after
+        `drain()` (or after waiting on the slot); with `to_host` the F-scores are also copied into a pinned fp64 buffer
+        on the side stream and THAT tensor is returned.  Use two slots alternately."""
         dev = db.features.device
         main, side, _ = self._streams(dev)
         st = self._slot(slot, db)
@@ -161,8 +168,16 @@ class Summarizer:
         with torch.cuda.stream(side):
             side.wait_event(ready)
             f = _engine.summarize(db.meta, st.scores.view(-1), db.cu_steps, self.eval_method)["f"]
+            if to_host:
+                if st.f_host is None or st.f_host.shape[0] < f.shape[0]:
+                    st.f_host = torch.empty(f.shape[0], dtype=torch.float64, pin_memory=True)
+                out = st.f_host[:f.shape[0]]
+                out.copy_(f, non_blocking=True)
+                f = out
             st.done = torch.cuda.Event()
             st.done.record(side)
+        if hasattr(db, "release"):
+            db.release(st.done)
         return f
 
     @torch.no_grad()
@@ -180,13 +195,14 @@ class Summarizer:
             st.copied = torch.cuda.Event()
             st.copied.record(copy)
         f = self.submit_device(db, slot)
-        if st.f_host is None or st.f_host.shape[0] != f.shape[0]:
+        if st.f_host is None or st.f_host.shape[0] < f.shape[0]:
             st.f_host = torch.empty(f.shape[0], dtype=torch.float64, pin_memory=True)
+        out = st.f_host[:f.shape[0]]
         with torch.cuda.stream(side):
-            st.f_host.copy_(f, non_blocking=True)
+            out.copy_(f, non_blocking=True)
             st.done = torch.cuda.Event()
             st.done.record(side)
-        return st.f_host
+        return out
 
     def drain(self, dev=None) -> None:
         """Make the current stream wait for everything queued on the side / copy streams."""
