@@ -77,7 +77,7 @@ class EvalBatch:
         self.h2d_bytes = int(lay.blob_bytes) + T * slot.features.shape[1] * slot.features.element_size() + \
             int(lay.us_elems) * (slot.users.element_size() if has_users else 0)
         self.ready: Optional[torch.cuda.Event] = None
-        self.collate_ms = 0.0
+        self.collate_ms = self.issue_ms = 0.0
 
     def wait(self):
         """Make the current stream wait for this batch's host-to-device copies."""
@@ -137,6 +137,7 @@ class PackedEvalLoader:
                                  torch.bfloat16 if dataset.features_bf16 else torch.float32,
                                  torch.uint8 if u8 else torch.float32) for _ in range(max(2, int(slots)))]
         self.collate_ms: List[float] = []
+        self.issue_ms: List[float] = []
 
     def __len__(self):
         return len(self._batches)
@@ -155,6 +156,8 @@ class PackedEvalLoader:
         _cabi.check(self._L.vsum_pack_eval_collate(self.ds._h, raw.ctypes.data, len(ids), slot.blob_host.data_ptr(),
                                                    slot.blob_host.numel(), C.byref(lay)), "vsum_pack_eval_collate")
         b = EvalBatch(slot, lay, ids, self.ds.names)
+        b.collate_ms = (time.perf_counter() - t0) * 1e3          # host time of the metadata gather
+        t1 = time.perf_counter()
         with torch.cuda.stream(self._stream):
             if slot.free_event is not None:
                 self._stream.wait_event(slot.free_event)          # the previous batch of this slot has been consumed
@@ -166,7 +169,7 @@ class PackedEvalLoader:
                                               self._stream.cuda_stream), "vsum_pack_h2d")
             b.ready = torch.cuda.Event()
             b.ready.record(self._stream)
-        b.collate_ms = (time.perf_counter() - t0) * 1e3          # host time of one batch: metadata gather + issuing the copies
+        b.issue_ms = (time.perf_counter() - t1) * 1e3            # issuing the copies (blocks while the stream's queue is full)
         return b
 
     def __iter__(self):
@@ -207,6 +210,7 @@ class PackedEvalLoader:
                 if isinstance(item, BaseException):
                     raise item
                 self.collate_ms.append(item.collate_ms)
+                self.issue_ms.append(item.issue_ms)
                 prev = item
                 yield item.wait()
         finally:
