@@ -175,6 +175,9 @@ class PackedEvalLoader:
     def __iter__(self):
         q: "queue.Queue" = queue.Queue(maxsize=max(1, len(self._slots) - 1))
         stop = threading.Event()
+        for slot in self._slots:          # slots of batches a previous (closed) iteration prepared but never handed out:
+            if not slot.free.is_set():    # their copies sit on the loader's stream, ahead of anything issued from now on
+                slot.free.set()
 
         def worker():
             try:
