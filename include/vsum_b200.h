@@ -359,6 +359,14 @@ VSUM_API int vsum_pack_h2d(vsum_pack_t pack, const void *blob_host, const vsum_e
  *     src/model/simnet.py:155-161.  The environment variable VSUM_ATTN_KERNEL sets the initial value.
  * ------------------------------------------------------------------------------------------ */
 VSUM_API int vsum_set_attention_kernel(int32_t version);
+/* Feed-forward block of an encoder layer (src/model/simnet.py:180-183 + 109-110): 2 (default) = ONE kernel for
+ * fc1 + ReLU + fc2 + residual + LayerNorm (+ regression head on the last layer), the [T,1024] hidden rows never leave the
+ * SM (csrc/vsum_ffn_tc05.cu); 1 = two GEMM launches with the hidden rows in HBM.  VSUM_FFN_KERNEL sets the initial value.
+ *   vsum_debug_ffn_tc05: out[M,256] bf16 = LayerNorm(relu(x W1^T + b1) W2^T + b2 + x) * gamma + beta; x [M,256],
+ *   W1 [1024,256], W2 [256,1024] bf16, biases / gamma / beta fp32. */
+VSUM_API int vsum_set_ffn_kernel(int32_t version);
+VSUM_API int vsum_debug_ffn_tc05(const void *x_bf16, const void *w1_bf16, const float *b1, const void *w2_bf16, const float *b2,
+                                 const float *gamma, const float *beta, void *out_bf16, int64_t M, void *stream);
 VSUM_API size_t vsum_attention_scratch_ints(int64_t T, int32_t B);
 VSUM_API int vsum_debug_gemm_tc05(const void *A, const void *W, const float *bias, const void *residual_bf16,
                          const float *gamma, const float *beta, void *out_bf16, int64_t M, int32_t N,

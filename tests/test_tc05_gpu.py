@@ -64,6 +64,33 @@ def test_gemm_residual_layernorm(M, K):
     torch.testing.assert_close(got, want, rtol=2e-2, atol=3e-2)
 
 
+@pytest.mark.parametrize("M", [128, 1, 127, 333, 4096, 40000, 148 * 128 * 3 + 5])
+def test_fused_ffn(M):
+    """simnet.py:180-183 + 109-110 in one kernel (vsum_ffn_tc05.cu): LayerNorm(relu(x W1^T + b1) W2^T + b2 + x) against
+    PyTorch fp32 on the same bf16-rounded operands, with the hidden activation rounded to bf16 where the kernel rounds
+    it (it is the bf16 A operand of the second product).  Ragged M: partial last tile, fewer tiles than CTAs, several
+    tiles per CTA."""
+    g = torch.Generator(device="cuda").manual_seed(M)
+    x = torch.randn((M, 256), device="cuda", generator=g).bfloat16()
+    w1 = (torch.randn((1024, 256), device="cuda", generator=g) / 16).bfloat16()
+    w2 = (torch.randn((256, 1024), device="cuda", generator=g) / 32).bfloat16()
+    b1 = torch.randn(1024, device="cuda", generator=g) * 0.5
+    b2 = torch.randn(256, device="cuda", generator=g)
+    gamma = 1 + 0.1 * torch.randn(256, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(256, device="cuda", generator=g)
+    hid = (x.float() @ w1.float().t() + b1).relu().bfloat16().float()
+    want = torch.nn.functional.layer_norm(hid @ w2.float().t() + b2 + x.float(), (256,), gamma, beta)
+    out = torch.full((M, 256), float("nan"), device="cuda").bfloat16()
+    L = _cabi.load()
+    _cabi.check(L.vsum_debug_ffn_tc05(x.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), gamma.data_ptr(),
+                                      beta.data_ptr(), out.data_ptr(), M, torch.cuda.current_stream().cuda_stream), "vsum_debug_ffn_tc05")
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out.float(), want, rtol=2e-2, atol=3e-2)
+    # and the two-launch form it replaces agrees to bf16 rounding of the output
+    two = gemm(gemm(x, w1, b1, 1).bfloat16(), w2, b2, 3, x, gamma, beta)
+    torch.testing.assert_close(out.float(), two, rtol=2e-2, atol=3e-2)
+
+
 def attention_ref(qkv, lens):
     out = torch.empty((qkv.shape[0], 256), device="cuda")
     off = 0

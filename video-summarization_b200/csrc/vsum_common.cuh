@@ -21,6 +21,7 @@ int set_error(int code, const char *fmt, ...);
 void count_launch(int n = 1);
 int eval_sm_budget();       // 0 = unlimited; else the evaluation kernels keep at most this many SMs busy
 int scorer_sm_reserve();    // persistent scorer GEMMs leave this many SMs free
+int ffn_kernel_version();         // 2 = fused fc1 + ReLU + fc2 + residual + LayerNorm kernel (default), 1 = two GEMM launches
 int attention_kernel_version();   // 2 = persistent two-query-tile forward kernel (default), 1 = one 128-query tile per CTA
 
 #define VSUM_CUDA_OK(expr)                                                                      \
@@ -62,7 +63,7 @@ int attention_kernel_version();   // 2 = persistent two-query-tile forward kerne
 
 // Optional per-kernel timing with CUDA events on the launching stream (vsum_profile_begin/end).
 enum ProfCategory {
-    PROF_EMBED = 0, PROF_QKV, PROF_ATTN, PROF_OPROJ_LN, PROF_FC1, PROF_FC2_LN, PROF_SHOT_MEAN, PROF_KNAPSACK,
+    PROF_EMBED = 0, PROF_QKV, PROF_ATTN, PROF_OPROJ_LN, PROF_FC1, PROF_FC2_LN, PROF_FFN, PROF_SHOT_MEAN, PROF_KNAPSACK,
     PROF_MASK, PROF_OVERLAP, PROF_FSCORE, PROF_OTHER, PROF_NUM
 };
 struct ProfScope {

@@ -42,6 +42,19 @@ int attention_kernel_version() {
     return v;
 }
 
+// Feed-forward block: 2 = fused kernel (vsum_ffn_tc05.cu, default), 1 = fc1 and fc2 + LayerNorm as two GEMM launches.
+// VSUM_FFN_KERNEL in the environment overrides the default at first use.
+static std::atomic<int> g_ffn_kernel{0};
+int ffn_kernel_version() {
+    int v = g_ffn_kernel.load(std::memory_order_relaxed);
+    if (v == 0) {
+        const char *e = getenv("VSUM_FFN_KERNEL");
+        v = (e && e[0] == '1') ? 1 : 2;
+        g_ffn_kernel.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
 // ---- profiling -------------------------------------------------------------------------------
 struct ProfRecord { int cat; cudaEvent_t a, b; };
 static std::mutex g_prof_mu;
@@ -66,7 +79,7 @@ ProfScope::~ProfScope() {
 }
 
 static const char *kProfNames[PROF_NUM] = {"embed_gemm", "qkv_gemm", "attention", "oproj_ln_gemm", "fc1_gemm",
-                                           "fc2_ln_gemm", "shot_mean", "knapsack", "summary_mask", "overlap",
+                                           "fc2_ln_gemm", "ffn_fused", "shot_mean", "knapsack", "summary_mask", "overlap",
                                            "fscore_finalize", "other"};
 
 }  // namespace vsum
@@ -107,6 +120,12 @@ extern "C" int vsum_set_sm_partition(int32_t eval_sms, int32_t scorer_reserved_s
 extern "C" int vsum_set_attention_kernel(int32_t version) {
     VSUM_REQUIRE(version == 1 || version == 2, VSUM_EINVAL, "vsum_set_attention_kernel: version %d (1 or 2)", version);
     vsum::g_attn_kernel.store(version);
+    return VSUM_OK;
+}
+
+extern "C" int vsum_set_ffn_kernel(int32_t version) {
+    VSUM_REQUIRE(version == 1 || version == 2, VSUM_EINVAL, "vsum_set_ffn_kernel: version %d (1 or 2)", version);
+    vsum::g_ffn_kernel.store(version);
     return VSUM_OK;
 }
 

@@ -138,6 +138,21 @@ struct Tc05GemmArgs {
 };
 int launch_gemm_tc05(const Tc05GemmArgs &a, cudaStream_t s);
 
+// Fused feed-forward block (vsum_ffn_tc05.cu): out = LN(relu(x W1^T + b1) W2^T + b2 + x) * gamma + beta, d_model 256,
+// d_ff 1024; head_w/head_b/scores_out (+ feats_out) as in the HEAD epilogue above; out may be NULL then.
+struct Tc05FfnArgs {
+    const __nv_bfloat16 *x;      // [M,256] bf16 (also the residual)
+    const __nv_bfloat16 *w1;     // [1024,256]
+    const __nv_bfloat16 *w2;     // [256,1024]
+    const float *b1, *b2, *gamma, *beta;
+    int64_t M;
+    __nv_bfloat16 *out;          // [M,256] or NULL
+    const float *head_w, *head_b;
+    float *scores_out, *feats_out;
+    int apply_sigmoid;
+};
+int launch_ffn_tc05(const Tc05FfnArgs &a, cudaStream_t s);
+
 // qkv [T,768] bf16 -> out [T,256] bf16, d_model 256, 4 heads of 64, scale = 1/16
 // lse2 != NULL: training variant (log2-domain log-sum-exp [T,4] out, dropout on P with the grouped hash,
 // `out` is then fp32 [T,256] instead of bf16)

@@ -249,6 +249,15 @@ static int forward_bf16(vsum_scorer_t h, const void *x, bool x_is_bf16, const in
         p.bias = h->w32 + o.bo; p.residual = w.xa; p.gamma = h->w32 + o.ln1g; p.beta = h->w32 + o.ln1b; p.out = w.xb;
         p.prof_cat = PROF_OPROJ_LN;
         RUN(launch_gemm_tc05(p, s));
+        if (ffn_kernel_version() == 2) {   // fc1 + ReLU + fc2 + residual + LayerNorm (+ head) in one kernel: the hidden rows stay on the SM
+            Tc05FfnArgs f{};
+            f.x = w.xb; f.w1 = h->w16 + o.h_fc1; f.w2 = h->w16 + o.h_fc2; f.b1 = h->w32 + o.fc1b; f.b2 = h->w32 + o.fc2b;
+            f.gamma = h->w32 + o.ln2g; f.beta = h->w32 + o.ln2b; f.M = T; f.out = last ? nullptr : w.xa;
+            if (last) { f.head_w = h->w32 + h->final_w; f.head_b = h->w32 + h->final_b; f.scores_out = scores; f.feats_out = feats; }
+            f.apply_sigmoid = sigm;
+            RUN(launch_ffn_tc05(f, s));
+            continue;
+        }
         Tc05GemmArgs f1{};
         f1.A = w.xb; f1.W = h->w16 + o.h_fc1; f1.M = T; f1.N = 1024; f1.K = 256; f1.epi = TC_EPI_BIAS_RELU;
         f1.bias = h->w32 + o.fc1b; f1.out = w.hid; f1.prof_cat = PROF_FC1;
@@ -580,6 +589,15 @@ extern "C" int vsum_debug_gemm_tc05(const void *A, const void *W, const float *b
     if (epi >= TC_EPI_BIAS_F32) g.out_f32 = (float *)out; else
     g.out = (__nv_bfloat16 *)out; g.residual = (const __nv_bfloat16 *)residual; g.gamma = gamma; g.beta = beta;
     return launch_gemm_tc05(g, (cudaStream_t)stream);
+}
+
+extern "C" int vsum_debug_ffn_tc05(const void *x, const void *w1, const float *b1, const void *w2, const float *b2,
+                                   const float *gamma, const float *beta, void *out, int64_t M, void *stream) {
+    VSUM_REQUIRE(x && w1 && b1 && w2 && b2 && gamma && beta && out, VSUM_EINVAL, "vsum_debug_ffn_tc05: null pointer");
+    Tc05FfnArgs f{};
+    f.x = (const __nv_bfloat16 *)x; f.w1 = (const __nv_bfloat16 *)w1; f.w2 = (const __nv_bfloat16 *)w2; f.b1 = b1; f.b2 = b2;
+    f.gamma = gamma; f.beta = beta; f.M = M; f.out = (__nv_bfloat16 *)out;
+    return launch_ffn_tc05(f, (cudaStream_t)stream);
 }
 
 extern "C" int vsum_debug_wgrad_tc05(const float *dY, const float *X, float *dW, float *db, int64_t M, int32_t N,

@@ -27,6 +27,7 @@ EXPORTS = (
     "vsum_scorer_set_train_mode", "vsum_scorer_tape_bytes", "vsum_scorer_train_workspace_bytes", "vsum_scorer_forward_train",
     "vsum_scorer_backward", "vsum_masked_mse",
     "vsum_debug_gemm_tc05", "vsum_debug_wgrad_tc05", "vsum_debug_attention_tc05", "vsum_debug_attention_scaled_tc05", "vsum_set_attention_kernel", "vsum_attention_scratch_ints",
+    "vsum_set_ffn_kernel", "vsum_debug_ffn_tc05",
     "vsum_debug_attention_train_tc05", "vsum_debug_attention_bwd_tc05",
     "vsum_linear_workspace_bytes", "vsum_linear_forward", "vsum_linear_backward",
     "vsum_kts_workspace_bytes", "vsum_kts_gram", "vsum_kts_dp",
@@ -136,6 +137,8 @@ def load():
     L.vsum_debug_attention_tc05.argtypes = [vp, vp, i32, i64, vp, vp, vp]
     L.vsum_debug_attention_scaled_tc05.argtypes = [vp, vp, i32, i64, C.c_float, vp, vp, vp]
     L.vsum_set_attention_kernel.argtypes = [i32]
+    L.vsum_set_ffn_kernel.argtypes = [i32]
+    L.vsum_debug_ffn_tc05.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
     L.vsum_attention_scratch_ints.argtypes = [i64, i32]
     L.vsum_attention_scratch_ints.restype = C.c_size_t
     L.vsum_debug_attention_train_tc05.argtypes = [vp, vp, i32, i64, vp, vp, C.c_float, C.c_uint64, vp, vp]
