@@ -316,6 +316,99 @@ def write_bench_pack(path, videos, feats_of, compact):
     write_pack(path, gen(), user_summary_u8=compact, features_bf16=compact)
 
 
+def train_records(world, rank, dev, steps=20, warmup=5):
+    """BASELINE configs 3 and 4 beside the headline: one training step = forward with activation tape + masked MSE + backward
+    through the C ABI + per-layer gradient all-reduce from a communication stream (world > 1) + fused Adam.  finetune: 4
+    videos / GPU of 200-400 frames (run_finetune.sh); pretrain-shaped: 8 videos / GPU of 2048 frames.  Features resident on
+    the device, CUDA events, max over ranks; weak scaling.  At world > 1 the data-parallel step is also checked against the
+    single-process step on the concatenated batch (rank 0 regenerates every shard)."""
+    import torch
+    import torch.distributed as dist
+    from vsum_b200 import _cabi
+    from vsum_b200.model import SimNet
+    from vsum_b200.sharding import DataParallel, scorer_cost
+    from vsum_b200.utils import mse_with_mask_loss
+
+    def shard(cfg, r):
+        rng = np.random.default_rng(99 + r)
+        lens = [int(n) for n in (rng.integers(200, 401, 4) if cfg == "finetune" else [2048] * 8)]
+        g = torch.Generator(device=dev).manual_seed(7 + r)
+        T = sum(lens)
+        feats = torch.randn((T, 1024), device=dev, generator=g)
+        tgt = torch.rand((1, T), device=dev, generator=g)
+        cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device=dev)
+        return lens, feats, tgt, cu
+
+    out = {}
+    for cfg in ("finetune", "pretrain_8x2048"):
+        lens, feats, tgt, cu = shard(cfg, rank)
+        T, bs = sum(lens), len(lens)
+        nopad = torch.zeros((1, T), dtype=torch.bool, device=dev)
+        torch.manual_seed(1234)
+        model = SimNet(**MODEL_KW).to(dev).train()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+        ddp = DataParallel(model)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            o, _ = model.forward_packed_train(feats, cu, lens)
+            ddp.loss(o.view(1, T, 1), tgt, nopad, batch=bs, nmax=max(lens)).backward()
+            loss = ddp.finish()
+            opt.step()
+            return loss
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        n0 = _cabi.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+        launches = (_cabi.launch_count() - n0) // steps
+        v = torch.tensor([e0.elapsed_time(e1) / steps, float(T), float(bs), sum(scorer_cost(n) for n in lens)], dtype=torch.float64, device=dev)
+        if world > 1:
+            mx = v.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(v, op=dist.ReduceOp.SUM)
+            v[0] = mx[0]
+        t_ms, frames, videos, fwd = (float(x) for x in v.tolist())
+        rec = {"ms_per_step": t_ms, "frames_per_s": frames / t_ms * 1e3, "videos_per_s": videos / t_ms * 1e3,
+               "train_tflops": 3.0 * fwd / t_ms / 1e9, "kernel_launches_per_step": int(launches), "final_loss": float(loss),
+               "steps": steps, "warmup": warmup, "dtype": "bf16 (tcgen05 linears tf32/bf16, attention bf16; fp32 master weights)"}
+        if world > 1 and cfg == "finetune":
+            # equality with the single-process step: dropout off, DP gradient vs rank 0's gradient on the concatenated batch
+            model.eval()
+            opt.zero_grad(set_to_none=True)
+            o, _ = model.forward_packed_train(feats, cu, lens)
+            ddp.loss(o.view(1, T, 1), tgt, nopad, batch=bs, nmax=max(lens)).backward()
+            ddp.finish()
+            got = torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone()
+            ddp.detach()
+            err = torch.zeros(1, device=dev)
+            if rank == 0:
+                parts = [shard(cfg, r) for r in range(world)]
+                all_lens = [n for p_ in parts for n in p_[0]]
+                f_all, t_all = torch.cat([p_[1] for p_ in parts]), torch.cat([p_[2] for p_ in parts], dim=1)
+                cu_all = torch.tensor(np.concatenate([[0], np.cumsum(all_lens)]), dtype=torch.int32, device=dev)
+                model.zero_grad(set_to_none=True)
+                o, _ = model.forward_packed_train(f_all, cu_all, all_lens)
+                mse_with_mask_loss(o.view(1, -1, 1), t_all, torch.zeros_like(t_all, dtype=torch.bool),
+                                   denom=float(len(all_lens) * max(all_lens))).backward()
+                want = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+                err[0] = (got - want).abs().max() / want.abs().max()
+            dist.broadcast(err, 0)
+            rec["dp_equals_single_process"] = {"max_abs_err_over_max_abs_grad": float(err), "ok": bool(float(err) < 2e-4),
+                                               "what": "all-reduced gradient of the sharded batch vs rank 0's gradient of the concatenated batch (dropout off)"}
+        ddp.detach()
+        out[cfg] = rec
+        del model, opt, ddp
+    return out
+
+
 def main_b200(args):
     import torch
     import torch.distributed as dist
@@ -502,6 +595,8 @@ def main_b200(args):
     probe_all = [float(x.item()) for x in probe_all]
     del src, dst
 
+    train = None if args.no_train else train_records(world, rank, dev)
+
     if world > 1:
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
         dist.all_reduce(lt)
@@ -531,7 +626,7 @@ def main_b200(args):
         kernel_ms = {k: round(v[0], 4) for k, v in prof_alone.items() if v[1]}
         kernel_ms_pipelined = {k: round(v[0] / args.steps, 4) for k, v in prof.items() if v[1]}
         gpu_ms = sum(kernel_ms.values())
-        scorer_ms = sum(v for k, v in kernel_ms.items() if k in ("embed_gemm", "qkv_gemm", "attention", "oproj_ln_gemm", "fc1_gemm", "fc2_ln_gemm", "ffn_gemm"))
+        scorer_ms = sum(v for k, v in kernel_ms.items() if k in ("embed_gemm", "qkv_gemm", "attention", "oproj_ln_gemm", "fc1_gemm", "fc2_ln_gemm", "ffn_fused"))
         m = hb.meta
         cells = float(sum((int(m.cu_shots[i + 1]) - int(m.cu_shots[i])) * (int((int(m.sum_offsets[i + 1]) - int(m.sum_offsets[i])) * 0.15) + 1)
                           for i in range(m.B)))
@@ -579,6 +674,7 @@ def main_b200(args):
             "kernel_ms_per_step_source": "one non-pipelined pass on a single stream (no contention between the scorer and the evaluation stream)",
             "kernel_ms_per_step_pipelined": kernel_ms_pipelined,
             "eval_kernels": ev,
+            "train": train,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], _ = run_cpu_baseline(1, 0, gpu_eager=True)
@@ -596,6 +692,7 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--videos", type=int, default=256, help="videos per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step sub-record (BASELINE configs 3 and 4)")
     ap.add_argument("--e2e-batches", type=int, default=4, help="distinct batches in the end-to-end legs' pack file (reduced when host memory is short)")
     ap.add_argument("--eval-sms", type=int, default=0, help="SMs left to the evaluation stream in pipelined mode (0 = no partition)")
     ap.add_argument("--len-lo", type=int, default=N_LO, help="shortest video (frames); default = BASELINE config 5")

@@ -39,8 +39,8 @@ def _model():
     return SimNet(num_heads=4, d_model=256, num_layers=2, sparsity=0., dropout=0.0)
 
 
-def _worker(rank, world, port, ret):
-    from vsum_b200.sharding import allreduce_gradients, global_loss_denominator
+def _worker(rank, world, port, ret, overlapped=False):
+    from vsum_b200.sharding import DataParallel, allreduce_gradients, global_loss_denominator
     from vsum_b200.utils import mse_with_mask_loss
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
@@ -49,23 +49,31 @@ def _worker(rank, world, port, ret):
     x, t = _batch(LENS[rank], 1300 + 10 * rank)
     x, t = x.cuda(), t.cuda()
     mask = x[:, :, 0] == 1000
-    denom = global_loss_denominator(x.shape[0], x.shape[1])
-    pred, _ = model(x, mask)
-    loss = mse_with_mask_loss(pred, t, mask, denom=denom)
-    loss.backward()
-    allreduce_gradients(model.parameters())
+    if overlapped:          # per-layer buckets from a communication stream, denominator derived on the device
+        ddp = DataParallel(model)
+        pred, _ = model(x, mask)
+        ddp.loss(pred, t, mask).backward()
+        ret[f"loss{rank}"] = float(ddp.finish())
+    else:
+        denom = global_loss_denominator(x.shape[0], x.shape[1])
+        pred, _ = model(x, mask)
+        loss = mse_with_mask_loss(pred, t, mask, denom=denom)
+        loss.backward()
+        allreduce_gradients(model.parameters())
+    torch.cuda.synchronize()
     ret[rank] = {k: p.grad.cpu().numpy() for k, p in model.named_parameters()}
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_rank_step_equals_single_process_step():
+@pytest.mark.parametrize("overlapped", [False, True], ids=["flat_allreduce", "bucketed_overlapped"])
+def test_two_rank_step_equals_single_process_step(overlapped):
     from vsum_b200.utils import mse_with_mask_loss
     port = _free_port()
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, ret, overlapped), nprocs=2, join=True)
     # single process, concatenated batch padded to the global maximum
     model = _model().cuda().train()
     lens = LENS[0] + LENS[1]
@@ -79,7 +87,11 @@ def test_two_rank_step_equals_single_process_step():
     x, t = torch.cat(xs).cuda(), torch.cat(ts).cuda()
     mask = x[:, :, 0] == 1000
     pred, _ = model(x, mask)
-    mse_with_mask_loss(pred, t, mask).backward()
+    single = mse_with_mask_loss(pred, t, mask)
+    single.backward()
+    if overlapped:
+        for rank in (0, 1):
+            assert abs(ret[f"loss{rank}"] - float(single)) <= 1e-5 * abs(float(single))
     for k, p in model.named_parameters():
         want = p.grad.cpu().numpy()
         for rank in (0, 1):

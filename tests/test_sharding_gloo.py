@@ -70,3 +70,33 @@ def test_gradient_allreduce_and_global_denominator_two_ranks():
         grads, denom = ret[rank]
         assert grads == [3.0, 6.0]                      # (1 + 2) * (i + 1): summed over the two ranks
         assert denom == float((4 + 3) * 150)            # sum of batch sizes x max padded length
+
+
+def _extras_worker(rank, world, port, ret):
+    import torch
+    from vsum_b200.sharding import dp_denominator, dp_extras, global_loss_denominator
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    bs, nmax, loss_sum = 4 - rank, 100 + 50 * rank, 2.5 * (rank + 1)
+    ext = dp_extras(loss_sum, bs, nmax, rank, world)
+    dist.all_reduce(ext, op=dist.ReduceOp.SUM)
+    ret[rank] = (dp_denominator(ext), float(ext[0]), global_loss_denominator(bs, nmax))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dp_extras_give_the_global_denominator_from_one_sum_allreduce():
+    """DataParallel's host-sync-free normalisation: batch size and a one-hot Nmax ride a SUM all-reduce; the denominator
+    derived from them equals global_loss_denominator (two blocking collectives) on every rank."""
+    from vsum_b200.sharding import bucket_slices
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_extras_worker, args=(2, port, ret), nprocs=2, join=True)
+    for rank in (0, 1):
+        d, s, want = ret[rank]
+        assert d == want == float(7 * 150) and s == 7.5
+    sl = bucket_slices(embed_n=10, layer_n=7, num_layers=3, total=10 + 21 + 4)
+    assert sl == {2: (24, 35), 1: (17, 24), 0: (10, 17), -1: (0, 10)}        # the last layer's bucket carries the head
+    covered = sorted(sl.values())
+    assert covered[0][0] == 0 and covered[-1][1] == 35 and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))

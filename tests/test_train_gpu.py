@@ -232,3 +232,37 @@ def test_pretrain_loss_kernels_forward_backward(lens, pen_met):
     assert (y.double() - ref_y).abs().max().item() <= 5e-3 * ref_y.abs().max().item()
     for a, r in zip(tc_in, (gy.double() @ w, gy.double().t() @ feats, gy.double().sum(0))):
         assert (a.grad.double() - r).abs().max().item() <= 2e-2 * r.abs().max().item()
+
+
+def test_data_parallel_wrapper_single_rank_equals_plain_step():
+    """sharding.DataParallel without a process group (world 1): hooked backward, bucket events, vsum_dp_finalize -- gradients
+    and loss equal the plain step's (mse_with_mask_loss normalised by bs * Nmax, utils.py:55) up to the fp32 rounding of
+    scaling after instead of before the backward."""
+    from vsum_b200.model import SimNet
+    from vsum_b200.sharding import DataParallel
+    from vsum_b200.utils import mse_with_mask_loss
+    lens, nmax = (140, 90, 33), 140
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.full((3, nmax, 1024), 1000.0, device="cuda")
+    t = torch.full((3, nmax), 1000.0, device="cuda")
+    for b, n in enumerate(lens):
+        x[b, :n] = torch.rand((n, 1024), device="cuda", generator=g)
+        t[b, :n] = torch.rand(n, device="cuda", generator=g)
+    mask = x[:, :, 0] == 1000
+    torch.manual_seed(21)
+    model = SimNet(num_heads=4, d_model=256, num_layers=2, sparsity=0., dropout=0.0).cuda().train()
+    pred, _ = model(x, mask)
+    want_loss = mse_with_mask_loss(pred, t, mask)
+    want_loss.backward()
+    want = {k: p.grad.clone() for k, p in model.named_parameters()}
+    model.zero_grad(set_to_none=True)
+    ddp = DataParallel(model)
+    pred, _ = model(x, mask)
+    ddp.loss(pred, t, mask).backward()
+    loss = ddp.finish()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(want_loss)) <= 1e-6 * abs(float(want_loss)) + 1e-9
+    for k, p in model.named_parameters():
+        torch.testing.assert_close(p.grad, want[k], rtol=1e-5, atol=1e-7 + 1e-6 * float(want[k].abs().max()))
+    ddp.detach()
+    assert model._dp is None

@@ -438,10 +438,10 @@ extern "C" int vsum_scorer_forward_train(vsum_scorer_t h, const float *x, const 
     return VSUM_OK;
 }
 
-extern "C" int vsum_scorer_backward(vsum_scorer_t h, const float *x, const int32_t *cu, int32_t B, int64_t T,
-                                    int32_t max_len, float p, uint64_t seed, const float *d_scores, const float *d_feats,
-                                    const void *tape_mem, const vsum_scorer_grads *g, void *ws_mem, size_t ws_bytes,
-                                    void *stream) {
+static int scorer_backward_impl(vsum_scorer_t h, const float *x, const int32_t *cu, int32_t B, int64_t T,
+                                int32_t max_len, float p, uint64_t seed, const float *d_scores, const float *d_feats,
+                                const void *tape_mem, const vsum_scorer_grads *g, void *ws_mem, size_t ws_bytes,
+                                void *stream, vsum_grad_bucket_hook hook, void *hook_user) {
     VSUM_REQUIRE(h && h->loaded && g, VSUM_EINVAL, "vsum_scorer_backward: bad handle / grads");
     VSUM_REQUIRE(B > 0 && T > 0 && x && cu && d_scores && tape_mem && ws_mem, VSUM_EINVAL, "vsum_scorer_backward: bad argument");
     VSUM_REQUIRE(ws_bytes >= vsum_scorer_train_workspace_bytes(h, T, B), VSUM_ENOMEM, "vsum_scorer_backward: workspace too small");
@@ -505,10 +505,48 @@ extern "C" int vsum_scorer_backward(vsum_scorer_t h, const float *x, const int32
             VSUM_CUDA_OK(cudaMemcpyAsync(wdst[i], w.dwqkv + i * d * d, d * d * sizeof(float), cudaMemcpyDeviceToDevice, s));
             VSUM_CUDA_OK(cudaMemcpyAsync(bdst[i], w.dbqkv + i * d, d * sizeof(float), cudaMemcpyDeviceToDevice, s));
         }
+        if (hook) hook(hook_user, l);          // every gradient of layer l (and, for the last layer, of the head) is queued on `stream`
     }
     // x0 = features We^T + be (+ positions)
     RUN(lin_wgrad(h, w.a, x, g->embed_w, g->embed_b, T, (int)d, c.in_features, w.y16, w.x16, s));
+    if (hook) hook(hook_user, -1);
 #undef ZERO
+    return VSUM_OK;
+}
+
+extern "C" int vsum_scorer_backward(vsum_scorer_t h, const float *x, const int32_t *cu, int32_t B, int64_t T,
+                                    int32_t max_len, float p, uint64_t seed, const float *d_scores, const float *d_feats,
+                                    const void *tape_mem, const vsum_scorer_grads *g, void *ws_mem, size_t ws_bytes,
+                                    void *stream) {
+    return scorer_backward_impl(h, x, cu, B, T, max_len, p, seed, d_scores, d_feats, tape_mem, g, ws_mem, ws_bytes, stream, nullptr, nullptr);
+}
+
+extern "C" int vsum_scorer_backward_hooked(vsum_scorer_t h, const float *x, const int32_t *cu, int32_t B, int64_t T,
+                                           int32_t max_len, float p, uint64_t seed, const float *d_scores, const float *d_feats,
+                                           const void *tape_mem, const vsum_scorer_grads *g, void *ws_mem, size_t ws_bytes,
+                                           void *stream, vsum_grad_bucket_hook hook, void *hook_user) {
+    return scorer_backward_impl(h, x, cu, B, T, max_len, p, seed, d_scores, d_feats, tape_mem, g, ws_mem, ws_bytes, stream, hook, hook_user);
+}
+
+// Data-parallel step, last stage (after the SUM all-reduces): ext = [sum of squared errors, sum of batch sizes, Nmax of rank 0,
+// ..., Nmax of rank world-1] -> D = (sum of batch sizes) * (max Nmax), the padded size mse_with_mask_loss divides by
+// (src/utils/utils.py:55) for the GLOBAL batch; grads *= 1 / D, loss_out = ext[0] / D.
+namespace {
+__global__ void dp_finalize_kernel(float *__restrict__ grads, int64_t n, const float *__restrict__ ext, int world, float *__restrict__ loss_out) {
+    float nmax = 0.f;
+    for (int r = 0; r < world; ++r) nmax = fmaxf(nmax, ext[2 + r]);
+    const float inv = 1.0f / (ext[1] * nmax);
+    if (loss_out && blockIdx.x == 0 && threadIdx.x == 0) *loss_out = ext[0] * inv;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) grads[i] *= inv;
+}
+}  // namespace
+
+extern "C" int vsum_dp_finalize(float *grads, int64_t n, const float *ext, int32_t world, float *loss_out, void *stream) {
+    VSUM_REQUIRE(grads && ext && n >= 0 && world >= 1, VSUM_EINVAL, "vsum_dp_finalize: bad argument");
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(148 * 4, (n + 255) / 256));
+    dp_finalize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(grads, n, ext, world, loss_out);
+    VSUM_LAUNCH_OK("dp_finalize_kernel");
     return VSUM_OK;
 }
 #undef RUN

@@ -159,10 +159,20 @@ class _ScorerTrainFn(torch.autograd.Function):
             _cabi.check(L.vsum_scorer_set_train_mode(model._handle, model._train_mode()), "vsum_scorer_set_train_mode")
             ws = model._workspace_for(L.vsum_scorer_train_workspace_bytes(model._handle, T, B), dev)
             wp = _al(ws)
-            _cabi.check(L.vsum_scorer_backward(model._handle, features.data_ptr(), cu_seqlens.data_ptr(), B, T, max_len,
-                                               drop_p, seed, d_scores.data_ptr(), None if d_feats is None else d_feats.data_ptr(),
-                                               _al(tape), C.byref(g), wp, ws.numel() - (wp - ws.data_ptr()), stream),
-                        "vsum_scorer_backward")
+            args = (model._handle, features.data_ptr(), cu_seqlens.data_ptr(), B, T, max_len,
+                    drop_p, seed, d_scores.data_ptr(), None if d_feats is None else d_feats.data_ptr(),
+                    _al(tape), C.byref(g), wp, ws.numel() - (wp - ws.data_ptr()), stream)
+            dp = getattr(model, "_dp", None)
+            if dp is None:
+                _cabi.check(L.vsum_scorer_backward(*args), "vsum_scorer_backward")
+            else:
+                # data-parallel step (sharding.DataParallel): the flat buffer is all-reduced bucket by bucket on the communication
+                # stream while the backward of the earlier layers is still running
+                layer_n = sum(sizes[f"0.{f}"] for f in _cabi._LAYER_FIELDS)
+                embed_n = sizes["embed_w"] + sizes["embed_b"]
+                dp._begin(flat, embed_n, layer_n, model.num_layers)
+                hook = _cabi.GRAD_BUCKET_HOOK(lambda _user, bucket: dp._bucket_ready(int(bucket)))
+                _cabi.check(L.vsum_scorer_backward_hooked(*args, hook, None), "vsum_scorer_backward_hooked")
         return (None, None, None, None, None, None, *grads)
 
 
@@ -214,6 +224,7 @@ class SimNet(nn.Module):
         # attention, "fp32" = SIMT kernels at reference accuracy
         self.train_precision = os.environ.get("VSUM_TRAIN_PRECISION", "bf16" if tc05 else "fp32")
         self._handle = None
+        self._dp = None                      # sharding.DataParallel attaches itself here
         self._weights_key = None
         self._table: Optional[Tensor] = None
         self._workspace: Optional[Tensor] = None

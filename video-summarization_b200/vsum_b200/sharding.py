@@ -111,3 +111,130 @@ def allreduce_gradients(params, group=None, average: bool = False) -> None:
         n = p.grad.numel()
         p.grad.copy_(flat[off:off + n].view_as(p.grad))
         off += n
+
+
+# ---------------------------------------------------------------------------------------------
+# data-parallel training step that overlaps: per-layer gradient buckets, no host round trip
+# ---------------------------------------------------------------------------------------------
+def bucket_slices(embed_n: int, layer_n: int, num_layers: int, total: int):
+    """Slices of the flat gradient buffer ([embedding | layer 0 | ... | layer L-1 | head], the layout
+    `_ScorerTrainFn.backward` hands out) in the order the backward completes them: bucket L-1 (with the head's
+    two tensors, adjacent in memory and finished first), L-2, ..., 0, then -1 = the embedding."""
+    out = {}
+    for l in range(num_layers - 1, -1, -1):
+        lo = embed_n + l * layer_n
+        out[l] = (lo, total if l == num_layers - 1 else lo + layer_n)
+    out[-1] = (0, embed_n)
+    return out
+
+
+def dp_extras(loss_sum, batch: int, nmax: int, rank: int, world: int) -> torch.Tensor:
+    """[sum of squared errors, batch size, Nmax one-hot over ranks]: after a SUM all-reduce every rank holds the global
+    sum, the global batch size and every rank's Nmax, so the padded-size denominator of `mse_with_mask_loss`
+    (src/utils/utils.py:55) for the GLOBAL batch comes out of the same kind of collective as the gradients."""
+    ext = torch.zeros(2 + world, dtype=torch.float32)
+    ext[0], ext[1], ext[2 + rank] = float(loss_sum), float(batch), float(nmax)
+    return ext
+
+
+def dp_denominator(ext_reduced: torch.Tensor) -> float:
+    """(sum of batch sizes) * (max Nmax) from SUM-reduced `dp_extras` (what vsum_dp_finalize computes on the device)."""
+    return float(ext_reduced[1]) * float(ext_reduced[2:].max())
+
+
+class DataParallel:
+    """Data-parallel wrapper of a `SimNet` for the training step of `src/train.py:111-131` on several GPUs (one process
+    per GPU, NCCL).  Equal to the single-process step on the concatenated batch, like `allreduce_gradients` +
+    `global_loss_denominator`, but
+
+    * the gradient all-reduce is issued PER LAYER from a communication stream as `vsum_scorer_backward_hooked` finishes
+      queuing each layer (the last layer's bucket also carries the head), so only the embedding bucket is exposed;
+    * nothing synchronises the host: every rank back-propagates the UN-normalised sum of squared errors, the global
+      denominator (sum of batch sizes) x (max Nmax) is derived on the device from extras that ride a SUM all-reduce of
+      their own, and `vsum_dp_finalize` scales the reduced gradients and the loss.
+
+        ddp = DataParallel(model)
+        out, _ = model(x, mask); ddp.loss(out, targets, mask).backward(); loss = ddp.finish(); optimizer.step()
+    """
+
+    def __init__(self, model, group=None):
+        from . import _cabi
+        self.model, self.group = model, group
+        self.active = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if self.active else 1
+        self.rank = dist.get_rank(group) if self.active else 0
+        self.device = next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise _cabi.VsumError("DataParallel needs the model on a CUDA device (no CPU fallback)")
+        self._comm = torch.cuda.Stream(self.device)
+        self._ext_host = torch.zeros(2 + self.world, dtype=torch.float32, pin_memory=True)
+        self._ext = torch.zeros(2 + self.world, dtype=torch.float32, device=self.device)
+        self._loss_out = torch.zeros((), dtype=torch.float32, device=self.device)
+        self._flat = None
+        self._works, self._error = [], None
+        model._dp = self
+
+    def detach(self):
+        self.model._dp = None
+
+    def loss(self, output, targets, mask, batch: int = None, nmax: int = None):
+        """Sum of squared errors of this rank's valid frames (what `.backward()` starts from); `finish()` returns the
+        global masked MSE.  `mask` bool [bs, Nmax], True = padded frame; callers that hold packed rows instead of a padded
+        batch pass `batch` (videos) and `nmax` (longest video) explicitly."""
+        from .utils import mse_with_mask_loss
+        s = mse_with_mask_loss(output, targets, mask, denom=1.0)
+        self._ext_host.zero_()
+        self._ext_host[1] = float(mask.shape[0] if batch is None else batch)
+        self._ext_host[2 + self.rank] = float(mask.shape[1] if nmax is None else nmax)
+        self._ext.copy_(self._ext_host, non_blocking=True)
+        self._ext[0:1].copy_(s.detach().view(1))
+        return s
+
+    # ---- called from _ScorerTrainFn.backward -------------------------------------------------
+    def _begin(self, flat, embed_n, layer_n, num_layers):
+        self._flat = flat
+        self._slices = bucket_slices(embed_n, layer_n, num_layers, flat.numel())
+        self._works, self._error = [], None
+        self._reduce(self._ext)                                    # extras first: ready before the backward starts
+
+    def _reduce(self, tensor):
+        main = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        if self.world == 1:
+            return
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(ev)
+            self._works.append(dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def _bucket_ready(self, bucket: int):
+        try:                                                        # (an exception must not unwind through the C caller)
+            lo, hi = self._slices[bucket]
+            self._reduce(self._flat[lo:hi])
+        except BaseException as e:
+            self._error = e
+
+    def finish(self) -> torch.Tensor:
+        """Queues the end of the step: wait for the bucket all-reduces on the communication stream, scale gradients and
+        loss by the global denominator there, make the current stream wait.  Returns the global loss (device scalar)."""
+        from . import _cabi
+        if self._error is not None:
+            raise self._error
+        if self._flat is None:
+            raise _cabi.VsumError("DataParallel.finish: no backward has run since the last step")
+        flat, self._flat = self._flat, None
+        main = torch.cuda.current_stream(self.device)
+        params = [p for p in self.model.parameters() if p.grad is not None]
+        st = flat.untyped_storage().data_ptr()
+        if not all(p.grad.untyped_storage().data_ptr() == st for p in params):
+            raise _cabi.VsumError("DataParallel.finish: a .grad no longer lives in the backward's flat buffer "
+                                  "(use optimizer.zero_grad(set_to_none=True) and one backward per step)")
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_stream(main)
+            for w in self._works:
+                w.wait()
+            _cabi.check(_cabi.load().vsum_dp_finalize(flat.data_ptr(), flat.numel(), self._ext.data_ptr(), self.world,
+                                                      self._loss_out.data_ptr(), self._comm.cuda_stream), "vsum_dp_finalize")
+        self._works = []
+        main.wait_stream(self._comm)
+        return self._loss_out
