@@ -146,12 +146,14 @@ VSUM_API int vsum_scorer_backward(vsum_scorer_t h, const float *features, const 
  * stream while the backward of the earlier layers runs.
  *   vsum_dp_finalize: grads[n] *= 1 / D and loss_out = ext[0] / D with D = ext[1] * max(ext[2 .. 2 + world)), i.e.
  *   (sum of batch sizes) * (largest Nmax): the padded size mse_with_mask_loss (src/utils/utils.py:55) divides by for the
- *   global batch, from SUM-reduced extras -- no host round trip for the denominator. */
+ *   global batch, from SUM-reduced extras -- no host round trip for the denominator.  vsum_dp_extras writes this rank's
+ *   extras, ext[2 + world] = [*loss_sum, batch, Nmax one-hot at rank], before that all-reduce. */
 typedef void (*vsum_grad_bucket_hook)(void *user, int32_t bucket);
 VSUM_API int vsum_scorer_backward_hooked(vsum_scorer_t h, const float *features, const int32_t *cu_seqlens, int32_t B, int64_t T,
                                          int32_t max_len, float drop_p, uint64_t seed, const float *d_scores, const float *d_feats,
                                          const void *tape, const vsum_scorer_grads *grads_host, void *workspace, size_t workspace_bytes,
                                          void *stream, vsum_grad_bucket_hook hook, void *hook_user);
+VSUM_API int vsum_dp_extras(float *ext, const float *loss_sum, int32_t batch, int32_t nmax, int32_t rank, int32_t world, void *stream);
 VSUM_API int vsum_dp_finalize(float *grads, int64_t n, const float *ext, int32_t world, float *loss_out, void *stream);
 /* Masked MSE of src/utils/utils.py:45-56 over n = bs*Nmax entries: *loss_out (device, pre-zeroed) +=
  * sum(((out - tgt) * !pad)^2) / denom; d_out (optional) = grad_scale * d(loss)/d(out). */

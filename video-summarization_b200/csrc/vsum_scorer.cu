@@ -542,6 +542,22 @@ __global__ void dp_finalize_kernel(float *__restrict__ grads, int64_t n, const f
 }
 }  // namespace
 
+namespace {
+__global__ void dp_extras_kernel(float *__restrict__ ext, const float *__restrict__ loss_sum, float batch, float nmax, int rank, int world) {
+    const int i = threadIdx.x;
+    if (i < 2 + world) ext[i] = i == 0 ? *loss_sum : (i == 1 ? batch : (i - 2 == rank ? nmax : 0.f));
+}
+}  // namespace
+
+// ext[2 + world] = [*loss_sum, batch, Nmax one-hot at `rank`]: the operand of the extras' SUM all-reduce (scalars travel as
+// kernel arguments, so a host that runs steps ahead of the device cannot overwrite them)
+extern "C" int vsum_dp_extras(float *ext, const float *loss_sum, int32_t batch, int32_t nmax, int32_t rank, int32_t world, void *stream) {
+    VSUM_REQUIRE(ext && loss_sum && world >= 1 && world <= 1022 && rank >= 0 && rank < world, VSUM_EINVAL, "vsum_dp_extras: bad argument");
+    dp_extras_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ext, loss_sum, (float)batch, (float)nmax, rank, world);
+    VSUM_LAUNCH_OK("dp_extras_kernel");
+    return VSUM_OK;
+}
+
 extern "C" int vsum_dp_finalize(float *grads, int64_t n, const float *ext, int32_t world, float *loss_out, void *stream) {
     VSUM_REQUIRE(grads && ext && n >= 0 && world >= 1, VSUM_EINVAL, "vsum_dp_finalize: bad argument");
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(148 * 4, (n + 255) / 256));

@@ -25,7 +25,7 @@ EXPORTS = (
     "vsum_scorer_workspace_bytes", "vsum_scorer_forward",
     "vsum_shot_mean", "vsum_knapsack_class_width", "vsum_knapsack_scratch_words", "vsum_knapsack", "vsum_summary_fscore",
     "vsum_scorer_set_train_mode", "vsum_scorer_tape_bytes", "vsum_scorer_train_workspace_bytes", "vsum_scorer_forward_train",
-    "vsum_scorer_backward", "vsum_scorer_backward_hooked", "vsum_dp_finalize", "vsum_masked_mse",
+    "vsum_scorer_backward", "vsum_scorer_backward_hooked", "vsum_dp_extras", "vsum_dp_finalize", "vsum_masked_mse",
     "vsum_debug_gemm_tc05", "vsum_debug_wgrad_tc05", "vsum_debug_attention_tc05", "vsum_debug_attention_scaled_tc05", "vsum_set_attention_kernel", "vsum_attention_scratch_ints",
     "vsum_set_ffn_kernel", "vsum_debug_ffn_tc05",
     "vsum_debug_attention_train_tc05", "vsum_debug_attention_bwd_tc05",
@@ -130,6 +130,7 @@ def load():
                                        C.POINTER(ScorerGrads), vp, C.c_size_t, vp]
     L.vsum_scorer_backward_hooked.argtypes = [vp, vp, vp, i32, i64, i32, C.c_float, C.c_uint64, vp, vp, vp,
                                               C.POINTER(ScorerGrads), vp, C.c_size_t, vp, GRAD_BUCKET_HOOK, vp]
+    L.vsum_dp_extras.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     L.vsum_dp_finalize.argtypes = [vp, i64, vp, i32, vp, vp]
     L.vsum_masked_mse.argtypes = [vp, vp, vp, i64, C.c_float, vp, C.c_float, vp, vp]
     L.vsum_shot_mean.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]

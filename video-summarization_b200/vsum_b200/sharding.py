@@ -167,7 +167,6 @@ class DataParallel:
         if self.device.type != "cuda":
             raise _cabi.VsumError("DataParallel needs the model on a CUDA device (no CPU fallback)")
         self._comm = torch.cuda.Stream(self.device)
-        self._ext_host = torch.zeros(2 + self.world, dtype=torch.float32, pin_memory=True)
         self._ext = torch.zeros(2 + self.world, dtype=torch.float32, device=self.device)
         self._loss_out = torch.zeros((), dtype=torch.float32, device=self.device)
         self._flat = None
@@ -182,12 +181,13 @@ class DataParallel:
         global masked MSE.  `mask` bool [bs, Nmax], True = padded frame; callers that hold packed rows instead of a padded
         batch pass `batch` (videos) and `nmax` (longest video) explicitly."""
         from .utils import mse_with_mask_loss
+        from . import _cabi
         s = mse_with_mask_loss(output, targets, mask, denom=1.0)
-        self._ext_host.zero_()
-        self._ext_host[1] = float(mask.shape[0] if batch is None else batch)
-        self._ext_host[2 + self.rank] = float(mask.shape[1] if nmax is None else nmax)
-        self._ext.copy_(self._ext_host, non_blocking=True)
-        self._ext[0:1].copy_(s.detach().view(1))
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.load().vsum_dp_extras(self._ext.data_ptr(), s.detach().data_ptr(),
+                                                    int(mask.shape[0] if batch is None else batch),
+                                                    int(mask.shape[1] if nmax is None else nmax), self.rank, self.world,
+                                                    torch.cuda.current_stream(self.device).cuda_stream), "vsum_dp_extras")
         return s
 
     # ---- called from _ScorerTrainFn.backward -------------------------------------------------
