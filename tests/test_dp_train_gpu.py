@@ -36,7 +36,9 @@ def _batch(lens, first_id):
 def _model():
     from vsum_b200.model import SimNet
     torch.manual_seed(21)
-    return SimNet(num_heads=4, d_model=256, num_layers=2, sparsity=0., dropout=0.0)
+    m = SimNet(num_heads=4, d_model=256, num_layers=2, sparsity=0., dropout=0.0)
+    m.train_precision = "fp32"      # the overlapped path scales AFTER the backward: exact in fp32 up to rounding, a different bf16 rounding otherwise
+    return m
 
 
 def _worker(rank, world, port, ret, overlapped=False):
@@ -50,7 +52,7 @@ def _worker(rank, world, port, ret, overlapped=False):
     x, t = x.cuda(), t.cuda()
     mask = x[:, :, 0] == 1000
     if overlapped:          # per-layer buckets from a communication stream, denominator derived on the device
-        ddp = DataParallel(model)
+        ddp = DataParallel(model, bucket_min_frames=0)        # per-layer buckets even for this small step
         pred, _ = model(x, mask)
         ddp.loss(pred, t, mask).backward()
         ret[f"loss{rank}"] = float(ddp.finish())

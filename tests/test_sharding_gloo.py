@@ -97,6 +97,6 @@ def test_dp_extras_give_the_global_denominator_from_one_sum_allreduce():
         d, s, want = ret[rank]
         assert d == want == float(7 * 150) and s == 7.5
     sl = bucket_slices(embed_n=10, layer_n=7, num_layers=3, total=10 + 21 + 4)
-    assert sl == {2: (24, 35), 1: (17, 24), 0: (10, 17), -1: (0, 10)}        # the last layer's bucket carries the head
+    assert sl == {2: (24, 35), 1: (17, 24), 0: (10, 17), -1: (0, 10)}        # the last layer's bucket carries the head (and the extras)
     covered = sorted(sl.values())
     assert covered[0][0] == 0 and covered[-1][1] == 35 and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))

