@@ -138,6 +138,35 @@ shot_mean_kernel(const float *__restrict__ scores, const int32_t *__restrict__ c
 // back-track test -- is packed with a warp ballot into a bit matrix in global memory (it stays in
 // L2); words whose capacities are all below the weight are never written and never read, because
 // the back-track (warp 0, 32 rows per probe) only probes rows with wt <= w.
+// One shot's update of the capacities a thread owns (cur[k] = K[i][k THREADS + tid]); KLO >= 0: the chunk that contains
+// w_min is known at compile time, KLO < 0: every chunk tests its capacities.  Each warp's ballot word (take bits of 32
+// consecutive capacities) leaves through a predicated store of lane 0 (inline PTX: no divergence bookkeeping).
+template <int THREADS, int EPT, int KLO>
+__device__ __forceinline__ void knapsack_row_update(double (&cur)[EPT], const double *__restrict__ rd, uint32_t *__restrict__ bw,
+                                                    double vi, int w_min, int tid, int lane) {
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        if (KLO >= 0 && k < KLO) continue;
+        const double b = cur[k];                          // K[i-1][w]
+        bool take;
+        double a;
+        if (KLO >= 0 && k > KLO) {
+            a = vi + rd[k * THREADS];
+            take = !(b >= a);
+        } else {
+            const bool can = k * THREADS + tid >= w_min;
+            a = vi + (can ? rd[k * THREADS] : 0.0);
+            take = can && !(b >= a);
+        }
+        // Python: m = max(a, b) keeps a unless b > a; take = (m != b).  With take = !(b >= a)
+        // and m = take ? a : b this is identical for every input incl. NaN (values equal when a == b).
+        cur[k] = take ? a : b;
+        const unsigned word = __ballot_sync(0xffffffffu, take);
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t@p st.global.u32 [%0], %1;\n\t}"
+                     ::"l"(bw + k * (THREADS / 32)), "r"(word), "r"(lane) : "memory");
+    }
+}
+
 template <int THREADS, int EPT>
 __global__ void __launch_bounds__(THREADS, 1)
 knapsack_kernel(const double *__restrict__ val, const int32_t *__restrict__ wt,
@@ -183,25 +212,17 @@ knapsack_kernel(const double *__restrict__ val, const int32_t *__restrict__ wt,
         const int w_min = wi > 1 ? wi : 1;                // K[i][0] stays 0 (line 14)
         const double *rd = row + tid - wi;                // rd[k*THREADS] = K[i-1][w - wt]
         uint32_t *bw = bits + (int64_t)i * WORDS + warp;  // this warp's ballot word of chunk k: bw[k*THREADS/32]
-        // Lane k keeps the ballot word of chunk k (and k + 32) in a register and the warp writes them with two
-        // predicated stores after the loop: a store by lane 0 inside the loop costs a divergent branch per chunk,
-        // which -- not shared memory or FP64 -- dominated the row update (profiles/r01_knapsack_phases.txt).
-        uint32_t my_lo = 0, my_hi = 0;
-#pragma unroll
-        for (int k = 0; k < EPT; ++k) {
-            const bool can = k * THREADS + tid >= w_min;
-            const double b = cur[k];                      // K[i-1][w]
-            const double a = vi + (can ? rd[k * THREADS] : 0.0);
-            // Python: m = max(a, b) keeps a unless b > a; take = (m != b).  With take = !(b >= a)
-            // and m = take ? a : b this is identical for every input incl. NaN (values equal when a == b).
-            const bool take = can && !(b >= a);
-            cur[k] = take ? a : b;
-            const unsigned word = __ballot_sync(0xffffffffu, take);
-            if (k < 32) my_lo = lane == k ? word : my_lo;
-            else my_hi = lane == k - 32 ? word : my_hi;
-        }
-        if (lane < (EPT < 32 ? EPT : 32)) bw[lane * (THREADS / 32)] = my_lo;
-        if (EPT > 32 && lane < EPT - 32) bw[(32 + lane) * (THREADS / 32)] = my_hi;
+        // Chunk k holds the capacities [k THREADS, k THREADS + THREADS): chunks below the one that contains w_min cannot
+        // change (no instruction at all: their words are never written and never read), chunks above it need no capacity
+        // test, only chunk k_lo = w_min / THREADS tests `w >= w_min` per thread.  The row update was ISSUE-bound at ~15
+        // instructions per capacity and warp (ncu: 52 % of the issue slots, shared memory at 12 %), most of them the
+        // per-capacity test; k_lo is 0 or 1 for every real shot length, so those two cases are compiled as straight-line
+        // code with the test in ONE chunk (LDS.64, DADD, DSETP, 2 FSEL, VOTE and the ballot word's predicated store per
+        // capacity), anything longer takes the generic form (profiles/r02_eval_kernels_ncu.txt).
+        const int k_lo = w_min / THREADS;
+        if (k_lo == 0) knapsack_row_update<THREADS, EPT, 0>(cur, rd, bw, vi, w_min, tid, lane);
+        else if (k_lo == 1) knapsack_row_update<THREADS, EPT, 1>(cur, rd, bw, vi, w_min, tid, lane);
+        else knapsack_row_update<THREADS, EPT, -1>(cur, rd, bw, vi, w_min, tid, lane);
         __syncthreads();                                  // everyone has read the old row
 #pragma unroll
         for (int k = 0; k < EPT; ++k) row[k * THREADS + tid] = cur[k];

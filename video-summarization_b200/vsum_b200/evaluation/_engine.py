@@ -177,6 +177,18 @@ def _scratch_buf(key: str, nbytes: int, dev: torch.device) -> torch.Tensor:
     return t
 
 
+_aux: dict = {}
+
+
+def _aux_streams(dev: torch.device, cur, n: int):
+    """`n` helper streams per (device, calling stream) for the knapsack class launches."""
+    k = (dev.index, cur.cuda_stream)
+    pool = _aux.setdefault(k, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(dev))
+    return pool[:n]
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -207,11 +219,22 @@ def summarize(db: DeviceEvalBatch, scores: torch.Tensor, cu_steps: torch.Tensor,
                                      db.cu_shots.data_ptr(), B, S, val.data_ptr(), wt.data_ptr(),
                                      cap.data_ptr(), stream), "vsum_shot_mean")
         bits = _scratch_buf("bits", int(hb.bit_offsets[-1]) * 4, dev)
-        for first, count, max_cap in hb.launches:
-            if count > 0:
-                _cabi.check(L.vsum_knapsack(val.data_ptr(), wt.data_ptr(), db.cu_shots.data_ptr(), cap.data_ptr(),
-                                            db.bit_offsets.data_ptr(), db.order.data_ptr() + 4 * first, count, max_cap,
-                                            bits.data_ptr(), selected.data_ptr(), stream), "vsum_knapsack")
+        # One launch per capacity class; the classes are independent (disjoint videos), so they run side by side on forked
+        # streams instead of one after the other: the widest class keeps only as many SMs busy as it has videos.
+        cur = torch.cuda.current_stream(dev)
+        launches = [l for l in hb.launches if l[1] > 0]
+        aux = _aux_streams(dev, cur, len(launches) - 1)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        for i, (first, count, max_cap) in enumerate(launches):
+            st = cur if i == 0 else aux[i - 1]
+            if i:
+                st.wait_event(fork)
+            _cabi.check(L.vsum_knapsack(val.data_ptr(), wt.data_ptr(), db.cu_shots.data_ptr(), cap.data_ptr(),
+                                        db.bit_offsets.data_ptr(), db.order.data_ptr() + 4 * first, count, max_cap,
+                                        bits.data_ptr(), selected.data_ptr(), st.cuda_stream), "vsum_knapsack")
+            if i:
+                cur.wait_stream(st)
         f = per_user = counts = None
         total_users = 0
         if want_f:
