@@ -371,7 +371,8 @@ VSUM_API int vsum_pack_h2d(vsum_pack_t pack, const void *blob_host, const vsum_e
  *     scratch_i32 holds vsum_attention_scratch_ints(T, B) int32 (all three attention entry points).
  *   vsum_set_attention_kernel: which forward kernel the scorer and these entry points run --
  *     2 (default): persistent kernel, two 128-query tiles per CTA, probabilities in tensor memory
- *     (csrc/vsum_attn2_tc05.cu); 1: one 128-query tile per CTA (csrc/vsum_attn_tc05.cu).  Both replace
+ *     (csrc/vsum_attn2_tc05.cu); 3: the same kernel with TWO softmax threads per query row (16 softmax warps) on the
+ *     pre-scaled inference fast pass; 1: one 128-query tile per CTA (csrc/vsum_attn_tc05.cu).  All replace
  *     src/model/simnet.py:155-161.  The environment variable VSUM_ATTN_KERNEL sets the initial value.
  * ------------------------------------------------------------------------------------------ */
 VSUM_API int vsum_set_attention_kernel(int32_t version);

@@ -103,9 +103,10 @@ def attention_ref(qkv, lens):
     return out
 
 
-@pytest.fixture(params=[2, 1], ids=["two_tile_persistent", "one_tile_per_cta"])
+@pytest.fixture(params=[2, 1, 3], ids=["two_tile_persistent", "one_tile_per_cta", "two_tile_two_threads_per_row"])
 def attn_kernel(request):
-    """Both forward kernels behind vsum_set_attention_kernel (2 is the default the scorer runs)."""
+    """The forward kernels behind vsum_set_attention_kernel: 2 / 3 = persistent two-tile kernel with one / two softmax threads
+    per query row (3 only differs on the pre-scaled inference fast pass), 1 = one tile per CTA."""
     L = _cabi.load()
     _cabi.check(L.vsum_set_attention_kernel(request.param), "vsum_set_attention_kernel")
     yield request.param
@@ -127,7 +128,8 @@ def test_attention(lens, attn_kernel):   # the last four have more work items th
     torch.testing.assert_close(out.float(), attention_ref(qkv, lens), rtol=2e-2, atol=2e-2)
 
 
-@pytest.mark.parametrize("lens", [[37], [300, 1, 127, 128, 513], [2048], [129, 128, 127] * 20])
+@pytest.mark.parametrize("lens", [[37], [1], [64], [65], [191], [300, 1, 127, 128, 513], [2048], [129, 128, 127] * 20, [8192, 4000, 77],
+                                  [1] * 700, [300] * 150])
 def test_attention_prescaled_q(lens, attn_kernel):
     """The form the scorer runs: d_model^-0.5 * log2(e) folded into Q (vsum_scorer_load_weights), scale = 1 / log2(e), so that
     the scores are base-2 exponents and the two-tile kernel exponentiates them as they are."""

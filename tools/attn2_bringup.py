@@ -108,3 +108,4 @@ if __name__ == "__main__":
     for p in libs:
         t0 = time.time()
         run_lib(p, 2, a.quick)
+        run_lib(p, 3, a.quick)

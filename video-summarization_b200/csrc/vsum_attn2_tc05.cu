@@ -43,8 +43,13 @@ namespace {
 constexpr int HD = 64, DM = 256, NH = 4;
 constexpr int BQ2 = 256, BKV = 128;
 constexpr int TILE_BYTES = 128 * 128;            // 128 rows x 64 bf16
-constexpr int A2_THREADS = 384;                  // 4 control warps + 8 softmax warps; 384 x 168 registers at launch
+constexpr int A2_THREADS = 384;                  // TPR 1: 4 control warps + 8 softmax warps; 384 x 168 registers at launch
 constexpr int A2_REGS_CONTROL = 80, A2_REGS_SOFTMAX = 208;   // setmaxnreg: 128 x (168 - 80) released >= 256 x (208 - 168) acquired
+// TPR 2 (two threads per query row, 64 key columns each): 16 softmax warps = four per SM sub-partition + 4 control warps;
+// 640 x 96 registers at launch, 128 x (96 - 64) released >= 512 x (104 - 96) acquired (setmaxnreg only moves registers inside
+// the CTA's own allocation: an increase that the releases do not cover never completes)
+constexpr int A2_THREADS2 = 640;
+constexpr int A2_REGS_CONTROL2 = 64, A2_REGS_SOFTMAX2 = 104;
 constexpr int A2_TMEM_COLS = 512;
 #ifndef VSUM_A2_STAGES
 #define VSUM_A2_STAGES 4
@@ -52,6 +57,7 @@ constexpr int A2_TMEM_COLS = 512;
 constexpr int KV_STAGES = VSUM_A2_STAGES;
 constexpr int SCHED_RING = 4;
 constexpr size_t A2_SMEM = (4 + 2 * (size_t)KV_STAGES) * TILE_BYTES + 512;   // Q (2 items x 2 tiles), K ring, V ring, barriers
+constexpr size_t A2_SMEM2 = A2_SMEM + 4096;                                  // + partial row sums of the two-threads-per-row variant
 #ifndef VSUM_A2_POLY_PERIOD
 #define VSUM_A2_POLY_PERIOD 3        // every k-th pair of exponentials is a polynomial on the FMA pipe (0 = none); swept 0 / 2..5 on B200
 #endif
@@ -151,8 +157,8 @@ __device__ __forceinline__ ItemInfo decode_item(int idx, const int32_t *__restri
 // item needs the exact pass (raised by the SAFE = false launch, consumed by the SAFE = true launch), counters[3] = how
 // many items are flagged.  Flags stay up until the next schedule: a later launch over the same batch (the next layer)
 // redoes those items in its exact pass too, which costs time, not correctness.
-template <bool TRAIN, bool SAFE, bool PRESCALED>
-__global__ void __launch_bounds__(A2_THREADS, 1)
+template <bool TRAIN, bool SAFE, bool PRESCALED, int TPR = 1>
+__global__ void __launch_bounds__(TPR == 2 ? A2_THREADS2 : A2_THREADS, 1)
 attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__restrict__ cu,
                   const int32_t *__restrict__ item_video, const int32_t *__restrict__ item_q0,
                   int32_t *__restrict__ counters, int32_t *__restrict__ flags, void *__restrict__ out_v, float scale_log2e,
@@ -175,25 +181,29 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
     uint64_t *sched_full = o_full + 2, *sched_empty = sched_full + SCHED_RING;
     int32_t *sched_idx = reinterpret_cast<int32_t *>(sched_empty + SCHED_RING);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sched_idx + SCHED_RING);
+    float *l_xch = reinterpret_cast<float *>(bars) + 128;         // TPR 2: [item parity][tile][half][128 rows] partial row sums (after 512 B of barriers)
+    static_assert(TPR == 1 || (TPR == 2 && !TRAIN && !SAFE), "two threads per row: inference fast pass only");
+    constexpr int NSOFT = 8 * TPR;                                // softmax warps; the control warps follow
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cw = warp - NSOFT;                                  // control warp index (0 producer, 1 QK issuer, 2 / 3 PV issuers)
     const int n_items = __ldg(counters) * NH;
 
-    if (warp == 8 && lane == 0) tc::tma_prefetch_desc(&tmQKV);
-    if (warp == 9 && lane == 0) {
+    if (cw == 0 && lane == 0) tc::tma_prefetch_desc(&tmQKV);
+    if (cw == 1 && lane == 0) {
         for (int i = 0; i < 2; ++i) { tc::mbar_init(q_full + i, 1); tc::mbar_init(q_empty + i, 1); }
         for (int s = 0; s < KV_STAGES; ++s) {
             tc::mbar_init(k_full + s, 1); tc::mbar_init(k_empty + s, 1);
             tc::mbar_init(v_full + s, 1); tc::mbar_init(v_empty + s, 2);
         }
-        for (int i = 0; i < 6; ++i) { tc::mbar_init(s_full + i, 1); tc::mbar_init(p_full + i, 128); }
+        for (int i = 0; i < 6; ++i) { tc::mbar_init(s_full + i, 1); tc::mbar_init(p_full + i, 128 * TPR); }
         for (int i = 0; i < 3; ++i) tc::mbar_init(buf_free + i, 1);
         for (int t = 0; t < 2; ++t) tc::mbar_init(o_full + t, 1);
         for (int t = 0; t < 2; ++t) tc::mbar_init(pv_done + t, 1);
-        for (int i = 0; i < SCHED_RING; ++i) { tc::mbar_init(sched_full + i, 1); tc::mbar_init(sched_empty + i, 11); }
+        for (int i = 0; i < SCHED_RING; ++i) { tc::mbar_init(sched_full + i, 1); tc::mbar_init(sched_empty + i, NSOFT + 3); }
         tc::fence_barrier_init();
     }
-    if (warp == 10) { tc::tmem_alloc(tmem_slot, A2_TMEM_COLS); tc::tmem_relinquish(); }
+    if (cw == 2) { tc::tmem_alloc(tmem_slot, A2_TMEM_COLS); tc::tmem_relinquish(); }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -208,9 +218,9 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
     };
     auto release_item = [&](int it) { tc::mbar_arrive(sched_empty + (it % SCHED_RING)); };
 
-    if (warp >= 8) {
-        tc::setmaxnreg_dec<A2_REGS_CONTROL>();
-        if (warp == 8) {                 // ===== work scheduler + TMA producer =====
+    if (cw >= 0) {
+        if (TPR == 2) tc::setmaxnreg_dec<A2_REGS_CONTROL2>(); else tc::setmaxnreg_dec<A2_REGS_CONTROL>();
+        if (cw == 0) {                   // ===== work scheduler + TMA producer =====
             if (lane == 0) {
                 uint32_t g = 0;                                           // running K/V tile counter (ring position)
                 for (int it = 0;; ++it) {
@@ -240,7 +250,7 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
                     }
                 }
             }
-        } else if (warp == 9) {          // ===== QK^T issuer (whole warp, warp-uniform control flow, one elected lane) =====
+        } else if (cw == 1) {            // ===== QK^T issuer (whole warp, warp-uniform control flow, one elected lane) =====
             // One thread cannot issue both products of both tiles fast enough (12 MMAs + commits + three waits cost it
             // ~1000 clk per unit, tools/microbench/mma_hazard.cu), so QK^T and the two tiles' PV have a warp each.
             constexpr uint32_t IDESC_QK = tc::make_idesc(1, 128, BKV, 0, 0);   // S[128 x 128], A and B K-major
@@ -286,7 +296,7 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
                 g0 += (uint32_t)w.nkv;
             }
         } else {                         // ===== PV issuer of tile t (warp 10: A, warp 11: B) =====
-            const int t = warp - 10;
+            const int t = cw - 2;
             constexpr uint32_t IDESC_PV = tc::make_idesc(1, 128, HD, 0, 1);    // O[128 x 64], A = P in TMEM, B = V MN-major
             const uint32_t v_lo = (uint32_t)tc::make_smem_desc_sw128(tc::smem_u32(sV), 16, 1024);
             const uint32_t hi = (uint32_t)(tc::make_smem_desc_sw128(tc::smem_u32(sV), 16, 1024) >> 32);
@@ -322,8 +332,10 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
                     if (tc::elect_one()) {
 #pragma unroll
                         for (int k = 0; k < BKV / 16; ++k)
-                            tc::mma_f16_ts(tO_t, tmem_base + buf * 128 + (uint32_t)(k * 8), desc_at(v_lo, (uint32_t)s * TILE16 + k * 128), IDESC_PV,
-                                           (j | k) != 0);
+                            // P of keys [16 k, 16 k + 16): 8 columns of packed pairs; with two threads per row the second thread's
+                            // probabilities (keys 64..127) sit in ITS half of the S buffer, columns 64..95
+                            tc::mma_f16_ts(tO_t, tmem_base + buf * 128 + (uint32_t)(TPR == 2 && k >= 4 ? 64 + (k - 4) * 8 : k * 8),
+                                           desc_at(v_lo, (uint32_t)s * TILE16 + k * 128), IDESC_PV, (j | k) != 0);
                         tc::mma_commit(pv_done + t);
                         if (j == w.nkv - 1) tc::mma_commit(o_full + t);
                         tc::mma_commit(buf_free + buf);
@@ -334,6 +346,104 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
                 }
                 g0 += (uint32_t)w.nkv;
             }
+        }
+    } else if constexpr (TPR == 2) {   // ===== softmax: TWO threads per query row, 64 key columns each =====
+        // Four softmax warps on every SM sub-partition instead of two: while one waits for S, for a tensor-memory load or
+        // on the MUFU queue, three others can issue.  The fixed exponent reference makes the two threads of a row fully
+        // independent inside an item -- no row maximum to agree on, no rescaling of the shared accumulator; they meet
+        // once per item to add their partial row sums.  Thread h of a row reads S columns [64 h, 64 h + 64) and writes
+        // its probabilities over the first 32 columns of that SAME half (packed pairs), so it only ever overwrites
+        // scores it has already loaded; the PV issuer reads keys 64..127 from columns 64..95.
+        tc::setmaxnreg_inc<A2_REGS_SOFTMAX2>();
+        const int hf = warp >> 3, t = (warp >> 2) & 1, qd = warp & 3;     // column half, tile, TMEM lane quarter
+        const int r = qd * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        const uint32_t tO_r = tO + lane_off + (uint32_t)(t * HD + hf * 32);    // my 32 of the tile's 64 output columns
+        const int pair_bar = 1 + t * 4 + qd;                              // named barrier of the two warps that share these rows
+        uint32_t c3 = 0, cpar = 0, n_unit0 = 0, n_done = 0;
+        for (int it = 0;; ++it) {
+            const int idx = next_item(it);
+            __syncwarp();
+            if (lane == 0) release_item(it);
+            if (idx >= n_items) break;
+            const ItemInfo w = decode_item(idx, cu, item_video, item_q0);
+            const int n_q = w.has_b ? 2 : 1;
+            const uint32_t unit0 = n_unit0;
+            n_unit0 += (uint32_t)(w.nkv * n_q);
+            if (t == 1 && !w.has_b) continue;
+            const int row = w.q0 + t * 128 + r;
+            float l_part = 0.f;
+            bool danger = false;
+            uint32_t ub = (unit0 + (uint32_t)t) % 3;
+            uint32_t sa[32], sb[32];
+            for (int j = 0; j < w.nkv; ++j) {
+                const uint32_t tS_r = tmem_base + lane_off + ub * 128 + (uint32_t)(hf * 64);   // my half of my row of the unit's S / P buffer
+                tc::mbar_wait(s_full + t * 3 + c3, cpar);
+                tc::tc_fence_after();
+                const int valid = w.n - j * BKV - hf * 64;        // keys of my half inside the video (<= 0: none)
+                float2 ps[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+                auto chunk = [&](uint32_t (&s)[32], int ch) {
+                    if (valid < 64) {                              // last tile of the video: keys past its end
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (ch * 32 + i >= valid) s[i] = 0xff800000u;
+                    }
+                    uint32_t wv[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        float2 x = make_float2(__uint_as_float(s[2 * e]), __uint_as_float(s[2 * e + 1]));
+                        if (!PRESCALED) x = ffma2(x, make_float2(scale_log2e, scale_log2e), make_float2(0.f, 0.f));
+                        const bool poly = VSUM_A2_POLY_PERIOD > 0 && (e % (VSUM_A2_POLY_PERIOD > 0 ? VSUM_A2_POLY_PERIOD : 1)) == VSUM_A2_POLY_PERIOD - 1;
+                        const float2 pp = poly ? exp2_poly2(x) : make_float2(ex2f(x.x), ex2f(x.y));
+                        ps[e & 3] = fadd2(ps[e & 3], pp);
+                        wv[e] = pack_bf16x2(pp.x, pp.y);
+                    }
+                    tmem_st16(tS_r + (uint32_t)(ch * 16), wv);
+                };
+                tc::tmem_ld32(tS_r, sa);
+                tmem_wait_ld_on(sa);
+                tc::tmem_ld32(tS_r + 32, sb);
+                chunk(sa, 0);
+                tmem_wait_ld_on(sb);
+                const uint32_t p_slot = t * 3 + c3;
+                ub += (uint32_t)n_q; if (ub >= 3) ub -= 3;
+                if (++c3 == 3) { c3 = 0; cpar ^= 1; }
+                chunk(sb, 1);
+                tc::tmem_wait_st();
+                tc::tc_fence_before();
+                tc::mbar_arrive(p_full + p_slot);
+                const float2 pq = fadd2(fadd2(ps[0], ps[1]), fadd2(ps[2], ps[3]));
+                const float psum = pq.x + pq.y;
+                danger |= !(psum < 1.2e27f);
+                l_part += psum;
+            }
+            // the two partial row sums meet (slots alternate with the item parity: the partner has read the previous value of a
+            // slot before it can arrive at the barrier that precedes the next write to it)
+            float *slot = l_xch + (((n_done & 1) * 2 + t) * 2) * 128 + r;
+            slot[hf * 128] = l_part;
+            tc::bar_sync(pair_bar, 64);
+            const float l_run = l_part + slot[(hf ^ 1) * 128];
+            if (row < w.n && (danger || !(l_run >= 8.3e-25f)) && atomicExch(flags + idx, 1) == 0) atomicAdd(counters + 3, 1);
+            tc::mbar_wait(o_full + t, n_done & 1);
+            ++n_done;
+            tc::tc_fence_after();
+            const float inv = 1.0f / l_run;
+            uint32_t o[32];
+            tc::tmem_ld32(tO_r, o);
+            tmem_wait_ld_on(o);
+            if (row < w.n) {
+                __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(out_v) + (int64_t)(w.base + row) * DM + w.head * HD + hf * 32;
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    uint4 pk;
+                    pk.x = pack_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
+                    pk.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+                    pk.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+                    pk.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+                    *reinterpret_cast<uint4 *>(dst + i) = pk;
+                }
+            }
+            tc::tc_fence_before();
         }
     } else {   // ===== softmax: one thread per query row =====
         tc::setmaxnreg_inc<A2_REGS_SOFTMAX>();
@@ -517,7 +627,7 @@ attn2_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t *__re
     __syncwarp();
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 10) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, A2_TMEM_COLS); }
+    if (cw == 2) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, A2_TMEM_COLS); }
     // The last CTA to leave rewinds the work counter, so one schedule serves every launch over the same batch.
     if (threadIdx.x == 0 && atomicAdd(counters + 2, 1) == (int)gridDim.x - 1) {
         counters[1] = 0;
@@ -595,6 +705,7 @@ int launch_attention2_tc05(const __nv_bfloat16 *qkv, const int32_t *cu_seqlens, 
         VSUM_CUDA_OK(cudaFuncSetAttribute(attn2_tc05_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A2_SMEM));
         VSUM_CUDA_OK(cudaFuncSetAttribute(attn2_tc05_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A2_SMEM));
         VSUM_CUDA_OK(cudaFuncSetAttribute(attn2_tc05_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A2_SMEM));
+        VSUM_CUDA_OK(cudaFuncSetAttribute(attn2_tc05_kernel<false, false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A2_SMEM2));
         VSUM_CUDA_OK(cudaDeviceGetAttribute(&n_sm[dev & 63], cudaDevAttrMultiProcessorCount, dev)));
     {   // setmaxnreg moves registers inside the CTA's own allocation: what the control warps release must cover what the softmax warps acquire
         static std::atomic<int> checked{0};
@@ -606,6 +717,10 @@ int launch_attention2_tc05(const __nv_bfloat16 *qkv, const int32_t *cu_seqlens, 
             const int e = fa.numRegs < fb.numRegs ? fa.numRegs : fb.numRegs;
             VSUM_REQUIRE(128 * (e - A2_REGS_CONTROL) >= 256 * (A2_REGS_SOFTMAX - e), VSUM_EUNSUPPORTED,
                          "attn2_tc05_kernel was compiled with %d registers per thread: the softmax warps could not grow to %d", e, A2_REGS_SOFTMAX);
+            cudaFuncAttributes fc;
+            VSUM_CUDA_OK(cudaFuncGetAttributes(&fc, attn2_tc05_kernel<false, false, true, 2>));
+            VSUM_REQUIRE(128 * (fc.numRegs - A2_REGS_CONTROL2) >= 512 * (A2_REGS_SOFTMAX2 - fc.numRegs), VSUM_EUNSUPPORTED,
+                         "attn2_tc05_kernel<TPR 2> was compiled with %d registers per thread: the softmax warps could not grow to %d", fc.numRegs, A2_REGS_SOFTMAX2);
             checked.store(1, std::memory_order_relaxed);
         }
     }
@@ -625,6 +740,10 @@ int launch_attention2_tc05(const __nv_bfloat16 *qkv, const int32_t *cu_seqlens, 
         VSUM_LAUNCH_OK("attn2_tc05_kernel");
         A2_LAUNCH(true, true, false, lse2, ks, thresh, seed);
     } else if (prescaled) {
+        if (attention_kernel_version() == 3)    // fast pass with two threads per row (16 softmax warps)
+            attn2_tc05_kernel<false, false, true, 2><<<grid, A2_THREADS2, A2_SMEM2, s>>>(tm, cu_seqlens, item_video, item_q0, counters, flags, out, sl2,
+                                                                                         nullptr, 1.0f, 0u, 0ull);
+        else
         A2_LAUNCH(false, false, true, nullptr, 1.0f, 0u, 0ull);
         VSUM_LAUNCH_OK("attn2_tc05_kernel");
         A2_LAUNCH(false, true, true, nullptr, 1.0f, 0u, 0ull);

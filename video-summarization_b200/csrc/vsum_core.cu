@@ -36,7 +36,7 @@ int attention_kernel_version() {
     int v = g_attn_kernel.load(std::memory_order_relaxed);
     if (v == 0) {
         const char *e = getenv("VSUM_ATTN_KERNEL");
-        v = (e && e[0] == '1') ? 1 : 2;
+        v = (e && e[0] == '1') ? 1 : ((e && e[0] == '3') ? 3 : 2);
         g_attn_kernel.store(v, std::memory_order_relaxed);
     }
     return v;
@@ -118,7 +118,7 @@ extern "C" int vsum_set_sm_partition(int32_t eval_sms, int32_t scorer_reserved_s
 }
 
 extern "C" int vsum_set_attention_kernel(int32_t version) {
-    VSUM_REQUIRE(version == 1 || version == 2, VSUM_EINVAL, "vsum_set_attention_kernel: version %d (1 or 2)", version);
+    VSUM_REQUIRE(version >= 1 && version <= 3, VSUM_EINVAL, "vsum_set_attention_kernel: version %d (1, 2 or 3)", version);
     vsum::g_attn_kernel.store(version);
     return VSUM_OK;
 }

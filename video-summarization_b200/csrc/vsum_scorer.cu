@@ -225,7 +225,7 @@ static int forward_bf16(vsum_scorer_t h, const void *x, bool x_is_bf16, const in
     carve16(c, T, max_tiles, ws, w);
     int rc;
     RUN(launch_row_positions(cu, B, T, w.row_pos, nullptr, s));
-    const bool attn2 = attention_kernel_version() == 2;
+    const bool attn2 = attention_kernel_version() >= 2;
     if (attn2) RUN(launch_attn2_schedule(cu, B, T, w.a2, s));
     else RUN(launch_attn_schedule(cu, B, w.tile_video, w.tile_q0, w.n_tiles, max_tiles, s));
     Tc05GemmArgs g{};
@@ -411,7 +411,7 @@ extern "C" int vsum_scorer_forward_train(vsum_scorer_t h, const float *x, const 
     const float scale = 1.0f / sqrtf((float)d);
     const float *xin = t.x0;
     const bool tc_attn = h->train_mode == 2;
-    const bool attn2 = tc_attn && attention_kernel_version() == 2;
+    const bool attn2 = tc_attn && attention_kernel_version() >= 2;
     if (attn2) RUN(launch_attn2_schedule(cu, B, T, w.a2, s));
     else if (tc_attn) RUN(launch_attn_schedule(cu, B, w.tile_video, w.tile_q0, w.n_tiles, w.max_tiles, s));
     for (int l = 0; l < c.num_layers; ++l) {
@@ -666,7 +666,7 @@ extern "C" int vsum_debug_attention_train_tc05(const void *qkv, const int32_t *c
     VSUM_REQUIRE(qkv && cu_seqlens && out && lse2 && scratch, VSUM_EINVAL, "vsum_debug_attention_train_tc05: null pointer");
     const int max_tiles = (int)(T / 128 + B);
     cudaStream_t s = (cudaStream_t)stream;
-    if (attention_kernel_version() == 2) {
+    if (attention_kernel_version() >= 2) {
         int rc2 = launch_attn2_schedule(cu_seqlens, B, T, scratch, s);
         if (rc2) return rc2;
         return launch_attention2_tc05((const __nv_bfloat16 *)qkv, cu_seqlens, B, T, 1.0f / 16.0f, out, scratch, s, lse2, drop_p, seed);
@@ -695,7 +695,7 @@ extern "C" int vsum_debug_attention_scaled_tc05(const void *qkv, const int32_t *
     VSUM_REQUIRE(qkv && cu_seqlens && out && scratch, VSUM_EINVAL, "vsum_debug_attention_scaled_tc05: null pointer");
     const int max_tiles = (int)(T / 128 + B);
     cudaStream_t s = (cudaStream_t)stream;
-    if (attention_kernel_version() == 2) {
+    if (attention_kernel_version() >= 2) {
         int rc2 = launch_attn2_schedule(cu_seqlens, B, T, scratch, s);
         if (rc2) return rc2;
         return launch_attention2_tc05((const __nv_bfloat16 *)qkv, cu_seqlens, B, T, scale, out, scratch, s);
