@@ -21,6 +21,7 @@ int set_error(int code, const char *fmt, ...);
 void count_launch(int n = 1);
 int eval_sm_budget();       // 0 = unlimited; else the evaluation kernels keep at most this many SMs busy
 int scorer_sm_reserve();    // persistent scorer GEMMs leave this many SMs free
+int *sched_slot();                // 16 zeroed ints of device memory for one launch's dynamic tile scheduler (nullptr: allocation failed)
 int ffn_kernel_version();         // 2 = fused fc1 + ReLU + fc2 + residual + LayerNorm kernel (default), 1 = two GEMM launches
 int attention_kernel_version();   // 2 = persistent two-query-tile forward kernel (default), 1 = one 128-query tile per CTA
 

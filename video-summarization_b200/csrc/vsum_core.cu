@@ -55,6 +55,28 @@ int ffn_kernel_version() {
     return v;
 }
 
+// Work counters of the persistent kernels' dynamic tile schedulers: every launch takes the next 64-byte slot (16 ints,
+// zero on entry; the last CTA of the launch zeroes it again) of a per-device ring.  A slot comes round again after 4096
+// launches, long after the launch that used it has retired.
+int *sched_slot() {
+    constexpr int SLOTS = 4096;
+    static int *ring[64] = {};
+    static std::atomic<unsigned> next[64];
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    dev &= 63;
+    if (!ring[dev]) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!ring[dev]) {
+            int *p = nullptr;
+            if (cudaMalloc(&p, SLOTS * 64) != cudaSuccess || cudaMemset(p, 0, SLOTS * 64) != cudaSuccess) return nullptr;
+            ring[dev] = p;
+        }
+    }
+    return ring[dev] + 16 * (next[dev].fetch_add(1, std::memory_order_relaxed) % SLOTS);
+}
+
 // ---- profiling -------------------------------------------------------------------------------
 struct ProfRecord { int cat; cudaEvent_t a, b; };
 static std::mutex g_prof_mu;

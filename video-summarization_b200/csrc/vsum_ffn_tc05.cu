@@ -14,8 +14,9 @@
 // parked in tensor memory, residual in / output out through TMA and a staging tile per column half).
 // Shared memory (227 KB): X tile 64 KB (4 k-blocks), weight ring 3 x 32 KB (half a W1 chunk or half a W2 chunk per stage,
 // in MMA issue order), H 32 KB, staging 2 x 16 KB.  Warp roles: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..11 epilogue.
-// Weights stream from L2 (1 MB per tile): at the sustained tensor rate that is ~40 B/clk/SM, the chip's L2 limit
-// (B300_MICROARCH: ~6300 B/clk) -- hence VSUM_FFN_CLUSTER: CTA pairs that each fetch half of every stage and multicast it.
+// Weights stream from L2 (1 MB per tile, ~40 B/clk/SM at the sustained tensor rate): ncu shows the L2 at 33 % of its peak and
+// the tensor pipe at 51 % (= 80 % of the sustained bf16 peak), so CTA pairs sharing weight stages by multicast were not built.
+// Tiles come from a dynamic scheduler (global counter -> shared-memory ring), see vsum_gemm_tc05.cu.
 #include "vsum_kernels.cuh"
 #include "vsum_tc05.cuh"
 
@@ -29,7 +30,7 @@ constexpr int STAGE = 2 * KB16;                               // 32 KB ring stag
 constexpr int NST = 3;
 constexpr int FFN_THREADS = 384;
 constexpr size_t OFF_X = 0, OFF_RING = 4 * (size_t)KB16, OFF_H = OFF_RING + (size_t)NST * STAGE, OFF_STG = OFF_H + 2 * (size_t)KB16,
-                 OFF_BARS = OFF_STG + 2 * (size_t)KB16, FFN_SMEM = OFF_BARS + 256 + 2560;
+                 OFF_BARS = OFF_STG + 2 * (size_t)KB16, FFN_SMEM = OFF_BARS + 384 + 2560;
 static_assert(FFN_SMEM <= 232448, "fused FFN: shared memory budget");
 constexpr int TM_Y = 0, TM_H = 256;                            // tensor-memory columns
 constexpr int EPI_BAR = 1;
@@ -39,7 +40,9 @@ struct FfnParams {
     const float *b1, *b2, *gamma, *beta, *head_w, *head_b;
     float *scores_out, *feats_out;
     int apply_sigmoid, store_out, head;
+    int *sched;               // dynamic tile scheduler: sched[0] = next tile, sched[8] = CTAs that have left
 };
+constexpr int SCHED_RING = 8;
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -64,8 +67,10 @@ ffn_tc05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     uint64_t *full = bars, *empty = bars + NST, *x_full = bars + 2 * NST, *x_free = x_full + 1;
     uint64_t *h_tfull = x_free + 1, *h_tfree = h_tfull + 2, *h_sfull = h_tfree + 2, *h_sfree = h_sfull + 1;
     uint64_t *y_full = h_sfree + 1, *y_free = y_full + 1, *rfull = y_free + 1;                 // rfull[2]: residual staging per half
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(rfull + 2);
-    float *xch = reinterpret_cast<float *>(bars) + 64;                                            // [2][128][2] sums + [128] head dots
+    uint64_t *sched_full = rfull + 2, *sched_empty = sched_full + SCHED_RING;
+    int32_t *sched_tile = reinterpret_cast<int32_t *>(sched_empty + SCHED_RING);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sched_tile + SCHED_RING);
+    float *xch = reinterpret_cast<float *>(bars) + 96;                                            // [2][128][2] sums + [128] head dots
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -77,6 +82,7 @@ ffn_tc05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         for (int b = 0; b < 2; ++b) { tc::mbar_init(h_tfull + b, 1); tc::mbar_init(h_tfree + b, 256); tc::mbar_init(rfull + b, 1); }
         tc::mbar_init(h_sfull, 256); tc::mbar_init(h_sfree, 1);
         tc::mbar_init(y_full, 1); tc::mbar_init(y_free, 256);
+        for (int a = 0; a < SCHED_RING; ++a) { tc::mbar_init(sched_full + a, 1); tc::mbar_init(sched_empty + a, 9); }
         tc::fence_barrier_init();
     }
     if (warp == 2) { tc::tmem_alloc(tmem_slot, 512); tc::tmem_relinquish(); }
@@ -84,20 +90,40 @@ ffn_tc05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int64_t first = blockIdx.x, step = gridDim.x;
+    // Dynamic tile scheduler (as in vsum_gemm_tc05.cu): the producer takes tiles from a global counter and hands them to
+    // the MMA and epilogue warps through a shared-memory ring; -1 ends the walk.
+    auto next_tile = [&](uint32_t n) -> int64_t {
+        const int slot = n % SCHED_RING;
+        tc::mbar_wait(sched_full + slot, (n / SCHED_RING) & 1);
+        const int64_t t = sched_tile[slot];
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(sched_empty + slot);
+        return t;
+    };
+    auto fetch_tile = [&](uint32_t n) -> int64_t {
+        const int slot = n % SCHED_RING;
+        tc::mbar_wait(sched_empty + slot, ((n / SCHED_RING) & 1) ^ 1);
+        const int64_t t = atomicAdd(p.sched, 1);
+        sched_tile[slot] = t < p.m_tiles ? (int32_t)t : -1;
+        tc::mbar_arrive(sched_full + slot);
+        return t < p.m_tiles ? t : -1;
+    };
 
     if (warp == 0) {
         if (lane == 0) {   // ===== TMA producer: X tile + weight ring in MMA issue order =====
-            uint32_t it = 0, tl = 0;
+            uint32_t it = 0, tl = 0, nf = 0;
             bool x_issued = false;                        // X of the tile about to start is already on its way
+            int64_t t_next = fetch_tile(nf++);
             auto load_x = [&](int64_t t) {
                 tc::mbar_arrive_expect_tx(x_full, 4 * KB16);
                 for (int kb = 0; kb < 4; ++kb) tc::tma_load_2d(sX + (size_t)kb * KB16, &tmX, x_full, kb * 64, (int)(t * BM));
             };
-            for (int64_t t = first; t < p.m_tiles; t += step, ++tl) {
+            for (; t_next >= 0; ++tl) {
+                const int64_t t = t_next;
+                t_next = fetch_tile(nf++);                // one tile ahead (the early X load below needs it)
                 if (!x_issued) { tc::mbar_wait(x_free, (tl & 1) ^ 1); load_x(t); }
                 x_issued = false;
-                const bool has_next = t + step < p.m_tiles;
+                const bool has_next = t_next >= 0;
                 auto stage_w1 = [&](int j, int hf) {      // k-blocks 2 hf, 2 hf + 1 of W1 chunk j
                     const int s = it % NST;
                     tc::mbar_wait(empty + s, ((it / NST) & 1) ^ 1);
@@ -113,7 +139,7 @@ ffn_tc05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                     tc::tma_load_2d(ring + (size_t)s * STAGE, &tmW2, full + s, j * CH + kb * 64, 0);
                     ++it;
                     // the next tile's X as soon as this tile's last G1 has released the buffer (not only after the ring drained)
-                    if (has_next && !x_issued && tc::mbar_test(x_free, tl & 1)) { load_x(t + step); x_issued = true; }
+                    if (has_next && !x_issued && tc::mbar_test(x_free, tl & 1)) { load_x(t_next); x_issued = true; }
                 };
                 stage_w1(0, 0); stage_w1(0, 1); stage_w1(1, 0); stage_w1(1, 1);
                 for (int j = 0; j < NCH; ++j) {
@@ -127,7 +153,8 @@ ffn_tc05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const uint64_t desc0 = tc::make_smem_desc_sw128(tc::smem_u32(smem), 16, 1024);
         const uint32_t x_off = (uint32_t)OFF_X >> 4, ring_off = (uint32_t)OFF_RING >> 4, h_off = (uint32_t)OFF_H >> 4;
         uint32_t it = 0, tl = 0, c1 = 0, c2 = 0;           // ring position, tile count, G1 chunks issued, G2 chunks issued
-        for (int64_t t = first; t < p.m_tiles; t += step, ++tl) {
+        for (;; ++tl) {
+            if (next_tile(tl) < 0) break;
             auto g1 = [&](int j) {
                 const uint32_t b = c1 & 1;
                 tc::mbar_wait(h_tfree + b, ((c1 >> 1) & 1) ^ 1);      // the epilogue has drained the chunk that used this TMEM buffer
@@ -201,7 +228,9 @@ ffn_tc05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         for (int ch = 0; ch < 8; ++ch) sw_off[ch] = (uint32_t)((ch ^ (r & 7)) << 4);
         uint32_t tl = 0, hc = 0, res_it = 0;
         uint32_t ra[32], rb[32];
-        for (int64_t t = first; t < p.m_tiles; t += step, ++tl) {
+        for (;; ++tl) {
+            const int64_t t = next_tile(tl);
+            if (t < 0) break;
             const int64_t row = t * BM + r;
             const bool valid = row < p.M;
             if (leader) {   // this half's first residual chunk on its way while the tile's products run
@@ -351,6 +380,11 @@ ffn_tc05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 2) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
+    if (threadIdx.x == 0 && atomicAdd(p.sched + 8, 1) == (int)gridDim.x - 1) {   // the last CTA hands the scheduler slot back zeroed
+        p.sched[0] = 0;
+        p.sched[8] = 0;
+        __threadfence();
+    }
 }
 
 }  // namespace
@@ -378,6 +412,8 @@ int launch_ffn_tc05(const Tc05FfnArgs &a, cudaStream_t s) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     sms = max(8, sms - scorer_sm_reserve());
     const unsigned grid = (unsigned)min(p.m_tiles, (int64_t)sms);
+    p.sched = sched_slot();
+    VSUM_REQUIRE(p.sched != nullptr, VSUM_ENOMEM, "ffn_tc05: no device memory for the tile scheduler");
     ProfScope prof(PROF_FFN, s);
     ffn_tc05_kernel<<<grid, FFN_THREADS, FFN_SMEM, s>>>(tmX, tmW1, tmW2, tmOut, p);
     VSUM_LAUNCH_OK("ffn_tc05_kernel");

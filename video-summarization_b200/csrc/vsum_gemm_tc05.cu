@@ -88,7 +88,7 @@ __host__ __device__ constexpr size_t gemm_ring_bytes(bool wres, bool dbl) {
                 : (size_t)gemm_ring_stages(dbl) * (A_STAGE + B_STAGE);
 }
 __host__ __device__ constexpr size_t gemm_smem(int epi, bool wres, bool dbl) {   // + 2.5 KB: row-statistics / head-dot exchange of the LayerNorm epilogues
-    return gemm_ring_bytes(wres, dbl) + (size_t)gemm_stg_tiles(dbl) * STG_BYTES + 256 /*barriers*/ + (epi_is_ln(epi) ? 2560 : 0);
+    return gemm_ring_bytes(wres, dbl) + (size_t)gemm_stg_tiles(dbl) * STG_BYTES + 384 /*barriers + scheduler ring*/ + (epi_is_ln(epi) ? 2560 : 0);
 }
 
 struct GemmParams {
@@ -104,7 +104,9 @@ struct GemmParams {
     float *scores_out, *feats_out;
     int apply_sigmoid;
     int store_out;
+    int *sched;               // dynamic tile scheduler: sched[y] = next m-tile of column block y (WRES) / next tile, sched[8] = CTAs that have left
 };
+constexpr int SCHED_RING = 8;
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -138,7 +140,9 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t *bars = reinterpret_cast<uint64_t *>(stg + (size_t)gemm_stg_tiles(DBL) * STG_BYTES);
     uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = tfull + 2;
     uint64_t *wfull = tempty + 2, *rfull = wfull + 1;     // rfull[4]: residual staging tiles (half, buffer)
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(rfull + 4);
+    uint64_t *sched_full = rfull + 4, *sched_empty = sched_full + SCHED_RING;
+    int32_t *sched_tile = reinterpret_cast<int32_t *>(sched_empty + SCHED_RING);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sched_tile + SCHED_RING);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int KELTS = TF32 ? 32 : 64;          // elements per 128-byte k-block
@@ -161,6 +165,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int s = 0; s < STAGES; ++s) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); }
         for (int a = 0; a < 2; ++a) { tc::mbar_init(tfull + a, 1); tc::mbar_init(tempty + a, EPI8 ? 256 : 128); }
         for (int a = 0; a < 4; ++a) tc::mbar_init(rfull + a, 1);
+        for (int a = 0; a < SCHED_RING; ++a) { tc::mbar_init(sched_full + a, 1); tc::mbar_init(sched_empty + a, 1 + (EPI8 ? 8 : 4)); }
         tc::mbar_init(wfull, 1);
         tc::fence_barrier_init();
     }
@@ -173,9 +178,28 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // tile walk shared by all roles
+    // Dynamic tile scheduler: the producer takes tiles from a global counter (one per column block in the weight-stationary
+    // variant) and hands them to the other roles through a small shared-memory ring, so a CTA that starts late -- the
+    // evaluation stream holds some SMs while the next batch's scorer runs -- simply takes fewer tiles instead of leaving
+    // its static share for a second wave.  -1 ends the walk.
     const int64_t total = WRES ? p.m_tiles : p.m_tiles * p.n_tiles;
-    const int64_t first = blockIdx.x, step = gridDim.x;
+    int *const counter = p.sched + (WRES ? blockIdx.y : 0);
+    auto next_tile = [&](uint32_t n) -> int64_t {          // consumers: n-th tile of this CTA
+        const int slot = n % SCHED_RING;
+        tc::mbar_wait(sched_full + slot, (n / SCHED_RING) & 1);
+        const int64_t t = sched_tile[slot];
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(sched_empty + slot);
+        return t;
+    };
+    auto fetch_tile = [&](uint32_t n) -> int64_t {         // producer: take the next tile and publish it as the CTA's n-th
+        const int slot = n % SCHED_RING;
+        tc::mbar_wait(sched_empty + slot, ((n / SCHED_RING) & 1) ^ 1);
+        const int64_t t = atomicAdd(counter, 1);
+        sched_tile[slot] = t < total ? (int32_t)t : -1;
+        tc::mbar_arrive(sched_full + slot);
+        return t < total ? t : -1;
+    };
 
     if (warp == 0) {
         if (lane == 0) {  // ===== TMA producer =====
@@ -184,8 +208,11 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int kb = 0; kb < p.num_kb; ++kb)
                     tc::tma_load_2d(ring + (size_t)kb * B_STAGE, &tmB, wfull, kb * KELTS, (int)blockIdx.y * BN);
             }
-            uint32_t it = 0;
-            for (int64_t t = first; t < total; t += step) {
+            uint32_t it = 0, nf = 0;
+            int64_t t_next = fetch_tile(nf++);
+            while (t_next >= 0) {
+                const int64_t t = t_next;
+                t_next = fetch_tile(nf++);                  // one tile ahead: the consumers find it in the ring, the L2 prefetch below uses it
                 const int64_t m_blk = WRES ? t : t / p.n_tiles;
                 const int n_blk = WRES ? (int)blockIdx.y : (int)(t % p.n_tiles);
                 for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
@@ -199,7 +226,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     // issued one tile period ahead at best.  Pull the rows of this CTA's NEXT tile into L2 now (one of the
                     // column-block CTAs walking the same rows does it): QKV GEMM -4 %, fc1 -2.5 % on the same box.  Not for
                     // K = 1024: there the ring already streams 16 k-blocks per tile and the extra requests cost 15-30 %.
-                    if (WRES && blockIdx.y == 0 && t + step < total) tc::tma_prefetch_l2_2d(&tmA, kb * KELTS, (int)((t + step) * BM));
+                    if (WRES && blockIdx.y == 0 && t_next >= 0) tc::tma_prefetch_l2_2d(&tmA, kb * KELTS, (int)(t_next * BM));
                 }
             }
         }
@@ -210,7 +237,8 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (WRES) { tc::mbar_wait(wfull, 0); }
         const uint64_t ring_desc = tc::make_smem_desc_sw128(tc::smem_u32(ring), 16, 1024);
         uint32_t it = 0, tl = 0;
-        for (int64_t t = first; t < total; t += step, ++tl) {
+        for (;; ++tl) {
+            if (next_tile(tl) < 0) break;
             const int acc = tl & 1;
             tc::mbar_wait(tempty + acc, ((tl >> 1) & 1) ^ 1);
             tc::tc_fence_after();
@@ -250,7 +278,9 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) sw_off[ch] = (uint32_t)((ch ^ (r & 7)) << 4);
         uint32_t tl = 0, res_it = 0;
-        for (int64_t t = first; t < total; t += step, ++tl) {
+        for (;; ++tl) {
+            const int64_t t = next_tile(tl);
+            if (t < 0) break;
             const int64_t m_blk = WRES ? t : t / p.n_tiles;
             const int n_blk = WRES ? (int)blockIdx.y : (int)(t % p.n_tiles);
             const int acc = tl & 1;
@@ -345,7 +375,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             } else {  // bias + residual + LayerNorm (+ head): N == 256, the tile is the whole row.  Two threads per row
                       // (columns [128 half, 128 half + 128) each) exchange their partial sums through shared memory.
-                float *xch = reinterpret_cast<float *>(bars) + 64;          // [2 halves][128 rows][2], after the 256 B of barriers
+                float *xch = reinterpret_cast<float *>(bars) + 96;          // [2 halves][128 rows][2], after the 384 B of barriers + scheduler ring
                 float sum = 0.f, sumsq = 0.f;
 #pragma unroll 1
                 for (int i = 0; i < 2; ++i) {
@@ -461,6 +491,11 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, TMEM_COLS);
     }
+    // the last CTA to leave hands the scheduler slot back zeroed
+    if (threadIdx.x == 0 && atomicAdd(p.sched + 8, 1) == (int)(gridDim.x * gridDim.y) - 1) {
+        for (int i = 0; i < 9; ++i) p.sched[i] = 0;
+        __threadfence();
+    }
 }
 
 template <bool TF32, int EPI, bool WRES, bool DBL = false>
@@ -476,8 +511,11 @@ int launch_variant(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtenso
     dim3 grid;
     if (WRES) grid = dim3((unsigned)max((int64_t)1, min(p.m_tiles, (int64_t)(sms / p.n_tiles))), (unsigned)p.n_tiles);
     else grid = dim3((unsigned)min(p.m_tiles * p.n_tiles, (int64_t)sms));
+    GemmParams q = p;
+    q.sched = sched_slot();
+    VSUM_REQUIRE(q.sched != nullptr, VSUM_ENOMEM, "gemm_tc05: no device memory for the tile scheduler");
     ProfScope prof(cat, s);
-    kern<<<grid, gemm_threads(EPI), SMEM, s>>>(tmA, tmB, tmOut, tmRes, p);
+    kern<<<grid, gemm_threads(EPI), SMEM, s>>>(tmA, tmB, tmOut, tmRes, q);
     VSUM_LAUNCH_OK("gemm_tc05_kernel");
     return VSUM_OK;
 }
