@@ -403,12 +403,15 @@ overlap_kernel(const int8_t *__restrict__ summary, const int64_t *__restrict__ s
         if (c + 3 < slen) o_cnt += (long long)sm[c + 3] & g3;
     };
     int q = threadIdx.x;
-    for (; q + (int)blockDim.x < nvec; q += 2 * blockDim.x) {
-        const float4 x0 = __ldcs(g4 + q), x1 = __ldcs(g4 + q + blockDim.x);          // streamed once
+    const int bd = blockDim.x;
+    for (; q + 3 * bd < nvec; q += 4 * bd) {              // four 16-byte loads in flight per thread, streamed once (two: 0.192 ms, four: 0.160 ms)
+        const float4 x0 = __ldcs(g4 + q), x1 = __ldcs(g4 + q + bd), x2 = __ldcs(g4 + q + 2 * bd), x3 = __ldcs(g4 + q + 3 * bd);
         add_group(x0, q);
-        add_group(x1, q + blockDim.x);
+        add_group(x1, q + bd);
+        add_group(x2, q + 2 * bd);
+        add_group(x3, q + 3 * bd);
     }
-    if (q < nvec) add_group(__ldcs(g4 + q), q);
+    for (; q < nvec; q += bd) add_group(__ldcs(g4 + q), q);
     for (int c = head + 4 * nvec + threadIdx.x; c < cols; c += blockDim.x) {
         const long long gi = (long long)__ldg(g + c);
         const long long si = c < slen ? (long long)sm[c] : 0;
@@ -483,7 +486,7 @@ overlap_u8_kernel(const int8_t *__restrict__ summary, const int64_t *__restrict_
     };
     int q = threadIdx.x;
     for (; q + (int)blockDim.x < nvec; q += 2 * blockDim.x) {
-        const uint4 x0 = __ldcs(g16 + q), x1 = __ldcs(g16 + q + blockDim.x);          // streamed once
+        const uint4 x0 = __ldcs(g16 + q), x1 = __ldcs(g16 + q + blockDim.x);          // streamed once (four in flight measured slower here: 0.100 -> 0.114 ms)
         add_group(x0, q);
         add_group(x1, q + blockDim.x);
     }
