@@ -172,3 +172,27 @@ def test_eval_collate_matches_the_host_batch_builder(tmp_path, u8):
     assert b"VSUM_PACK_PINNED" in L.vsum_last_error()
     bad = np.asarray([99], np.int32)
     assert L.vsum_pack_eval_collate(ds._h, bad.ctypes.data, 1, None, 0, C.byref(lay)) != 0
+
+
+def test_eval_collate_edge_cases(tmp_path):
+    """Empty batch, a one-video batch and a pack without user summaries."""
+    import ctypes as C
+    vids = _videos((33, 300), first=950)
+    for v in vids:
+        del v["user_summary"], v["user_scores"]
+    path = str(tmp_path / "d.vspack")
+    write_pack(path, vids)
+    ds = PackedDataset(path, split="val")
+    L = _cabi.load()
+    lay = _cabi.EvalBatchLayout()
+    _cabi.check(L.vsum_pack_eval_collate(ds._h, None, 0, None, 0, C.byref(lay)), "empty")
+    assert (lay.B, lay.T, lay.total_shots, lay.total_users, lay.n_launches) == (0, 0, 0, 0, 0)
+    raw = np.asarray([1], np.int32)
+    _cabi.check(L.vsum_pack_eval_collate(ds._h, raw.ctypes.data, 1, None, 0, C.byref(lay)), "one")
+    blob = np.zeros(int(lay.blob_bytes), np.uint8)
+    _cabi.check(L.vsum_pack_eval_collate(ds._h, raw.ctypes.data, 1, blob.ctypes.data, blob.nbytes, C.byref(lay)), "one")
+    assert (lay.B, lay.T, lay.total_users, lay.us_elems, lay.n_launches) == (1, 300, 0, 0, 1)
+    assert np.frombuffer(blob, np.int32, 2, int(lay.off_cu_steps)).tolist() == [0, 300]
+    assert np.array_equal(np.frombuffer(blob, np.int32, 300, int(lay.off_picks)), vids[1]["picks"])
+    small = np.zeros(16, np.uint8)                                     # a blob that is too small is refused
+    assert L.vsum_pack_eval_collate(ds._h, raw.ctypes.data, 1, small.ctypes.data, small.nbytes, C.byref(lay)) != 0
