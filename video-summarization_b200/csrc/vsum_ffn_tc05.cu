@@ -103,7 +103,7 @@ ffn_tc05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     auto fetch_tile = [&](uint32_t n) -> int64_t {
         const int slot = n % SCHED_RING;
         tc::mbar_wait(sched_empty + slot, ((n / SCHED_RING) & 1) ^ 1);
-        const int64_t t = atomicAdd(p.sched, 1);
+        const int64_t t = n == 0 ? (int64_t)blockIdx.x : (int64_t)gridDim.x + atomicAdd(p.sched, 1);   // first tile: the static one, no atomic round trip
         sched_tile[slot] = t < p.m_tiles ? (int32_t)t : -1;
         tc::mbar_arrive(sched_full + slot);
         return t < p.m_tiles ? t : -1;
@@ -120,9 +120,9 @@ ffn_tc05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             };
             for (; t_next >= 0; ++tl) {
                 const int64_t t = t_next;
-                t_next = fetch_tile(nf++);                // one tile ahead (the early X load below needs it)
                 if (!x_issued) { tc::mbar_wait(x_free, (tl & 1) ^ 1); load_x(t); }
                 x_issued = false;
+                t_next = fetch_tile(nf++);                // one tile ahead (the early X load below needs it), after this tile's X is on its way
                 const bool has_next = t_next >= 0;
                 auto stage_w1 = [&](int j, int hf) {      // k-blocks 2 hf, 2 hf + 1 of W1 chunk j
                     const int s = it % NST;

@@ -195,7 +195,8 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto fetch_tile = [&](uint32_t n) -> int64_t {         // producer: take the next tile and publish it as the CTA's n-th
         const int slot = n % SCHED_RING;
         tc::mbar_wait(sched_empty + slot, ((n / SCHED_RING) & 1) ^ 1);
-        const int64_t t = atomicAdd(counter, 1);
+        // the CTA's first tile is its static one (no atomic round trip before the first loads), the rest come from the counter
+        const int64_t t = n == 0 ? (int64_t)blockIdx.x : (int64_t)gridDim.x + atomicAdd(counter, 1);
         sched_tile[slot] = t < total ? (int32_t)t : -1;
         tc::mbar_arrive(sched_full + slot);
         return t < total ? t : -1;
@@ -212,7 +213,6 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int64_t t_next = fetch_tile(nf++);
             while (t_next >= 0) {
                 const int64_t t = t_next;
-                t_next = fetch_tile(nf++);                  // one tile ahead: the consumers find it in the ring, the L2 prefetch below uses it
                 const int64_t m_blk = WRES ? t : t / p.n_tiles;
                 const int n_blk = WRES ? (int)blockIdx.y : (int)(t % p.n_tiles);
                 for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
@@ -222,6 +222,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tc::mbar_arrive_expect_tx(full + s, WRES ? A_STAGE : A_STAGE + B_STAGE);
                     tc::tma_load_2d(a_stage(s), &tmA, full + s, kb * KELTS, (int)(m_blk * BM));
                     if (!WRES) tc::tma_load_2d(b_stage(s), &tmB, full + s, kb * KELTS, n_blk * BN);
+                    if (kb == 0) t_next = fetch_tile(nf++);   // one tile ahead, after this tile's first loads are on their way: the consumers find it in the ring, the L2 prefetch below uses it
                     // Weight-stationary variant (K = 256): the activation ring holds exactly one tile, so a tile's loads are
                     // issued one tile period ahead at best.  Pull the rows of this CTA's NEXT tile into L2 now (one of the
                     // column-block CTAs walking the same rows does it): QKV GEMM -4 %, fc1 -2.5 % on the same box.  Not for
