@@ -336,6 +336,9 @@ extern "C" int vsum_pack_h2d(vsum_pack_t p, const void *blob_host, const vsum_ev
     for (int k = 0; k < lay->B; ++k) {
         VSUM_REQUIRE(vid[k] >= 0 && (uint32_t)vid[k] < p->hdr->n_videos, VSUM_EINVAL, "vsum_pack_h2d: corrupt blob (video %d)", vid[k]);
         const IndexEntry &e = p->index[vid[k]];
+        // the blob must be the one vsum_pack_eval_collate wrote for this pack: row and element offsets advance by this video's sizes
+        VSUM_REQUIRE(cu[k + 1] - cu[k] == e.n_steps && (!user_summary_dev || uso[k + 1] - uso[k] == (int64_t)e.n_users * e.n_frames), VSUM_EINVAL,
+                     "vsum_pack_h2d: blob and pack disagree on video %d", vid[k]);
         if (features_dev)
             VSUM_CUDA_OK(cudaMemcpyAsync((uint8_t *)features_dev + (uint64_t)cu[k] * row, p->base + e.off[VSUM_PACK_FEATURES],
                                          (uint64_t)e.n_steps * row, cudaMemcpyHostToDevice, s));
