@@ -92,6 +92,11 @@ VSUM_API int vsum_scorer_create(vsum_scorer_t *out, const vsum_scorer_config *cf
 VSUM_API int vsum_scorer_destroy(vsum_scorer_t h);
 /* Copies (and for the bf16 path converts/packs) the weights into handle-owned device memory. */
 VSUM_API int vsum_scorer_load_weights(vsum_scorer_t h, const vsum_scorer_weights *w_host, void *stream);
+/* The same with flags.  VSUM_WEIGHTS_TRAIN_ONLY: refresh only what the training entry points read (fp32 copies and their
+ * transposes) -- the per-step refresh after optimizer.step() (src/train.py:127); the bf16 inference path then refuses to
+ * run until a full vsum_scorer_load_weights. */
+#define VSUM_WEIGHTS_TRAIN_ONLY 1
+VSUM_API int vsum_scorer_load_weights_ex(vsum_scorer_t h, const vsum_scorer_weights *w_host, int32_t flags, void *stream);
 /* Bytes of scratch vsum_scorer_forward needs for T packed frames in B videos. */
 VSUM_API size_t vsum_scorer_workspace_bytes(vsum_scorer_t h, int64_t T, int32_t B, int32_t mode);
 /* features [T,in_features] fp32 (bf16 with VSUM_MODE_BF16_FEATURES), cu_seqlens int32[B+1].  Key masking follows simnet.py:156-157:

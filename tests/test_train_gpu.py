@@ -267,3 +267,38 @@ def test_data_parallel_wrapper_single_rank_equals_plain_step():
         torch.testing.assert_close(p.grad, want[k], rtol=2e-4, atol=1e-7 + 2e-5 * float(want[k].abs().max()))
     ddp.detach()
     assert model._dp is None
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_optimizer_updates_reach_the_kernels(fused):
+    """`torch.optim.Adam(fused=True)` updates the parameters without bumping their version counters: the differentiable
+    forward must refresh the kernels' copy of the weights every step regardless (a stale copy trains on the initial weights
+    for ever: constant loss), and an inference call after training must see the trained weights."""
+    from vsum_b200.model import SimNet
+    from vsum_b200.utils import mse_with_mask_loss
+    torch.manual_seed(0)
+    model = SimNet(num_heads=4, d_model=256, num_layers=2, sparsity=0., dropout=0.0).cuda().train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=fused)
+    T = 400
+    g = torch.Generator(device="cuda").manual_seed(5)
+    feats = torch.rand((T, 1024), device="cuda", generator=g)
+    tgt = torch.rand((1, T), device="cuda", generator=g)
+    cu = torch.tensor([0, 150, 400], dtype=torch.int32, device="cuda")
+    nopad = torch.zeros((1, T), dtype=torch.bool, device="cuda")
+    with torch.no_grad():
+        before, _ = model.forward_packed(feats, cu, [150, 250])
+        before = before.clone()
+    losses = []
+    for _ in range(4):
+        opt.zero_grad(set_to_none=True)
+        out, _ = model.forward_packed_train(feats, cu, [150, 250])
+        loss = mse_with_mask_loss(out.view(1, T, 1), tgt, nopad)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert len(set(losses)) == 4, losses                      # every step saw the previous step's update
+    with torch.no_grad():
+        after, _ = model.forward_packed(feats, cu, [150, 250])
+    assert not torch.equal(before, after)                      # inference after training runs on the trained weights
+    want, _ = model.forward_packed_train(feats, cu, [150, 250])
+    torch.testing.assert_close(after, want.detach(), rtol=2e-2, atol=2e-2)

@@ -28,6 +28,8 @@ struct vsum_scorer {
     size_t h_embed = 0;            // bf16 copy of embed_w in the bf16 blob (VSUM_MODE_BF16_FEATURES)
     LayerOffsets L[VSUM_MAX_LAYERS];
     bool loaded = false;
+    bool bf16_valid = false;       // the bf16 inference copies match w32 (false after a VSUM_WEIGHTS_TRAIN_ONLY refresh)
+    const float *pos_src = nullptr;   // caller's table the handle's copy was taken from
     bool tc05_shape = false;
     int train_mode = 0;            // 0: fp32 SIMT linears; 1: tf32 tcgen05 linears (forward, dgrad, wgrad)
     float *zeros = nullptr;        // zero bias for the dgrad GEMMs
@@ -96,29 +98,68 @@ extern "C" int vsum_scorer_destroy(vsum_scorer_t h) {
     return VSUM_OK;
 }
 
-extern "C" int vsum_scorer_load_weights(vsum_scorer_t h, const vsum_scorer_weights *w, void *stream) {
+namespace {
+// One launch copies a group of parameter tensors into the handle's fp32 blob (a training step refreshes 69 tensors: one
+// cudaMemcpyAsync each made the weight refresh the largest block of launches of the launch-bound finetune step).
+struct GatherArgs { const float *src[20]; float *dst[20]; int n[20]; int count; };
+__global__ void __launch_bounds__(256) gather_copy_kernel(const GatherArgs a) {
+    const int i = blockIdx.y;
+    if (i >= a.count) return;
+    const float *__restrict__ src = a.src[i];
+    float *__restrict__ dst = a.dst[i];
+    const int n = a.n[i], stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+        const int n4 = n >> 2;
+        for (int k = t0; k < n4; k += stride) reinterpret_cast<float4 *>(dst)[k] = __ldg(reinterpret_cast<const float4 *>(src) + k);
+        for (int k = 4 * n4 + t0; k < n; k += stride) dst[k] = __ldg(src + k);
+    } else {
+        for (int k = t0; k < n; k += stride) dst[k] = __ldg(src + k);
+    }
+}
+struct Gather {
+    GatherArgs a{};
+    int add(const float *src, float *dst, size_t n, const char *what) {
+        VSUM_REQUIRE(src != nullptr, VSUM_EINVAL, "vsum_scorer_load_weights: null tensor %s", what);
+        VSUM_REQUIRE(a.count < 20 && n < ((size_t)1 << 31), VSUM_EINVAL, "vsum_scorer_load_weights: gather group overflow");
+        a.src[a.count] = src; a.dst[a.count] = dst; a.n[a.count] = (int)n; ++a.count;
+        return VSUM_OK;
+    }
+    int run(cudaStream_t s) {
+        if (a.count == 0) return VSUM_OK;
+        gather_copy_kernel<<<dim3(32, (unsigned)a.count), 256, 0, s>>>(a);
+        VSUM_LAUNCH_OK("gather_copy_kernel");
+        a.count = 0;
+        return VSUM_OK;
+    }
+};
+}  // namespace
+
+extern "C" int vsum_scorer_load_weights_ex(vsum_scorer_t h, const vsum_scorer_weights *w, int32_t flags, void *stream) {
     VSUM_REQUIRE(h && w, VSUM_EINVAL, "vsum_scorer_load_weights: null argument");
+    VSUM_REQUIRE((flags & ~VSUM_WEIGHTS_TRAIN_ONLY) == 0, VSUM_EINVAL, "vsum_scorer_load_weights_ex: unknown flags %d", flags);
+    const bool train_only = (flags & VSUM_WEIGHTS_TRAIN_ONLY) != 0;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t d = h->cfg.d_model, ff = h->cfg.d_ff, in = h->cfg.in_features, C = h->cfg.num_classes;
-#define CP(dst_off, src, n)                                                                              \
-    do {                                                                                                 \
-        VSUM_REQUIRE((src) != nullptr, VSUM_EINVAL, "vsum_scorer_load_weights: null tensor " #src);      \
-        VSUM_CUDA_OK(cudaMemcpyAsync(h->w32 + (dst_off), (src), (n) * sizeof(float),                     \
-                                     cudaMemcpyDeviceToDevice, s));                                      \
-    } while (0)
+    int rc;
+    Gather g;
+#define CP(dst_off, src, n) do { if ((rc = g.add((src), h->w32 + (dst_off), (n), #src))) return rc; } while (0)
     CP(h->embed_w, w->embed_w, d * in); CP(h->embed_b, w->embed_b, d);
     CP(h->final_w, w->final_w, C * d); CP(h->final_b, w->final_b, C);
+    if ((rc = g.run(s))) return rc;
     if (h->cfg.use_pos) {
         VSUM_REQUIRE(w->pos_table && w->pos_rows > 0, VSUM_EINVAL, "vsum_scorer_load_weights: use_pos needs pos_table");
+        const bool same_table = train_only && h->pos_src == w->pos_table && w->pos_rows == h->pos_rows;   // a training step does not touch the table
         if (w->pos_rows != h->pos_rows) {
             cudaFree(h->pos_table); h->pos_table = nullptr; h->pos_rows = 0;
             VSUM_CUDA_OK(cudaMalloc(&h->pos_table, (size_t)w->pos_rows * d * sizeof(float)));
             h->pos_rows = w->pos_rows;
         }
-        VSUM_CUDA_OK(cudaMemcpyAsync(h->pos_table, w->pos_table, (size_t)w->pos_rows * d * sizeof(float),
-                                     cudaMemcpyDeviceToDevice, s));
+        if (!same_table)
+            VSUM_CUDA_OK(cudaMemcpyAsync(h->pos_table, w->pos_table, (size_t)w->pos_rows * d * sizeof(float),
+                                         cudaMemcpyDeviceToDevice, s));
+        h->pos_src = w->pos_table;
     }
-    if (int rc = launch_f32_to_bf16(h->w32 + h->embed_w, h->w16 + h->h_embed, d * in, s)) return rc;
+    if (!train_only && (rc = launch_f32_to_bf16(h->w32 + h->embed_w, h->w16 + h->h_embed, d * in, s))) return rc;
     for (int l = 0; l < h->cfg.num_layers; ++l) {
         const vsum_layer_weights &lw = w->layers[l];
         const LayerOffsets &o = h->L[l];
@@ -129,17 +170,19 @@ extern "C" int vsum_scorer_load_weights(vsum_scorer_t h, const vsum_scorer_weigh
         CP(o.fc1w, lw.fc1_w, ff * d); CP(o.fc1b, lw.fc1_b, ff);
         CP(o.fc2w, lw.fc2_w, d * ff); CP(o.fc2b, lw.fc2_b, d);
         CP(o.ln2g, lw.ln2_g, d); CP(o.ln2b, lw.ln2_b, d);
-        int rc;
-        // bf16 inference copy of [Wq; Wk; Wv]: the softmax scale d_model^-0.5 (simnet.py:126) and log2(e) are folded into the q
-        // rows and the q bias, so that a score Q K^T already is the base-2 exponent the attention kernel needs
-        const float qs = kQPrescale / sqrtf((float)d);
-        if ((rc = launch_scale_convert(h->w32 + o.wqkv, h->w16 + o.h_wqkv, nullptr, d * d, qs, s))) return rc;
-        if ((rc = launch_f32_to_bf16(h->w32 + o.wqkv + d * d, h->w16 + o.h_wqkv + d * d, 2 * d * d, s))) return rc;
-        if ((rc = launch_scale_convert(h->w32 + o.bqkv, nullptr, h->w32 + o.bqkv_s, d, qs, s))) return rc;
-        if ((rc = launch_scale_convert(h->w32 + o.bqkv + d, nullptr, h->w32 + o.bqkv_s + d, 2 * d, 1.0f, s))) return rc;
-        if ((rc = launch_f32_to_bf16(h->w32 + o.wo, h->w16 + o.h_wo, d * d, s))) return rc;
-        if ((rc = launch_f32_to_bf16(h->w32 + o.fc1w, h->w16 + o.h_fc1, ff * d, s))) return rc;
-        if ((rc = launch_f32_to_bf16(h->w32 + o.fc2w, h->w16 + o.h_fc2, d * ff, s))) return rc;
+        if ((rc = g.run(s))) return rc;
+        if (!train_only) {
+            // bf16 inference copy of [Wq; Wk; Wv]: the softmax scale d_model^-0.5 (simnet.py:126) and log2(e) are folded into the q
+            // rows and the q bias, so that a score Q K^T already is the base-2 exponent the attention kernel needs
+            const float qs = kQPrescale / sqrtf((float)d);
+            if ((rc = launch_scale_convert(h->w32 + o.wqkv, h->w16 + o.h_wqkv, nullptr, d * d, qs, s))) return rc;
+            if ((rc = launch_f32_to_bf16(h->w32 + o.wqkv + d * d, h->w16 + o.h_wqkv + d * d, 2 * d * d, s))) return rc;
+            if ((rc = launch_scale_convert(h->w32 + o.bqkv, nullptr, h->w32 + o.bqkv_s, d, qs, s))) return rc;
+            if ((rc = launch_scale_convert(h->w32 + o.bqkv + d, nullptr, h->w32 + o.bqkv_s + d, 2 * d, 1.0f, s))) return rc;
+            if ((rc = launch_f32_to_bf16(h->w32 + o.wo, h->w16 + o.h_wo, d * d, s))) return rc;
+            if ((rc = launch_f32_to_bf16(h->w32 + o.fc1w, h->w16 + o.h_fc1, ff * d, s))) return rc;
+            if ((rc = launch_f32_to_bf16(h->w32 + o.fc2w, h->w16 + o.h_fc2, d * ff, s))) return rc;
+        }
         // [out,in] -> [in,out] copies: the dgrad GEMMs dX = dY W run as dY (W^T)^T on the K-major kernel
         if ((rc = launch_transpose_f32(h->w32 + o.wqkv, h->w32 + o.t_wqkv, (int)(3 * d), (int)d, s))) return rc;
         if ((rc = launch_transpose_f32(h->w32 + o.wo, h->w32 + o.t_wo, (int)d, (int)d, s))) return rc;
@@ -148,7 +191,12 @@ extern "C" int vsum_scorer_load_weights(vsum_scorer_t h, const vsum_scorer_weigh
     }
 #undef CP
     h->loaded = true;
+    h->bf16_valid = !train_only;
     return VSUM_OK;
+}
+
+extern "C" int vsum_scorer_load_weights(vsum_scorer_t h, const vsum_scorer_weights *w, void *stream) {
+    return vsum_scorer_load_weights_ex(h, w, 0, stream);
 }
 
 namespace {
@@ -220,6 +268,8 @@ static int forward_bf16(vsum_scorer_t h, const void *x, bool x_is_bf16, const in
                  "the sm_100a tcgen05 scorer is built for d_model=256, heads=4, d_ff=1024, num_classes=1 "
                  "(got d_model=%d heads=%d d_ff=%d classes=%d); use VSUM_MODE_FP32",
                  c.d_model, c.num_heads, c.d_ff, c.num_classes);
+    VSUM_REQUIRE(h->bf16_valid, VSUM_EINVAL, "vsum_scorer_forward: the weights were last refreshed with VSUM_WEIGHTS_TRAIN_ONLY; "
+                 "call vsum_scorer_load_weights before the bf16 inference path");
     const int max_tiles = max_attn_tiles(T, B);
     Ws16 w;
     carve16(c, T, max_tiles, ws, w);

@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("VSUM_LIB", os.path.join(_HERE, "libvsum_b200.so"))   
 
 VSUM_MAX_LAYERS = 16
 MODE_FP32, MODE_BF16, MODE_BF16_FEATURES = 0, 1, 2
+WEIGHTS_TRAIN_ONLY = 1
 FSCORE_AVG, FSCORE_MAX = 0, 1
 USER_SUMMARY_F32, USER_SUMMARY_U8 = 0, 1
 FEATURES_F32, FEATURES_BF16 = 0, 1
@@ -21,7 +22,7 @@ FEATURES_F32, FEATURES_BF16 = 0, 1
 # every symbol include/vsum_b200.h declares (checked by tests/test_cabi_symbols.py)
 EXPORTS = (
     "vsum_abi_version", "vsum_last_error", "vsum_launch_count", "vsum_set_sm_partition",
-    "vsum_scorer_create", "vsum_scorer_destroy", "vsum_scorer_load_weights",
+    "vsum_scorer_create", "vsum_scorer_destroy", "vsum_scorer_load_weights", "vsum_scorer_load_weights_ex",
     "vsum_scorer_workspace_bytes", "vsum_scorer_forward",
     "vsum_shot_mean", "vsum_knapsack_class_width", "vsum_knapsack_scratch_words", "vsum_knapsack", "vsum_summary_fscore",
     "vsum_scorer_set_train_mode", "vsum_scorer_tape_bytes", "vsum_scorer_train_workspace_bytes", "vsum_scorer_forward_train",
@@ -115,6 +116,7 @@ def load():
     L.vsum_scorer_create.argtypes = [C.POINTER(vp), C.POINTER(ScorerConfig)]
     L.vsum_scorer_destroy.argtypes = [vp]
     L.vsum_scorer_load_weights.argtypes = [vp, C.POINTER(ScorerWeights), vp]
+    L.vsum_scorer_load_weights_ex.argtypes = [vp, C.POINTER(ScorerWeights), i32, vp]
     L.vsum_scorer_workspace_bytes.restype = C.c_size_t
     L.vsum_scorer_workspace_bytes.argtypes = [vp, i64, i32, i32]
     L.vsum_scorer_forward.argtypes = [vp, vp, vp, i32, i64, i32, i32, i32, vp, vp, vp, C.c_size_t, vp]

@@ -103,7 +103,7 @@ class _ScorerTrainFn(torch.autograd.Function):
         L = _cabi.load()
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            model._sync_weights(max_len, dev, stream)
+            model._sync_weights(max_len, dev, stream, train_only=True, force=True)   # every step: see _sync_weights
             h = model._handle
             _cabi.check(L.vsum_scorer_set_train_mode(h, model._train_mode()), "vsum_scorer_set_train_mode")
             tape = torch.empty(L.vsum_scorer_tape_bytes(h, T) + 1024, dtype=torch.uint8, device=dev)
@@ -157,7 +157,7 @@ class _ScorerTrainFn(torch.autograd.Function):
         g.pre_zeroed = 1
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            model._sync_weights(max_len, dev, stream)          # the optimiser may not have stepped yet: no-op
+            model._sync_weights(max_len, dev, stream, train_only=True)   # the optimiser may not have stepped yet: no-op
             _cabi.check(L.vsum_scorer_set_train_mode(model._handle, model._train_mode()), "vsum_scorer_set_train_mode")
             ws = model._workspace_for(L.vsum_scorer_train_workspace_bytes(model._handle, T, B), dev)
             wp = _al(ws)
@@ -227,6 +227,7 @@ class SimNet(nn.Module):
         self._handle = None
         self._dp = None                      # sharding.DataParallel attaches itself here
         self._weights_key = None
+        self._weights_key_train = None
         self._table: Optional[Tensor] = None
         self._workspace: Optional[Tensor] = None
 
@@ -262,15 +263,25 @@ class SimNet(nn.Module):
         if self._table is None or self._table.shape[0] < rows_needed or self._table.device != device:
             rows = 1 << (rows_needed - 1).bit_length()
             self._table = sinusoid_table(rows, self.d_model).to(device)
-            self._weights_key = None
+            self._weights_key = self._weights_key_train = None
         return self._table
 
-    def _sync_weights(self, max_len: int, device, stream: int):
+    def mark_weights_dirty(self):
+        """Force the next forward to hand the parameters to the kernels again.  Inference calls detect updates through the
+        tensors' version counters; an update that does not bump them (a fused optimizer, a CUDA-graph replay, writes through
+        `.data`) outside the differentiable forward -- which always refreshes -- has to be announced here."""
+        self._weights_key = self._weights_key_train = None
+
+    def _sync_weights(self, max_len: int, device, stream: int, train_only: bool = False, force: bool = False):
+        """Hand the current parameter values to the handle.  `train_only`: the per-step refresh of a training loop -- fp32
+        copies and transposes only (VSUM_WEIGHTS_TRAIN_ONLY); the bf16 inference copies are rebuilt by the next inference
+        call.  `force`: do not trust the version counters (the differentiable forward: `torch.optim.Adam(fused=True)` updates
+        the parameters without bumping them, and a stale copy would silently train on the old weights)."""
         params = list(self.parameters())
         table = self._table_for(max_len, device) if self.use_pos else None
         key = (tuple((p.data_ptr(), p._version) for p in params),
                None if table is None else (table.data_ptr(), table.shape[0]))
-        if key == self._weights_key:
+        if not force and (key == self._weights_key or (train_only and key == self._weights_key_train)):
             return
         for p in params:
             if p.device != device or p.dtype != torch.float32 or not p.is_contiguous():
@@ -292,9 +303,11 @@ class SimNet(nn.Module):
             lw.fc1_w, lw.fc1_b = blk.mlp.fc1.weight.data_ptr(), blk.mlp.fc1.bias.data_ptr()
             lw.fc2_w, lw.fc2_b = blk.mlp.fc2.weight.data_ptr(), blk.mlp.fc2.bias.data_ptr()
             lw.ln2_g, lw.ln2_b = blk.norm2.weight.data_ptr(), blk.norm2.bias.data_ptr()
-        _cabi.check(_cabi.load().vsum_scorer_load_weights(self._ensure_handle(), C.byref(w), C.c_void_p(stream)),
-                    "vsum_scorer_load_weights")
-        self._weights_key = key
+        _cabi.check(_cabi.load().vsum_scorer_load_weights_ex(self._ensure_handle(), C.byref(w),
+                                                             _cabi.WEIGHTS_TRAIN_ONLY if train_only else 0, C.c_void_p(stream)),
+                    "vsum_scorer_load_weights_ex")
+        self._weights_key_train = key
+        self._weights_key = None if train_only else key
 
     def _workspace_for(self, nbytes: int, device) -> Tensor:
         ws = self._workspace
