@@ -382,6 +382,7 @@ def train_records(world, rank, dev, steps=20, warmup=5):
         if world > 1 and cfg == "finetune":
             # equality with the single-process step: dropout off, DP gradient vs rank 0's gradient on the concatenated batch
             model.eval()
+            model.train_precision = "fp32"      # the check is about the data-parallel logic: fp32 SIMT kernels, where scaling before / after the backward commutes up to rounding
             opt.zero_grad(set_to_none=True)
             o, _ = model.forward_packed_train(feats, cu, lens)
             ddp.loss(o.view(1, T, 1), tgt, nopad, batch=bs, nmax=max(lens)).backward()
@@ -402,7 +403,7 @@ def train_records(world, rank, dev, steps=20, warmup=5):
                 err[0] = (got - want).abs().max() / want.abs().max()
             dist.broadcast(err, 0)
             rec["dp_equals_single_process"] = {"max_abs_err_over_max_abs_grad": float(err), "ok": bool(float(err) < 2e-4),
-                                               "what": "all-reduced gradient of the sharded batch vs rank 0's gradient of the concatenated batch (dropout off)"}
+                                               "what": "all-reduced gradient of the sharded batch vs rank 0's gradient of the concatenated batch (dropout off, fp32 kernels)"}
         ddp.detach()
         out[cfg] = rec
         del model, opt, ddp
