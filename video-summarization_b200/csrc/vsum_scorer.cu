@@ -101,13 +101,35 @@ extern "C" int vsum_scorer_destroy(vsum_scorer_t h) {
 namespace {
 // One launch copies a group of parameter tensors into the handle's fp32 blob (a training step refreshes 69 tensors: one
 // cudaMemcpyAsync each made the weight refresh the largest block of launches of the launch-bound finetune step).
-struct GatherArgs { const float *src[20]; float *dst[20]; int n[20]; int count; };
+struct GatherArgs { const float *src[20]; float *dst[20]; float *tdst[20]; int n[20]; int cols[20]; int tstride[20]; int count; };
 __global__ void __launch_bounds__(256) gather_copy_kernel(const GatherArgs a) {
+    __shared__ float tile[32][33];
     const int i = blockIdx.y;
     if (i >= a.count) return;
     const float *__restrict__ src = a.src[i];
     float *__restrict__ dst = a.dst[i];
-    const int n = a.n[i], stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = a.n[i];
+    if (a.tdst[i]) {   // weight matrix [rows, cols] (both multiples of 32): straight copy + [cols, rows] transpose for the dgrad GEMMs
+        float *__restrict__ tdst = a.tdst[i];
+        const int cols = a.cols[i], rows = n / cols, tc = cols >> 5, n_tiles = (rows >> 5) * tc, ts = a.tstride[i];
+        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8 threads
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int r0 = (t / tc) << 5, c0 = (t % tc) << 5;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r = r0 + ty + 8 * k;
+                const float v = __ldg(src + (size_t)r * cols + c0 + tx);
+                dst[(size_t)r * cols + c0 + tx] = v;
+                tile[ty + 8 * k][tx] = v;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tdst[(size_t)(c0 + ty + 8 * k) * ts + r0 + tx] = tile[tx][ty + 8 * k];
+            __syncthreads();
+        }
+        return;
+    }
+    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
     if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
         const int n4 = n >> 2;
         for (int k = t0; k < n4; k += stride) reinterpret_cast<float4 *>(dst)[k] = __ldg(reinterpret_cast<const float4 *>(src) + k);
@@ -118,10 +140,11 @@ __global__ void __launch_bounds__(256) gather_copy_kernel(const GatherArgs a) {
 }
 struct Gather {
     GatherArgs a{};
-    int add(const float *src, float *dst, size_t n, const char *what) {
+    // tdst != nullptr: also write the [cols, n / cols] transpose there (rows and cols must be multiples of 32, else tdst is ignored by the caller)
+    int add(const float *src, float *dst, size_t n, const char *what, float *tdst = nullptr, int cols = 0, int tstride = 0) {
         VSUM_REQUIRE(src != nullptr, VSUM_EINVAL, "vsum_scorer_load_weights: null tensor %s", what);
         VSUM_REQUIRE(a.count < 20 && n < ((size_t)1 << 31), VSUM_EINVAL, "vsum_scorer_load_weights: gather group overflow");
-        a.src[a.count] = src; a.dst[a.count] = dst; a.n[a.count] = (int)n; ++a.count;
+        a.src[a.count] = src; a.dst[a.count] = dst; a.tdst[a.count] = tdst; a.n[a.count] = (int)n; a.cols[a.count] = cols; a.tstride[a.count] = tstride; ++a.count;
         return VSUM_OK;
     }
     int run(cudaStream_t s) {
@@ -163,13 +186,20 @@ extern "C" int vsum_scorer_load_weights_ex(vsum_scorer_t h, const vsum_scorer_we
     for (int l = 0; l < h->cfg.num_layers; ++l) {
         const vsum_layer_weights &lw = w->layers[l];
         const LayerOffsets &o = h->L[l];
-        CP(o.wqkv, lw.q_w, d * d); CP(o.wqkv + d * d, lw.k_w, d * d); CP(o.wqkv + 2 * d * d, lw.v_w, d * d);
+        // weight matrices go out straight and transposed ([out,in] -> [in,out]: the dgrad GEMMs dX = dY W run as dY (W^T)^T on the
+        // K-major kernel) in the same launch when their sides are multiples of 32
+        const bool fuse_t = d % 32 == 0 && ff % 32 == 0;
+#define CPT(dst_off, src, rows, cols, t_off, tstride) do { if ((rc = g.add((src), h->w32 + (dst_off), (size_t)(rows) * (cols), #src, \
+                                                                           fuse_t ? h->w32 + (t_off) : nullptr, (int)(cols), (int)(tstride)))) return rc; } while (0)
+        CPT(o.wqkv, lw.q_w, d, d, o.t_wqkv, 3 * d); CPT(o.wqkv + d * d, lw.k_w, d, d, o.t_wqkv + d, 3 * d);
+        CPT(o.wqkv + 2 * d * d, lw.v_w, d, d, o.t_wqkv + 2 * d, 3 * d);
         CP(o.bqkv, lw.q_b, d); CP(o.bqkv + d, lw.k_b, d); CP(o.bqkv + 2 * d, lw.v_b, d);
-        CP(o.wo, lw.o_w, d * d); CP(o.bo, lw.o_b, d);
+        CPT(o.wo, lw.o_w, d, d, o.t_wo, d); CP(o.bo, lw.o_b, d);
         CP(o.ln1g, lw.ln1_g, d); CP(o.ln1b, lw.ln1_b, d);
-        CP(o.fc1w, lw.fc1_w, ff * d); CP(o.fc1b, lw.fc1_b, ff);
-        CP(o.fc2w, lw.fc2_w, d * ff); CP(o.fc2b, lw.fc2_b, d);
+        CPT(o.fc1w, lw.fc1_w, ff, d, o.t_fc1, ff); CP(o.fc1b, lw.fc1_b, ff);
+        CPT(o.fc2w, lw.fc2_w, d, ff, o.t_fc2, d); CP(o.fc2b, lw.fc2_b, d);
         CP(o.ln2g, lw.ln2_g, d); CP(o.ln2b, lw.ln2_b, d);
+#undef CPT
         if ((rc = g.run(s))) return rc;
         if (!train_only) {
             // bf16 inference copy of [Wq; Wk; Wv]: the softmax scale d_model^-0.5 (simnet.py:126) and log2(e) are folded into the q
@@ -183,11 +213,12 @@ extern "C" int vsum_scorer_load_weights_ex(vsum_scorer_t h, const vsum_scorer_we
             if ((rc = launch_f32_to_bf16(h->w32 + o.fc1w, h->w16 + o.h_fc1, ff * d, s))) return rc;
             if ((rc = launch_f32_to_bf16(h->w32 + o.fc2w, h->w16 + o.h_fc2, d * ff, s))) return rc;
         }
-        // [out,in] -> [in,out] copies: the dgrad GEMMs dX = dY W run as dY (W^T)^T on the K-major kernel
-        if ((rc = launch_transpose_f32(h->w32 + o.wqkv, h->w32 + o.t_wqkv, (int)(3 * d), (int)d, s))) return rc;
-        if ((rc = launch_transpose_f32(h->w32 + o.wo, h->w32 + o.t_wo, (int)d, (int)d, s))) return rc;
-        if ((rc = launch_transpose_f32(h->w32 + o.fc1w, h->w32 + o.t_fc1, (int)ff, (int)d, s))) return rc;
-        if ((rc = launch_transpose_f32(h->w32 + o.fc2w, h->w32 + o.t_fc2, (int)d, (int)ff, s))) return rc;
+        if (!fuse_t) {
+            if ((rc = launch_transpose_f32(h->w32 + o.wqkv, h->w32 + o.t_wqkv, (int)(3 * d), (int)d, s))) return rc;
+            if ((rc = launch_transpose_f32(h->w32 + o.wo, h->w32 + o.t_wo, (int)d, (int)d, s))) return rc;
+            if ((rc = launch_transpose_f32(h->w32 + o.fc1w, h->w32 + o.t_fc1, (int)ff, (int)d, s))) return rc;
+            if ((rc = launch_transpose_f32(h->w32 + o.fc2w, h->w32 + o.t_fc2, (int)d, (int)ff, s))) return rc;
+        }
     }
 #undef CP
     h->loaded = true;
