@@ -112,10 +112,24 @@ wgrad_tc05_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
     if (warp == 2) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, WG_BN); }
 }
 
-// One pass over dY: db[n] += sum_m dY[m, n] (when db != NULL) and the bf16 copy the wgrad MMAs consume.
+// One launch prepares both wgrad operands.  blockIdx.z == 0: one pass over dY -- db[n] += sum_m dY[m, n] (when db != NULL) and
+// the bf16 copy the wgrad MMAs consume; blockIdx.z == 1: the bf16 copy of X (grid-stride, four elements per thread).
 __global__ void __launch_bounds__(256)
 colsum_convert_kernel(const float *__restrict__ dY, __nv_bfloat16 *__restrict__ dY16, float *__restrict__ db, int64_t M, int N,
-                      int64_t rows_per_block) {
+                      int64_t rows_per_block, const float *__restrict__ X, __nv_bfloat16 *__restrict__ X16, int64_t nx) {
+    if (blockIdx.z == 1) {
+        const int64_t stride = (int64_t)gridDim.x * gridDim.y * 256, t0 = ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 256 + threadIdx.x;
+        const int64_t n4 = nx >> 2;                       // X and X16 are 16-byte aligned (workspace carve) and K is a multiple of 256
+        for (int64_t k = t0; k < n4; k += stride) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(X) + k);
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t *>(&lo); pk.y = *reinterpret_cast<uint32_t *>(&hi);
+            reinterpret_cast<uint2 *>(X16)[k] = pk;
+        }
+        for (int64_t k = 4 * n4 + t0; k < nx; k += stride) X16[k] = __float2bfloat16_rn(X[k]);
+        return;
+    }
     const int n = blockIdx.x * 256 + threadIdx.x;
     if (n >= N) return;
     const int64_t m0 = (int64_t)blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
@@ -159,13 +173,14 @@ int launch_linear_wgrad_tc05(const float *dY, const float *X, float *dW, float *
     if (M == 0) return VSUM_OK;
     int rc;
     VSUM_REQUIRE(dY16 && X16, VSUM_EINVAL, "wgrad_tc05: bf16 scratch buffers are required");
-    {   // dY -> bf16 and its column sums in one pass
+    {   // dY -> bf16 with its column sums, and X -> bf16, in one launch
         const int64_t rpb = ceil_div(M, 512);
-        dim3 g2((unsigned)ceil_div(N, 256), (unsigned)ceil_div(M, rpb));
-        colsum_convert_kernel<<<g2, 256, 0, s>>>(dY, dY16, db, M, N, rpb);
+        const bool x_vec = (((uintptr_t)X | (uintptr_t)X16) & 15) == 0;
+        dim3 g2((unsigned)ceil_div(N, 256), (unsigned)ceil_div(M, rpb), x_vec ? 2 : 1);
+        colsum_convert_kernel<<<g2, 256, 0, s>>>(dY, dY16, db, M, N, rpb, X, X16, M * (int64_t)K);
         VSUM_LAUNCH_OK("colsum_convert_kernel");
+        if (!x_vec && (rc = launch_f32_to_bf16(X, X16, M * K, s))) return rc;
     }
-    if ((rc = launch_f32_to_bf16(X, X16, M * K, s))) return rc;
     return launch_wgrad<true>(dY16, X16, dW, M, N, K, s);
 }
 
