@@ -125,39 +125,32 @@ class _ScorerTrainFn(torch.autograd.Function):
         features, cu_seqlens, B, T, max_len, drop_p, seed = ctx.args
         dev = features.device
         L = _cabi.load()
-        params = list(model._train_params())
         # one flat, zeroed gradient buffer; every .grad is a view of it (sharding.allreduce_gradients reduces it
         # in place) and q|k|v of a layer are adjacent so the fused QKV weight gradient is written in place
-        names = ["embed_w", "embed_b"] + [f"{i}.{f}" for i in range(model.num_layers) for f in _cabi._LAYER_FIELDS] + ["final_w", "final_b"]
-        sizes = dict(zip(names, (p.numel() for p in params)))
-        order = ["embed_w", "embed_b"]
-        for i in range(model.num_layers):
-            first = [f"{i}.{f}" for f in ("q_w", "k_w", "v_w", "q_b", "k_b", "v_b")]
-            order += first + [f"{i}.{f}" for f in _cabi._LAYER_FIELDS if f"{i}.{f}" not in first]
-        order += ["final_w", "final_b"]
+        lay = model._grad_layout()
         dp = getattr(model, "_dp", None)
-        n_grads = sum(sizes.values())
+        n_grads = lay["n_grads"]
         flat = torch.zeros(n_grads + (dp.ext_n if dp is not None else 0), dtype=torch.float32, device=dev)   # + sharding.DataParallel's extras
-        views, off = {}, 0
-        for k in order:
-            views[k] = flat[off:off + sizes[k]]
-            off += sizes[k]
-        grads = [views[k].view_as(p) for k, p in zip(names, params)]
+        grads = [flat[o:o + n].view(shape) for o, n, shape in lay["views"]]
         if d_scores is None:
             d_scores = torch.zeros((T, model.num_classes), dtype=torch.float32, device=dev)
         d_scores = d_scores.contiguous().float()
         d_feats = None if d_feats is None else d_feats.contiguous().float()
         g = _cabi.ScorerGrads()
-        it = iter(grads)
-        g.embed_w, g.embed_b = next(it).data_ptr(), next(it).data_ptr()
+        base = flat.data_ptr()
+        ptrs = [base + 4 * o for o, _, _ in lay["views"]]           # same order as SimNet._train_params
+        g.embed_w, g.embed_b = ptrs[0], ptrs[1]
+        k = 2
         for i in range(model.num_layers):
+            gl = g.layers[i]
             for name in _cabi._LAYER_FIELDS:
-                setattr(g.layers[i], name, next(it).data_ptr())
-        g.final_w, g.final_b = next(it).data_ptr(), next(it).data_ptr()
+                setattr(gl, name, ptrs[k])
+                k += 1
+        g.final_w, g.final_b = ptrs[k], ptrs[k + 1]
         g.pre_zeroed = 1
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            model._sync_weights(max_len, dev, stream, train_only=True)   # the optimiser may not have stepped yet: no-op
+            # (the handle holds the weights of this step's forward: nothing to refresh between forward and backward)
             _cabi.check(L.vsum_scorer_set_train_mode(model._handle, model._train_mode()), "vsum_scorer_set_train_mode")
             ws = model._workspace_for(L.vsum_scorer_train_workspace_bytes(model._handle, T, B), dev)
             wp = _al(ws)
@@ -169,9 +162,7 @@ class _ScorerTrainFn(torch.autograd.Function):
             else:
                 # data-parallel step (sharding.DataParallel): the flat buffer is all-reduced bucket by bucket on the communication
                 # stream while the backward of the earlier layers is still running
-                layer_n = sum(sizes[f"0.{f}"] for f in _cabi._LAYER_FIELDS)
-                embed_n = sizes["embed_w"] + sizes["embed_b"]
-                dp._begin(flat, n_grads, embed_n, layer_n, model.num_layers, T)
+                dp._begin(flat, n_grads, lay["embed_n"], lay["layer_n"], model.num_layers, T)
                 hook = _cabi.GRAD_BUCKET_HOOK(lambda _user, bucket: dp._bucket_ready(int(bucket)))
                 _cabi.check(L.vsum_scorer_backward_hooked(*args, hook, None), "vsum_scorer_backward_hooked")
         return (None, None, None, None, None, None, *grads)
@@ -266,6 +257,44 @@ class SimNet(nn.Module):
             self._weights_key = self._weights_key_train = None
         return self._table
 
+    def _param_list(self):
+        """Parameters in module order, cached (the module tree is fixed after construction; walking it costs ~0.2 ms)."""
+        pl = self.__dict__.get("_params_cache")
+        if pl is None:
+            pl = list(self.parameters())
+            self.__dict__["_params_cache"] = pl
+        return pl
+
+    def _apply(self, fn, *args, **kwargs):
+        """`.to()` / `.cuda()` / `.float()` may replace parameter tensors: drop everything cached about them."""
+        for k in ("_params_cache", "_train_params_cache", "_grad_layout_cache", "_weights_struct"):
+            self.__dict__.pop(k, None)
+        self._weights_key = self._weights_key_train = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def _grad_layout(self):
+        """Offsets of every parameter's gradient inside the flat buffer `_ScorerTrainFn.backward` hands out, in
+        `_train_params` order: [embedding | per layer q_w k_w v_w q_b k_b v_b, then the rest | head]."""
+        lay = self.__dict__.get("_grad_layout_cache")
+        if lay is not None:
+            return lay
+        params = list(self._train_params())
+        names = ["embed_w", "embed_b"] + [f"{i}.{f}" for i in range(self.num_layers) for f in _cabi._LAYER_FIELDS] + ["final_w", "final_b"]
+        sizes = dict(zip(names, (p.numel() for p in params)))
+        order = ["embed_w", "embed_b"]
+        for i in range(self.num_layers):
+            first = [f"{i}.{f}" for f in ("q_w", "k_w", "v_w", "q_b", "k_b", "v_b")]
+            order += first + [f"{i}.{f}" for f in _cabi._LAYER_FIELDS if f"{i}.{f}" not in first]
+        order += ["final_w", "final_b"]
+        offs, off = {}, 0
+        for k in order:
+            offs[k] = off
+            off += sizes[k]
+        lay = dict(n_grads=off, views=[(offs[k], sizes[k], tuple(p.shape)) for k, p in zip(names, params)],
+                   embed_n=sizes["embed_w"] + sizes["embed_b"], layer_n=sum(sizes[f"0.{f}"] for f in _cabi._LAYER_FIELDS))
+        self.__dict__["_grad_layout_cache"] = lay
+        return lay
+
     def mark_weights_dirty(self):
         """Force the next forward to hand the parameters to the kernels again.  Inference calls detect updates through the
         tensors' version counters; an update that does not bump them (a fused optimizer, a CUDA-graph replay, writes through
@@ -277,11 +306,20 @@ class SimNet(nn.Module):
         copies and transposes only (VSUM_WEIGHTS_TRAIN_ONLY); the bf16 inference copies are rebuilt by the next inference
         call.  `force`: do not trust the version counters (the differentiable forward: `torch.optim.Adam(fused=True)` updates
         the parameters without bumping them, and a stale copy would silently train on the old weights)."""
-        params = list(self.parameters())
+        params = self._param_list()
         table = self._table_for(max_len, device) if self.use_pos else None
         key = (tuple((p.data_ptr(), p._version) for p in params),
                None if table is None else (table.data_ptr(), table.shape[0]))
         if not force and (key == self._weights_key or (train_only and key == self._weights_key_train)):
+            return
+        ptr_key = (tuple(k[0] for k in key[0]), key[1], str(device))
+        cached = self.__dict__.get("_weights_struct")
+        if cached is not None and cached[0] == ptr_key:      # same tensors as last time: the filled struct is still right
+            _cabi.check(_cabi.load().vsum_scorer_load_weights_ex(self._ensure_handle(), C.byref(cached[1]),
+                                                                 _cabi.WEIGHTS_TRAIN_ONLY if train_only else 0, C.c_void_p(stream)),
+                        "vsum_scorer_load_weights_ex")
+            self._weights_key_train = key
+            self._weights_key = None if train_only else key
             return
         for p in params:
             if p.device != device or p.dtype != torch.float32 or not p.is_contiguous():
@@ -306,6 +344,7 @@ class SimNet(nn.Module):
         _cabi.check(_cabi.load().vsum_scorer_load_weights_ex(self._ensure_handle(), C.byref(w),
                                                              _cabi.WEIGHTS_TRAIN_ONLY if train_only else 0, C.c_void_p(stream)),
                     "vsum_scorer_load_weights_ex")
+        self.__dict__["_weights_struct"] = (ptr_key, w, table)          # (the table tensor is kept alive with the struct that points at it)
         self._weights_key_train = key
         self._weights_key = None if train_only else key
 
@@ -323,6 +362,14 @@ class SimNet(nn.Module):
 
     def _train_params(self):
         """Parameters in the order _ScorerTrainFn returns their gradients."""
+        tp = self.__dict__.get("_train_params_cache")
+        if tp is not None:
+            return iter(tp)
+        tp = list(self._train_params_walk())
+        self.__dict__["_train_params_cache"] = tp
+        return iter(tp)
+
+    def _train_params_walk(self):
         emb = self.embedding_layer.feature_transform
         yield emb.weight
         yield emb.bias
