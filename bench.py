@@ -424,7 +424,7 @@ def main_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device; the B200 path has no CPU fallback (use --impl reference)")
-    rank_cores = pin_rank_to_cores(local, world)
+    rank_cores = None if args.no_pin else pin_rank_to_cores(local, world)
     if rank_cores:
         torch.set_num_threads(rank_cores)
     torch.cuda.set_device(local)
@@ -434,6 +434,15 @@ def main_b200(args):
             os.environ["NCCL_DEBUG"] = "WARN"                      # no version banner: stdout is the one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
+
+    if args.only_train:
+        rec = train_records(world, rank, dev, steps=50, warmup=10)
+        if rank == 0:
+            print(json.dumps({"train": rec, "host_cores_per_rank": rank_cores, "n_gpus": world}), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     # ---- workload: weak scaling, rank r owns videos [r*V*NB, (r+1)*V*NB) of the global id space: NB distinct batches of V
     # videos; the resident leg (`value`) runs on the first of them
@@ -693,6 +702,8 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--videos", type=int, default=256, help="videos per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pin", action="store_true", help="do not restrict each rank to its slice of the host cores")
+    ap.add_argument("--only-train", action="store_true", help="print only the training-step sub-record (experiments)")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step sub-record (BASELINE configs 3 and 4)")
     ap.add_argument("--e2e-batches", type=int, default=4, help="distinct batches in the end-to-end legs' pack file (reduced when host memory is short)")
     ap.add_argument("--eval-sms", type=int, default=0, help="SMs left to the evaluation stream in pipelined mode (0 = no partition)")

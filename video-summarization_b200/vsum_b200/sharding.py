@@ -219,8 +219,10 @@ class DataParallel:
             if self._bucketed:
                 lo, hi = self._slices[bucket]
                 self._reduce(self._flat[lo:hi])
-            elif bucket == -1:
-                self._reduce(self._flat)
+            elif bucket == -1 and self.world > 1:
+                # launch-bound step: nothing to overlap with -- one all-reduce on the compute stream itself, no events, no
+                # second stream (the host, not the GPU, is what such a step waits for)
+                dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.group)
         except BaseException as e:
             self._error = e
 
@@ -234,11 +236,16 @@ class DataParallel:
             raise _cabi.VsumError("DataParallel.finish: no backward has run since the last step")
         flat, self._flat = self._flat, None
         main = torch.cuda.current_stream(self.device)
-        params = [p for p in self.model.parameters() if p.grad is not None]
+        plist = self.model._param_list() if hasattr(self.model, "_param_list") else list(self.model.parameters())
+        params = [p for p in plist if p.grad is not None]
         st = flat.untyped_storage().data_ptr()
         if not all(p.grad.untyped_storage().data_ptr() == st for p in params):
             raise _cabi.VsumError("DataParallel.finish: a .grad no longer lives in the backward's flat buffer "
                                   "(use optimizer.zero_grad(set_to_none=True) and one backward per step)")
+        if not self._bucketed:                                      # everything already sits on the compute stream
+            _cabi.check(_cabi.load().vsum_dp_finalize(flat.data_ptr(), self._n_grads, flat.data_ptr() + 4 * self._n_grads, self.world,
+                                                      self._loss_out.data_ptr(), main.cuda_stream), "vsum_dp_finalize")
+            return self._loss_out
         with torch.cuda.stream(self._comm):
             self._comm.wait_stream(main)
             for w in self._works:
