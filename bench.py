@@ -561,7 +561,7 @@ def main_b200(args):
         stop()
         h2d.clear()
         n_col = len(loader.collate_ms)
-        steps = max(2 * NB, args.steps)                     # enough steps that the cold start (one exposed copy) weighs little
+        steps = max(4 * NB, args.steps)                     # enough steps that the cold start (one exposed copy) weighs little
         ms = timed(step, steps) / steps                     # cold pipeline at the start, everything drained at the end
         col, iss = loader.collate_ms[n_col:n_col + steps], loader.issue_ms[n_col:n_col + steps]
         stop()
