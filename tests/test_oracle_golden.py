@@ -46,6 +46,11 @@ def test_python_port_matches_golden(eval_golden):
         for k, method in enumerate(("avg", "max")):
             f = ref_port.fscore_video(summary, v.user_summary, method)
             assert bits_equal(np.float64(f), np.float64(eval_golden[f"f_{vid}"][k]))
+            if n <= 400:      # the timing arm's form: builtin sum() counts like evaluation_metrics.py:23-24 -- same bits, ~100x the time
+                assert bits_equal(np.float64(ref_port.fscore_video(summary, v.user_summary, method, builtin_sums=True)), np.float64(f))
+        if n <= 400:          # ... and the multiprocessing worker of bench.py's `fair` CPU figure
+            got = ref_port.pool_eval_video((v.change_points, make_scores(vid, n), v.n_frames, v.picks, v.user_summary, "avg"))
+            assert bits_equal(np.float64(got), np.float64(eval_golden[f"f_{vid}"][0]))
 
 
 def test_pairwise_sum_matches_numpy():
