@@ -251,7 +251,9 @@ def run_gpu_eager(sd, sample):
         ref_port.pool_eval_video((v.change_points, sc, v.n_frames, v.picks, v.user_summary, "avg"))
     dt_ev = time.perf_counter() - t0
     return {"scorer_only_videos_per_s": len(sample) / dt_sc, "with_python_eval_videos_per_s": len(sample) / (dt_sc + dt_ev),
-            "what": "torch fp32 eager scorer on cuda:0 (oracle restatement of simnet.py), one video per forward; evaluation stages pure Python on the host"}
+            "what": "torch fp32 eager scorer on cuda:0 (oracle restatement of simnet.py, without the reference's per-layer "
+                    "attention_weight.detach().cpu() copy of simnet.py:164, i.e. a faster reference), one video per forward; evaluation stages "
+                    "pure Python on the host"}
 
 
 def main_reference(args):
