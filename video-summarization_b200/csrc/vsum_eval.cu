@@ -132,12 +132,14 @@ shot_mean_kernel(const float *__restrict__ scores, const int32_t *__restrict__ c
 // ---------------------------------------------------------------------------------------------
 // One video per CTA.  Thread t owns the capacities w = t + k*THREADS and keeps K[i][w] for them in
 // REGISTERS across shots; shared memory holds a copy of the previous row only so that other threads
-// can read K[i-1][w - wt].  Per shot and capacity that is one 8-byte shared load and, only where the
-// value changed, one 8-byte shared store (two barriers per shot).  Capacities below the shot's
+// can read K[i-1][w - wt].  Per shot and capacity that is one 8-byte shared load and one 8-byte shared
+// store (two barriers per shot; storing only the capacities that changed was measured and is slower:
+// the bookkeeping costs more instructions than the stores it saves).  Capacities below the shot's
 // weight cannot change and are skipped.  take[i][w] = (K[i][w] != K[i-1][w]) -- the reference's own
 // back-track test -- is packed with a warp ballot into a bit matrix in global memory (it stays in
 // L2); words whose capacities are all below the weight are never written and never read, because
 // the back-track (warp 0, 32 rows per probe) only probes rows with wt <= w.
+
 // One shot's update of the capacities a thread owns (cur[k] = K[i][k THREADS + tid]); KLO >= 0: the chunk that contains
 // w_min is known at compile time, KLO < 0: every chunk tests its capacities.  Each warp's ballot word (take bits of 32
 // consecutive capacities) leaves through a predicated store of lane 0 (inline PTX: no divergence bookkeeping).
